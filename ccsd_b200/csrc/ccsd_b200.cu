@@ -1,0 +1,579 @@
+// ccsd_b200.cu -- host side of the C ABI (include/ccsd_b200.h): plan validation, shared-memory and
+// workspace layout, the per-step launch sequences of the PC and S4 samplers.
+//
+// Reference call structure being replaced: ccsd/src/solver.py:961-1003 / 1109-1174 (pc_sampler),
+// :1267-1371 / 1409-1561 (s4_solver).  Launch sequence per PC step with the Langevin corrector:
+//   corrector:  gram(F0) [proj1] xa(SCORE) apply(SCORE) coef update      -> (x1, adj1, F1)
+//   predictor:  gram(F1) [proj1] xa(PRED)  apply(PRED)                   -> (x2, adj2, F2)
+// and per S4 step:  gram [proj1] xa(SCORE) apply(SCORE) coef update(S4 chain).
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "r2_kernels.cuh"
+#include "xa_kernel.cuh"
+#ifndef CCSD_EMU
+#include "tc_gram.cuh"
+#endif
+
+#ifdef CCSD_EMU
+thread_local ccsd_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local float *ccsd_emu_smem = nullptr;
+#endif
+
+using namespace ccsd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#ifdef CCSD_EMU
+static int dev_copy(void *dst, const void *src, size_t bytes, void *) {
+  memcpy(dst, src, bytes);
+  return 0;
+}
+static int dev_check(const char *) { return 0; }
+#else
+static int dev_copy(void *dst, const void *src, size_t bytes, void *stream) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(CCSD_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e));
+  return 0;
+}
+static int dev_check(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CCSD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+#endif
+
+struct ccsd_plan {
+  DevPlan hp;  // host copy; device copy lives at the start of the workspace
+  std::vector<ccsd_objcoef_t> sched;
+  std::vector<unsigned long long> cell_mask;
+  std::vector<int> edge_ij;
+  const float *weights = nullptr;
+  size_t n_weights = 0;
+  // workspace
+  char *ws = nullptr;
+  size_t ws_bytes = 0;
+  DevPlan *dP = nullptr;
+  float *flags = nullptr, *x = nullptr, *adj = nullptr, *r2 = nullptr;
+  float *mx = nullptr, *madj = nullptr, *mr2 = nullptr;
+  float *sx = nullptr, *sadj = nullptr, *sr2 = nullptr;
+  float *H = nullptr, *P0 = nullptr, *P1 = nullptr, *norm_part = nullptr, *coef = nullptr;
+  float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
+  bool bound = false, inited = false;
+  unsigned long long seed = 0;
+  long long sample_offset = 0;
+  size_t xa_smem = 0, apply_smem = 0;
+  int64_t launches = 0;
+  int use_tc = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+static int a4(int v) { return (v + 3) & ~3; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+static int check_mlp(const ccsd_mlp_t &m, size_t nw, const char *name, int small) {
+  if (m.nl < 1 || m.nl > CCSD_MAX_MLP) return fail(CCSD_ERR_UNSUPPORTED, std::string(name) + ": 1..4 linears supported");
+  for (int l = 0; l < m.nl; ++l) {
+    const int din = l == 0 ? m.din : m.dhid, dout = l == m.nl - 1 ? m.dout : m.dhid;
+    const int opad = (dout + 7) / 8 * 8;
+    if (m.w[l] < 0 || (m.w[l] & 3) || (size_t)m.w[l] + (size_t)din * opad > nw || m.b[l] < 0 || (m.b[l] & 3) ||
+        (size_t)m.b[l] + opad > nw)
+      return fail(CCSD_ERR_INVALID, std::string(name) + ": weight offsets out of range / unaligned");
+    if (small && (din > SMALL_MAX || dout > SMALL_MAX))
+      return fail(CCSD_ERR_UNSUPPORTED, std::string(name) + ": layer wider than 32 is not supported on this path");
+  }
+  return 0;
+}
+static int check_gcn(const ccsd_gcn_t &g, size_t nw, const char *name) {
+  const int opad = (g.dout + 7) / 8 * 8;
+  if (g.w < 0 || (g.w & 3) || (size_t)g.w + (size_t)g.din * opad > nw || g.b < 0 || (size_t)g.b + opad > nw)
+    return fail(CCSD_ERR_INVALID, std::string(name) + ": weight offsets out of range / unaligned");
+  return 0;
+}
+
+static int validate(const ccsd_plan_desc_t &d, size_t nw) {
+  if (d.B < 1 || d.N < 2 || d.F < 1) return fail(CCSD_ERR_INVALID, "B, N, F must be positive (N >= 2)");
+  if (d.N > 64) return fail(CCSD_ERR_UNSUPPORTED, "max_node_num > 64 is not supported by the per-graph-tile kernels yet");
+  if (d.sampler != CCSD_SAMPLER_PC && d.sampler != CCSD_SAMPLER_S4) return fail(CCSD_ERR_INVALID, "unknown sampler");
+  if (d.n_lang_steps != 1) return fail(CCSD_ERR_UNSUPPORTED, "Langevin n_steps != 1 is not implemented");
+  if (d.n_diff_steps < 1) return fail(CCSD_ERR_INVALID, "n_diff_steps must be >= 1");
+  const ccsd_netx_t &X = d.netx;
+  if (d.nets & 1) {
+  if (X.nfeat != d.F || X.depth < 1 || X.depth > CCSD_MAX_LAYERS) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkX: depth 1..8, nfeat == F");
+  if (X.fdim != X.nfeat + X.depth * X.nhid) return fail(CCSD_ERR_INVALID, "ScoreNetworkX: fdim mismatch");
+  for (int k = 0; k < X.depth; ++k)
+    if (int r = check_gcn(X.gcn[k], nw, "ScoreNetworkX.layers")) return r;
+  if (int r = check_mlp(X.fin, nw, "ScoreNetworkX.final", 0)) return r;
+  if (X.fin.din != X.fdim || X.fin.dout != d.F) return fail(CCSD_ERR_INVALID, "ScoreNetworkX.final dims mismatch");
+  }
+  const ccsd_neta_t &A = d.neta;
+  if (d.is_cc && (d.E != d.N * (d.N - 1) / 2 || d.K < 1)) return fail(CCSD_ERR_INVALID, "rank-2 dims mismatch");
+  if (d.nets & 2) {
+  if (A.num_layers < 1 || A.num_layers > CCSD_MAX_LAYERS || A.c_init < 1 || A.c_init > CCSD_MAX_CH)
+    return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA: num_layers 1..8, c_init 1..8");
+  int ch = A.c_init, cin = A.c_init, kin = d.F;
+  for (int l = 0; l < A.num_layers; ++l) {
+    const ccsd_attn_layer_t &ly = A.layer[l];
+    if (ly.c_in != cin || ly.conv_in != kin) return fail(CCSD_ERR_INVALID, "ScoreNetworkA: layer chaining mismatch");
+    if (ly.c_in > CCSD_MAX_CH || ly.c_out > CCSD_MAX_CH || ly.c_out < 1) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA: more than 8 channels per layer");
+    if (ly.attn_dim < A.num_heads || A.num_heads < 1) return fail(CCSD_ERR_INVALID, "ScoreNetworkA: attn_dim < num_heads");
+    for (int c = 0; c < ly.c_in; ++c) {
+      if (int r = check_gcn(ly.q[c], nw, "attn.gnn_q")) return r;
+      if (int r = check_gcn(ly.k[c], nw, "attn.gnn_k")) return r;
+      if (int r = check_gcn(ly.v[c], nw, "attn.gnn_v")) return r;
+    }
+    if (int r = check_mlp(ly.mlp, nw, "AttentionLayer.mlp", 0)) return r;
+    if (int r = check_mlp(ly.multi_channel, nw, "AttentionLayer.multi_channel", 0)) return r;
+    if (ly.mlp.din != 2 * ly.c_in || ly.mlp.dout != ly.c_out || ly.multi_channel.din != ly.c_in * ly.conv_out ||
+        ly.multi_channel.dout != ly.conv_out)
+      return fail(CCSD_ERR_INVALID, "AttentionLayer: MLP dims mismatch");
+    ch += ly.c_out; cin = ly.c_out; kin = ly.conv_out;
+  }
+  if (A.is_cc && !d.is_cc) return fail(CCSD_ERR_INVALID, "ScoreNetworkA_CC needs a combinatorial-complex plan (is_cc)");
+  if (A.is_cc) {
+    if (A.num_layers_h < 1 || A.num_layers_h > CCSD_MAX_HODGE_LAYERS)
+      return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA_CC: num_layers_h must be 1 or 2 (the dense H @ rank2 value path of deeper stacks is not implemented)");
+    int hin = A.c_init;
+    for (int l = 0; l < A.num_layers_h; ++l) {
+      const ccsd_hodge_layer_t &h = A.hodge[l];
+      if (h.c_in != hin || h.c_in > CCSD_MAX_CH || h.c_out > CCSD_MAX_CH || h.attn_dim > SMALL_MAX || h.attn_dim < A.num_heads_h || A.num_heads_h < 1)
+        return fail(CCSD_ERR_UNSUPPORTED, "HodgeAdjAttentionLayer: channels <= 8, attn_dim <= 32");
+      if (A.n_proj_rows[l] != h.c_in * 2 * h.attn_dim) return fail(CCSD_ERR_INVALID, "hodge projection rows mismatch");
+      if (int r = check_mlp(h.mlp_attention, nw, "mlp_attention", 1)) return r;
+      if (int r = check_mlp(h.mlp_value, nw, "mlp_value", 1)) return r;
+      ch += h.c_out; hin = h.c_out;
+    }
+    ch += A.c_init;
+    const int Kw = a4(d.K);
+    const size_t rows = (size_t)A.n_proj_rows[0] + (A.num_layers_h == 2 ? A.n_proj_rows[1] : 0);
+    if (A.proj_w < 0 || (A.proj_w & 3) || (size_t)A.proj_w + rows * Kw > nw) return fail(CCSD_ERR_INVALID, "hodge projection weights out of range");
+  }
+  if (ch != A.fdim) return fail(CCSD_ERR_INVALID, "ScoreNetworkA: fdim does not match the channel stack (the reference would raise a shape error too)");
+  if (int r = check_mlp(A.fin, nw, "ScoreNetworkA.final", 0)) return r;
+  if (A.fin.din != A.fdim || A.fin.dout != 1) return fail(CCSD_ERR_INVALID, "ScoreNetworkA.final dims mismatch");
+  }
+  if (d.is_cc && (d.nets & 4)) {
+    const ccsd_netf_t &Fn = d.netf;
+    if (Fn.cnum != 2) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkF: only cnum == 2 (F, H F) is implemented");
+    if (Fn.num_layers < 1 || Fn.num_layers > CCSD_MAX_F_LAYERS) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkF: num_layers 1..4");
+    int fd = Fn.cnum, fin = Fn.cnum;
+    for (int l = 0; l < Fn.num_layers; ++l) {
+      if (int r = check_mlp(Fn.layer[l], nw, "HodgeNetworkLayer", 1)) return r;
+      if (Fn.layer[l].din != fin) return fail(CCSD_ERR_INVALID, "ScoreNetworkF: layer chaining mismatch");
+      fin = Fn.layer[l].dout; fd += fin;
+    }
+    if (fd != Fn.fdim || fd > SMALL_MAX) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkF: fdim mismatch or > 32");
+    if (int r = check_mlp(Fn.fin, nw, "ScoreNetworkF.final", 1)) return r;
+    if (Fn.fin.din != fd || Fn.fin.dout != 1) return fail(CCSD_ERR_INVALID, "ScoreNetworkF.final dims mismatch");
+  }
+  return 0;
+}
+
+static void make_layout(const ccsd_plan_desc_t &d, XaLayout &L) {
+  memset(&L, 0, sizeof(L));
+  const int N = d.N, F = d.F, NP = N * N;
+  L.ldn = N | 1;
+  L.ldp = NP | 1;
+  const ccsd_netx_t &X = d.netx;
+  const ccsd_neta_t &A = d.neta;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += a4(n); return r; };
+  L.flags = take(N);
+  L.dvec = take(N);
+  L.hcat = take(imax(X.fdim, F) * L.ldn);
+  L.an = take(N * L.ldn);
+  L.stack = take(imax(A.fdim, 1) * L.ldp);
+  int nh_max = 1, ad_max = 1, vc_max = 1, cin_max = 1, xw_max = a4(X.nhid), hsz = X.fin.dhid * L.ldn;
+  for (int l = 0; l < A.num_layers; ++l) {
+    const ccsd_attn_layer_t &ly = A.layer[l];
+    nh_max = imax(nh_max, ly.conv_out);
+    ad_max = imax(ad_max, ly.attn_dim);
+    vc_max = imax(vc_max, ly.c_in * ly.conv_out);
+    cin_max = imax(cin_max, ly.c_in);
+    xw_max = imax(xw_max, 2 * a4(ly.attn_dim) + a4(ly.conv_out));
+    hsz = imax(hsz, ly.multi_channel.dhid * L.ldn);
+    hsz = imax(hsz, ly.mlp.dhid * L.ldp);
+  }
+  for (int k = 0; k < X.depth; ++k) xw_max = imax(xw_max, a4(X.gcn[k].dout));
+  L.xa = take(nh_max * L.ldn);
+  L.xb = take(nh_max * L.ldn);
+  L.sx = take(F * L.ldn);
+  L.sadj = take(NP);
+  L.red = take(40);
+  L.scratch = o;
+  // final MLP row chunk
+  const int fin_h = imax(A.fin.dhid, 1);
+  hsz = imax(hsz, fin_h * 65);
+  int rows = hsz / fin_h - 1;
+  if (rows > NP) rows = NP;
+  L.fin_rows = rows;
+  L.fin_ld = rows | 1;
+  if (L.fin_ld * fin_h > hsz) hsz = L.fin_ld * fin_h;
+  int s = 0;
+  auto stake = [&](int n) { int r = s; s += a4(n); return r; };
+  L.ldxw = xw_max;
+  L.xw = stake(N * L.ldxw);
+  L.ldq = a4(ad_max);
+  L.qn = stake(N * L.ldq);
+  L.kf = stake(ad_max * L.ldn);
+  L.vcat = stake(vc_max * L.ldn);
+  L.att = stake(cin_max * L.ldp);
+  L.hA = stake(hsz);
+  L.hB = stake(hsz);
+  int s_layers = s;
+  int s_hodge = 0;
+  if (d.is_cc && A.is_cc && A.num_layers_h == 2) {
+    int h = 0;
+    auto htake = [&](int n) { int r = h; h += a4(n); return r; };
+    const int E = d.E;
+    L.lde = E | 1;
+    L.hq = htake(A.c_init * E * A.hodge[0].attn_dim);
+    L.hk = htake(A.c_init * E * A.hodge[0].attn_dim);
+    L.h1 = htake(A.hodge[0].c_out * E * L.lde);
+    L.hdeg = htake(A.hodge[0].c_out * E);
+    s_hodge = h;
+  }
+  L.total = L.scratch + imax(s_layers, s_hodge);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int ccsd_plan_desc_size(void) { return (int)sizeof(ccsd_plan_desc_t); }
+int ccsd_objcoef_size(void) { return (int)sizeof(ccsd_objcoef_t); }
+const char *ccsd_last_error(void) { return g_err.c_str(); }
+const char *ccsd_version(void) {
+#ifdef CCSD_EMU
+  return "ccsd_b200 0.1 (HOST EMULATION BUILD - tests only)";
+#else
+  return "ccsd_b200 0.1 (sm_100a)";
+#endif
+}
+
+static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct WsLayout {
+  size_t plan, sched, cells, edges, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+};
+static WsLayout ws_layout(const ccsd_plan *p) {
+  const ccsd_plan_desc_t &d = p->hp.d;
+  WsLayout w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+  const size_t B = d.B, N = d.N, F = d.F, E = d.E, K = d.K;
+  w.plan = take(sizeof(DevPlan));
+  w.sched = take(p->sched.size() * sizeof(ccsd_objcoef_t));
+  w.cells = take(imax(1, d.K) * sizeof(unsigned long long));
+  w.edges = take(imax(1, d.E) * 2 * sizeof(int));
+  w.flags = take(B * N * 4);
+  w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
+  w.mx = take(B * N * F * 4); w.madj = take(B * N * N * 4); w.mr2 = take(B * E * K * 4 + 16);
+  w.sx = take(B * N * F * 4); w.sadj = take(B * N * N * 4); w.sr2 = take(B * E * K * 4 + 16);
+  w.H = take(B * E * E * 4 + 16);
+  w.P0 = take(B * E * (size_t)imax(1, p->hp.PR0) * 4);
+  w.P1 = take(B * E * (size_t)imax(1, p->hp.PR1) * 4);
+  w.norm = take(3 * B * (size_t)p->hp.ntile_max * 2 * 4);
+  w.coef = take(64);
+  w.total = o;
+  return w;
+}
+
+int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedule_host, const float *weights_dev,
+                     size_t n_weights, ccsd_plan_t **out) {
+  if (!desc || !schedule_host || !weights_dev || !out) return fail(CCSD_ERR_INVALID, "null argument");
+  if (int r = validate(*desc, n_weights)) return r;
+  ccsd_plan *p = new ccsd_plan();
+  p->hp.d = *desc;
+  const ccsd_plan_desc_t &d = p->hp.d;
+  make_layout(d, p->hp.xa);
+  p->xa_smem = (size_t)p->hp.xa.total * 4;
+  p->weights = weights_dev;
+  p->n_weights = n_weights;
+  p->sched.assign(schedule_host, schedule_host + (size_t)d.n_diff_steps * 3);
+  const bool hodge = d.is_cc && (d.nets & 2) && d.neta.is_cc;
+  p->hp.PR0 = hodge ? d.neta.n_proj_rows[0] : 0;
+  p->hp.PR1 = (hodge && d.neta.num_layers_h == 2) ? d.neta.n_proj_rows[1] : 0;
+  p->hp.Kp = a4(d.K);
+  p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
+  p->hp.ntile_max = imax(1, p->hp.ntile_r2);
+  p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40) * 4 : 0;
+  if (p->xa_smem > 227 * 1024 || p->apply_smem > 227 * 1024) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "graph tile does not fit shared memory (xa %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
+             p->xa_smem, p->apply_smem);
+    delete p;
+    return fail(CCSD_ERR_UNSUPPORTED, buf);
+  }
+  // tables
+  if (d.is_cc) {
+    const int N = d.N;
+    p->edge_ij.resize((size_t)d.E * 2);
+    int e = 0;
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) { p->edge_ij[2 * e] = i; p->edge_ij[2 * e + 1] = j; ++e; }
+    // cells: combinations(range(N), dd) for dd = d_min..d_max, lexicographic (cc_utils.py:72-76)
+    p->cell_mask.reserve(d.K);
+    for (int dd = d.d_min; dd <= d.d_max; ++dd) {
+      if (dd < 1 || dd > N) continue;
+      std::vector<int> c(dd);
+      for (int i = 0; i < dd; ++i) c[i] = i;
+      while (true) {
+        unsigned long long m = 0;
+        for (int i = 0; i < dd; ++i) m |= 1ull << c[i];
+        p->cell_mask.push_back(m);
+        int i = dd - 1;
+        while (i >= 0 && c[i] == N - dd + i) --i;
+        if (i < 0) break;
+        ++c[i];
+        for (int j = i + 1; j < dd; ++j) c[j] = c[j - 1] + 1;
+      }
+    }
+    if ((int)p->cell_mask.size() != d.K) {
+      delete p;
+      return fail(CCSD_ERR_INVALID, "K does not equal sum_d C(N, d) for d_min..d_max");
+    }
+  }
+#ifndef CCSD_EMU
+  cudaError_t e1 = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->xa_smem);
+  cudaError_t e2 = cudaSuccess;
+  if (d.is_cc) e2 = cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    delete p;
+    return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
+  if (p->use_tc) {
+    if (int r = tc_gram_prepare()) { delete p; return fail(CCSD_ERR_CUDA, "tc_gram_prepare failed"); }
+  }
+#endif
+  *out = p;
+  return 0;
+}
+
+void ccsd_plan_destroy(ccsd_plan_t *plan) { delete plan; }
+
+size_t ccsd_plan_workspace_bytes(const ccsd_plan_t *plan) { return plan ? ws_layout(plan).total : 0; }
+
+int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stream) {
+  if (!p || !workspace_dev) return fail(CCSD_ERR_INVALID, "null argument");
+  const WsLayout w = ws_layout(p);
+  if (bytes < w.total) return fail(CCSD_ERR_INVALID, "workspace too small");
+  if (((uintptr_t)workspace_dev) & 255) return fail(CCSD_ERR_INVALID, "workspace must be 256-byte aligned");
+  char *ws = (char *)workspace_dev;
+  p->ws = ws; p->ws_bytes = bytes;
+  p->dP = (DevPlan *)(ws + w.plan);
+  p->flags = (float *)(ws + w.flags);
+  p->x = (float *)(ws + w.x); p->adj = (float *)(ws + w.adj); p->r2 = (float *)(ws + w.r2);
+  p->mx = (float *)(ws + w.mx); p->madj = (float *)(ws + w.madj); p->mr2 = (float *)(ws + w.mr2);
+  p->sx = (float *)(ws + w.sx); p->sadj = (float *)(ws + w.sadj); p->sr2 = (float *)(ws + w.sr2);
+  p->H = (float *)(ws + w.H); p->P0 = (float *)(ws + w.P0); p->P1 = (float *)(ws + w.P1);
+  p->norm_part = (float *)(ws + w.norm); p->coef = (float *)(ws + w.coef);
+  p->hp.W = p->weights;
+  p->hp.sched = (const ccsd_objcoef_t *)(ws + w.sched);
+  p->hp.cell_mask = (const unsigned long long *)(ws + w.cells);
+  p->hp.edge_ij = (const int *)(ws + w.edges);
+  if (int r = dev_copy(ws + w.plan, &p->hp, sizeof(DevPlan), stream)) return r;
+  if (int r = dev_copy(ws + w.sched, p->sched.data(), p->sched.size() * sizeof(ccsd_objcoef_t), stream)) return r;
+  if (!p->cell_mask.empty())
+    if (int r = dev_copy(ws + w.cells, p->cell_mask.data(), p->cell_mask.size() * 8, stream)) return r;
+  if (!p->edge_ij.empty())
+    if (int r = dev_copy(ws + w.edges, p->edge_ij.data(), p->edge_ij.size() * 4, stream)) return r;
+  p->bound = true;
+  p->inited = false;
+  return 0;
+}
+
+int ccsd_plan_set_traj(ccsd_plan_t *p, float *tx, float *tadj, float *tr2) {
+  if (!p) return fail(CCSD_ERR_INVALID, "null plan");
+  p->traj_x = tx; p->traj_adj = tadj; p->traj_r2 = tr2;
+  return 0;
+}
+
+static int grid_for(size_t n) {
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, const float *padj, const float *pr2,
+                   uint64_t seed, int64_t sample_offset, void *stream) {
+  if (!p || !flags_dev) return fail(CCSD_ERR_INVALID, "null argument");
+  if (!p->bound) return fail(CCSD_ERR_STATE, "ccsd_plan_bind must be called before ccsd_plan_init");
+  const ccsd_plan_desc_t &d = p->hp.d;
+  if (int r = dev_copy(p->flags, flags_dev, (size_t)d.B * d.N * 4, stream)) return r;
+  p->seed = seed; p->sample_offset = sample_offset;
+  InitArgs a;
+  a.flags = p->flags; a.px = px; a.padj = padj; a.pr2 = pr2; a.x = p->x; a.adj = p->adj; a.r2 = p->r2;
+  a.nz.seed = seed; a.nz.sample_offset = sample_offset; a.nz.step = -1;
+  const size_t units = d.is_cc ? (size_t)d.B * d.E * (p->hp.Kp / 4) : (size_t)d.B * d.N * d.N;
+  CCSD_LAUNCH(init_kernel, dim3(grid_for(units), d.is_cc ? 3 : 2, 1), 256, 0, stream, p->dP, a);
+  p->launches++;
+  // means start as the prior (returned if zero steps are run)
+  if (int r = dev_copy(p->mx, p->x, (size_t)d.B * d.N * d.F * 4, stream)) return r;
+  if (int r = dev_copy(p->madj, p->adj, (size_t)d.B * d.N * d.N * 4, stream)) return r;
+  if (d.is_cc)
+    if (int r = dev_copy(p->mr2, p->r2, (size_t)d.B * d.E * d.K * 4, stream)) return r;
+  p->inited = true;
+  return dev_check("init_kernel");
+}
+
+// H, P0 (and P1) of the rank-2 tensor `r2` (+ adj for P1)
+static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, const float *flags, void *stream) {
+  const ccsd_plan_desc_t &d = p->hp.d;
+#ifndef CCSD_EMU
+  if (p->use_tc) {
+    if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, stream)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
+    p->launches++;
+  } else
+#endif
+  {
+    GramArgs g; g.r2 = r2; g.H = p->H; g.P0 = p->P0;
+    const int ncols = d.E + p->hp.PR0;
+    CCSD_LAUNCH(gram_kernel, dim3((ncols + GRAM_BN - 1) / GRAM_BN, (d.E + GRAM_BM - 1) / GRAM_BM, d.B), 256,
+                2 * GRAM_BK * (GRAM_BM + 4) * 4, stream, p->dP, g);
+    p->launches++;
+  }
+  if (p->hp.PR1 > 0) {
+    Proj1Args q; q.r2 = r2; q.adj = adj; q.flags = flags; q.P1 = p->P1;
+    CCSD_LAUNCH(proj1_kernel, dim3(d.E, d.B, 1), 128, (2 * 64 + 16 + p->hp.Kp + 4) * 4, stream, p->dP, q);
+    p->launches++;
+  }
+  return dev_check("rank2 pre-pass");
+}
+
+static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, const float *nr2, int write_mean,
+                   void *stream) {
+  const ccsd_plan_desc_t &d = p->hp.d;
+  if ((d.nets & 3) != 3 || (d.is_cc && !(d.nets & 4)))
+    return fail(CCSD_ERR_STATE, "sampling needs ScoreNetworkX, ScoreNetworkA and (for CC) ScoreNetworkF in the plan");
+  const size_t sx = (size_t)d.B * d.N * d.F, sa = (size_t)d.B * d.N * d.N, sr = (size_t)d.B * d.E * d.K;
+  const int s4 = d.sampler == CCSD_SAMPLER_S4;
+  NoiseCtx nz; nz.seed = p->seed; nz.sample_offset = p->sample_offset; nz.step = step;
+  float *tx = p->traj_x ? p->traj_x + (size_t)step * d.N * d.F : nullptr;
+  float *ta = p->traj_adj ? p->traj_adj + (size_t)step * d.N * d.N : nullptr;
+  float *tr = (p->traj_r2 && d.is_cc) ? p->traj_r2 + (size_t)step * d.E * d.K : nullptr;
+
+  auto score_phase = [&](int mode, int slot) -> int {
+    if (d.is_cc)
+      if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
+    XaArgs a; memset(&a, 0, sizeof a);
+    a.x = p->x; a.adj = p->adj; a.flags = p->flags; a.P0 = p->P0; a.P1 = p->P1;
+    a.mode = mode; a.which = 3; a.slot = slot; a.denoise = d.denoise; a.nz = nz;
+    a.norm_part = p->norm_part;
+    a.noise_x = nx ? nx + (size_t)slot * sx : nullptr;
+    a.noise_adj = nadj ? nadj + (size_t)slot * sa : nullptr;
+    if (mode == MODE_SCORE) { a.out_x = p->sx; a.out_adj = p->sadj; }
+    else { a.out_x = p->x; a.out_adj = p->adj; a.mean_x = p->mx; a.mean_adj = p->madj; a.traj_x = tx; a.traj_adj = ta; }
+    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), XA_THREADS, p->xa_smem, stream, p->dP, a);
+    p->launches++;
+    if (d.is_cc) {
+      ApplyArgs q; memset(&q, 0, sizeof q);
+      q.r2 = p->r2; q.H = p->H; q.flags = p->flags; q.mode = mode; q.slot = slot; q.denoise = d.denoise; q.nz = nz;
+      q.norm_part = p->norm_part;
+      q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
+      if (mode == MODE_SCORE) q.out = p->sr2;
+      else { q.out = p->r2; q.mean = p->mr2; q.write_mean = write_mean; q.traj = tr; }
+      CCSD_LAUNCH(apply_kernel, dim3(p->hp.ntile_r2, d.B, 1), 256, p->apply_smem, stream, p->dP, q);
+      p->launches++;
+    }
+    return dev_check("score phase");
+  };
+  auto update_phase = [&]() -> int {
+    CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4;
+    CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
+    UpdateArgs u; memset(&u, 0, sizeof u);
+    u.flags = p->flags; u.x = p->x; u.adj = p->adj; u.r2 = p->r2; u.sx = p->sx; u.sadj = p->sadj; u.sr2 = p->sr2;
+    u.coef = p->coef; u.mx = p->mx; u.madj = p->madj; u.mr2 = p->mr2; u.nx = nx; u.nadj = nadj; u.nr2 = nr2;
+    u.tx = tx; u.tadj = ta; u.tr2 = tr; u.s4 = s4; u.denoise = d.denoise; u.write_mean_r2 = write_mean; u.nz = nz;
+    const size_t units = d.is_cc ? (size_t)d.B * d.E * (p->hp.Kp / 4) : sa;
+    CCSD_LAUNCH(update_kernel, dim3(grid_for(units), d.is_cc ? 3 : 2, 1), 256, 0, stream, p->dP, u);
+    p->launches += 2;
+    return dev_check("update phase");
+  };
+
+  if (s4) {
+    if (int r = score_phase(MODE_SCORE, 0)) return r;
+    return update_phase();
+  }
+  int slot = 0;
+  if (d.use_corrector) {
+    if (int r = score_phase(MODE_SCORE, 0)) return r;
+    if (int r = update_phase()) return r;
+    slot = d.n_lang_steps;
+  }
+  return score_phase(MODE_PRED, slot);
+}
+
+int ccsd_plan_step(ccsd_plan_t *p, int step, const float *nx, const float *nadj, const float *nr2, void *stream) {
+  if (!p) return fail(CCSD_ERR_INVALID, "null plan");
+  if (!p->inited) return fail(CCSD_ERR_STATE, "ccsd_plan_init must be called before stepping");
+  if (step < 0 || step >= p->hp.d.n_diff_steps) return fail(CCSD_ERR_INVALID, "step out of range");
+  return do_step(p, step, nx, nadj, nr2, 1, stream);
+}
+
+int ccsd_plan_run(ccsd_plan_t *p, int step_begin, int step_end, void *stream) {
+  if (!p) return fail(CCSD_ERR_INVALID, "null plan");
+  if (!p->inited) return fail(CCSD_ERR_STATE, "ccsd_plan_init must be called before running");
+  if (step_begin < 0 || step_end > p->hp.d.n_diff_steps || step_begin > step_end) return fail(CCSD_ERR_INVALID, "step range out of bounds");
+  for (int s = step_begin; s < step_end; ++s)
+    if (int r = do_step(p, s, nullptr, nullptr, nullptr, s == step_end - 1, stream)) return r;
+  return 0;
+}
+
+int ccsd_plan_read(ccsd_plan_t *p, int want_mean, float *ox, float *oadj, float *or2, void *stream) {
+  if (!p || !p->inited) return fail(CCSD_ERR_STATE, "plan not initialised");
+  const ccsd_plan_desc_t &d = p->hp.d;
+  if (ox) if (int r = dev_copy(ox, want_mean ? p->mx : p->x, (size_t)d.B * d.N * d.F * 4, stream)) return r;
+  if (oadj) if (int r = dev_copy(oadj, want_mean ? p->madj : p->adj, (size_t)d.B * d.N * d.N * 4, stream)) return r;
+  if (or2 && d.is_cc) if (int r = dev_copy(or2, want_mean ? p->mr2 : p->r2, (size_t)d.B * d.E * d.K * 4, stream)) return r;
+  return 0;
+}
+
+int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj, const float *r2, const float *flags,
+                    float *out, void *stream) {
+  if (!p || !x || !adj || !flags || !out) return fail(CCSD_ERR_INVALID, "null argument");
+  if (!p->bound) return fail(CCSD_ERR_STATE, "ccsd_plan_bind must be called first");
+  const ccsd_plan_desc_t &d = p->hp.d;
+  if (d.is_cc && which != CCSD_NET_X && !r2) return fail(CCSD_ERR_INVALID, "rank2 is required for CC plans");
+  if (which == CCSD_NET_RANK2 && !d.is_cc) return fail(CCSD_ERR_INVALID, "graph plans have no rank-2 network");
+  if (which < 0 || which > 2 || !(d.nets & (1 << which))) return fail(CCSD_ERR_INVALID, "that network is not part of this plan");
+  if (which == CCSD_NET_X || which == CCSD_NET_ADJ) {
+    if (which == CCSD_NET_ADJ && d.is_cc)
+      if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
+    XaArgs a; memset(&a, 0, sizeof a);
+    a.x = x; a.adj = adj; a.flags = flags; a.P0 = p->P0; a.P1 = p->P1; a.mode = MODE_EVAL;
+    a.which = which == CCSD_NET_X ? 1 : 2;
+    a.out_x = out; a.out_adj = out;
+    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), XA_THREADS, p->xa_smem, stream, p->dP, a);
+    p->launches++;
+    return dev_check("xa_kernel");
+  }
+  if (which == CCSD_NET_RANK2) {
+    if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
+    ApplyArgs q; memset(&q, 0, sizeof q);
+    q.r2 = r2; q.H = p->H; q.flags = flags; q.mode = MODE_EVAL; q.out = out;
+    CCSD_LAUNCH(apply_kernel, dim3(p->hp.ntile_r2, d.B, 1), 256, p->apply_smem, stream, p->dP, q);
+    p->launches++;
+    return dev_check("apply_kernel");
+  }
+  return fail(CCSD_ERR_INVALID, "unknown network id");
+}
+
+int ccsd_quantize(const float *in, uint8_t *out, size_t n, float thr, int mol, void *stream) {
+  if (!in || !out) return fail(CCSD_ERR_INVALID, "null argument");
+  if (n == 0) return 0;
+  CCSD_LAUNCH(quantize_kernel, dim3(grid_for(n), 1, 1), 256, 0, stream, in, out, n, thr, mol);
+  return dev_check("quantize_kernel");
+}
+
+int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }
+
+}  // extern "C"

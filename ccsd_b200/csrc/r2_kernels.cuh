@@ -1,0 +1,553 @@
+// r2_kernels.cuh -- the rank-2 (incidence tensor, B x E x K) side of the score evaluation, fp32 FMA
+// path, plus the element-wise sampler kernels (prior, Langevin coefficients, corrector / S4 update).
+//
+//   gram_kernel   G = F [F ; Wp]^T  ->  H = (F F^T) (1 - I)   (cc_utils.py:917-979, hodge_laplacian +
+//                 default_mask) and P0 = F Wp^T, the hodge-attention projections rank2 @ W_{q,k}
+//                 (hodge_layers.py:185) as extra Gram columns.
+//   proj1_kernel  P1 = rank2' Wp1^T for a second hodge layer; rank2' is the first layer's value
+//                 output, an element-wise function of F because the layer-0 Hodge dual is diagonal
+//                 (hodge_attention.py:107, 322-323).
+//   apply_kernel  H F, the per-entry channel MLPs (hodge_layers.py:70-92), final MLP, masks
+//                 (ScoreNetwork_F.py:175-217) and the sampler epilogue.
+#pragma once
+#include "prims.cuh"
+
+namespace ccsd {
+
+__device__ __forceinline__ unsigned long long zero_mask_of(const float *flags, int N) {
+  unsigned long long m = 0ull;
+  for (int n = 0; n < N; ++n)
+    if (flags[n] == 0.f) m |= (1ull << n);
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct GramArgs {
+  const float *r2;   // [B,E,K]
+  float *H;          // [B,E,E]
+  float *P0;         // [B,E,PR0]
+};
+
+__global__ void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P, GramArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp;
+  const int b = blockIdx.z, m0 = blockIdx.y * GRAM_BM, n0 = blockIdx.x * GRAM_BN;
+  const float *Fb = a.r2 + (size_t)b * E * K;
+  const float *Wp = P->W + d.neta.proj_w;  // [PR_total x Kw], rows 0..PR0-1 = hodge layer 0
+  constexpr int LDT = GRAM_BM + 4;
+  float *As = sm;                      // [BK][LDT]
+  float *Bs = sm + GRAM_BK * LDT;      // [BK][LDT]
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+#ifdef CCSD_EMU
+  const int nthr = 256;  // emulate the 256 logical threads of the tile serially
+  for (int k0 = 0; k0 < K; k0 += GRAM_BK) {
+    for (int t = 0; t < nthr; ++t) {
+      const int r = t >> 2, kq = (t & 3) << 2;
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + kq + q;
+        const int m = m0 + r, n = n0 + r;
+        As[(kq + q) * LDT + r] = (m < E && k < K) ? Fb[(size_t)m * K + k] : 0.f;
+        float bv = 0.f;
+        if (k < K) {
+          if (n < E) bv = Fb[(size_t)n * K + k];
+          else if (n - E < PR0) bv = Wp[(size_t)(n - E) * Kw + k];
+        }
+        Bs[(kq + q) * LDT + r] = bv;
+      }
+    }
+    // serial tile product written straight to the outputs via a static accumulator tile
+    static thread_local float tile[GRAM_BM][GRAM_BN];
+    if (k0 == 0) memset(tile, 0, sizeof(tile));
+    for (int kk = 0; kk < GRAM_BK; ++kk)
+      for (int i = 0; i < GRAM_BM; ++i)
+        for (int j = 0; j < GRAM_BN; ++j) tile[i][j] += As[kk * LDT + i] * Bs[kk * LDT + j];
+    if (k0 + GRAM_BK >= K) {
+      for (int i = 0; i < GRAM_BM; ++i)
+        for (int j = 0; j < GRAM_BN; ++j) {
+          const int m = m0 + i, n = n0 + j;
+          if (m >= E) continue;
+          if (n < E) a.H[((size_t)b * E + m) * E + n] = (d.netf.use_hodge_mask && m == n) ? 0.f : tile[i][j];
+          else if (n - E < PR0) a.P0[((size_t)b * E + m) * PR0 + (n - E)] = tile[i][j];
+        }
+    }
+  }
+  (void)acc;
+#else
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int r = t >> 2, kq = (t & 3) << 2;
+  for (int k0 = 0; k0 < K; k0 += GRAM_BK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + kq + q;
+      const int m = m0 + r, n = n0 + r;
+      As[(kq + q) * LDT + r] = (m < E && k < K) ? __ldg(Fb + (size_t)m * K + k) : 0.f;
+      float bv = 0.f;
+      if (k < K) {
+        if (n < E) bv = __ldg(Fb + (size_t)n * K + k);
+        else if (n - E < PR0) bv = __ldg(Wp + (size_t)(n - E) * Kw + k);
+      }
+      Bs[(kq + q) * LDT + r] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GRAM_BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4 *>(As + kk * LDT + ty * 4);
+      const float4 bv = *reinterpret_cast<const float4 *>(Bs + kk * LDT + tx * 4);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += aa[i] * bb[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m >= E) continue;
+      if (n < E) a.H[((size_t)b * E + m) * E + n] = (d.netf.use_hodge_mask && m == n) ? 0.f : acc[i][j];
+      else if (n - E < PR0) a.P0[((size_t)b * E + m) * PR0 + (n - E)] = acc[i][j];
+    }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Proj1Args {
+  const float *r2, *adj, *flags;  // [B,E,K] [B,N,N] [B,N]
+  float *P1;                      // [B,E,PR1]
+};
+
+__global__ void __launch_bounds__(128) proj1_kernel(const DevPlan *__restrict__ P, Proj1Args a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const ccsd_neta_t &A = d.neta;
+  const int N = d.N, E = d.E, K = d.K, PR0 = P->PR0, PR1 = P->PR1, Kw = P->Kp;
+  const int e = blockIdx.x, b = blockIdx.y;
+  const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+  const float *adj = a.adj + (size_t)b * N * N;
+  const float *fl = a.flags + (size_t)b * N;
+  float *vrow = sm;            // [2][N] ping-pong: row i of A^c
+  float *ac = sm + 2 * 64;     // [c0]
+  float *r2v = sm + 2 * 64 + 16;  // [Kw]
+  const int c0 = A.c_init;
+  // a_c[e] = (A^c)[i][j]
+  for (int n = threadIdx.x; n < N; n += blockDim.x) vrow[n] = adj[i * N + n];
+  __syncthreads();
+  if (threadIdx.x == 0) ac[0] = vrow[j];
+  for (int c = 1; c < c0; ++c) {
+    const float *src = vrow + ((c - 1) & 1) * 64;
+    float *dst = vrow + (c & 1) * 64;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < N; ++k) s += src[k] * adj[k * N + n];
+      dst[n] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ac[c] = dst[j];
+  }
+  __syncthreads();
+  const unsigned long long zm = zero_mask_of(fl, N);
+  const float fe = fl[i] * fl[j];
+  const float *Fr = a.r2 + ((size_t)b * E + e) * K;
+  const ccsd_hodge_layer_t &h0 = A.hodge[0];
+  for (int k = threadIdx.x; k < Kw; k += blockDim.x) {
+    float v = 0.f;
+    if (k < K) {
+      float in[CCSD_MAX_CH], out[SMALL_MAX];
+      const float f = Fr[k];
+      for (int c = 0; c < c0; ++c) in[c] = ac[c] * f;  // V_c = diag(a_c) rank2  (hodge_attention.py:107)
+      small_mlp(h0.mlp_value, P->W, in, out, ACT_ELU);
+      const float fc = (P->cell_mask[k] & zm) ? 0.f : 1.f;
+      v = out[0] * fe * fc;  // mask_rank2 (hodge_attention.py:323)
+    }
+    r2v[k] = v;
+  }
+  __syncthreads();
+#ifdef CCSD_EMU
+  const int lane = 0, nlane = 1, warp = 0, nwarp = 1;
+#else
+  const int lane = threadIdx.x & 31, nlane = 32, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#endif
+  const float *Wp = P->W + A.proj_w + (size_t)PR0 * Kw;  // rows of hodge layer 1
+  for (int r = warp; r < PR1; r += nwarp) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += nlane) s += r2v[k] * __ldg(Wp + (size_t)r * Kw + k);
+#ifndef CCSD_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#endif
+    if (lane == 0) a.P1[((size_t)b * E + e) * PR1 + r] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ScoreNetworkF on one entry: channels [f, (H f)], HodgeNetworkLayer MLPs with mask, final MLP.
+__device__ __forceinline__ float netf_entry(const ccsd_netf_t &Fn, const float *__restrict__ W, float f, float hf,
+                                            float m) {
+  float lst[SMALL_MAX], cur[SMALL_MAX], nxt[SMALL_MAX];
+  lst[0] = f; lst[1] = hf;
+  cur[0] = f; cur[1] = hf;
+  int nl = 2;
+  for (int l = 0; l < Fn.num_layers; ++l) {
+    small_mlp(Fn.layer[l], W, cur, nxt, ACT_ELU);
+    const int O = Fn.layer[l].dout;
+    for (int o = 0; o < O; ++o) { cur[o] = nxt[o] * m; lst[nl + o] = cur[o]; }
+    nl += O;
+  }
+  float out[SMALL_MAX];
+  small_mlp(Fn.fin, W, lst, out, ACT_ELU);
+  return out[0] * m;
+}
+
+struct ApplyArgs {
+  const float *r2, *H, *flags;   // [B,E,K] [B,E,E] [B,N]
+  int mode;
+  float *out;                    // EVAL: raw output; SCORE: scaled score; PRED: new state (may alias r2)
+  float *mean;                   // PRED: means (written when write_mean)
+  float *norm_part;
+  const float *noise;            // raw normals [B,E,K] for this draw or nullptr
+  float *traj;                   // PRED: sample 0 destination or nullptr
+  int slot, denoise, write_mean;
+  NoiseCtx nz;
+};
+
+__global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int N = d.N, E = d.E, K = d.K;
+  const int b = blockIdx.y, n0 = blockIdx.x * APPLY_TN;
+  const float *Fb = a.r2 + (size_t)b * E * K;
+  const float *Hb = a.H + (size_t)b * E * E;
+  const float *fl = a.flags + (size_t)b * N;
+  const float *W = P->W;
+  constexpr int LDF = APPLY_TN + 4, LDH = 64 + 4;
+  float *Fs = sm;                         // [E][LDF]
+  float *Hs = sm + (size_t)E * LDF;       // [16][LDH]
+  float *red = Hs + 16 * LDH;             // [40]
+  const unsigned long long zm = zero_mask_of(fl, N);
+  const ccsd_objcoef_t co = (a.mode == MODE_EVAL) ? ccsd_objcoef_t{} : P->sched[a.nz.step * 3 + 2];
+  const unsigned long long gs = (unsigned long long)(a.nz.sample_offset + b);
+  const int Kg = P->Kp >> 2;
+
+  for (int p = threadIdx.x; p < E * APPLY_TN; p += blockDim.x) {
+    const int e = p / APPLY_TN, c = p - e * APPLY_TN;
+    const int k = n0 + c;
+    Fs[e * LDF + c] = (k < K) ? Fb[(size_t)e * K + k] : 0.f;
+  }
+  __syncthreads();
+
+  float s2 = 0.f, z2 = 0.f;
+
+  // per-element epilogue shared by both builds
+  auto finish = [&](int e, int cq, const float hf4[4]) {
+    // e: edge row, cq: first of 4 consecutive tile columns
+    const int k0 = n0 + cq;
+    if (e >= E || k0 >= K) return;
+    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+    const float fe = fl[i] * fl[j];
+    float z4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.mode != MODE_EVAL) {
+      if (a.noise) {
+        for (int q = 0; q < 4; ++q)
+          if (k0 + q < K) z4[q] = a.noise[((size_t)b * E + e) * K + k0 + q];
+      } else {
+        normal4(a.nz.seed, gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(e * Kg + (k0 >> 2)), z4);
+      }
+    }
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + q;
+      if (k >= K) break;
+      const float fc = (P->cell_mask[k] & zm) ? 0.f : 1.f;
+      const float m = fe * fc;
+      const float f = Fs[e * LDF + cq + q];
+      const float o = netf_entry(d.netf, W, f, hf4[q], m);
+      const size_t g = ((size_t)b * E + e) * K + k;
+      if (a.mode == MODE_EVAL) {
+        a.out[g] = o;
+      } else {
+        const float s = co.score_scale * o;
+        const float z = z4[q] * m;
+        if (a.mode == MODE_SCORE) {
+          a.out[g] = s;
+          s2 += s * s;
+          z2 += z * z;
+        } else {
+          const float mu = co.pa * f + co.pb * s;
+          const float v = mu + co.pc * z;
+          a.out[g] = v;
+          if (a.write_mean) a.mean[g] = mu;
+          if (a.traj && b == 0) a.traj[(size_t)e * K + k] = a.denoise ? mu : v;
+        }
+      }
+    }
+  };
+
+#ifdef CCSD_EMU
+  (void)Hs;
+  for (int e = 0; e < E; ++e)
+    for (int cq = 0; cq < APPLY_TN; cq += 4) {
+      float hf4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int e2 = 0; e2 < E; ++e2) {
+        const float h = Hb[(size_t)e * E + e2];
+        for (int q = 0; q < 4; ++q) hf4[q] += h * Fs[e2 * LDF + cq + q];
+      }
+      finish(e, cq, hf4);
+    }
+#else
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int lr = t >> 2, lq = (t & 3) << 2;
+  for (int m0 = 0; m0 < E; m0 += 64) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int e0 = 0; e0 < E; e0 += 16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + lr, e2 = e0 + lq + q;
+        Hs[(lq + q) * LDH + lr] = (m < E && e2 < E) ? __ldg(Hb + (size_t)m * E + e2) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const int e2 = e0 + kk;
+        if (e2 < E) {
+          const float4 av = *reinterpret_cast<const float4 *>(Hs + kk * LDH + ty * 4);
+          const float4 bv = *reinterpret_cast<const float4 *>(Fs + e2 * LDF + tx * 4);
+          const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += aa[i] * bb[j];
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) finish(m0 + ty * 4 + i, tx * 4, acc[i]);
+  }
+#endif
+  if (a.mode == MODE_SCORE) {
+    s2 = block_sum(s2, red);
+    z2 = block_sum(z2, red);
+    if (threadIdx.x == 0) {
+      float *np = a.norm_part + ((size_t)(2 * d.B + b) * P->ntile_max + blockIdx.x) * 2;
+      np[0] = s2; np[1] = z2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prior: state = mask(raw normal)  (solver.py:963-968, 1111-1118; sde.py:436, 448-449)
+struct InitArgs {
+  const float *flags;
+  const float *px, *padj, *pr2;  // raw normals or nullptr
+  float *x, *adj, *r2;
+  NoiseCtx nz;
+};
+
+__global__ void __launch_bounds__(256) init_kernel(const DevPlan *__restrict__ P, InitArgs a) {
+  const ccsd_plan_desc_t &d = P->d;
+  const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
+  const int obj = blockIdx.y;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj == 0) {
+    for (size_t g = start; g < (size_t)d.B * N * F; g += stride) {
+      const int b = (int)(g / (N * F)), p = (int)(g - (size_t)b * N * F), i = p / F;
+      const float z = a.px ? a.px[g] : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, -1, 0), p);
+      a.x[g] = z * a.flags[(size_t)b * N + i];
+    }
+  } else if (obj == 1) {
+    for (size_t g = start; g < (size_t)d.B * N * N; g += stride) {
+      const int b = (int)(g / (N * N)), p = (int)(g - (size_t)b * N * N), i = p / N, j = p - i * N;
+      float z = 0.f;
+      if (i != j) {
+        const int q = (i < j) ? i * N + j : j * N + i;
+        z = a.padj ? a.padj[(size_t)b * N * N + q] : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, -1, 0), q);
+      }
+      a.adj[g] = z * a.flags[(size_t)b * N + i] * a.flags[(size_t)b * N + j];
+    }
+  } else if (d.is_cc) {
+    for (size_t u = start; u < (size_t)d.B * E * Kg; u += stride) {
+      const int b = (int)(u / ((size_t)E * Kg));
+      const int rem = (int)(u - (size_t)b * E * Kg), e = rem / Kg, kg = rem - e * Kg;
+      const float *fl = a.flags + (size_t)b * N;
+      const unsigned long long zm = zero_mask_of(fl, N);
+      const float fe = fl[P->edge_ij[2 * e]] * fl[P->edge_ij[2 * e + 1]];
+      float z4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!a.pr2) normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, -1, 0), (uint32_t)(e * Kg + kg), z4);
+      for (int q = 0; q < 4; ++q) {
+        const int k = kg * 4 + q;
+        if (k >= K) break;
+        const size_t g = ((size_t)b * E + e) * K + k;
+        const float z = a.pr2 ? a.pr2[g] : z4[q];
+        a.r2[g] = z * fe * ((P->cell_mask[k] & zm) ? 0.f : 1.f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Langevin / S4 step sizes from the batch means of the per-sample norms
+// (solver.py:695-701, 763-769, 1300-1316):  cs = (snr*mean||z||/mean||g||)^2 * 2*alpha, cn = sqrt(2 cs)*eps
+struct CoefArgs {
+  const float *norm_part;  // [3][B][ntile_max][2]
+  float *coef;             // [3][2]
+  int step, s4;
+};
+
+__global__ void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ P, CoefArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int nobj = d.is_cc ? 3 : 2;
+  for (int obj = 0; obj < nobj; ++obj) {
+    const int nt = (obj == 2) ? P->ntile_r2 : 1;
+    float gs = 0.f, zs = 0.f;
+    for (int b = threadIdx.x; b < d.B; b += blockDim.x) {
+      const float *np = a.norm_part + ((size_t)(obj * d.B + b) * P->ntile_max) * 2;
+      float g2 = 0.f, z2 = 0.f;
+      for (int t = 0; t < nt; ++t) { g2 += np[2 * t]; z2 += np[2 * t + 1]; }
+      gs += sqrtf(g2);
+      zs += sqrtf(z2);
+    }
+    gs = block_sum(gs, sm);
+    zs = block_sum(zs, sm);
+    if (threadIdx.x == 0) {
+      const ccsd_objcoef_t co = P->sched[a.step * 3 + obj];
+      const float alpha = a.s4 ? co.s4_alpha : co.lg_alpha;
+      const float gm = gs / (float)d.B, zm = zs / (float)d.B;
+      const float r = d.snr * zm / gm;
+      const float cs = r * r * 2.f * alpha;
+      a.coef[obj * 2 + 0] = cs;
+      a.coef[obj * 2 + 1] = sqrtf(cs * 2.f) * d.scale_eps;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Corrector update (PC) or the whole S4 chain after the scores are known.
+struct UpdateArgs {
+  const float *flags;
+  float *x, *adj, *r2;                 // state, updated in place
+  const float *sx, *sadj, *sr2;        // scaled scores
+  const float *coef;                   // [3][2] from coef_kernel
+  float *mx, *madj, *mr2;              // means (S4)
+  const float *nx, *nadj, *nr2;        // injected raw normals [n_draws][B][...] or nullptr
+  float *tx, *tadj, *tr2;              // traj destinations (S4) or nullptr
+  int s4, denoise, write_mean_r2;
+  NoiseCtx nz;
+};
+
+__device__ __forceinline__ float upd_elem(const ccsd_objcoef_t &co, float cs, float cn, int s4, float v, float s,
+                                          const float z[3], float *mean) {
+  float o = v + cs * s + cn * z[0];  // Langevin (solver.py:700-701) / S4 correction (:1312-1316)
+  if (!s4) { *mean = v + cs * s; return o; }
+  o = co.s4_m1 * o + co.s4_s1 * z[1];       // transition(t, dt/2)      (solver.py:1339-1342)
+  o = o + co.s4_sd * s;                     // + Sdrift * dt            (:1344-1345)
+  const float mu = co.s4_m2 * o;            // transition(t+dt/2, dt/2) (:1347-1350)
+  *mean = mu;
+  return mu + co.s4_s2 * z[2];
+}
+
+__global__ void __launch_bounds__(256) update_kernel(const DevPlan *__restrict__ P, UpdateArgs a) {
+  const ccsd_plan_desc_t &d = P->d;
+  const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
+  const int obj = blockIdx.y;
+  const int ndraw = a.s4 ? 3 : 1;
+  const ccsd_objcoef_t co = P->sched[a.nz.step * 3 + obj];
+  const float cs = a.coef[obj * 2], cn = a.coef[obj * 2 + 1];
+  const size_t stride = (size_t)gridDim.x * blockDim.x, start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj == 0) {
+    const size_t tot = (size_t)d.B * N * F;
+    for (size_t g = start; g < tot; g += stride) {
+      const int b = (int)(g / (N * F)), p = (int)(g - (size_t)b * N * F), i = p / F;
+      const float f = a.flags[(size_t)b * N + i];
+      float z[3] = {0.f, 0.f, 0.f};
+      for (int s = 0; s < ndraw; ++s)
+        z[s] = f * (a.nx ? a.nx[(size_t)s * tot + g]
+                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, a.nz.step, s), p));
+      float mean;
+      const float v = upd_elem(co, cs, cn, a.s4, a.x[g], a.sx[g], z, &mean);
+      a.x[g] = v;
+      if (a.s4) {
+        a.mx[g] = mean;
+        if (a.tx && b == 0) a.tx[p] = a.denoise ? mean : v;
+      }
+    }
+  } else if (obj == 1) {
+    const size_t tot = (size_t)d.B * N * N;
+    for (size_t g = start; g < tot; g += stride) {
+      const int b = (int)(g / (N * N)), p = (int)(g - (size_t)b * N * N), i = p / N, j = p - i * N;
+      const float f = a.flags[(size_t)b * N + i] * a.flags[(size_t)b * N + j];
+      float z[3] = {0.f, 0.f, 0.f};
+      if (i != j) {
+        const int q = (i < j) ? i * N + j : j * N + i;
+        for (int s = 0; s < ndraw; ++s)
+          z[s] = f * (a.nadj ? a.nadj[(size_t)s * tot + (size_t)b * N * N + q]
+                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, a.nz.step, s), q));
+      }
+      float mean;
+      const float v = upd_elem(co, cs, cn, a.s4, a.adj[g], a.sadj[g], z, &mean);
+      a.adj[g] = v;
+      if (a.s4) {
+        a.madj[g] = mean;
+        if (a.tadj && b == 0) a.tadj[p] = a.denoise ? mean : v;
+      }
+    }
+  } else if (d.is_cc) {
+    const size_t tot = (size_t)d.B * E * K;
+    for (size_t u = start; u < (size_t)d.B * E * Kg; u += stride) {
+      const int b = (int)(u / ((size_t)E * Kg));
+      const int rem = (int)(u - (size_t)b * E * Kg), e = rem / Kg, kg = rem - e * Kg;
+      const float *fl = a.flags + (size_t)b * N;
+      const unsigned long long zm = zero_mask_of(fl, N);
+      const float fe = fl[P->edge_ij[2 * e]] * fl[P->edge_ij[2 * e + 1]];
+      float zz[3][4];
+      for (int s = 0; s < 3; ++s)
+        for (int q = 0; q < 4; ++q) zz[s][q] = 0.f;
+      if (!a.nr2)
+        for (int s = 0; s < ndraw; ++s)
+          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, a.nz.step, s), (uint32_t)(e * Kg + kg), zz[s]);
+      for (int q = 0; q < 4; ++q) {
+        const int k = kg * 4 + q;
+        if (k >= K) break;
+        const size_t g = ((size_t)b * E + e) * K + k;
+        const float m = fe * ((P->cell_mask[k] & zm) ? 0.f : 1.f);
+        float z[3] = {0.f, 0.f, 0.f};
+        for (int s = 0; s < ndraw; ++s) z[s] = m * (a.nr2 ? a.nr2[(size_t)s * tot + g] : zz[s][q]);
+        float mean;
+        const float v = upd_elem(co, cs, cn, a.s4, a.r2[g], a.sr2[g], z, &mean);
+        a.r2[g] = v;
+        if (a.s4) {
+          if (a.write_mean_r2) a.mr2[g] = mean;
+          if (a.tr2 && b == 0) a.tr2[(size_t)e * K + k] = a.denoise ? mean : v;
+        }
+      }
+    }
+  }
+}
+
+// quantize / quantize_mol (graph_utils.py:181-213)
+__global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__ in, uint8_t *__restrict__ out,
+                                                        size_t n, float thr, int mol) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+    const float v = in[g];
+    uint8_t q;
+    if (mol) q = v >= 2.5f ? 3 : (v >= 1.5f ? 2 : (v >= 0.5f ? 1 : 0));
+    else q = v < thr ? 0 : 1;
+    out[g] = q;
+  }
+}
+
+}  // namespace ccsd
