@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: sampled complexes/sec of the full PC sampler.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (torchrun for N > 1) prints ONE
+JSON line.  Workload = BASELINE.json configs[1]: community_small_CC (N=20, F=11, E=190, K=1140),
+ScoreNetworkX + ScoreNetworkA_CC + ScoreNetworkF, VP x3, Euler predictor + Langevin corrector
+(snr .05, scale_eps .7), batch 1024 PER GPU, shipped-checkpoint weights (tests/golden), synthetic
+node-count flags, Philox noise.  A "step" is one sampler iteration (corrector + predictor, 2 score
+triples) over the whole batch on the real 1000-step schedule; ``value`` = complexes/sec of the full
+1000-step sampler = B_total / (ms_per_step * 1000 steps).  With the default K = 1000 the timed
+region IS the whole sampler run (prior sampling included).
+
+``--impl reference`` times the reference algorithm's CPU port (oracle/ccsd_oracle.py, validated
+against the unmodified reference in the build container -- the reference itself is Python and
+cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (golden weights, per-GPU batch, CPU-baseline batch [reference's own per-call batch, SURVEY 8d])
+    "community_small_cc": ("community_small_cc", 1024, 32),
+    "qm9_cc": ("qm9_cc", 10000, 2500),
+    "enzymes_small_cc": ("enzymes_small_cc", 4096, 64),
+    "community_small": ("community_small", 128, 128),
+    "qm9": ("qm9", 1024, 1024),
+}
+
+
+class Holder:
+    def __init__(self, kind, hp, sd):
+        self.__dict__.update(hp)
+        self.model_type = kind
+        self._sd = sd
+
+    def state_dict(self):
+        return self._sd
+
+    def eval(self):
+        return self
+
+
+def load_workload(name):
+    z = np.load(ROOT / "tests" / "golden" / f"weights_{name}.npz")
+    meta = json.loads(bytes(z["meta"]).decode())
+    keys = ["x", "adj"] + (["rank2"] if meta["is_cc"] else [])
+    holders = []
+    for k in keys:
+        hp = meta["params"][k]
+        sd = {kk[len(k) + 1:]: torch.from_numpy(z[kk]) for kk in z.files if kk.startswith(k + "/")}
+        holders.append(Holder(hp["model_type"], hp, sd))
+    return meta, keys, holders
+
+
+def make_flags(N, B, seed=0):
+    """Synthetic node-count mask: n_b uniform on [ceil(N/2), N] (SURVEY 8d fallback)."""
+    rng = np.random.RandomState(seed)
+    n = rng.randint((N + 1) // 2, N + 1, size=B)
+    return torch.from_numpy((np.arange(N)[None, :] < n[:, None]).astype(np.float32))
+
+
+def dims(meta):
+    from ccsd_b200.packer import rank2_dim
+    d = meta["data"]
+    N, F = d["max_node_num"], d["max_feat_num"]
+    if meta["is_cc"]:
+        E, K = rank2_dim(N, d["d_min"], d["d_max"])
+        return N, F, E, K, d["d_min"], d["d_max"]
+    return N, F, 0, 0, None, None
+
+
+def shapes_of(meta, B):
+    N, F, E, K, _, _ = dims(meta)
+    return [(B, N, F), (B, N, N)] + ([(B, E, K)] if meta["is_cc"] else [])
+
+
+# ---- algorithmic FLOPs (dense-matmul 2mnk only) ------------------------------------
+def mlp_flops(rows, dims_):
+    return sum(2 * rows * a * b for a, b in zip(dims_[:-1], dims_[1:]))
+
+
+def xa_flops(meta):
+    N, F, E, K, _, _ = dims(meta)
+    px, pa = meta["params"]["x"], meta["params"]["adj"]
+    fl = 0
+    din = F
+    for _ in range(px["depth"]):
+        fl += 2 * N * din * px["nhid"] + 2 * N * N * px["nhid"]
+        din = px["nhid"]
+    fd = F + px["depth"] * px["nhid"]
+    fl += mlp_flops(N, [fd, 2 * fd, 2 * fd, F])
+    L, nl, c0, ch, cf, nh, ad = (pa[k] for k in ("num_layers", "num_linears", "c_init", "c_hid", "c_final", "nhid", "adim"))
+    fl += (c0 - 1) * 2 * N ** 3
+    cin, kin, fdA = c0, F, c0
+    for l in range(L):
+        cout = ch if l < L - 1 or L == 1 else cf
+        a = nh if l == 0 else ad
+        fl += cin * (2 * N * kin * (2 * a + nh) + 2 * N * N * (2 * a + nh) + 2 * N * N * a)
+        hid = 2 * max(cin, cout)
+        fl += mlp_flops(N, [cin * nh, hid, nh])
+        fl += mlp_flops(N * N, [2 * cin] + [hid] * (nl - 1) + [cout])
+        cin, kin = cout, nh
+        fdA += cout
+    if meta["is_cc"] and pa["model_type"] == "ScoreNetworkA_CC":
+        fdA += c0 + (pa["c_hid_h"] if pa["num_layers_h"] > 1 else 0) + (pa["c_final_h"] if pa["num_layers_h"] > 1 else pa["c_hid_h"])
+    fl += mlp_flops(N * N, [fdA, 2 * fdA, 2 * fdA, 1])
+    return fl
+
+
+def kernel_alg_flops(meta, B, pr0):
+    N, F, E, K, _, _ = dims(meta)
+    out = {"xa_kernel": B * xa_flops(meta)}
+    if meta["is_cc"]:
+        out["gram_kernel"] = B * 2 * E * (E + pr0) * K
+        out["tc_gram_kernel"] = out["gram_kernel"]
+        out["apply_kernel"] = B * 2 * E * E * K
+    return out
+
+
+# ---- clocks -----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU baseline (oracle port) ---------------------------------------------------------------
+def cpu_baseline(workload, budget_s=20.0, threads=None):
+    from oracle import ccsd_oracle as O
+    wname, _, B = WORKLOADS[workload]
+    meta, keys, holders = load_workload(wname)
+    N, F, E, K, d_min, d_max = dims(meta)
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    models = [O.Model(h.model_type, meta["params"][k], h.state_dict(), is_cc=meta["is_cc"]) for k, h in zip(keys, holders)]
+    s = meta["sde"]
+    sdes = [O.make_sde(s[k]["type"], s[k]["beta_min"], s[k]["beta_max"], s[k]["num_scales"]) for k in keys]
+    sh = meta["shipped_sampler"]
+    flags = make_flags(N, B)
+    shapes = shapes_of(meta, B)
+
+    def run(steps):
+        kw = dict(snr=sh["snr"], scale_eps=sh["scale_eps"], denoise=True, eps=1e-4, d_min=d_min, d_max=d_max,
+                  noise=O.NoiseSource(0), max_steps=steps)
+        t0 = time.perf_counter()
+        if sh["predictor"] == "S4":
+            O.s4_solver(models, sdes, shapes, flags, **kw)
+        else:
+            O.pc_sampler(models, sdes, shapes, flags, predictor=sh["predictor"], corrector=sh["corrector"], n_steps=1, **kw)
+        return time.perf_counter() - t0
+
+    t1 = run(1)  # also warms the allocator; includes prior sampling
+    steps = int(max(2, min(50, budget_s / max(t1, 1e-3))))
+    t = run(steps)
+    ms_step = 1000.0 * t / steps
+    value = B / (ms_step * 1e-3 * 1000)
+    return {"value": value, "unit": "complexes/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} sampler steps of the real 1000-step schedule at B={B} (the reference's own per-call batch), "
+                      f"oracle port of ccsd/src/solver.py on torch CPU fp32, {ms_step:.1f} ms/step, extrapolated to 1000 steps",
+            "ms_per_step": ms_step, "batch": B}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    # steps/warmup are honoured as bounded samples: each "step" is one sampler iteration at the CPU batch
+    cb = cpu_baseline(args.workload, budget_s=float(os.environ.get("CCSD_CPU_BUDGET_S", "45")))
+    wname, B_gpu, _ = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "sampled complexes/sec (full PC sampler)", "value": cb["value"],
+        "unit": "complexes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic flags + torch CPU noise; shipped-checkpoint weights",
+        "config": {"workload": f"{wname} PC sampler, CPU port of the reference at B={cb['batch']}", "timed": cb["sample"]},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "complexes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ---- main -------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="community_small_cc", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: BASELINE size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from ccsd_b200 import build as _build
+    _build.build_cuda()  # no-op when the in-tree .so is current
+    from ccsd_b200.solver import Engine, get_pc_sampler, S4_solver, quantize
+    from ccsd_b200 import sde as bsde
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback. Use --impl reference for the CPU port.")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    wname, B, _ = WORKLOADS[args.workload]
+    B = args.batch or B
+    meta, keys, holders = load_workload(wname)
+    N, F, E, K, d_min, d_max = dims(meta)
+    s = meta["sde"]
+    mk = {"VP": bsde.VPSDE, "VE": bsde.VESDE, "subVP": bsde.subVPSDE}
+    sdes = [mk[s[k]["type"]](s[k]["beta_min"], s[k]["beta_max"], s[k]["num_scales"]) for k in keys]
+    sh = meta["shipped_sampler"]
+    shapes = shapes_of(meta, B)
+    sampler = "S4" if sh["predictor"] == "S4" else "PC"
+    n_total = sdes[1].N
+    K_steps = max(1, min(args.steps, n_total))
+    flags_host = make_flags(N, B, seed=rank).pin_memory()
+    flags = flags_host.to(dev, non_blocking=True)
+    eng = Engine(holders, sdes, shapes, sampler=sampler, predictor=sh["predictor"], corrector=sh["corrector"],
+                 snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1, denoise=True, eps=1e-4, device=dev, d_min=d_min,
+                 d_max=d_max)
+    eng.enable_traj()  # the reference records sample 0 every step (solver.py:1149-1165); so do we
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(outs):
+        """single NCCL gather of the (quantised) results, BASELINE.json north_star"""
+        if world == 1:
+            return
+        q = [outs[0]] + [quantize(t) for t in outs[1:]]
+        for t in q:
+            bufs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(bufs, t)
+
+    # warm-up: W untimed steps
+    eng.init(flags, seed=1234, sample_offset=rank * B)
+    eng.run(0, max(args.warmup, 3))
+    gather(eng.read(True))
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    eng.init(flags, seed=1234, sample_offset=rank * B)
+    eng.run(0, K_steps)
+    outs = eng.read(True)
+    gather(outs)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / K_steps
+    value = (B * world) / (ms_per_step * 1e-3 * n_total)
+
+    # ---- e2e: public API, host buffers, H2D of the inputs and D2H of the results in the timed region
+    fac = S4_solver if sampler == "S4" else get_pc_sampler
+    kw = dict(predictor=sh["predictor"], corrector=sh["corrector"], snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1,
+              probability_flow=False, continuous=True, denoise=True, eps=1e-4, device=dev)
+    if meta["is_cc"]:
+        kw.update(is_cc=True, sde_rank2=sdes[2], shape_rank2=shapes[2], d_min=d_min, d_max=d_max)
+    del eng
+    torch.cuda.empty_cache()
+    fn = fac(sdes[0], sdes[1], shapes[0], shapes[1], **kw)
+    host_out = [torch.empty(sh_, dtype=torch.float32).pin_memory() for sh_ in shapes]
+    fn(*holders, flags_host.to(dev, non_blocking=True), seed=1, sample_offset=rank * B, max_steps=3)  # builds the plan
+    barrier()
+    t0 = time.perf_counter()
+    res = fn(*holders, flags_host.to(dev, non_blocking=True), seed=1234, sample_offset=rank * B, max_steps=K_steps)
+    for h, t in zip(host_out, res[: len(shapes)]):
+        h.copy_(t, non_blocking=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = (B * world) / (e2e_s / K_steps * n_total)
+    h2d = flags_host.numel() * 4
+    d2h = sum(int(np.prod(s_)) for s_ in shapes) * 4
+
+    # ---- per-kernel device times (CUDA events on the launching stream) + roofline of the dominant kernel
+    roofline = None
+    prof_summary = {}
+    if rank == 0:
+        eng2 = Engine(holders, sdes, shapes, sampler=sampler, predictor=sh["predictor"], corrector=sh["corrector"],
+                      snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1, denoise=True, eps=1e-4, device=dev,
+                      d_min=d_min, d_max=d_max)
+        eng2.init(flags, seed=1234, sample_offset=0)
+        eng2.run(0, 3)
+        torch.cuda.synchronize()
+        eng2.set_profiling(True)
+        eng2.run(3, 3 + args.profile_steps)
+        recs = eng2.get_profile()
+        eng2.set_profiling(False)
+        for nm, t in recs:
+            a = prof_summary.setdefault(nm, [0.0, 0])
+            a[0] += t
+            a[1] += 1
+        tot = sum(v[0] for v in prof_summary.values()) or 1.0
+        dom = max(prof_summary, key=lambda k_: prof_summary[k_][0])
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        src = "measured (MEASURED_PEAKS.json, sustained)"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        if not pk.exists():
+            src = "fallback (B200_PROFILING.md)"
+        alg = kernel_alg_flops(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
+        avg_ms = prof_summary[dom][0] / prof_summary[dom][1]
+        ach = alg.get(dom, 0) / (avg_ms * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None, "peak_source": src, "avg_launch_ms": avg_ms,
+                    "share_of_step": prof_summary[dom][0] / tot,
+                    "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / tot,
+                                     "alg_tflops": alg.get(k_, 0) / (v[0] / v[1] * 1e-3) / 1e12}
+                                for k_, v in prof_summary.items()}}
+        del eng2
+
+    if rank == 0:
+        line = {
+            "metric": "sampled complexes/sec (full PC sampler)", "value": value, "unit": "complexes/s",
+            "n_gpus": world, "steps": K_steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "us_per_score_step": ms_per_step * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic node-count flags + Philox noise; shipped-checkpoint weights (tests/golden)",
+            "config": {"workload": f"{wname}: N={N} F={F} E={E} K={K}, {sampler} sampler {sh['predictor']}+{sh['corrector']} "
+                                   f"snr={sh['snr']} scale_eps={sh['scale_eps']}, {n_total}-step schedule, batch {B} per GPU",
+                       "global_batch": B * world, "parallelism": f"dp{world} (batch shards, no per-step collective, one NCCL gather)",
+                       "l2": "state per step (>= 0.9 GB of rank-2 tensors) is larger than L2; no flush needed",
+                       "timed": f"{K_steps} sampler steps incl. prior sampling" + (" = the whole sampler run" if K_steps == n_total else " (scaled to 1000)")},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "complexes/s", "h2d_bytes_per_step": h2d / K_steps, "d2h_bytes_per_step": d2h / K_steps,
+                    "seconds": e2e_s, "call": "ccsd_b200.get_pc_sampler(...)(models, init_flags) with pinned host flags in, pinned host results out"},
+            "roofline": roofline,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload).items() if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,11 +30,6 @@ def _stale(target: Path) -> bool:
     return any(s.stat().st_mtime > t for s in _sources())
 
 
-def _cuda_include() -> list:
-    """Driver-API header location for the TMA tensor-map types (cuda.h ships with the toolkit)."""
-    return []
-
-
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale(LIB):
         return LIB
@@ -42,7 +37,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     LIB.parent.mkdir(parents=True, exist_ok=True)
     cmd = [
         nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-        "-Xcompiler", "-fPIC", "-shared", "-o", str(LIB), str(CSRC / "ccsd_b200.cu"), "-lcuda",
+        "-Xcompiler", "-fPIC", "-shared", "-o", str(LIB), str(CSRC / "ccsd_b200.cu"),
     ]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -72,7 +72,30 @@ struct ccsd_plan {
   size_t xa_smem = 0, apply_smem = 0;
   int64_t launches = 0;
   int use_tc = 0;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool profiling = false;
+  struct ProfRec { const char *name; void *e0, *e1; };
+  std::vector<ProfRec> prof;
 };
+
+#ifdef CCSD_EMU
+#define PROF_BEGIN(p, nm, stream) ((void)0)
+#define PROF_END(p, stream) ((void)0)
+#else
+static void prof_begin(ccsd_plan *p, const char *name, void *stream) {
+  if (!p->profiling) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, (cudaStream_t)stream);
+  p->prof.push_back({name, (void *)a, (void *)b});
+}
+static void prof_end(ccsd_plan *p, void *stream) {
+  if (!p->profiling) return;
+  cudaEventRecord((cudaEvent_t)p->prof.back().e1, (cudaStream_t)stream);
+}
+#define PROF_BEGIN(p, nm, stream) prof_begin(p, nm, stream)
+#define PROF_END(p, stream) prof_end(p, stream)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 static int a4(int v) { return (v + 3) & ~3; }
@@ -341,9 +364,17 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     }
   }
 #ifndef CCSD_EMU
-  cudaError_t e1 = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->xa_smem);
-  cudaError_t e2 = cudaSuccess;
-  if (d.is_cc) e2 = cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+  // the attribute is per function, not per plan: only ever raise it (several plans may coexist)
+  static size_t xa_attr = 0, apply_attr = 0;
+  cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+  if (p->xa_smem > xa_attr) {
+    e1 = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->xa_smem);
+    if (e1 == cudaSuccess) xa_attr = p->xa_smem;
+  }
+  if (d.is_cc && p->apply_smem > apply_attr) {
+    e2 = cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+    if (e2 == cudaSuccess) apply_attr = p->apply_smem;
+  }
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     delete p;
     return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -430,20 +461,26 @@ static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, con
   const ccsd_plan_desc_t &d = p->hp.d;
 #ifndef CCSD_EMU
   if (p->use_tc) {
+    PROF_BEGIN(p, "tc_gram_kernel", stream);
     if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, stream)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
+    PROF_END(p, stream);
     p->launches++;
   } else
 #endif
   {
     GramArgs g; g.r2 = r2; g.H = p->H; g.P0 = p->P0;
     const int ncols = d.E + p->hp.PR0;
+    PROF_BEGIN(p, "gram_kernel", stream);
     CCSD_LAUNCH(gram_kernel, dim3((ncols + GRAM_BN - 1) / GRAM_BN, (d.E + GRAM_BM - 1) / GRAM_BM, d.B), 256,
                 2 * GRAM_BK * (GRAM_BM + 4) * 4, stream, p->dP, g);
+    PROF_END(p, stream);
     p->launches++;
   }
   if (p->hp.PR1 > 0) {
     Proj1Args q; q.r2 = r2; q.adj = adj; q.flags = flags; q.P1 = p->P1;
+    PROF_BEGIN(p, "proj1_kernel", stream);
     CCSD_LAUNCH(proj1_kernel, dim3(d.E, d.B, 1), 128, (2 * 64 + 16 + p->hp.Kp + 4) * 4, stream, p->dP, q);
+    PROF_END(p, stream);
     p->launches++;
   }
   return dev_check("rank2 pre-pass");
@@ -472,7 +509,9 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     a.noise_adj = nadj ? nadj + (size_t)slot * sa : nullptr;
     if (mode == MODE_SCORE) { a.out_x = p->sx; a.out_adj = p->sadj; }
     else { a.out_x = p->x; a.out_adj = p->adj; a.mean_x = p->mx; a.mean_adj = p->madj; a.traj_x = tx; a.traj_adj = ta; }
+    PROF_BEGIN(p, "xa_kernel", stream);
     CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), XA_THREADS, p->xa_smem, stream, p->dP, a);
+    PROF_END(p, stream);
     p->launches++;
     if (d.is_cc) {
       ApplyArgs q; memset(&q, 0, sizeof q);
@@ -481,20 +520,26 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
       q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
       if (mode == MODE_SCORE) q.out = p->sr2;
       else { q.out = p->r2; q.mean = p->mr2; q.write_mean = write_mean; q.traj = tr; }
+      PROF_BEGIN(p, "apply_kernel", stream);
       CCSD_LAUNCH(apply_kernel, dim3(p->hp.ntile_r2, d.B, 1), 256, p->apply_smem, stream, p->dP, q);
+      PROF_END(p, stream);
       p->launches++;
     }
     return dev_check("score phase");
   };
   auto update_phase = [&]() -> int {
     CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4;
+    PROF_BEGIN(p, "coef_kernel", stream);
     CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
+    PROF_END(p, stream);
     UpdateArgs u; memset(&u, 0, sizeof u);
     u.flags = p->flags; u.x = p->x; u.adj = p->adj; u.r2 = p->r2; u.sx = p->sx; u.sadj = p->sadj; u.sr2 = p->sr2;
     u.coef = p->coef; u.mx = p->mx; u.madj = p->madj; u.mr2 = p->mr2; u.nx = nx; u.nadj = nadj; u.nr2 = nr2;
     u.tx = tx; u.tadj = ta; u.tr2 = tr; u.s4 = s4; u.denoise = d.denoise; u.write_mean_r2 = write_mean; u.nz = nz;
     const size_t units = d.is_cc ? (size_t)d.B * d.E * (p->hp.Kp / 4) : sa;
+    PROF_BEGIN(p, "update_kernel", stream);
     CCSD_LAUNCH(update_kernel, dim3(grid_for(units), d.is_cc ? 3 : 2, 1), 256, 0, stream, p->dP, u);
+    PROF_END(p, stream);
     p->launches += 2;
     return dev_check("update phase");
   };
@@ -575,5 +620,32 @@ int ccsd_quantize(const float *in, uint8_t *out, size_t n, float thr, int mol, v
 }
 
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }
+
+int ccsd_plan_set_profiling(ccsd_plan_t *p, int on) {
+  if (!p) return fail(CCSD_ERR_INVALID, "null plan");
+#ifndef CCSD_EMU
+  for (auto &r : p->prof) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
+#endif
+  p->prof.clear();
+  p->profiling = on != 0;
+  return 0;
+}
+
+int ccsd_plan_get_profile(ccsd_plan_t *p, int max_records, char *names, int name_stride, float *ms) {
+  if (!p || !names || !ms) return fail(CCSD_ERR_INVALID, "null argument");
+  int n = 0;
+#ifndef CCSD_EMU
+  for (auto &r : p->prof) {
+    if (n >= max_records) break;
+    if (cudaEventSynchronize((cudaEvent_t)r.e1) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaEventSynchronize failed");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, (cudaEvent_t)r.e0, (cudaEvent_t)r.e1);
+    ms[n] = t;
+    snprintf(names + (size_t)n * name_stride, name_stride, "%s", r.name);
+    ++n;
+  }
+#endif
+  return n;
+}
 
 }  // extern "C"

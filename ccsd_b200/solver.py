@@ -206,6 +206,19 @@ class Engine:
                                            _ptr(out), self._stream()))
         return out
 
+    def set_profiling(self, on: bool) -> None:
+        nat.check(self.lib.ccsd_plan_set_profiling(self.handle, int(on)))
+
+    def get_profile(self, max_records: int = 65536):
+        """[(kernel name, ms)] for every launch since set_profiling(True) (waits for the events)."""
+        names = C.create_string_buffer(max_records * 32)
+        ms = (C.c_float * max_records)()
+        n = self.lib.ccsd_plan_get_profile(self.handle, max_records, names, 32, ms)
+        if n < 0:
+            nat.check(n)
+        raw = names.raw
+        return [(raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]
+
     @property
     def launches(self) -> int:
         return int(self.lib.ccsd_plan_launch_count(self.handle))

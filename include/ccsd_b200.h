@@ -189,6 +189,12 @@ int ccsd_quantize(const float *in_dev, uint8_t *out_dev, size_t n, float thr, in
 /* Number of kernel launches issued by this plan so far (bench.py's gpu_launches). */
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *plan);
 
+/* Per-kernel device timing for bench.py's roofline: when on, every launch of ccsd_plan_step /
+ * ccsd_plan_run is bracketed by CUDA events on the launching stream.  ccsd_plan_get_profile waits
+ * for them and returns the number of records written (name_stride bytes per name). */
+int ccsd_plan_set_profiling(ccsd_plan_t *plan, int on);
+int ccsd_plan_get_profile(ccsd_plan_t *plan, int max_records, char *names, int name_stride, float *ms);
+
 const char *ccsd_last_error(void);
 const char *ccsd_version(void);
 

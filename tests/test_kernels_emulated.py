@@ -1,0 +1,49 @@
+"""CPU-side check of the kernels' index arithmetic, weight packing and masks: the SAME kernel
+sources compiled for the host (one thread per block, tests/_emu) against the oracle.  This is not
+a product path -- it only exists so that a box without a GPU can catch layout bugs; the parity
+tests proper are tests/test_parity_gpu.py."""
+import pytest
+import torch
+
+from ccsd_b200 import _native as nat
+from tests.parity_cases import SCORE_TOL, sampler_parity, score_parity
+
+pytestmark = pytest.mark.skipif(torch.cuda.is_available(), reason="host emulation is only used where there is no GPU")
+
+
+def test_emulation_build_is_flagged():
+    assert nat.is_emulation()
+    assert b"EMULATION" in nat.load().ccsd_version()
+
+
+@pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1)])
+def test_scores(name, B):
+    for k, e in score_parity(name, B, "cpu").items():
+        assert e < SCORE_TOL, (name, k, e)
+
+
+def test_scores_community_small_cc():
+    for k, e in score_parity("community_small_cc", 1, "cpu").items():
+        assert e < SCORE_TOL, (k, e)
+
+
+@pytest.mark.parametrize("name,sampler,pred,corr", [
+    ("qm9", "PC", "Reverse", "Langevin"),
+    ("qm9", "PC", "Euler", "None"),
+    ("qm9", "S4", "None", "None"),
+    ("qm9_cc", "PC", "Reverse", "Langevin"),
+    ("qm9_cc", "PC", "Euler", "Langevin"),
+    ("qm9_cc", "S4", "None", "None"),
+    ("enzymes_small_cc", "S4", "None", "None"),
+])
+def test_sampler_steps(name, sampler, pred, corr):
+    res = sampler_parity(name, sampler, pred, corr, B=2, steps=2, device="cpu")
+    for k, (e_ret, e_state, agree) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4, (name, k, e_ret, e_state)
+        assert agree >= 0.999
+
+
+def test_sampler_not_denoised():
+    res = sampler_parity("qm9_cc", "PC", "Reverse", "Langevin", B=2, steps=2, device="cpu", denoise=False)
+    for k, (e_ret, e_state, _) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4
