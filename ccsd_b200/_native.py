@@ -57,7 +57,7 @@ class NetA(C.Structure):
 class NetF(C.Structure):
     _fields_ = [
         ("num_layers", i32), ("cnum", i32), ("fdim", i32), ("use_hodge_mask", i32),
-        ("layer", Mlp * MAX_F_LAYERS), ("fin", Mlp),
+        ("layer", Mlp * MAX_F_LAYERS), ("fin", Mlp), ("affine", i32), ("aff", f32 * 3),
     ]
 
 

@@ -326,7 +326,20 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.Kp = a4(d.K);
   p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
   p->hp.ntile_max = imax(1, p->hp.ntile_r2);
-  p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40) * 4 : 0;
+  p->hp.f_mode = 0; p->hp.f_nlin = 0;
+  if (d.is_cc && (d.nets & 4)) {
+    const ccsd_netf_t &Fn = d.netf;
+    bool w8 = Fn.fin.nl == 1 && Fn.fdim <= 40;
+    int nlin = 0;
+    for (int l = 0; l < Fn.num_layers; ++l) {
+      const ccsd_mlp_t &M = Fn.layer[l];
+      if (M.din > 8 || M.dout > 8 || (M.nl > 1 && M.dhid > 8)) w8 = false;
+      nlin += M.nl;
+    }
+    if (Fn.affine) p->hp.f_mode = 1;
+    else if (w8) { p->hp.f_mode = 2; p->hp.f_nlin = nlin; }
+  }
+  p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)p->hp.f_nlin * 72 + 48) * 4 : 0;
   if (p->xa_smem > 227 * 1024 || p->apply_smem > 227 * 1024) {
     char buf[160];
     snprintf(buf, sizeof buf, "graph tile does not fit shared memory (xa %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
@@ -372,7 +385,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     if (e1 == cudaSuccess) xa_attr = p->xa_smem;
   }
   if (d.is_cc && p->apply_smem > apply_attr) {
-    e2 = cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+    e2 = cudaFuncSetAttribute(apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
     if (e2 == cudaSuccess) apply_attr = p->apply_smem;
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -456,6 +471,13 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
   return dev_check("init_kernel");
 }
 
+static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
+  const dim3 grid(p->hp.ntile_r2, p->hp.d.B, 1);
+  if (p->hp.f_mode == 1) CCSD_LAUNCH(apply_kernel<1>, grid, 256, p->apply_smem, stream, p->dP, q);
+  else if (p->hp.f_mode == 2) CCSD_LAUNCH(apply_kernel<2>, grid, 256, p->apply_smem, stream, p->dP, q);
+  else CCSD_LAUNCH(apply_kernel<0>, grid, 256, p->apply_smem, stream, p->dP, q);
+}
+
 // H, P0 (and P1) of the rank-2 tensor `r2` (+ adj for P1)
 static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, const float *flags, void *stream) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -521,7 +543,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
       if (mode == MODE_SCORE) q.out = p->sr2;
       else { q.out = p->r2; q.mean = p->mr2; q.write_mean = write_mean; q.traj = tr; }
       PROF_BEGIN(p, "apply_kernel", stream);
-      CCSD_LAUNCH(apply_kernel, dim3(p->hp.ntile_r2, d.B, 1), 256, p->apply_smem, stream, p->dP, q);
+      launch_apply(p, q, stream);
       PROF_END(p, stream);
       p->launches++;
     }
@@ -605,7 +627,7 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
     if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
     ApplyArgs q; memset(&q, 0, sizeof q);
     q.r2 = r2; q.H = p->H; q.flags = flags; q.mode = MODE_EVAL; q.out = out;
-    CCSD_LAUNCH(apply_kernel, dim3(p->hp.ntile_r2, d.B, 1), 256, p->apply_smem, stream, p->dP, q);
+    launch_apply(p, q, stream);
     p->launches++;
     return dev_check("apply_kernel");
   }

@@ -49,6 +49,8 @@ struct DevPlan {
   int Kp;                         // K rounded up to 4 (Philox groups per rank-2 row = Kp/4)
   int ntile_r2;                   // apply-kernel column tiles per sample
   int ntile_max;                  // stride of the per-object norm partials
+  int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled
+  int f_nlin;                     // number of Linears staged for f_mode 2
 };
 
 // modes of the score kernels

@@ -207,6 +207,64 @@ __device__ __forceinline__ float netf_entry(const ccsd_netf_t &Fn, const float *
   return out[0] * m;
 }
 
+// Fast path for networks whose every layer is at most 8 wide and whose final MLP is one Linear:
+// weights staged in shared memory as zero-padded 8x8 blocks (72 floats per Linear: W[8][8], b[8]),
+// then the final weights (40 floats) and bias; everything unrolled into registers.
+__device__ __forceinline__ float netf_entry_w8(const ccsd_netf_t &Fn, const float *fw, int nlin, float f, float hf,
+                                               float m) {
+  const float *wf = fw + nlin * 72;
+  float cur[8] = {f, hf, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float acc = wf[40] + wf[0] * f + wf[1] * hf;
+  int off = 2, li = 0;
+  for (int l = 0; l < Fn.num_layers; ++l) {
+    const int nl = Fn.layer[l].nl;
+    for (int i = 0; i < nl; ++i, ++li) {
+      const float *Wm = fw + li * 72;
+      float t[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) t[o] = Wm[64 + o];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) t[o] += cur[k] * Wm[k * 8 + o];
+      if (i == nl - 1) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) cur[o] = t[o] * m;
+      } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) cur[o] = t[o] > 0.f ? t[o] : expm1f(t[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc += wf[off + o] * cur[o];
+    off += Fn.layer[l].dout;
+  }
+  return acc * m;
+}
+
+__device__ __forceinline__ void netf_stage_w8(const ccsd_netf_t &Fn, const float *__restrict__ W, float *fw) {
+  int li = 0;
+  for (int l = 0; l < Fn.num_layers; ++l) {
+    const ccsd_mlp_t &M = Fn.layer[l];
+    for (int i = 0; i < M.nl; ++i, ++li) {
+      const int din = (i == 0) ? M.din : M.dhid;
+      for (int p = threadIdx.x; p < 72; p += blockDim.x) {
+        float v;
+        if (p < 64) v = (p / 8 < din) ? __ldg(W + M.w[i] + p) : 0.f;   // rows are 8 floats (out_pad = 8)
+        else v = __ldg(W + M.b[i] + (p - 64));
+        fw[li * 72 + p] = v;
+      }
+    }
+  }
+  // final Linear: (fd, out_pad=8) with out = 1 -> column 0
+  for (int p = threadIdx.x; p < 41; p += blockDim.x) {
+    float v = 0.f;
+    if (p < 40) v = (p < Fn.fin.din) ? __ldg(W + Fn.fin.w[0] + p * 8) : 0.f;
+    else v = __ldg(W + Fn.fin.b[0]);
+    fw[li * 72 + p] = v;
+  }
+}
+
 struct ApplyArgs {
   const float *r2, *H, *flags;   // [B,E,K] [B,E,E] [B,N]
   int mode;
@@ -219,6 +277,72 @@ struct ApplyArgs {
   NoiseCtx nz;
 };
 
+// Per-CTA epilogue context (everything the per-entry work needs), shared by the fp32 and the
+// tensor-core apply kernels.
+struct R2Epi {
+  const DevPlan *P;
+  const float *fl;       // flags of this sample
+  const float *fw;       // staged ScoreNetworkF weights (f_mode 2) in shared memory
+  unsigned long long zm; // zero-flag node mask
+  unsigned long long gs; // global sample index
+  ccsd_objcoef_t co;
+  int b, E, K, Kg, f_nlin;
+  float aff0, aff1, aff2;
+};
+
+// 4 consecutive cells k0..k0+3 of edge row e: network -> score -> mode-specific output.
+// f4: state entries, hf4: (H F) entries.  Accumulates the squared norms for MODE_SCORE.
+template <int FMODE>
+__device__ __forceinline__ void r2_epilogue4(const R2Epi &c, const ApplyArgs &a, int e, int k0, const float f4[4],
+                                             const float hf4[4], float &s2, float &z2) {
+  const DevPlan *P = c.P;
+  const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+  const float fe = c.fl[i] * c.fl[j];
+  float z4[4] = {0.f, 0.f, 0.f, 0.f};
+  const size_t g0 = ((size_t)c.b * c.E + e) * c.K + k0;
+  if (a.mode != MODE_EVAL) {
+    if (a.noise) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (k0 + q < c.K) z4[q] = a.noise[g0 + q];
+    } else {
+      normal4(a.nz.seed, c.gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(e * c.Kg + (k0 >> 2)), z4);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = k0 + q;
+    if (k < c.K) {
+      const float fc = (P->cell_mask[k] & c.zm) ? 0.f : 1.f;
+      const float m = fe * fc;
+      const float f = f4[q];
+      float o;
+      if (FMODE == 1) o = m * (c.aff0 * f + c.aff1 * hf4[q] + c.aff2);
+      else if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf4[q], m);
+      else o = netf_entry(P->d.netf, P->W, f, hf4[q], m);
+      const size_t g = g0 + q;
+      if (a.mode == MODE_EVAL) {
+        a.out[g] = o;
+      } else {
+        const float s = c.co.score_scale * o;
+        const float z = z4[q] * m;
+        if (a.mode == MODE_SCORE) {
+          a.out[g] = s;
+          s2 += s * s;
+          z2 += z * z;
+        } else {
+          const float mu = c.co.pa * f + c.co.pb * s;
+          const float v = mu + c.co.pc * z;
+          a.out[g] = v;
+          if (a.write_mean) a.mean[g] = mu;
+          if (a.traj && c.b == 0) a.traj[(size_t)e * c.K + k] = a.denoise ? mu : v;
+        }
+      }
+    }
+  }
+}
+
+template <int FMODE>
 __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
@@ -227,79 +351,38 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
   const float *Fb = a.r2 + (size_t)b * E * K;
   const float *Hb = a.H + (size_t)b * E * E;
   const float *fl = a.flags + (size_t)b * N;
-  const float *W = P->W;
   constexpr int LDF = APPLY_TN + 4, LDH = 64 + 4;
   float *Fs = sm;                         // [E][LDF]
   float *Hs = sm + (size_t)E * LDF;       // [16][LDH]
   float *red = Hs + 16 * LDH;             // [40]
-  const unsigned long long zm = zero_mask_of(fl, N);
-  const ccsd_objcoef_t co = (a.mode == MODE_EVAL) ? ccsd_objcoef_t{} : P->sched[a.nz.step * 3 + 2];
-  const unsigned long long gs = (unsigned long long)(a.nz.sample_offset + b);
-  const int Kg = P->Kp >> 2;
+  float *fw = red + 40;                   // staged ScoreNetworkF weights (f_mode 2)
+  if (FMODE == 2) netf_stage_w8(d.netf, P->W, fw);
+  R2Epi c;
+  c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
+  c.gs = (unsigned long long)(a.nz.sample_offset + b);
+  if (a.mode != MODE_EVAL) c.co = P->sched[a.nz.step * 3 + 2];
+  c.b = b; c.E = E; c.K = K; c.Kg = P->Kp >> 2; c.f_nlin = P->f_nlin;
+  c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
 
   for (int p = threadIdx.x; p < E * APPLY_TN; p += blockDim.x) {
-    const int e = p / APPLY_TN, c = p - e * APPLY_TN;
-    const int k = n0 + c;
-    Fs[e * LDF + c] = (k < K) ? Fb[(size_t)e * K + k] : 0.f;
+    const int e = p / APPLY_TN, cc = p - e * APPLY_TN;
+    const int k = n0 + cc;
+    Fs[e * LDF + cc] = (k < K) ? Fb[(size_t)e * K + k] : 0.f;
   }
   __syncthreads();
 
   float s2 = 0.f, z2 = 0.f;
-
-  // per-element epilogue shared by both builds
-  auto finish = [&](int e, int cq, const float hf4[4]) {
-    // e: edge row, cq: first of 4 consecutive tile columns
-    const int k0 = n0 + cq;
-    if (e >= E || k0 >= K) return;
-    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
-    const float fe = fl[i] * fl[j];
-    float z4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a.mode != MODE_EVAL) {
-      if (a.noise) {
-        for (int q = 0; q < 4; ++q)
-          if (k0 + q < K) z4[q] = a.noise[((size_t)b * E + e) * K + k0 + q];
-      } else {
-        normal4(a.nz.seed, gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(e * Kg + (k0 >> 2)), z4);
-      }
-    }
-    for (int q = 0; q < 4; ++q) {
-      const int k = k0 + q;
-      if (k >= K) break;
-      const float fc = (P->cell_mask[k] & zm) ? 0.f : 1.f;
-      const float m = fe * fc;
-      const float f = Fs[e * LDF + cq + q];
-      const float o = netf_entry(d.netf, W, f, hf4[q], m);
-      const size_t g = ((size_t)b * E + e) * K + k;
-      if (a.mode == MODE_EVAL) {
-        a.out[g] = o;
-      } else {
-        const float s = co.score_scale * o;
-        const float z = z4[q] * m;
-        if (a.mode == MODE_SCORE) {
-          a.out[g] = s;
-          s2 += s * s;
-          z2 += z * z;
-        } else {
-          const float mu = co.pa * f + co.pb * s;
-          const float v = mu + co.pc * z;
-          a.out[g] = v;
-          if (a.write_mean) a.mean[g] = mu;
-          if (a.traj && b == 0) a.traj[(size_t)e * K + k] = a.denoise ? mu : v;
-        }
-      }
-    }
-  };
-
 #ifdef CCSD_EMU
   (void)Hs;
   for (int e = 0; e < E; ++e)
     for (int cq = 0; cq < APPLY_TN; cq += 4) {
+      if (n0 + cq >= K) continue;
       float hf4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int e2 = 0; e2 < E; ++e2) {
         const float h = Hb[(size_t)e * E + e2];
         for (int q = 0; q < 4; ++q) hf4[q] += h * Fs[e2 * LDF + cq + q];
       }
-      finish(e, cq, hf4);
+      r2_epilogue4<FMODE>(c, a, e, n0 + cq, Fs + e * LDF + cq, hf4, s2, z2);
     }
 #else
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -323,17 +406,23 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
         if (e2 < E) {
           const float4 av = *reinterpret_cast<const float4 *>(Hs + kk * LDH + ty * 4);
           const float4 bv = *reinterpret_cast<const float4 *>(Fs + e2 * LDF + tx * 4);
-          const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += aa[i] * bb[j];
+          acc[0][0] += av.x * bv.x; acc[0][1] += av.x * bv.y; acc[0][2] += av.x * bv.z; acc[0][3] += av.x * bv.w;
+          acc[1][0] += av.y * bv.x; acc[1][1] += av.y * bv.y; acc[1][2] += av.y * bv.z; acc[1][3] += av.y * bv.w;
+          acc[2][0] += av.z * bv.x; acc[2][1] += av.z * bv.y; acc[2][2] += av.z * bv.z; acc[2][3] += av.z * bv.w;
+          acc[3][0] += av.w * bv.x; acc[3][1] += av.w * bv.y; acc[3][2] += av.w * bv.z; acc[3][3] += av.w * bv.w;
         }
       }
       __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) finish(m0 + ty * 4 + i, tx * 4, acc[i]);
+    for (int i = 0; i < 4; ++i) {
+      const int e = m0 + ty * 4 + i;
+      if (e < E && n0 + tx * 4 < K) {
+        const float4 fv = *reinterpret_cast<const float4 *>(Fs + e * LDF + tx * 4);
+        const float f4[4] = {fv.x, fv.y, fv.z, fv.w};
+        r2_epilogue4<FMODE>(c, a, e, n0 + tx * 4, f4, acc[i], s2, z2);
+      }
+    }
   }
 #endif
   if (a.mode == MODE_SCORE) {

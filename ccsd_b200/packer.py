@@ -221,6 +221,25 @@ def pack_netf(dst: nat.NetF, blob: Blob, model) -> None:
     dst.use_hodge_mask = 1 if getattr(m, "use_hodge_mask", True) else 0
     if int(getattr(m, "cnum", dst.cnum)) != dst.cnum:
         raise ValueError("ScoreNetworkF: cnum attribute disagrees with the first layer's input width")
+    # affine fold: all MLPs single Linears -> score = m * (a f + b (H f) + c)   (masks are {0,1})
+    dst.affine = 0
+    if dst.cnum == 2 and dst.fin.nl == 1 and all(dst.layer[l].nl == 1 for l in range(L)):
+        def lin(prefix):
+            return sd[f"{prefix}.linear.weight"].astype(np.float64), sd[f"{prefix}.linear.bias"].astype(np.float64)
+        A = np.eye(2)            # current channels as an affine map of v = [f, H f]:  cur = A v + c
+        c = np.zeros(2)
+        rows_A, rows_c = [A], [c]
+        for l in range(L):
+            W, b = lin(f"layers.{l}.layer")
+            A, c = W @ A, W @ c + b
+            rows_A.append(A)
+            rows_c.append(c)
+        Wf, bf = lin("final")
+        A_all, c_all = np.concatenate(rows_A, 0), np.concatenate(rows_c, 0)
+        coef = Wf @ A_all            # (1, 2)
+        gamma = float(Wf @ c_all + bf)
+        dst.affine = 1
+        dst.aff[0], dst.aff[1], dst.aff[2] = float(coef[0, 0]), float(coef[0, 1]), gamma
 
 
 def rank2_dim(N: int, d_min: int, d_max: int) -> Tuple[int, int]:

@@ -103,6 +103,12 @@ typedef struct {
   int32_t num_layers, cnum, fdim, use_hodge_mask;
   ccsd_mlp_t layer[CCSD_MAX_F_LAYERS]; /* HodgeNetworkLayer MLPs (hodge_layers.py:17-92) */
   ccsd_mlp_t fin;
+  /* When every MLP of the network is a single Linear (num_linears == 1 and num_layers_mlp == 1, as in
+   * the shipped community_small / ego_small / grid_small / QM9 CC checkpoints) there is no activation
+   * anywhere and, the masks being {0,1}, the score is m * (aff[0]*f + aff[1]*(H f) + aff[2]).  The
+   * packer folds the chain on the host (float64) and sets affine = 1. */
+  int32_t affine;
+  float aff[3];
 } ccsd_netf_t;
 
 /* Per-step, per-object scalars, computed on the host with the reference's own torch fp32
