@@ -7,6 +7,7 @@
 //   predictor:  gram(F1) [proj1] xa(PRED)  apply(PRED)                   -> (x2, adj2, F2)
 // and per S4 step:  gram [proj1] xa(SCORE) apply(SCORE) coef update(S4 chain).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -395,6 +396,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = 0;  // A/B switch for tests and profiling
   if (p->use_tc) {
     if (int r = tc_gram_prepare()) { delete p; return fail(CCSD_ERR_CUDA, "tc_gram_prepare failed"); }
   }
@@ -642,6 +644,23 @@ int ccsd_quantize(const float *in, uint8_t *out, size_t n, float thr, int mol, v
 }
 
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }
+
+int ccsd_debug_gram(ccsd_plan_t *p, const float *r2, float *H_out, float *P0_out, int use_tc, void *stream) {
+  if (!p || !r2 || !p->bound || !p->hp.d.is_cc) return fail(CCSD_ERR_INVALID, "ccsd_debug_gram: bound CC plan required");
+  const ccsd_plan_desc_t &d = p->hp.d;
+  const int saved = p->use_tc;
+#ifndef CCSD_EMU
+  if (use_tc && !tc_gram_supported(d.E, d.K, p->hp.PR0)) return fail(CCSD_ERR_UNSUPPORTED, "tensor-core Gram kernel does not cover this shape");
+  if (use_tc) tc_gram_prepare();
+#endif
+  p->use_tc = use_tc;
+  int r = launch_rank2_pre(p, r2, p->adj, p->flags, stream);
+  p->use_tc = saved;
+  if (r) return r;
+  if (H_out) if (int e = dev_copy(H_out, p->H, (size_t)d.B * d.E * d.E * 4, stream)) return e;
+  if (P0_out && p->hp.PR0) if (int e = dev_copy(P0_out, p->P0, (size_t)d.B * d.E * p->hp.PR0 * 4, stream)) return e;
+  return 0;
+}
 
 int ccsd_plan_set_profiling(ccsd_plan_t *p, int on) {
   if (!p) return fail(CCSD_ERR_INVALID, "null plan");

@@ -206,6 +206,17 @@ class Engine:
                                            _ptr(out), self._stream()))
         return out
 
+    def debug_gram(self, rank2: torch.Tensor, use_tc: bool):
+        """(H, P0) of `rank2` through the fp32 FMA or the tcgen05 Gram kernel (test seam)."""
+        d = self.desc
+        r2 = self._dev(rank2)
+        pr0 = d.neta.n_proj_rows[0] if (d.nets & 2 and d.neta.is_cc) else 0
+        H = torch.empty(d.B, d.E, d.E, dtype=torch.float32, device=self.device)
+        P0 = torch.empty(d.B, d.E, max(pr0, 1), dtype=torch.float32, device=self.device)
+        nat.check(self.lib.ccsd_debug_gram(self.handle, _ptr(r2), _ptr(H), _ptr(P0) if pr0 else None, int(use_tc),
+                                           self._stream()))
+        return H, P0[:, :, :pr0]
+
     def set_profiling(self, on: bool) -> None:
         nat.check(self.lib.ccsd_plan_set_profiling(self.handle, int(on)))
 

@@ -201,6 +201,10 @@ int64_t ccsd_plan_launch_count(const ccsd_plan_t *plan);
 int ccsd_plan_set_profiling(ccsd_plan_t *plan, int on);
 int ccsd_plan_get_profile(ccsd_plan_t *plan, int max_records, char *names, int name_stride, float *ms);
 
+/* Test seam: H = (F F^T)(1-I) and P0 = F Wp^T of `r2` ([B,E,K]) through the fp32 FMA kernel
+ * (use_tc = 0) or the tcgen05 kernel (use_tc = 1); outputs [B,E,E] and [B,E,PR0] (either may be NULL). */
+int ccsd_debug_gram(ccsd_plan_t *plan, const float *r2, float *H_out, float *P0_out, int use_tc, void *stream);
+
 const char *ccsd_last_error(void);
 const char *ccsd_version(void);
 
