@@ -8,14 +8,14 @@
 // product is accumulated as hi.hi + hi.lo + lo.hi in the fp32 TMEM accumulator (dropped lo.lo term
 // ~2^-18 relative) -- "bf16x3".
 //
-// One persistent CTA per SM, 9 warps:
-//   warps 0-3  producers: coalesced fp32 loads of F rows (+ the projection rows of the weight blob),
+// One persistent CTA per SM, 13 warps:
+//   warps 0-7  producers (all loads of a k-block are issued before the split, >= 56 KB in flight per SM): coalesced fp32 loads of F rows (+ the projection rows of the weight blob),
 //              hi/lo split, st.shared into the canonical K-major SWIZZLE_128B operand layout
 //              (row r, 16-byte chunk c at (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16)), one stage =
 //              64 k-values x 256 rows x {hi, lo} = 64 KB, 3-stage mbarrier ring;
-//   warp  8    one elected thread issues tcgen05.mma (M=128, N=ncols, K=16; 2 M tiles x 3 terms x 4
+//   warp  12   one elected thread issues tcgen05.mma (M=128, N=ncols, K=16; 2 M tiles x 3 terms x 4
 //              k-steps per stage), tcgen05.commit frees the stage / publishes the accumulator;
-//   warps 4-7  epilogue: tcgen05.ld (32 lanes x 16 columns) -> masked stores of H and P0.
+//   warps 8-11 epilogue: tcgen05.ld (32 lanes x 16 columns) -> masked stores of H and P0.
 // A and B read the SAME shared-memory rows (rows < E are F; rows wp0.. are Wp), so F is converted once.
 #pragma once
 #include "plan_dev.h"
@@ -23,7 +23,9 @@
 
 namespace ccsd {
 
-constexpr int TG_THREADS = 288;
+constexpr int TG_PROD_WARPS = 8;
+constexpr int TG_PROD = TG_PROD_WARPS * 32;
+constexpr int TG_THREADS = TG_PROD + 128 + 32;   // producers, 4 epilogue warps, 1 MMA warp
 constexpr int TG_STAGES = 3;
 constexpr int TG_BK = 64;
 constexpr uint32_t TG_HALF = 256 * 128;   // bytes of the hi (or lo) half of a stage
@@ -40,7 +42,7 @@ static inline int tc_gram_wp0(int E) { return (E + 7) & ~7; }
 static inline int tc_gram_ncols(int E, int PR0) { return (tc_gram_wp0(E) + PR0 + 15) & ~15; }
 static inline int tc_gram_supported(int E, int K, int PR0) {
   (void)K;
-  return E >= 8 && E <= 248 && tc_gram_ncols(E, PR0) <= 256;
+  return E >= 8 && E <= 192 && PR0 <= 32 && tc_gram_ncols(E, PR0) <= 256;
 }
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *__restrict__ P, TcGramArgs a) {
@@ -63,71 +65,92 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
-      tc::mbar_init(full0 + 8 * s, 128);  // every producer thread arrives
+      tc::mbar_init(full0 + 8 * s, 128);      // every thread of the producer group that fills it
       tc::mbar_init(empty0 + 8 * s, 1);   // tcgen05.commit
     }
     tc::mbar_init(tfull, 1);
     tc::mbar_init(tempty, 128);           // every epilogue thread arrives
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(tslot, 512);
+  if (warp == TG_PROD_WARPS + 4) tc::tmem_alloc(tslot, 512);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tslot_gen;
 
-  if (warp < 4) {
+  if (warp < TG_PROD_WARPS) {
     // ===================== producers =====================
+    // Two independent groups of 4 warps fill alternate k-blocks, so two k-blocks (~100 KB of loads)
+    // are in flight per SM without register double buffering.  Within a group, thread t owns the
+    // 16-byte chunk c = t & 7 of rows (t >> 3) + 16 j: global and shared addresses advance by constant
+    // strides and the 24 loads of a k-block are independent.
     const float *Wp = P->W + d.neta.proj_w;
-    const int tasks = (E + PR0) * 8;
     const bool vec = (K & 3) == 0;
-    uint32_t it = 0;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    constexpr int NT = 12;                      // 16 * 12 = 192 rows of F per k-block (E <= 192)
+    const int grp = warp >> 2, tg = threadIdx.x & 127;
+    const int c = tg & 7, r0 = tg >> 3;
+    const uint32_t off0 = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
+    const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long total = (long)nmine * nkb;
+    for (long g = grp; g < total; g += 2) {
+      const int b = (int)blockIdx.x + (int)(g / nkb) * (int)gridDim.x;
+      const int kb = (int)(g % nkb);
       const float *Fb = a.r2 + (size_t)b * E * K;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % TG_STAGES;
-        const uint32_t ph = (it / TG_STAGES) & 1;
-        tc::mbar_wait(empty0 + 8 * s, ph ^ 1);
-        uint8_t *st = gen_base + (size_t)s * TG_STAGE;
-        for (int t = threadIdx.x; t < tasks; t += 128) {
-          const int rr = t >> 3, c = t & 7;
-          const int k = kb * TG_BK + c * 8;
-          float x[8];
-          int row;
-          if (rr < E) {
-            row = rr;
-            const float *src = Fb + (size_t)rr * K + k;
-            if (vec && k + 8 <= K) {
-              const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src));
-              const float4 v1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
-              x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            } else {
+      const int k = kb * TG_BK + c * 8;
+      const bool fast = vec && (kb * TG_BK + TG_BK <= K);
+      const float *src = Fb + (size_t)r0 * K + k;
+      float x[NT][8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) x[q] = (k + q < K) ? __ldg(src + q) : 0.f;
-            }
+      for (int j = 0; j < NT; ++j) {
+        if (r0 + 16 * j < E) {
+          const float *sj = src + (size_t)(16 * j) * K;
+          if (fast) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sj));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sj + 4));
+            x[j][0] = v0.x; x[j][1] = v0.y; x[j][2] = v0.z; x[j][3] = v0.w;
+            x[j][4] = v1.x; x[j][5] = v1.y; x[j][6] = v1.z; x[j][7] = v1.w;
           } else {
-            row = wp0 + (rr - E);
-            const float *src = Wp + (size_t)(rr - E) * Kw + k;   // rows are zero padded to Kw (multiple of 4)
-            if (k + 8 <= Kw) {
-              const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src));
-              const float4 v1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
-              x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) x[q] = (k + q < Kw) ? __ldg(src + q) : 0.f;
-            }
+            for (int q = 0; q < 8; ++q) x[j][q] = (k + q < K) ? __ldg(sj + q) : 0.f;
           }
-          uint4 hi, lo;
-          tc::split8(x, hi, lo);
-          const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4 *>(st + off) = hi;
-          *reinterpret_cast<uint4 *>(st + TG_HALF + off) = lo;
         }
-        tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-        tc::mbar_arrive(full0 + 8 * s);
       }
+      const int s = (int)(g % TG_STAGES);
+      const uint32_t ph = (uint32_t)(g / TG_STAGES) & 1;
+      tc::mbar_wait(empty0 + 8 * s, ph ^ 1);
+      uint8_t *st = gen_base + (size_t)s * TG_STAGE;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (r0 + 16 * j < E) {
+          uint4 hi, lo;
+          tc::split8(x[j], hi, lo);
+          *reinterpret_cast<uint4 *>(st + off0 + j * 2048u) = hi;
+          *reinterpret_cast<uint4 *>(st + TG_HALF + off0 + j * 2048u) = lo;
+        }
+      }
+      // projection rows of the weight blob (zero padded to Kw, L1/L2 resident)
+      for (int rw = r0; rw < PR0; rw += 16) {
+        const float *sw = Wp + (size_t)rw * Kw + k;
+        float y[8];
+        if (k + 8 <= Kw) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sw));
+          const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sw + 4));
+          y[0] = v0.x; y[1] = v0.y; y[2] = v0.z; y[3] = v0.w; y[4] = v1.x; y[5] = v1.y; y[6] = v1.z; y[7] = v1.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) y[q] = (k + q < Kw) ? __ldg(sw + q) : 0.f;
+        }
+        const int row = wp0 + rw;
+        const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+        uint4 hi, lo;
+        tc::split8(y, hi, lo);
+        *reinterpret_cast<uint4 *>(st + off) = hi;
+        *reinterpret_cast<uint4 *>(st + TG_HALF + off) = lo;
+      }
+      tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      tc::mbar_arrive(full0 + 8 * s);
     }
-  } else if (warp == 8) {
+  } else if (warp == TG_PROD_WARPS + 4) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = tc::make_idesc_bf16(128, ncols, 0, 0);
     uint32_t it = 0, tile = 0;
@@ -162,7 +185,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       }
     }
   } else {
-    // ===================== epilogue (warps 4-7 -> TMEM lane quarters 0-3) =====================
+    // ===================== epilogue (warps 8-11 -> TMEM lane quarters 0-3) =====================
     const int q = warp & 3;
     const int mask_diag = d.netf.use_hodge_mask;
     uint32_t tile = 0;
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == TG_PROD_WARPS + 4) tc::tmem_dealloc(tmem, 512);
 }
 
 static inline int tc_gram_prepare() {
