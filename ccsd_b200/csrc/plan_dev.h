@@ -5,7 +5,7 @@
 
 namespace ccsd {
 
-constexpr int XA_THREADS = 256;
+constexpr int XA_THREADS = 512;
 constexpr int SMALL_MAX = 32;     // widest layer of the per-entry / per-edge "small" MLPs
 constexpr int GRAM_BM = 64, GRAM_BN = 64, GRAM_BK = 16;
 constexpr int APPLY_TN = 64;      // cell columns per apply-kernel CTA

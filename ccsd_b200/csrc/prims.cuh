@@ -27,21 +27,37 @@ __device__ __forceinline__ void dense2(const float *in1, int ld1, int K1, const 
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     }
     const float *wp = W + oc;
-    for (int k = 0; k < K1; ++k) {
-      const float v = in1[k * ld1 + r];
-      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wp));
-      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
-      acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-      acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
-      wp += Opad;
-    }
-    for (int k = 0; k < K2; ++k) {
-      const float v = in2[k * ld2 + r];
-      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wp));
-      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
-      acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-      acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
-      wp += Opad;
+    // the two input segments are walked with the same code; k is unrolled by 4 with every load of
+    // the group issued before the FMAs (the weights come from L1/L2: latency, not bandwidth, bound)
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {
+      const float *in = seg ? in2 : in1;
+      const int ld = seg ? ld2 : ld1, K = seg ? K2 : K1;
+      int k = 0;
+      for (; k + 4 <= K; k += 4) {
+        float v[4];
+        float4 w0[4], w1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = in[(k + u) * ld + r];
+          w0[u] = __ldg(reinterpret_cast<const float4 *>(wp + u * Opad));
+          w1[u] = __ldg(reinterpret_cast<const float4 *>(wp + u * Opad + 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[0] += v[u] * w0[u].x; acc[1] += v[u] * w0[u].y; acc[2] += v[u] * w0[u].z; acc[3] += v[u] * w0[u].w;
+          acc[4] += v[u] * w1[u].x; acc[5] += v[u] * w1[u].y; acc[6] += v[u] * w1[u].z; acc[7] += v[u] * w1[u].w;
+        }
+        wp += 4 * Opad;
+      }
+      for (; k < K; ++k) {
+        const float v = in[k * ld + r];
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
+        acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
+        acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+        wp += Opad;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)

@@ -196,7 +196,7 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(XA_THREADS) xa_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+__global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XaLayout &L = P->xa;
