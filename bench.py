@@ -128,6 +128,7 @@ def kernel_alg_flops(meta, B, pr0):
         out["gram_kernel"] = B * 2 * E * (E + pr0) * K
         out["tc_gram_kernel"] = out["gram_kernel"]
         out["apply_kernel"] = B * 2 * E * E * K
+        out["tc_apply_kernel"] = out["apply_kernel"]
     return out
 
 

@@ -17,6 +17,7 @@
 #include "xa_kernel.cuh"
 #ifndef CCSD_EMU
 #include "tc_gram.cuh"
+#include "tc_apply.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -72,7 +73,7 @@ struct ccsd_plan {
   long long sample_offset = 0;
   size_t xa_smem = 0, apply_smem = 0;
   int64_t launches = 0;
-  int use_tc = 0;
+  int use_tc = 0, use_tc_apply = 0;
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
   struct ProfRec { const char *name; void *e0, *e1; };
@@ -396,7 +397,11 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = 0;  // A/B switch for tests and profiling
+  p->use_tc_apply = (d.is_cc && (d.nets & 4)) ? tc_apply_supported(d.E, d.K) : 0;
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = 0;  // A/B switch for tests and profiling
+  if (p->use_tc_apply) {
+    if (int r = tc_apply_prepare()) { delete p; return fail(CCSD_ERR_CUDA, "tc_apply_prepare failed"); }
+  }
   if (p->use_tc) {
     if (int r = tc_gram_prepare()) { delete p; return fail(CCSD_ERR_CUDA, "tc_gram_prepare failed"); }
   }
@@ -474,6 +479,9 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
 }
 
 static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
+#ifndef CCSD_EMU
+  if (p->use_tc_apply) { tc_apply_launch(p->dP, p->hp, q, stream); return; }
+#endif
   const dim3 grid(p->hp.ntile_r2, p->hp.d.B, 1);
   if (p->hp.f_mode == 1) CCSD_LAUNCH(apply_kernel<1>, grid, 256, p->apply_smem, stream, p->dP, q);
   else if (p->hp.f_mode == 2) CCSD_LAUNCH(apply_kernel<2>, grid, 256, p->apply_smem, stream, p->dP, q);
@@ -544,7 +552,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
       q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
       if (mode == MODE_SCORE) q.out = p->sr2;
       else { q.out = p->r2; q.mean = p->mr2; q.write_mean = write_mean; q.traj = tr; }
-      PROF_BEGIN(p, "apply_kernel", stream);
+      PROF_BEGIN(p, p->use_tc_apply ? "tc_apply_kernel" : "apply_kernel", stream);
       launch_apply(p, q, stream);
       PROF_END(p, stream);
       p->launches++;
