@@ -43,6 +43,8 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 static inline float __uint2float_rn(uint32_t v) { return (float)v; }
 static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
 static inline float __shfl_sync(unsigned, float v, int) { return v; }
+#define CCSD_FAST_LOGF(v) logf(v)
+#define CCSD_FAST_SINCOSF(v, s, c) sincosf(v, s, c)
 #define CCSD_SMEM(name) float *name = ccsd_emu_smem
 typedef void *cudaStream_t;
 template <class Fn> static inline void ccsd_emu_launch(dim3 grid, size_t smem_bytes, Fn fn) {
@@ -64,6 +66,8 @@ template <class Fn> static inline void ccsd_emu_launch(dim3 grid, size_t smem_by
   ccsd_emu_launch(dim3(grid), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
 #else
 #include <cuda_runtime.h>
+#define CCSD_FAST_LOGF(v) __logf(v)
+#define CCSD_FAST_SINCOSF(v, s, c) __sincosf(v, s, c)
 #define CCSD_SMEM(name) extern __shared__ __align__(16) float name[]
 #define CCSD_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
@@ -134,11 +138,13 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t sample, uint32_t
   const float u1 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u2 = ((float)(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u3 = ((float)(r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  // Box-Muller with the SFU intrinsics (|err| ~1e-6 on a unit normal: irrelevant for noise, and 4x
+  // fewer instructions than the IEEE-accurate libm paths -- the draw is on the per-entry hot path)
+  const float ra = sqrtf(-2.0f * CCSD_FAST_LOGF(u0)), rb = sqrtf(-2.0f * CCSD_FAST_LOGF(u2));
   float s, c;
-  sincosf(6.283185307179586f * u1, &s, &c);
+  CCSD_FAST_SINCOSF(6.283185307179586f * u1, &s, &c);
   z[0] = ra * c; z[1] = ra * s;
-  sincosf(6.283185307179586f * u3, &s, &c);
+  CCSD_FAST_SINCOSF(6.283185307179586f * u3, &s, &c);
   z[2] = rb * c; z[3] = rb * s;
 }
 

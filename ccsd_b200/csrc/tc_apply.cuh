@@ -30,7 +30,7 @@ constexpr uint32_t TA_B = 2u * TA_BHALF;         // 147456
 constexpr uint32_t TA_AHALF = 2u * 8192u;        // 16384: hi (or lo) half of one A stage
 constexpr uint32_t TA_ASTAGE = 2u * TA_AHALF;    // 32768
 constexpr int TA_STAGES = 2;
-constexpr size_t TA_SMEM = (size_t)TA_B + TA_STAGES * TA_ASTAGE + 1024 + 512 + 6144 /*staged F-net weights*/;
+constexpr size_t TA_SMEM = (size_t)TA_B + TA_STAGES * TA_ASTAGE + 1024 + 1024 + 6144 /*staged F-net weights*/;
 
 static inline int tc_apply_supported(int E, int K) { return E >= 8 && E <= TA_NE && K >= 8; }
 
@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   uint8_t *gen_bars = gen + TA_B + TA_STAGES * TA_ASTAGE;
   uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen_bars + 80);
   float *red = reinterpret_cast<float *>(gen_bars + 128);   // [2][8] warp partials
-  float *fw = reinterpret_cast<float *>(gen_bars + 512);    // staged ScoreNetworkF weights (FMODE 2)
+  float *fes = reinterpret_cast<float *>(gen_bars + 256);   // [192] per-edge flag products of the sample
+  float *fw = reinterpret_cast<float *>(gen_bars + 1024);   // staged ScoreNetworkF weights (FMODE 2)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TA_STAGES; ++s) {
@@ -228,52 +229,63 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       c.b = b; c.E = E; c.K = K; c.Kg = Kg; c.f_nlin = P->f_nlin;
       c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
       const float *Fb = a.r2 + (size_t)b * E * K;
+      const float *Nb = a.noise ? a.noise + (size_t)b * E * K : nullptr;
+      // per-edge node-mask products for this sample (shared by the 8 epilogue warps)
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous sample's readers are done
+      for (int e = et; e < TA_NE; e += TA_EPI)
+        fes[e] = e < E ? fl[P->edge_ij[2 * e]] * fl[P->edge_ij[2 * e + 1]] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       float s2 = 0.f, z2 = 0.f;
       for (int ct = 0; ct < ntile; ++ct, ++tit) {
         const int tb = tit & 1;
-        tc::mbar_wait(t_full + 8 * tb, (tit >> 1) & 1);
-        tc::tc_fence_after_sync();
         const int k = ct * 128 + q * 32 + lane;
         const bool kval = k < K;
-        const float fc = (kval && !(P->cell_mask[kval ? k : 0] & c.zm)) ? 1.f : 0.f;
+        const int kk = kval ? k : 0;
+        const float fc = (kval && !(P->cell_mask[kk] & c.zm)) ? 1.f : 0.f;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * TA_NE);
+        bool waited = false;
         for (int ch = 0; ch < 6; ++ch) {
           const int e0 = half * 96 + ch * 16;
-          float v[16];
-          tc::tmem_ld16(trow + (uint32_t)e0, v);   // all 32 lanes (sync.aligned), even past E
-          if (e0 >= E) continue;
+          if (e0 < E) {
+            // every global load of the chunk is issued before the accumulator is touched
+            float f16[16], n16[16];
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            // Philox: lane i of each aligned 4-lane group draws the normals of edge e0+4*g4+i for the
-            // group's 4 cells; a 4x4 exchange hands every lane its own cell's value for the 4 edges.
-            float zz[4] = {0.f, 0.f, 0.f, 0.f};
-            if (a.mode != MODE_EVAL && !a.noise) {
-              float z4[4];
-              const int em = e0 + 4 * g4 + (lane & 3);
-              normal4(a.nz.seed, c.gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(em * Kg + (k >> 2)), z4);
+            for (int j = 0; j < 16; ++j) {
+              const int e = (e0 + j < E) ? e0 + j : E - 1;
+              f16[j] = Fb[(size_t)e * K + kk];
+              n16[j] = (Nb && a.mode != MODE_EVAL) ? Nb[(size_t)e * K + kk] : 0.f;
+            }
+            if (!waited) { tc::mbar_wait(t_full + 8 * tb, (tit >> 1) & 1); tc::tc_fence_after_sync(); waited = true; }
+            float v[16];
+            tc::tmem_ld16(trow + (uint32_t)e0, v);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              // Philox: lane i of each aligned 4-lane group draws the normals of edge e0+4*g4+i for the
+              // group's 4 cells; a 4x4 exchange hands every lane its own cell's value for the 4 edges.
+              float zz[4] = {n16[4 * g4], n16[4 * g4 + 1], n16[4 * g4 + 2], n16[4 * g4 + 3]};
+              if (a.mode != MODE_EVAL && !Nb) {
+                float z4[4];
+                const int em = e0 + 4 * g4 + (lane & 3);
+                normal4(a.nz.seed, c.gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(em * Kg + (k >> 2)), z4);
+                const int i = lane & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int srcl = (lane & ~3) | j;
+                  const float t0 = __shfl_sync(0xffffffffu, z4[0], srcl), t1 = __shfl_sync(0xffffffffu, z4[1], srcl);
+                  const float t2 = __shfl_sync(0xffffffffu, z4[2], srcl), t3 = __shfl_sync(0xffffffffu, z4[3], srcl);
+                  zz[j] = i == 0 ? t0 : (i == 1 ? t1 : (i == 2 ? t2 : t3));
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int srcl = (lane & ~3) | j;
-                const float t0 = __shfl_sync(0xffffffffu, z4[0], srcl), t1 = __shfl_sync(0xffffffffu, z4[1], srcl);
-                const float t2 = __shfl_sync(0xffffffffu, z4[2], srcl), t3 = __shfl_sync(0xffffffffu, z4[3], srcl);
-                const int i = lane & 3;
-                zz[j] = i == 0 ? t0 : (i == 1 ? t1 : (i == 2 ? t2 : t3));
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int e = e0 + 4 * g4 + j;
-              if (e < E && kval) {
-                const int ni = P->edge_ij[2 * e], nj = P->edge_ij[2 * e + 1];
-                const float fe = fl[ni] * fl[nj];
-                const float f = Fb[(size_t)e * K + k];
-                float zr = zz[j];
-                if (a.mode != MODE_EVAL && a.noise) zr = a.noise[((size_t)b * E + e) * K + k];
-                r2_epilogue1<FMODE>(c, a, e, k, f, v[4 * g4 + j], zr, fe, fc, s2, z2);
+                const int e = e0 + 4 * g4 + j;
+                if (e < E && kval)
+                  r2_epilogue1<FMODE>(c, a, e, k, f16[4 * g4 + j], v[4 * g4 + j], zz[j], fes[e], fc, s2, z2);
               }
             }
           }
         }
+        if (!waited) { tc::mbar_wait(t_full + 8 * tb, (tit >> 1) & 1); tc::tc_fence_after_sync(); }
         tc::tc_fence_before_sync();
         tc::mbar_arrive(t_empty + 8 * tb);
       }
