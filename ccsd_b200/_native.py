@@ -123,6 +123,8 @@ def load():
     lib.ccsd_quantize.argtypes = [vp, vp, sz, C.c_float, C.c_int, vp]
     lib.ccsd_plan_launch_count.restype = C.c_int64
     lib.ccsd_plan_launch_count.argtypes = [vp]
+    lib.ccsd_plan_info.restype = C.c_int
+    lib.ccsd_plan_info.argtypes = [vp, C.c_int]
     lib.ccsd_plan_set_profiling.restype = C.c_int
     lib.ccsd_plan_set_profiling.argtypes = [vp, C.c_int]
     lib.ccsd_plan_get_profile.restype = C.c_int

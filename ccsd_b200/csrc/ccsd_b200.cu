@@ -203,56 +203,61 @@ static int validate(const ccsd_plan_desc_t &d, size_t nw) {
 
 static void make_layout(const ccsd_plan_desc_t &d, XaLayout &L) {
   memset(&L, 0, sizeof(L));
-  const int N = d.N, F = d.F, NP = N * N;
-  L.ldn = N | 1;
-  L.ldp = NP | 1;
+  const int N = d.N, F = d.F;
   const ccsd_netx_t &X = d.netx;
   const ccsd_neta_t &A = d.neta;
+  const int N4 = a4(N), NT = N * (N + 1) / 2, ldp = a4(NT);
+  L.N4 = N4; L.NT = NT; L.ldp = ldp;
+  L.T = NT >= 96 ? 128 : 64;
   int o = 0;
   auto take = [&](int n) { int r = o; o += a4(n); return r; };
-  L.flags = take(N);
-  L.dvec = take(N);
-  L.hcat = take(imax(X.fdim, F) * L.ldn);
-  L.an = take(N * L.ldn);
-  L.stack = take(imax(A.fdim, 1) * L.ldp);
-  int nh_max = 1, ad_max = 1, vc_max = 1, cin_max = 1, xw_max = a4(X.nhid), hsz = X.fin.dhid * L.ldn;
+  int nh_max = 1, ad_max = 1, cin_max = 1, kin_max = F, mc_hid = 1, eh = 1, eh_bufs = 1, heads = imax(A.num_heads, 1);
   for (int l = 0; l < A.num_layers; ++l) {
     const ccsd_attn_layer_t &ly = A.layer[l];
     nh_max = imax(nh_max, ly.conv_out);
     ad_max = imax(ad_max, ly.attn_dim);
-    vc_max = imax(vc_max, ly.c_in * ly.conv_out);
     cin_max = imax(cin_max, ly.c_in);
-    xw_max = imax(xw_max, 2 * a4(ly.attn_dim) + a4(ly.conv_out));
-    hsz = imax(hsz, ly.multi_channel.dhid * L.ldn);
-    hsz = imax(hsz, ly.mlp.dhid * L.ldp);
+    kin_max = imax(kin_max, ly.conv_in);
+    mc_hid = imax(mc_hid, imax(ly.multi_channel.dhid, ly.multi_channel.dout));
+    if (ly.mlp.nl > 1) eh = imax(eh, ly.mlp.dhid);
+    if (ly.mlp.nl > 2) eh_bufs = 2;
   }
-  for (int k = 0; k < X.depth; ++k) xw_max = imax(xw_max, a4(X.gcn[k].dout));
-  L.xa = take(nh_max * L.ldn);
-  L.xb = take(nh_max * L.ldn);
-  L.sx = take(F * L.ldn);
-  L.sadj = take(NP);
+  // torch.split: ceil(ad / (ad / heads)) chunks
+  int nch_max = 1;
+  for (int l = 0; l < A.num_layers; ++l) {
+    const int ad = A.layer[l].attn_dim, ds = imax(ad / heads, 1);
+    nch_max = imax(nch_max, (ad + ds - 1) / ds);
+  }
+  L.flags = take(N4);
+  L.dvec = take(N4);
+  L.pij = take(ldp);
+  L.an = take(N * N4);
+  L.x0 = take(F * N4);
+  L.xa = take(nh_max * N4);
+  L.xb = take(nh_max * N4);
+  L.sx = take(F * N4);
+  L.sadj = take(ldp);
   L.red = take(40);
+  L.stack = take(imax(A.fdim, 1) * ldp);
   L.scratch = o;
-  // final MLP row chunk
-  const int fin_h = imax(A.fin.dhid, 1);
-  hsz = imax(hsz, fin_h * 65);
-  int rows = hsz / fin_h - 1;
-  if (rows > NP) rows = NP;
-  L.fin_rows = rows;
-  L.fin_ld = rows | 1;
-  if (L.fin_ld * fin_h > hsz) hsz = L.fin_ld * fin_h;
+  // ---- A-net layers (scratch-relative) ----
   int s = 0;
   auto stake = [&](int n) { int r = s; s += a4(n); return r; };
-  L.ldxw = xw_max;
-  L.xw = stake(N * L.ldxw);
-  L.ldq = a4(ad_max);
-  L.qn = stake(N * L.ldq);
-  L.kf = stake(ad_max * L.ldn);
-  L.vcat = stake(vc_max * L.ldn);
-  L.att = stake(cin_max * L.ldp);
-  L.hA = stake(hsz);
-  L.hB = stake(hsz);
-  int s_layers = s;
+  L.att = stake(cin_max * ldp);
+  L.ax = stake(kin_max * N4);
+  L.hmc = stake(mc_hid * N4);
+  L.hmc2 = stake(mc_hid * N4);
+  const int work = s;
+  L.q = stake(ad_max * N4);
+  L.k = stake(ad_max * N4);
+  L.v = stake(nh_max * N4);
+  L.atp = stake(nch_max * ldp);
+  const int s_attn = s;
+  s = work;
+  L.eh_a = stake(eh * ldp);
+  L.eh_b = eh_bufs == 2 ? stake(eh * ldp) : L.eh_a;
+  const int s_layers = imax(s_attn, s);
+  // ---- hodge, two layers (scratch-relative; the attention-layer buffers are dead by then) ----
   int s_hodge = 0;
   if (d.is_cc && A.is_cc && A.num_layers_h == 2) {
     int h = 0;
@@ -265,7 +270,27 @@ static void make_layout(const ccsd_plan_desc_t &d, XaLayout &L) {
     L.hdeg = htake(A.hodge[0].c_out * E);
     s_hodge = h;
   }
-  L.total = L.scratch + imax(s_layers, s_hodge);
+  int a_end = L.scratch + imax(s_layers, s_hodge);
+  // ---- X-net (absolute; from stack channel 1 on) ----
+  int xo = L.stack + ldp;
+  auto xtake = [&](int n) { int r = xo; xo += a4(n); return r; };
+  int din_max = F;
+  for (int k = 0; k < X.depth; ++k) din_max = imax(din_max, X.gcn[k].din);
+  L.xh_cat = xtake(imax(X.depth * X.nhid, 1) * N4);
+  L.xh_ax = xtake(din_max * N4);
+  L.xh_a = xtake(imax(X.fin.dhid, 1) * N4);
+  L.xh_b = X.fin.nl > 2 ? xtake(imax(X.fin.dhid, 1) * N4) : L.xh_a;
+  int total = imax(a_end, xo);
+  // ---- final per-edge MLP: as many rows per chunk as the scratch already paid for, at least 32 ----
+  const int fin_h = imax(A.fin.nl > 1 ? A.fin.dhid : 1, 1), fin_bufs = A.fin.nl > 2 ? 2 : 1;
+  int rows = ((total - L.scratch) / (fin_bufs * fin_h)) & ~3;
+  if (rows < 32) rows = 32;
+  if (rows > ldp) rows = ldp;
+  L.fin_rows = rows;
+  L.fh_a = 0;
+  L.fh_b = fin_bufs == 2 ? a4(fin_h * rows) : 0;
+  total = imax(total, L.scratch + fin_bufs * a4(fin_h * rows));
+  L.total = total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -542,7 +567,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     if (mode == MODE_SCORE) { a.out_x = p->sx; a.out_adj = p->sadj; }
     else { a.out_x = p->x; a.out_adj = p->adj; a.mean_x = p->mx; a.mean_adj = p->madj; a.traj_x = tx; a.traj_adj = ta; }
     PROF_BEGIN(p, "xa_kernel", stream);
-    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), XA_THREADS, p->xa_smem, stream, p->dP, a);
+    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), p->hp.xa.T, p->xa_smem, stream, p->dP, a);
     PROF_END(p, stream);
     p->launches++;
     if (d.is_cc) {
@@ -629,7 +654,7 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
     a.x = x; a.adj = adj; a.flags = flags; a.P0 = p->P0; a.P1 = p->P1; a.mode = MODE_EVAL;
     a.which = which == CCSD_NET_X ? 1 : 2;
     a.out_x = out; a.out_adj = out;
-    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), XA_THREADS, p->xa_smem, stream, p->dP, a);
+    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), p->hp.xa.T, p->xa_smem, stream, p->dP, a);
     p->launches++;
     return dev_check("xa_kernel");
   }
@@ -652,6 +677,20 @@ int ccsd_quantize(const float *in, uint8_t *out, size_t n, float thr, int mol, v
 }
 
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }
+
+int ccsd_plan_info(const ccsd_plan_t *p, int what) {
+  if (!p) return -1;
+  switch (what) {
+    case 0: return (int)p->xa_smem;
+    case 1: return p->hp.xa.T;
+    case 2: return (int)p->apply_smem;
+    case 3: return p->use_tc;
+    case 4: return p->use_tc_apply;
+    case 5: return p->hp.f_mode;
+    case 6: return p->hp.xa.fin_rows;
+    default: return -1;
+  }
+}
 
 int ccsd_debug_gram(ccsd_plan_t *p, const float *r2, float *H_out, float *P0_out, int use_tc, void *stream) {
   if (!p || !r2 || !p->bound || !p->hp.d.is_cc) return fail(CCSD_ERR_INVALID, "ccsd_debug_gram: bound CC plan required");

@@ -1,159 +1,219 @@
 // prims.cuh -- block-cooperative building blocks over shared memory (fp32 FMA path).
-// Conventions: "feature-major" buffers are buf[f*ld + row]; "node-major" are buf[row*ld + f].
-// Every primitive strides work items over the block and does NOT synchronise at the end.
+//
+// Conventions
+//   * "feature-major" buffers are buf[f*ld + row] with ld a multiple of 4 and every buffer starting
+//     at a multiple of 4 floats, so that 4 consecutive rows of one feature are one 16-byte load.
+//   * Rows are processed in groups of 4; rows past the valid count (up to the next multiple of 4)
+//     may hold anything -- their results are computed and discarded, never stored.
+//   * Work items are strided over the block (`for (it = threadIdx.x; it < items; it += blockDim.x)`)
+//     and no primitive synchronises at its end unless its comment says so.
+//   * Node pairs (i <= j) of an N-node graph are stored in upper-triangle row-major order
+//     ("tri" index); every adjacency-shaped quantity of the score networks is symmetric
+//     (ScoreNetwork_A.py:505-541: powers of a symmetric matrix, symmetrised attention, M + M^T).
 #pragma once
 #include "plan_dev.h"
 
 namespace ccsd {
 
-// out(r, o) = act(bias[o] + sum_k in(k, r) * W[k*Opad + o]),  Opad = round_up(O, 8)
-// in(k, r) = k < K1 ? in1[k*ld1 + r] : in2[(k-K1)*ld2 + r]      (feature-major inputs)
-// out(r, o) stored at out[r*sro + o*soo].  W, bias in global memory (read-only path).
-__device__ __forceinline__ void dense2(const float *in1, int ld1, int K1, const float *in2, int ld2, int K2,
-                                       const float *__restrict__ W, const float *__restrict__ bias, int O,
-                                       float *out, int sro, int soo, int R, int act) {
-  const int Opad = round_up(O, 8);
-  const int nchunk = Opad >> 3;
-  const int items = nchunk * R;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int chunk = it / R, r = it - chunk * R;
-    const int oc = chunk << 3;
-    float acc[8];
-    if (bias) {
+#ifdef CCSD_EMU
+__device__ __forceinline__ float fast_tanh(float v) { return tanhf(v); }
+__device__ __forceinline__ float fast_elu(float v) { return v > 0.f ? v : expm1f(v); }
+#else
+// tanh(v) = 1 - 2 / (exp(2v) + 1): two SFU ops; absolute error ~1e-7 (the libm path is ~25 instructions)
+__device__ __forceinline__ float fast_tanh(float v) {
+  const float e = __expf(2.0f * v);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+// elu: absolute error ~1e-7 for v < 0
+__device__ __forceinline__ float fast_elu(float v) { return v > 0.f ? v : __expf(v) - 1.0f; }
+#endif
+
+__device__ __forceinline__ float act_fast(float v, int act) {
+  if (act == ACT_ELU) return fast_elu(v);
+  if (act == ACT_TANH) return fast_tanh(v);
+  return v;
+}
+
+__device__ __forceinline__ int tri_index(int i, int j, int N) {  // i <= j
+  return i * N - (i * (i - 1)) / 2 + (j - i);
+}
+__device__ __forceinline__ int tri_index_any(int i, int j, int N) { return i <= j ? tri_index(i, j, N) : tri_index(j, i, N); }
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// ---------------------------------------------------------------------------------------------
+// One 4-row x 8-output register tile of a Linear:
+//   acc[rr][j] = sum_k in(k, r0 + rr) * W[k*Opad + oc + j]
+//   in(k, r) = k < K1 ? in1[k*ld1 + r] : in2[(k-K1)*ld2 + r]   (feature-major, r0 % 4 == 0)
+// W in global memory (read-only path; shared by every CTA, so L1/L2 resident).  32 FMAs per three
+// 16-byte loads; k is unrolled by two so that six loads are in flight per thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_fma(float acc[4][8], const float4 a, const float4 w0, const float4 w1) {
+  const float av[4] = {a.x, a.y, a.z, a.w};
+  const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + oc + j);
-    } else {
+  for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    }
-    const float *wp = W + oc;
-    // the two input segments are walked with the same code; k is unrolled by 4 with every load of
-    // the group issued before the FMAs (the weights come from L1/L2: latency, not bandwidth, bound)
+    for (int j = 0; j < 8; ++j) acc[rr][j] += av[rr] * wv[j];
+}
+
+__device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, int ld1, int K1, const float *in2, int ld2,
+                                           int K2, const float *__restrict__ W, int Opad, int r0, int oc) {
+  const float *wp = W + oc;
 #pragma unroll 1
-    for (int seg = 0; seg < 2; ++seg) {
-      const float *in = seg ? in2 : in1;
-      const int ld = seg ? ld2 : ld1, K = seg ? K2 : K1;
-      int k = 0;
-      for (; k + 4 <= K; k += 4) {
-        float v[4];
-        float4 w0[4], w1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v[u] = in[(k + u) * ld + r];
-          w0[u] = __ldg(reinterpret_cast<const float4 *>(wp + u * Opad));
-          w1[u] = __ldg(reinterpret_cast<const float4 *>(wp + u * Opad + 4));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          acc[0] += v[u] * w0[u].x; acc[1] += v[u] * w0[u].y; acc[2] += v[u] * w0[u].z; acc[3] += v[u] * w0[u].w;
-          acc[4] += v[u] * w1[u].x; acc[5] += v[u] * w1[u].y; acc[6] += v[u] * w1[u].z; acc[7] += v[u] * w1[u].w;
-        }
-        wp += 4 * Opad;
-      }
-      for (; k < K; ++k) {
-        const float v = in[k * ld + r];
-        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wp));
-        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
-        acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-        acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
-        wp += Opad;
-      }
+  for (int seg = 0; seg < 2; ++seg) {
+    const float *in = (seg ? in2 : in1) + r0;
+    const int ld = seg ? ld2 : ld1, K = seg ? K2 : K1;
+    int k = 0;
+#pragma unroll 1
+    for (; k + 2 <= K; k += 2) {
+      const float4 a0 = ld4(in + k * ld), a1 = ld4(in + (k + 1) * ld);
+      const float4 w00 = __ldg(reinterpret_cast<const float4 *>(wp)), w01 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
+      const float4 w10 = __ldg(reinterpret_cast<const float4 *>(wp + Opad)), w11 = __ldg(reinterpret_cast<const float4 *>(wp + Opad + 4));
+      tile_fma(acc, a0, w00, w01);
+      tile_fma(acc, a1, w10, w11);
+      wp += 2 * Opad;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (oc + j < O) out[r * sro + (oc + j) * soo] = act_apply(acc[j], act);
+    if (k < K) {
+      const float4 a0 = ld4(in + k * ld);
+      const float4 w00 = __ldg(reinterpret_cast<const float4 *>(wp)), w01 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
+      tile_fma(acc, a0, w00, w01);
+      wp += Opad;
+    }
   }
 }
 
-// A whole MLP over R rows.  Hidden activations ping-pong between hA/hB ([dhid x ldh], feature-major).
-// Ends with a __syncthreads() after every layer (including the last).
-__device__ __forceinline__ void mlp_rows(const ccsd_mlp_t &m, const float *__restrict__ W, const float *in1,
-                                         int ld1, int K1, const float *in2, int ld2, int K2, int R, float *hA,
-                                         float *hB, int ldh, float *out, int sro, int soo, int hidden_act,
-                                         int out_act) {
+// out(r, o) = act(bias[o] + sum_k in(k, r) W[k, o]),  r < R, o < O, stored at out[r*sro + o*soo].
+// bias may be nullptr.  When `accum` the previous out(r, o) is added (and act / bias are the caller's
+// business): used to fold a Linear over a channel-concatenated input channel by channel.
+__device__ __forceinline__ void dense_fm(const float *in1, int ld1, int K1, const float *in2, int ld2, int K2,
+                                         const float *__restrict__ W, const float *__restrict__ bias, int O,
+                                         float *out, int sro, int soo, int R, int act, bool accum = false) {
+  const int Opad = round_up(O, 8);
+  const int nchunk = Opad >> 3, ngrp = (R + 3) >> 2;
+  const int items = nchunk * ngrp;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int chunk = it / ngrp, g = it - chunk * ngrp;
+    const int oc = chunk << 3, r0 = g << 2;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bv = bias ? __ldg(bias + oc + j) : 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) acc[rr][j] = bv;
+    }
+    dense_tile(acc, in1, ld1, K1, in2, ld2, K2, W, Opad, r0, oc);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = r0 + rr;
+      if (r < R) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (oc + j < O) {
+            float *dst = out + r * sro + (oc + j) * soo;
+            *dst = accum ? *dst + acc[rr][j] : act_fast(acc[rr][j], act);
+          }
+      }
+    }
+  }
+}
+
+// A whole MLP over R rows (feature-major in / hidden).  Hidden activations ping-pong between hA and hB
+// ([dhid x ldh]).  __syncthreads() after every layer, including the last.
+__device__ __forceinline__ void mlp_fm(const ccsd_mlp_t &m, const float *__restrict__ W, const float *in1, int ld1,
+                                       int K1, const float *in2, int ld2, int K2, int R, float *hA, float *hB, int ldh,
+                                       float *out, int sro, int soo, int hidden_act, int out_act) {
   const float *cur1 = in1, *cur2 = in2;
   int c_ld1 = ld1, c_K1 = K1, c_ld2 = ld2, c_K2 = K2;
   for (int l = 0; l < m.nl; ++l) {
     const bool last = (l == m.nl - 1);
     const int O = last ? m.dout : m.dhid;
     float *dst = last ? out : ((l & 1) ? hB : hA);
-    dense2(cur1, c_ld1, c_K1, cur2, c_ld2, c_K2, W + m.w[l], W + m.b[l], O, dst, last ? sro : 1,
-           last ? soo : ldh, R, last ? out_act : hidden_act);
+    dense_fm(cur1, c_ld1, c_K1, cur2, c_ld2, c_K2, W + m.w[l], W + m.b[l], O, dst, last ? sro : 1, last ? soo : ldh, R,
+             last ? out_act : hidden_act);
     __syncthreads();
     cur1 = dst; c_ld1 = ldh; c_K1 = O; cur2 = nullptr; c_ld2 = 0; c_K2 = 0;
   }
 }
 
-// DenseGCNConv normalisation (layers.py:139-147): A^ = adj with unit diagonal,
-// d = rowsum(A^).clamp(min=1)^-1/2, an[i][j] = d_i * A^_ij * d_j.  adj: row-major N x N (ld = N).
-// Contains two __syncthreads (dvec is ready after the first; `an` after the second).
-__device__ __forceinline__ void gcn_norm(const float *adj, int N, float *dvec, float *an, int ldn) {
+// DenseGCNConv normalisation (layers.py:139-147) of one symmetric adjacency channel in tri storage:
+// A^ = adj with unit diagonal, d = rowsum(A^).clamp(min=1)^-1/2, an[i][j] = d_i A^_ij d_j (full,
+// symmetric, [N x N4]).  Two __syncthreads (dvec after the first, `an` after the second).
+__device__ __forceinline__ void gcn_norm_tri(const float *adj_tri, int N, int N4, float *dvec, float *an) {
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     float s = 0.f;
-    for (int j = 0; j < N; ++j) s += (j == i) ? 1.f : adj[i * N + j];
+    for (int j = 0; j < N; ++j) s += (j == i) ? 1.f : adj_tri[tri_index_any(i, j, N)];
     dvec[i] = 1.0f / sqrtf(fmaxf(s, 1.f));
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < N * N; p += blockDim.x) {
-    const int i = p / N, j = p - i * N;
-    const float a = (i == j) ? 1.f : adj[p];
-    an[i * ldn + j] = dvec[i] * a * dvec[j];
+  for (int p = threadIdx.x; p < N * N4; p += blockDim.x) {
+    const int i = p / N4, j = p - i * N4;
+    float v = 0.f;
+    if (j < N) v = dvec[i] * ((i == j) ? 1.f : adj_tri[tri_index_any(i, j, N)]) * dvec[j];
+    an[p] = v;
   }
   __syncthreads();
 }
 
-// out(i, f) = act(bias[f] + sum_j an[i][j] * xw[j*ldxw + f0 + f]),  f < nf, stored at out[i*sro + f*sfo].
-// f0 and ldxw are multiples of 4 (float4 loads along f).
-__device__ __forceinline__ void gcn_aggregate(const float *an, int ldn, int N, const float *xw, int ldxw, int f0,
-                                              int nf, const float *__restrict__ bias, float *out, int sro,
-                                              int sfo, int act) {
-  const int ng = (nf + 3) >> 2;
-  for (int it = threadIdx.x; it < ng * N; it += blockDim.x) {
-    const int i = it / ng, g = it - i * ng;
-    const int f = g << 2;
+// ax(k, i) = sum_j an[i][j] * xin(k, j): the GCN aggregation applied BEFORE the feature transform
+// ((A x) W = A (x W), layers.py:144-156; K_in <= K_out for every layer here so this order is cheaper
+// and needs no node-major intermediate).  xin, ax feature-major [K x N4].  `an` symmetric.
+__device__ __forceinline__ void gcn_aggregate_fm(const float *an, int N, int N4, const float *xin, int K, float *ax) {
+  const int ngrp = N4 >> 2;
+  for (int it = threadIdx.x; it < K * ngrp; it += blockDim.x) {
+    const int k = it / ngrp, i0 = (it - k * ngrp) << 2;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float *row = an + i * ldn;
-    const float *xp = xw + f0 + f;
+    const float *xr = xin + k * N4;
     for (int j = 0; j < N; ++j) {
-      const float w = row[j];
-      const float4 v = *reinterpret_cast<const float4 *>(xp + j * ldxw);
-      a0 += w * v.x; a1 += w * v.y; a2 += w * v.z; a3 += w * v.w;
+      const float xv = xr[j];
+      const float4 w = ld4(an + j * N4 + i0);   // an[j][i0..i0+3] = an[i0..i0+3][j]
+      a0 += w.x * xv; a1 += w.y * xv; a2 += w.z * xv; a3 += w.w * xv;
     }
-    const float r[4] = {a0, a1, a2, a3};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (f + q < nf) out[i * sro + (f + q) * sfo] = act_apply(r[q] + __ldg(bias + f + q), act);
+    float *dst = ax + k * N4 + i0;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
   }
 }
 
-// Attention.forward score part (attention.py:111-130): heads are chunks of ds = ad / heads features
-// (torch.split semantics: ceil(ad/ds) chunks), tanh(q.k * scale) averaged over chunks, symmetrised.
-// qn: node-major [N x ldq]; kf: feature-major [ad x ldn]; att: row-major N x N.
-__device__ __forceinline__ void attn_scores(const float *qn, int ldq, const float *kf, int ldn, int N, int ad,
-                                            int heads, float scale, float *att) {
+// Attention.forward score part (attention.py:111-130) for one channel.  Q, K feature-major
+// [ad x N4].  Heads are chunks of ds = ad / heads features (torch.split: ceil(ad/ds) chunks).
+// Item = (4x4 node block I <= J, head): both orientations q_i.k_j and q_j.k_i are accumulated in
+// registers (32 FMAs per four 16-byte loads), tanh'ed, and the symmetrised value
+// 0.5 (tanh(s_ij) + tanh(s_ji)) / n_heads goes to atp[head][tri(i, j)].  The caller sums atp over heads.
+__device__ __forceinline__ void attn_scores_blk(const float *Q, const float *Kf, int N, int N4, int ad, int heads,
+                                                float scale, float *atp, int ldp) {
   const int ds = ad / heads;
   const int nch = (ad + ds - 1) / ds;
-  const float inv = 1.0f / (float)nch;
-  const int npair = N * (N + 1) / 2;
-  for (int p = threadIdx.x; p < npair; p += blockDim.x) {
-    // p -> (i <= j), row-major over the upper triangle
-    int i = 0, rem = p;
-    while (rem >= N - i) { rem -= N - i; ++i; }
-    const int j = i + rem;
-    float sij = 0.f, sji = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      const int d0 = c * ds, d1 = (d0 + ds < ad) ? d0 + ds : ad;
-      float a = 0.f, b2 = 0.f;
-      for (int dd = d0; dd < d1; ++dd) {
-        a += qn[i * ldq + dd] * kf[dd * ldn + j];
-        b2 += qn[j * ldq + dd] * kf[dd * ldn + i];
-      }
-      sij += tanhf(a * scale);
-      sji += tanhf(b2 * scale);
+  const float inv = 0.5f / (float)nch;
+  const int nb = N4 >> 2, nblk = nb * (nb + 1) / 2;
+  for (int it = threadIdx.x; it < nblk * nch; it += blockDim.x) {
+    const int blk = it / nch, h = it - blk * nch;
+    int I = 0, rem = blk;
+    while (rem >= nb - I) { rem -= nb - I; ++I; }
+    const int J = I + rem;
+    const int i0 = I << 2, j0 = J << 2;
+    float a[4][4], b[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { a[u][v] = 0.f; b[u][v] = 0.f; }
+    const int d0 = h * ds, d1 = (d0 + ds < ad) ? d0 + ds : ad;
+    for (int dd = d0; dd < d1; ++dd) {
+      const float4 qi = ld4(Q + dd * N4 + i0), kj = ld4(Kf + dd * N4 + j0);
+      const float4 qj = ld4(Q + dd * N4 + j0), ki = ld4(Kf + dd * N4 + i0);
+      const float qiv[4] = {qi.x, qi.y, qi.z, qi.w}, kjv[4] = {kj.x, kj.y, kj.z, kj.w};
+      const float qjv[4] = {qj.x, qj.y, qj.z, qj.w}, kiv[4] = {ki.x, ki.y, ki.z, ki.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { a[u][v] += qiv[u] * kjv[v]; b[u][v] += qjv[v] * kiv[u]; }
     }
-    const float v = 0.5f * (sij * inv + sji * inv);
-    att[i * N + j] = v;
-    att[j * N + i] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = i0 + u, j = j0 + v;
+        if (i <= j && j < N) atp[h * ldp + tri_index(i, j, N)] = inv * (fast_tanh(a[u][v] * scale) + fast_tanh(b[u][v] * scale));
+      }
   }
 }
 

@@ -5,6 +5,14 @@
 // Reference: ScoreNetwork_X.py:102-133, ScoreNetwork_A.py:505-541, ScoreNetwork_A_CC.py:275-332,
 // attention.py:84-132,270-304, hodge_attention.py:80-129,290-325, layers.py:115-158.
 //
+// Shape of the kernel: the graphs are tiny (N <= 64), so a CTA is small (64 or 128 threads, chosen
+// per plan) and several CTAs share an SM; every phase has on the order of 100 work items (4x8
+// register tiles of the feature transforms, 4x4 node blocks of the attention products), and the
+// barrier bubbles of one graph are filled by the other graphs resident on the SM.  To make that
+// residency possible every adjacency-shaped tensor lives in upper-triangle storage (N(N+1)/2 node
+// pairs instead of N^2): the adjacency state is symmetric, and so is every channel derived from it
+// (matrix powers, symmetrised attention, M + M^T) -- which also halves the per-edge MLP work.
+//
 // Hodge branch (ScoreNetworkA_CC): the Hodge-dual adjacency built by adj_to_hodgedual
 // (cc_utils.py:1503-1538) is diagonal and hodgedual_to_adj (cc_utils.py:1541-1588) reads only
 // diagonals back, so layer 0 is a per-edge row scaling of the projections rank2 @ W_{q,k}
@@ -32,10 +40,6 @@ struct XaArgs {
   NoiseCtx nz;
 };
 
-__device__ __forceinline__ int edge_index(int i, int j, int N) {  // i < j
-  return i * N - (i * (i + 1)) / 2 + (j - i - 1);
-}
-
 // ---- hodge branch -----------------------------------------------------------------------------
 __device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, int ad, int heads, float scale) {
   const int ds = ad / heads;
@@ -54,7 +58,7 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
   const ccsd_plan_desc_t &d = P->d;
   const XaLayout &L = P->xa;
   const ccsd_neta_t &A = d.neta;
-  const int N = d.N, E = d.E, ldp = L.ldp;
+  const int N = d.N, E = d.E, ldp = L.ldp, NT = L.NT;
   const float *W = P->W;
   float *stack = sm + L.stack;
   const float *flags = sm + L.flags;
@@ -64,19 +68,18 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
   const int ad0 = h0.attn_dim;
   const int PR0 = P->PR0;
   const float *P0 = a.P0 + (size_t)b * E * PR0;
+  const int *pij = reinterpret_cast<const int *>(sm + L.pij);
 
-  // channels [ch_hodge0, ch_hodge0 + c0): hodgedual_to_adj(adj_to_hodgedual(adjc)) = adjc with zero diagonal
-  for (int p = threadIdx.x; p < c0 * N * N; p += blockDim.x) {
-    const int c = p / (N * N), ij = p - c * N * N;
-    const int i = ij / N, j = ij - i * N;
-    stack[(ch_hodge0 + c) * ldp + ij] = (i == j) ? 0.f : stack[c * ldp + ij];
-  }
-  // zero the diagonals / whole planes of the hodge output channels (off-diagonals are filled per edge)
+  // channels [ch_hodge0, ch_hodge0 + c0): hodgedual_to_adj(adj_to_hodgedual(adjc)) = adjc with zero diagonal;
+  // the hodge output channels start as zero (diagonals stay zero, off-diagonals are filled per edge)
   {
-    int nout = h0.c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
-    for (int p = threadIdx.x; p < nout * N; p += blockDim.x) {
-      const int c = p / N, i = p - c * N;
-      stack[(ch_hodge0 + c0 + c) * ldp + i * N + i] = 0.f;
+    const int nout = h0.c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
+    for (int p = threadIdx.x; p < (c0 + nout) * NT; p += blockDim.x) {
+      const int c = p / NT, t = p - c * NT;
+      const int ij = pij[t];
+      float v = 0.f;
+      if (c < c0 && (ij >> 8) != (ij & 255)) v = stack[c * ldp + t];
+      stack[(ch_hodge0 + c) * ldp + t] = v;
     }
   }
   __syncthreads();
@@ -84,10 +87,11 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
   if (A.num_layers_h == 1) {
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+      const int t = tri_index(i, j, N);
       const float fe = flags[i] * flags[j];
       float att[CCSD_MAX_CH], q[SMALL_MAX], k[SMALL_MAX], out[SMALL_MAX];
       for (int c = 0; c < c0; ++c) {
-        const float av = stack[c * ldp + i * N + j];
+        const float av = stack[c * ldp + t];
         const float dg = 1.0f / sqrtf(fmaxf(av, 1.f));
         const float nrm = dg * av * dg;
         const float *pq = P0 + (size_t)e * PR0 + h0.proj_row + (c * 2 + 0) * ad0;
@@ -99,11 +103,7 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
         att[c] = hodge_diag_att(q, k, ad0, A.num_heads_h, scale);
       }
       small_mlp(h0.mlp_attention, W, att, out, ACT_ELU);
-      for (int c = 0; c < h0.c_out; ++c) {
-        const float v = 2.0f * tanhf(fe * fe * out[c]);
-        stack[(ch_hodge0 + c0 + c) * ldp + i * N + j] = v;
-        stack[(ch_hodge0 + c0 + c) * ldp + j * N + i] = v;
-      }
+      for (int c = 0; c < h0.c_out; ++c) stack[(ch_hodge0 + c0 + c) * ldp + t] = 2.0f * tanhf(fe * fe * out[c]);
     }
     __syncthreads();
     return;
@@ -119,7 +119,7 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
   for (int p = threadIdx.x; p < c0 * E; p += blockDim.x) {
     const int c = p / E, e = p - c * E;
     const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
-    const float av = stack[c * ldp + i * N + j];
+    const float av = stack[c * ldp + tri_index(i, j, N)];
     const float dg = 1.0f / sqrtf(fmaxf(av, 1.f));
     const float nrm = dg * av * dg;
     const float *pq = P0 + (size_t)e * PR0 + h0.proj_row + (c * 2 + 0) * ad0;
@@ -159,9 +159,7 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
     float s = 0.f;
     for (int e2 = 0; e2 < E; ++e2) s += row[e2];
     hdeg[c * E + e] = 1.0f / sqrtf(fmaxf(s, 1.f));
-    const float v = row[e];
-    stack[(ch_hodge0 + c0 + c) * ldp + i * N + j] = v;
-    stack[(ch_hodge0 + c0 + c) * ldp + j * N + i] = v;
+    stack[(ch_hodge0 + c0 + c) * ldp + tri_index(i, j, N)] = row[e];
   }
   __syncthreads();
   // layer 1 (last): only diag(attention) is read back (cc_utils.py:1571)
@@ -186,57 +184,61 @@ __device__ void hodge_branch(const DevPlan *__restrict__ P, const XaArgs &a, flo
       att[c] = hodge_diag_att(q, k, ad1, A.num_heads_h, scale);
     }
     small_mlp(h1.mlp_attention, W, att, out, ACT_ELU);
-    for (int c = 0; c < h1.c_out; ++c) {
-      const float v = 2.0f * tanhf(fe * fe * out[c]);
-      stack[(ch_hodge0 + c0 + c1 + c) * ldp + i * N + j] = v;
-      stack[(ch_hodge0 + c0 + c1 + c) * ldp + j * N + i] = v;
-    }
+    for (int c = 0; c < h1.c_out; ++c)
+      stack[(ch_hodge0 + c0 + c1 + c) * ldp + tri_index(i, j, N)] = 2.0f * tanhf(fe * fe * out[c]);
   }
   __syncthreads();
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+__global__ void __launch_bounds__(XA_MAX_THREADS, XA_MIN_BLOCKS) xa_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XaLayout &L = P->xa;
   const int b = blockIdx.x;
-  const int N = d.N, F = d.F, NP = N * N, ldn = L.ldn, ldp = L.ldp;
+  const int N = d.N, F = d.F, NP = N * N, N4 = L.N4, NT = L.NT, ldp = L.ldp;
   const float *W = P->W;
-  float *flags = sm + L.flags, *dvec = sm + L.dvec, *hcat = sm + L.hcat, *an = sm + L.an;
+  float *flags = sm + L.flags, *dvec = sm + L.dvec, *an = sm + L.an, *x0 = sm + L.x0;
   float *stack = sm + L.stack, *sx = sm + L.sx, *sadj = sm + L.sadj, *red = sm + L.red;
   float *scr = sm + L.scratch;
-  float *xw = scr + L.xw, *hA = scr + L.hA, *hB = scr + L.hB;
-  const int ldxw = L.ldxw;
+  int *pij = reinterpret_cast<int *>(sm + L.pij);
 
   // ---- load the graph tile ----
-  for (int i = threadIdx.x; i < N; i += blockDim.x) flags[i] = a.flags[(size_t)b * N + i];
-  for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
-    const int i = p / F, f = p - i * F;
-    hcat[f * ldn + i] = a.x[(size_t)b * N * F + p];
+  for (int i = threadIdx.x; i < N4; i += blockDim.x) flags[i] = i < N ? a.flags[(size_t)b * N + i] : 0.f;
+  for (int p = threadIdx.x; p < F * N4; p += blockDim.x) {
+    const int f = p / N4, i = p - f * N4;
+    x0[p] = i < N ? a.x[((size_t)b * N + i) * F + f] : 0.f;
   }
-  for (int p = threadIdx.x; p < NP; p += blockDim.x) stack[p] = a.adj[(size_t)b * NP + p];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int t0 = tri_index(i, i, N);
+    for (int j = i; j < N; ++j) {
+      pij[t0 + j - i] = (i << 8) | j;
+      stack[t0 + j - i] = a.adj[(size_t)b * NP + i * N + j];
+    }
+  }
   __syncthreads();
 
   // ================= ScoreNetworkX =================
   if (a.which & 1) {
     const ccsd_netx_t &X = d.netx;
-    gcn_norm(stack, N, dvec, an, ldn);
-    int row_in = 0, din = F;
+    float *hcat = sm + L.xh_cat, *ax = sm + L.xh_ax, *hA = sm + L.xh_a, *hB = sm + L.xh_b;
+    gcn_norm_tri(stack, N, N4, dvec, an);
+    const float *in = x0;
+    int din = F, row = 0;
     for (int k = 0; k < X.depth; ++k) {
       const ccsd_gcn_t &g = X.gcn[k];
-      dense2(hcat + row_in * ldn, ldn, din, nullptr, 0, 0, W + g.w, nullptr, g.dout, xw, ldxw, 1, N, ACT_NONE);
+      gcn_aggregate_fm(an, N, N4, in, din, ax);
       __syncthreads();
-      const int row_out = row_in + din;
-      gcn_aggregate(an, ldn, N, xw, ldxw, 0, g.dout, W + g.b, hcat + row_out * ldn, 1, ldn, ACT_TANH);
+      dense_fm(ax, N4, din, nullptr, 0, 0, W + g.w, W + g.b, g.dout, hcat + row * N4, 1, N4, N, ACT_TANH);
       __syncthreads();
-      row_in = row_out;
+      in = hcat + row * N4;
       din = g.dout;
+      row += g.dout;
     }
-    mlp_rows(X.fin, W, hcat, ldn, X.fdim, nullptr, 0, 0, N, hA, hB, ldn, sx, 1, ldn, ACT_ELU, ACT_NONE);
-    for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
-      const int f = p / N, i = p - f * N;
-      sx[f * ldn + i] *= flags[i];
+    mlp_fm(X.fin, W, x0, N4, F, hcat, N4, row, N, hA, hB, N4, sx, 1, N4, ACT_ELU, ACT_NONE);
+    for (int p = threadIdx.x; p < F * N4; p += blockDim.x) {
+      const int i = p % N4;
+      if (i < N) sx[p] *= flags[i];
     }
     __syncthreads();
   }
@@ -244,66 +246,113 @@ __global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__rest
   // ================= ScoreNetworkA / ScoreNetworkA_CC =================
   if (a.which & 2) {
     const ccsd_neta_t &A = d.neta;
-    float *qn = scr + L.qn, *kf = scr + L.kf, *vcat = scr + L.vcat, *att = scr + L.att;
-    const int ldq = L.ldq;
-    // pow_tensor (graph_utils.py:274-292)
+    float *att = scr + L.att, *ax = scr + L.ax, *hmc = scr + L.hmc, *hmc2 = scr + L.hmc2;
+    float *q = scr + L.q, *kf = scr + L.k, *v = scr + L.v, *atp = scr + L.atp;
+    float *ehA = scr + L.eh_a, *ehB = scr + L.eh_b;
+    // pow_tensor (graph_utils.py:274-292): A^c = A^(c-1) . A, symmetric
     for (int c = 1; c < A.c_init; ++c) {
-      for (int p = threadIdx.x; p < NP; p += blockDim.x) {
-        const int i = p / N, j = p - i * N;
+      for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+        const int ij = pij[t], i = ij >> 8, j = ij & 255;
         float s = 0.f;
-        for (int k = 0; k < N; ++k) s += stack[(c - 1) * ldp + i * N + k] * stack[k * N + j];
-        stack[c * ldp + p] = s;
+        for (int k = 0; k < N; ++k) s += stack[(c - 1) * ldp + tri_index_any(i, k, N)] * stack[tri_index_any(k, j, N)];
+        stack[c * ldp + t] = s;
       }
       __syncthreads();
     }
-    const float *xin = hcat;  // layer 0 reads the raw node features (feature-major, rows 0..F-1)
+    const float *xin = x0;  // layer 0 reads the raw node features
     int kin = F;
-    float *xcur = sm + L.xa, *xnext = sm + L.xb;
+    float *xnext = sm + L.xa, *xother = sm + L.xb;
     int ch_in = 0, ch_out = A.c_init;
     for (int l = 0; l < A.num_layers; ++l) {
       const ccsd_attn_layer_t &ly = A.layer[l];
       const int ad = ly.attn_dim, nh = ly.conv_out;
-      const int adp = round_up(ad, 4);
       const float scale = 1.0f / sqrtf((float)nh);  // / sqrt(out_dim)  (attention.py:125)
+      const ccsd_mlp_t &mc = ly.multi_channel;
+      const int mc_o1 = mc.nl == 1 ? mc.dout : mc.dhid, mc_o1p = round_up(mc_o1, 8);
+      const int nch = (ad + ad / A.num_heads - 1) / (ad / A.num_heads);
       for (int c = 0; c < ly.c_in; ++c) {
-        gcn_norm(stack + (ch_in + c) * ldp, N, dvec, an, ldn);
-        dense2(xin, ldn, kin, nullptr, 0, 0, W + ly.q[c].w, nullptr, ad, xw, ldxw, 1, N, ACT_NONE);
-        dense2(xin, ldn, kin, nullptr, 0, 0, W + ly.k[c].w, nullptr, ad, xw + adp, ldxw, 1, N, ACT_NONE);
-        dense2(xin, ldn, kin, nullptr, 0, 0, W + ly.v[c].w, nullptr, nh, xw + 2 * adp, ldxw, 1, N, ACT_NONE);
+        gcn_norm_tri(stack + (ch_in + c) * ldp, N, N4, dvec, an);
+        gcn_aggregate_fm(an, N, N4, xin, kin, ax);
         __syncthreads();
-        gcn_aggregate(an, ldn, N, xw, ldxw, 0, ad, W + ly.q[c].b, qn, ldq, 1, ACT_NONE);
-        gcn_aggregate(an, ldn, N, xw, ldxw, adp, ad, W + ly.k[c].b, kf, 1, ldn, ACT_NONE);
-        gcn_aggregate(an, ldn, N, xw, ldxw, 2 * adp, nh, W + ly.v[c].b, vcat + c * nh * ldn, 1, ldn, ACT_NONE);
+        {
+          // Q | K | V = A x W_{q,k,v} + b as one item space (same input tile, three weight matrices)
+          const int ngrp = N4 >> 2;
+          const int nq = (round_up(ad, 8) >> 3) * ngrp, nv = (round_up(nh, 8) >> 3) * ngrp;
+          for (int it = threadIdx.x; it < 2 * nq + nv; it += blockDim.x) {
+            const int w = it < nq ? 0 : (it < 2 * nq ? 1 : 2);
+            const int li = it - (w == 0 ? 0 : (w == 1 ? nq : 2 * nq));
+            const ccsd_gcn_t &g = w == 0 ? ly.q[c] : (w == 1 ? ly.k[c] : ly.v[c]);
+            float *dst = w == 0 ? q : (w == 1 ? kf : v);
+            const int O = g.dout, Opad = round_up(O, 8);
+            const int chunk = li / ngrp, r0 = (li - chunk * ngrp) << 2, oc = chunk << 3;
+            float acc[4][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float bv = __ldg(W + g.b + oc + j);
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) acc[rr][j] = bv;
+            }
+            dense_tile(acc, ax, N4, kin, nullptr, 0, 0, W + g.w, Opad, r0, oc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (oc + j < O) {
+                // padded node rows are written too (finite values: the attention blocks read them)
+                float *o = dst + (oc + j) * N4 + r0;
+                o[0] = acc[0][j]; o[1] = acc[1][j]; o[2] = acc[2][j]; o[3] = acc[3][j];
+              }
+          }
+        }
         __syncthreads();
-        attn_scores(qn, ldq, kf, ldn, N, ad, A.num_heads, scale, att + c * ldp);
+        attn_scores_blk(q, kf, N, N4, ad, A.num_heads, scale, atp, ldp);
+        // node branch, first Linear of multi_channel folded over the channel concat (attention.py:292):
+        // hmc(o, i) += sum_f V_c(i, f) W1[c*nh + f, o]
+        dense_fm(v, N4, nh, nullptr, 0, 0, W + mc.w[0] + (size_t)c * nh * mc_o1p, nullptr, mc_o1, hmc, 1, N4, N, ACT_NONE,
+                 c > 0);
         __syncthreads();
+        for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+          float s = 0.f;
+          for (int h = 0; h < nch; ++h) s += atp[h * ldp + t];
+          att[c * ldp + t] = s;
+        }
       }
       // node branch: x_out = tanh(mask_x(MLP(cat V)))  (attention.py:292-293)
-      mlp_rows(ly.multi_channel, W, vcat, ldn, ly.c_in * nh, nullptr, 0, 0, N, hA, hB, ldn, xnext, 1, ldn,
-               ACT_ELU, ACT_NONE);
-      for (int p = threadIdx.x; p < nh * N; p += blockDim.x) {
-        const int f = p / N, i = p - f * N;
-        xnext[f * ldn + i] = tanhf(xnext[f * ldn + i] * flags[i]);
+      {
+        float *cur = hmc, *oth = hmc2;
+        for (int p = threadIdx.x; p < mc_o1 * N4; p += blockDim.x) {
+          const int o = p / N4;
+          const float t = cur[p] + __ldg(W + mc.b[0] + o);
+          cur[p] = mc.nl == 1 ? t : fast_elu(t);
+        }
+        __syncthreads();
+        for (int li = 1; li < mc.nl; ++li) {
+          const bool last = li == mc.nl - 1;
+          const int O = last ? mc.dout : mc.dhid;
+          dense_fm(cur, N4, li == 1 ? mc_o1 : mc.dhid, nullptr, 0, 0, W + mc.w[li], W + mc.b[li], O, oth, 1, N4, N,
+                   last ? ACT_NONE : ACT_ELU);
+          __syncthreads();
+          float *t = cur; cur = oth; oth = t;
+        }
+        for (int p = threadIdx.x; p < nh * N4; p += blockDim.x) {
+          const int i = p % N4;
+          xnext[p] = i < N ? fast_tanh(cur[p] * flags[i]) : 0.f;
+        }
       }
       // edge branch: M = MLP(cat[A_1..A_c, adj_1..adj_c]) ; adj_out = mask_adjs(M + M^T)  (attention.py:295-302)
-      mlp_rows(ly.mlp, W, att, ldp, ly.c_in, stack + ch_in * ldp, ldp, ly.c_in, NP, hA, hB, ldp,
-               stack + ch_out * ldp, 1, ldp, ACT_ELU, ACT_NONE);
-      for (int p = threadIdx.x; p < ly.c_out * (N * (N + 1) / 2); p += blockDim.x) {
-        const int c = p / (N * (N + 1) / 2);
-        int rem = p - c * (N * (N + 1) / 2), i = 0;
-        while (rem >= N - i) { rem -= N - i; ++i; }
-        const int j = i + rem;
-        float *pl = stack + (ch_out + c) * ldp;
-        const float v = (pl[i * N + j] + pl[j * N + i]) * flags[i] * flags[j];
-        pl[i * N + j] = v;
-        pl[j * N + i] = v;
+      // (the head sums of the last channel are ordered before this by the __syncthreads above)
+      mlp_fm(ly.mlp, W, att, ldp, ly.c_in, stack + ch_in * ldp, ldp, ly.c_in, NT, ehA, ehB, ldp, stack + ch_out * ldp, 1,
+             ldp, ACT_ELU, ACT_NONE);
+      for (int p = threadIdx.x; p < ly.c_out * NT; p += blockDim.x) {
+        const int c = p / NT, t = p - c * NT;
+        const int ij = pij[t];
+        float *pl = stack + (ch_out + c) * ldp + t;
+        *pl = 2.0f * *pl * flags[ij >> 8] * flags[ij & 255];
       }
       __syncthreads();
       ch_in = ch_out;
       ch_out += ly.c_out;
       xin = xnext;
       kin = nh;
-      float *t = xcur; xcur = xnext; xnext = t;
+      float *t = xnext; xnext = xother; xother = t;
     }
     int fd_have = ch_out;
     if (A.is_cc) {
@@ -311,15 +360,17 @@ __global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__rest
       fd_have += A.c_init + A.hodge[0].c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
     }
     // final per-edge MLP, (1 - I) mask, mask_adjs  (ScoreNetwork_A.py:529-539)
-    const int RC = L.fin_rows;
-    for (int r0 = 0; r0 < NP; r0 += RC) {
-      const int R = (NP - r0 < RC) ? NP - r0 : RC;
-      mlp_rows(A.fin, W, stack + r0, ldp, fd_have, nullptr, 0, 0, R, hA, hB, L.fin_ld, sadj + r0, 1, 0, ACT_ELU,
-               ACT_NONE);
+    {
+      float *fA = scr + L.fh_a, *fB = scr + L.fh_b;
+      const int RC = L.fin_rows;
+      for (int r0 = 0; r0 < NT; r0 += RC) {
+        const int R = (NT - r0 < RC) ? NT - r0 : RC;
+        mlp_fm(A.fin, W, stack + r0, ldp, fd_have, nullptr, 0, 0, R, fA, fB, RC, sadj + r0, 1, 0, ACT_ELU, ACT_NONE);
+      }
     }
-    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
-      const int i = p / N, j = p - i * N;
-      sadj[p] = (i == j) ? 0.f : sadj[p] * flags[i] * flags[j];
+    for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+      const int ij = pij[t], i = ij >> 8, j = ij & 255;
+      sadj[t] = (i == j) ? 0.f : sadj[t] * flags[i] * flags[j];
     }
     __syncthreads();
   }
@@ -330,10 +381,13 @@ __global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__rest
     if (a.which & 1)
       for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
         const int i = p / F, f = p - i * F;
-        a.out_x[gx + p] = sx[f * ldn + i];
+        a.out_x[gx + p] = sx[f * N4 + i];
       }
     if (a.which & 2)
-      for (int p = threadIdx.x; p < NP; p += blockDim.x) a.out_adj[ga + p] = sadj[p];
+      for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+        const int i = p / N, j = p - i * N;
+        a.out_adj[ga + p] = sadj[tri_index_any(i, j, N)];
+      }
     return;
   }
   const ccsd_objcoef_t cx = P->sched[a.nz.step * 3 + 0], ca = P->sched[a.nz.step * 3 + 1];
@@ -343,7 +397,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__rest
     float s2 = 0.f, z2 = 0.f;
     for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
       const int i = p / F, f = p - i * F;
-      const float s = cx.score_scale * sx[f * ldn + i];
+      const float s = cx.score_scale * sx[f * N4 + i];
       a.out_x[gx + p] = s;
       const float z = (a.noise_x ? a.noise_x[gx + p] : normal1(a.nz.seed, gs, draw_id(0, a.nz.step, a.slot), p)) *
                       flags[i];
@@ -357,18 +411,18 @@ __global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__rest
       np[0] = s2; np[1] = z2;
     }
     s2 = 0.f; z2 = 0.f;
-    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
-      const int i = p / N, j = p - i * N;
-      const float s = ca.score_scale * sadj[p];
-      a.out_adj[ga + p] = s;
-      float z = 0.f;
+    for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+      const int ij = pij[t], i = ij >> 8, j = ij & 255;
+      const float s = ca.score_scale * sadj[t];
+      a.out_adj[ga + i * N + j] = s;
       if (i != j) {
-        const int q = (i < j) ? i * N + j : j * N + i;
-        z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gs, draw_id(1, a.nz.step, a.slot), q)) *
-            flags[i] * flags[j];
+        a.out_adj[ga + j * N + i] = s;
+        const int q = i * N + j;
+        const float z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gs, draw_id(1, a.nz.step, a.slot), q)) *
+                        flags[i] * flags[j];
+        s2 += 2.f * s * s;
+        z2 += 2.f * z * z;
       }
-      s2 += s * s;
-      z2 += z * z;
     }
     s2 = block_sum(s2, red);
     z2 = block_sum(z2, red);
@@ -381,29 +435,34 @@ __global__ void __launch_bounds__(XA_THREADS, 1) xa_kernel(const DevPlan *__rest
   // MODE_PRED: mean = pa*obj + pb*score ; new = mean + pc*z   (solver.py:230-244, 386-398; sde.py:200-235)
   for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
     const int i = p / F, f = p - i * F;
-    const float s = cx.score_scale * sx[f * ldn + i];
+    const float s = cx.score_scale * sx[f * N4 + i];
     const float z = (a.noise_x ? a.noise_x[gx + p] : normal1(a.nz.seed, gs, draw_id(0, a.nz.step, a.slot), p)) *
                     flags[i];
-    const float m = cx.pa * hcat[f * ldn + i] + cx.pb * s;
+    const float m = cx.pa * x0[f * N4 + i] + cx.pb * s;
     const float v = m + cx.pc * z;
     a.out_x[gx + p] = v;
     a.mean_x[gx + p] = m;
     if (a.traj_x && b == 0) a.traj_x[p] = a.denoise ? m : v;
   }
-  for (int p = threadIdx.x; p < NP; p += blockDim.x) {
-    const int i = p / N, j = p - i * N;
-    const float s = ca.score_scale * sadj[p];
+  for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+    const int ij = pij[t], i = ij >> 8, j = ij & 255;
+    const float s = ca.score_scale * sadj[t];
     float z = 0.f;
     if (i != j) {
-      const int q = (i < j) ? i * N + j : j * N + i;
-      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gs, draw_id(1, a.nz.step, a.slot), q)) *
-          flags[i] * flags[j];
+      const int q = i * N + j;
+      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gs, draw_id(1, a.nz.step, a.slot), q)) * flags[i] *
+          flags[j];
     }
-    const float m = ca.pa * stack[p] + ca.pb * s;
+    const float m = ca.pa * stack[t] + ca.pb * s;
     const float v = m + ca.pc * z;
-    a.out_adj[ga + p] = v;
-    a.mean_adj[ga + p] = m;
-    if (a.traj_adj && b == 0) a.traj_adj[p] = a.denoise ? m : v;
+    a.out_adj[ga + i * N + j] = v;
+    a.mean_adj[ga + i * N + j] = m;
+    if (a.traj_adj && b == 0) a.traj_adj[i * N + j] = a.denoise ? m : v;
+    if (i != j) {
+      a.out_adj[ga + j * N + i] = v;
+      a.mean_adj[ga + j * N + i] = m;
+      if (a.traj_adj && b == 0) a.traj_adj[j * N + i] = a.denoise ? m : v;
+    }
   }
 }
 

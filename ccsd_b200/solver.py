@@ -230,6 +230,10 @@ class Engine:
         raw = names.raw
         return [(raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]
 
+    def info(self) -> dict:
+        names = ("xa_smem_bytes", "xa_threads", "apply_smem_bytes", "tc_gram", "tc_apply", "f_mode", "fin_rows")
+        return {n: int(self.lib.ccsd_plan_info(self.handle, i)) for i, n in enumerate(names)}
+
     @property
     def launches(self) -> int:
         return int(self.lib.ccsd_plan_launch_count(self.handle))

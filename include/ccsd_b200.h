@@ -195,6 +195,11 @@ int ccsd_quantize(const float *in_dev, uint8_t *out_dev, size_t n, float thr, in
 /* Number of kernel launches issued by this plan so far (bench.py's gpu_launches). */
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *plan);
 
+/* Introspection for tests / DESIGN.md tables: what = 0 xa-kernel dynamic shared memory (bytes), 1 xa-kernel
+ * threads per CTA, 2 fp32 apply-kernel shared memory, 3 / 4 whether the tcgen05 Gram / apply kernels are
+ * selected, 5 ScoreNetworkF entry path (0 generic, 1 affine fold, 2 <= 8-wide unrolled), 6 final-MLP row chunk. */
+int ccsd_plan_info(const ccsd_plan_t *plan, int what);
+
 /* Per-kernel device timing for bench.py's roofline: when on, every launch of ccsd_plan_step /
  * ccsd_plan_run is bracketed by CUDA events on the launching stream.  ccsd_plan_get_profile waits
  * for them and returns the number of records written (name_stride bytes per name). */
