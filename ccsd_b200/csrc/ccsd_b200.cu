@@ -326,7 +326,7 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
   w.mx = take(B * N * F * 4); w.madj = take(B * N * N * 4); w.mr2 = take(B * E * K * 4 + 16);
   w.sx = take(B * N * F * 4); w.sadj = take(B * N * N * 4); w.sr2 = take(B * E * K * 4 + 16);
-  w.H = take(B * E * E * 4 + 16);
+  w.H = take(B * E * (size_t)a4((int)E) * 4 + 64);
   w.P0 = take(B * E * (size_t)imax(1, p->hp.PR0) * 4);
   w.P1 = take(B * E * (size_t)imax(1, p->hp.PR1) * 4);
   w.norm = take(3 * B * (size_t)p->hp.ntile_max * 2 * 4);
@@ -351,6 +351,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.PR0 = hodge ? d.neta.n_proj_rows[0] : 0;
   p->hp.PR1 = (hodge && d.neta.num_layers_h == 2) ? d.neta.n_proj_rows[1] : 0;
   p->hp.Kp = a4(d.K);
+  p->hp.Ep = a4(d.E);
   p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
   p->hp.ntile_max = imax(1, p->hp.ntile_r2);
   p->hp.f_mode = 0; p->hp.f_nlin = 0;
@@ -555,7 +556,23 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
   float *ta = p->traj_adj ? p->traj_adj + (size_t)step * d.N * d.N : nullptr;
   float *tr = (p->traj_r2 && d.is_cc) ? p->traj_r2 + (size_t)step * d.E * d.K : nullptr;
 
-  auto score_phase = [&](int mode, int slot) -> int {
+  // rank-2 apply pass: H F + ScoreNetworkF + the mode's epilogue
+  auto apply_pass = [&](int mode, int slot) -> int {
+    ApplyArgs q; memset(&q, 0, sizeof q);
+    q.r2 = p->r2; q.H = p->H; q.flags = p->flags; q.mode = mode; q.slot = slot; q.denoise = d.denoise; q.nz = nz;
+    q.norm_part = p->norm_part; q.coef = p->coef;
+    q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
+    if (mode == MODE_SCORE) q.out = p->sr2;
+    else if (mode == MODE_CORR) q.out = p->r2;
+    else if (mode == MODE_PRED) { q.out = p->r2; q.mean = p->mr2; q.write_mean = write_mean; q.traj = tr; }
+    PROF_BEGIN(p, p->use_tc_apply ? "tc_apply_kernel" : "apply_kernel", stream);
+    launch_apply(p, q, stream);
+    PROF_END(p, stream);
+    p->launches++;
+    return dev_check("apply pass");
+  };
+  // x / adj networks (+ the Gram pre-pass their hodge branch and the rank-2 network need)
+  auto score_phase = [&](int mode, int slot, int r2_mode) -> int {
     if (d.is_cc)
       if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
     XaArgs a; memset(&a, 0, sizeof a);
@@ -570,21 +587,13 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), p->hp.xa.T, p->xa_smem, stream, p->dP, a);
     PROF_END(p, stream);
     p->launches++;
-    if (d.is_cc) {
-      ApplyArgs q; memset(&q, 0, sizeof q);
-      q.r2 = p->r2; q.H = p->H; q.flags = p->flags; q.mode = mode; q.slot = slot; q.denoise = d.denoise; q.nz = nz;
-      q.norm_part = p->norm_part;
-      q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
-      if (mode == MODE_SCORE) q.out = p->sr2;
-      else { q.out = p->r2; q.mean = p->mr2; q.write_mean = write_mean; q.traj = tr; }
-      PROF_BEGIN(p, p->use_tc_apply ? "tc_apply_kernel" : "apply_kernel", stream);
-      launch_apply(p, q, stream);
-      PROF_END(p, stream);
-      p->launches++;
-    }
-    return dev_check("score phase");
+    if (int r = dev_check("xa_kernel")) return r;
+    if (d.is_cc) return apply_pass(r2_mode, slot);
+    return 0;
   };
-  auto update_phase = [&]() -> int {
+  // Langevin step sizes, then the corrector update (PC: x and adj here, the rank-2 state in its own CORR
+  // apply pass) or the whole S4 chain for every object
+  auto update_phase = [&](int nobj) -> int {
     CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4;
     PROF_BEGIN(p, "coef_kernel", stream);
     CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
@@ -593,25 +602,29 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     u.flags = p->flags; u.x = p->x; u.adj = p->adj; u.r2 = p->r2; u.sx = p->sx; u.sadj = p->sadj; u.sr2 = p->sr2;
     u.coef = p->coef; u.mx = p->mx; u.madj = p->madj; u.mr2 = p->mr2; u.nx = nx; u.nadj = nadj; u.nr2 = nr2;
     u.tx = tx; u.tadj = ta; u.tr2 = tr; u.s4 = s4; u.denoise = d.denoise; u.write_mean_r2 = write_mean; u.nz = nz;
-    const size_t units = d.is_cc ? (size_t)d.B * d.E * (p->hp.Kp / 4) : sa;
+    const size_t units = nobj == 3 ? (size_t)d.B * d.E * (p->hp.Kp / 4) : sa;
     PROF_BEGIN(p, "update_kernel", stream);
-    CCSD_LAUNCH(update_kernel, dim3(grid_for(units), d.is_cc ? 3 : 2, 1), 256, 0, stream, p->dP, u);
+    CCSD_LAUNCH(update_kernel, dim3(grid_for(units), nobj, 1), 256, 0, stream, p->dP, u);
     PROF_END(p, stream);
     p->launches += 2;
     return dev_check("update phase");
   };
 
   if (s4) {
-    if (int r = score_phase(MODE_SCORE, 0)) return r;
-    return update_phase();
+    if (int r = score_phase(MODE_SCORE, 0, MODE_SCORE)) return r;
+    return update_phase(d.is_cc ? 3 : 2);
   }
   int slot = 0;
   if (d.use_corrector) {
-    if (int r = score_phase(MODE_SCORE, 0)) return r;
-    if (int r = update_phase()) return r;
+    // corrector: the rank-2 score is never written to HBM -- a NORM pass produces the norms, and after
+    // the step sizes are known a CORR pass recomputes the score and updates the state in place
+    if (int r = score_phase(MODE_SCORE, 0, MODE_NORM)) return r;
+    if (int r = update_phase(2)) return r;
+    if (d.is_cc)
+      if (int r = apply_pass(MODE_CORR, 0)) return r;
     slot = d.n_lang_steps;
   }
-  return score_phase(MODE_PRED, slot);
+  return score_phase(MODE_PRED, slot, MODE_PRED);
 }
 
 int ccsd_plan_step(ccsd_plan_t *p, int step, const float *nx, const float *nadj, const float *nr2, void *stream) {
@@ -704,7 +717,15 @@ int ccsd_debug_gram(ccsd_plan_t *p, const float *r2, float *H_out, float *P0_out
   int r = launch_rank2_pre(p, r2, p->adj, p->flags, stream);
   p->use_tc = saved;
   if (r) return r;
-  if (H_out) if (int e = dev_copy(H_out, p->H, (size_t)d.B * d.E * d.E * 4, stream)) return e;
+  if (H_out) {
+    const size_t rows = (size_t)d.B * d.E, rb = (size_t)d.E * 4, pitch = (size_t)p->hp.Ep * 4;
+#ifdef CCSD_EMU
+    for (size_t r = 0; r < rows; ++r) memcpy((char *)H_out + r * rb, (const char *)p->H + r * pitch, rb);
+#else
+    if (cudaMemcpy2DAsync(H_out, rb, p->H, pitch, rb, rows, cudaMemcpyDefault, (cudaStream_t)stream) != cudaSuccess)
+      return fail(CCSD_ERR_CUDA, "cudaMemcpy2DAsync failed");
+#endif
+  }
   if (P0_out && p->hp.PR0) if (int e = dev_copy(P0_out, p->P0, (size_t)d.B * d.E * p->hp.PR0 * 4, stream)) return e;
   return 0;
 }

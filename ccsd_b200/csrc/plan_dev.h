@@ -58,6 +58,7 @@ struct DevPlan {
   const int *edge_ij;             // [E][2]
   int PR0, PR1;                   // projection rows of hodge layer 0 / 1
   int Kp;                         // K rounded up to 4 (Philox groups per rank-2 row = Kp/4)
+  int Ep;                         // E rounded up to 4: row pitch of the H buffer [B][E][Ep]
   int ntile_r2;                   // apply-kernel column tiles per sample
   int ntile_max;                  // stride of the per-object norm partials
   int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled
@@ -65,7 +66,10 @@ struct DevPlan {
 };
 
 // modes of the score kernels
-enum { MODE_EVAL = 0, MODE_SCORE = 1, MODE_PRED = 2 };
+// EVAL: raw network output.  SCORE: scaled score to `out` + norm partials.  PRED: predictor update.
+// NORM: norm partials only (nothing written).  CORR: Langevin correction with the step sizes in `coef`
+// (rank-2 apply kernels only; x / adj are corrected by update_kernel).
+enum { MODE_EVAL = 0, MODE_SCORE = 1, MODE_PRED = 2, MODE_NORM = 3, MODE_CORR = 4 };
 
 struct NoiseCtx {
   unsigned long long seed;

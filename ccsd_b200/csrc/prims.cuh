@@ -57,6 +57,18 @@ __device__ __forceinline__ void tile_fma(float acc[4][8], const float4 a, const 
     for (int j = 0; j < 8; ++j) acc[rr][j] += av[rr] * wv[j];
 }
 
+struct TileOps {   // operands of two consecutive k-steps
+  float4 a0, a1, w00, w01, w10, w11;
+};
+__device__ __forceinline__ void tile_load2(TileOps &t, const float *in, int ld, const float *__restrict__ wp, int Opad) {
+  t.a0 = ld4(in); t.a1 = ld4(in + ld);
+  t.w00 = __ldg(reinterpret_cast<const float4 *>(wp)); t.w01 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
+  t.w10 = __ldg(reinterpret_cast<const float4 *>(wp + Opad)); t.w11 = __ldg(reinterpret_cast<const float4 *>(wp + Opad + 4));
+}
+
+// Software pipelined: the six loads of k-steps (k+2, k+3) are issued before the 64 FMAs of (k, k+1), so a
+// weight load that misses L1 (the weights are shared by every CTA and live in L2) is covered by this warp's
+// own FMAs plus the other resident warps'.
 __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, int ld1, int K1, const float *in2, int ld2,
                                            int K2, const float *__restrict__ W, int Opad, int r0, int oc) {
   const float *wp = W + oc;
@@ -64,22 +76,27 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
   for (int seg = 0; seg < 2; ++seg) {
     const float *in = (seg ? in2 : in1) + r0;
     const int ld = seg ? ld2 : ld1, K = seg ? K2 : K1;
-    int k = 0;
+    const int npair = K >> 1;
+    if (npair > 0) {
+      TileOps cur, nxt;
+      tile_load2(cur, in, ld, wp, Opad);
 #pragma unroll 1
-    for (; k + 2 <= K; k += 2) {
-      const float4 a0 = ld4(in + k * ld), a1 = ld4(in + (k + 1) * ld);
-      const float4 w00 = __ldg(reinterpret_cast<const float4 *>(wp)), w01 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
-      const float4 w10 = __ldg(reinterpret_cast<const float4 *>(wp + Opad)), w11 = __ldg(reinterpret_cast<const float4 *>(wp + Opad + 4));
-      tile_fma(acc, a0, w00, w01);
-      tile_fma(acc, a1, w10, w11);
-      wp += 2 * Opad;
+      for (int p = 1; p < npair; ++p) {
+        tile_load2(nxt, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
+        tile_fma(acc, cur.a0, cur.w00, cur.w01);
+        tile_fma(acc, cur.a1, cur.w10, cur.w11);
+        cur = nxt;
+      }
+      tile_fma(acc, cur.a0, cur.w00, cur.w01);
+      tile_fma(acc, cur.a1, cur.w10, cur.w11);
     }
-    if (k < K) {
+    if (K & 1) {
+      const int k = K - 1;
       const float4 a0 = ld4(in + k * ld);
-      const float4 w00 = __ldg(reinterpret_cast<const float4 *>(wp)), w01 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
+      const float4 w00 = __ldg(reinterpret_cast<const float4 *>(wp + k * Opad)), w01 = __ldg(reinterpret_cast<const float4 *>(wp + k * Opad + 4));
       tile_fma(acc, a0, w00, w01);
-      wp += Opad;
     }
+    wp += K * Opad;
   }
 }
 
@@ -88,11 +105,14 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
 // business): used to fold a Linear over a channel-concatenated input channel by channel.
 __device__ __forceinline__ void dense_fm(const float *in1, int ld1, int K1, const float *in2, int ld2, int K2,
                                          const float *__restrict__ W, const float *__restrict__ bias, int O,
-                                         float *out, int sro, int soo, int R, int act, bool accum = false) {
+                                         float *out, int sro, int soo, int R, int act, bool accum = false,
+                                         int tid0 = 0) {
   const int Opad = round_up(O, 8);
   const int nchunk = Opad >> 3, ngrp = (R + 3) >> 2;
   const int items = nchunk * ngrp;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+  // tid0: the thread that takes item 0 (lets two primitives in one barrier window start on different warps)
+  const int vt = ((int)threadIdx.x + (int)blockDim.x - tid0 % (int)blockDim.x) % (int)blockDim.x;
+  for (int it = vt; it < items; it += blockDim.x) {
     const int chunk = it / ngrp, g = it - chunk * ngrp;
     const int oc = chunk << 3, r0 = g << 2;
     float acc[4][8];

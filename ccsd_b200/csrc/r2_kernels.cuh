@@ -31,7 +31,7 @@ struct GramArgs {
 __global__ void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P, GramArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
-  const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp;
+  const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp, Ep = P->Ep;
   const int b = blockIdx.z, m0 = blockIdx.y * GRAM_BM, n0 = blockIdx.x * GRAM_BN;
   const float *Fb = a.r2 + (size_t)b * E * K;
   const float *Wp = P->W + d.neta.proj_w;  // [PR_total x Kw], rows 0..PR0-1 = hodge layer 0
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P
         for (int j = 0; j < GRAM_BN; ++j) {
           const int m = m0 + i, n = n0 + j;
           if (m >= E) continue;
-          if (n < E) a.H[((size_t)b * E + m) * E + n] = (d.netf.use_hodge_mask && m == n) ? 0.f : tile[i][j];
+          if (n < E) a.H[((size_t)b * E + m) * Ep + n] = (d.netf.use_hodge_mask && m == n) ? 0.f : tile[i][j];
           else if (n - E < PR0) a.P0[((size_t)b * E + m) * PR0 + (n - E)] = tile[i][j];
         }
     }
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P
     for (int j = 0; j < 4; ++j) {
       const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
       if (m >= E) continue;
-      if (n < E) a.H[((size_t)b * E + m) * E + n] = (d.netf.use_hodge_mask && m == n) ? 0.f : acc[i][j];
+      if (n < E) a.H[((size_t)b * E + m) * Ep + n] = (d.netf.use_hodge_mask && m == n) ? 0.f : acc[i][j];
       else if (n - E < PR0) a.P0[((size_t)b * E + m) * PR0 + (n - E)] = acc[i][j];
     }
 #endif
@@ -271,6 +271,7 @@ struct ApplyArgs {
   float *out;                    // EVAL: raw output; SCORE: scaled score; PRED: new state (may alias r2)
   float *mean;                   // PRED: means (written when write_mean)
   float *norm_part;
+  const float *coef;             // CORR: [3][2] Langevin step sizes from coef_kernel
   const float *noise;            // raw normals [B,E,K] for this draw or nullptr
   float *traj;                   // PRED: sample 0 destination or nullptr
   int slot, denoise, write_mean;
@@ -326,10 +327,12 @@ __device__ __forceinline__ void r2_epilogue4(const R2Epi &c, const ApplyArgs &a,
       } else {
         const float s = c.co.score_scale * o;
         const float z = z4[q] * m;
-        if (a.mode == MODE_SCORE) {
-          a.out[g] = s;
+        if (a.mode == MODE_SCORE || a.mode == MODE_NORM) {
+          if (a.mode == MODE_SCORE) a.out[g] = s;
           s2 += s * s;
           z2 += z * z;
+        } else if (a.mode == MODE_CORR) {
+          a.out[g] = f + a.coef[4] * s + a.coef[5] * z;   // Langevin (solver.py:784-785)
         } else {
           const float mu = c.co.pa * f + c.co.pb * s;
           const float v = mu + c.co.pc * z;
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
   const int N = d.N, E = d.E, K = d.K;
   const int b = blockIdx.y, n0 = blockIdx.x * APPLY_TN;
   const float *Fb = a.r2 + (size_t)b * E * K;
-  const float *Hb = a.H + (size_t)b * E * E;
+  const float *Hb = a.H + (size_t)b * E * P->Ep;
   const float *fl = a.flags + (size_t)b * N;
   constexpr int LDF = APPLY_TN + 4, LDH = 64 + 4;
   float *Fs = sm;                         // [E][LDF]
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
       if (n0 + cq >= K) continue;
       float hf4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int e2 = 0; e2 < E; ++e2) {
-        const float h = Hb[(size_t)e * E + e2];
+        const float h = Hb[(size_t)e * P->Ep + e2];
         for (int q = 0; q < 4; ++q) hf4[q] += h * Fs[e2 * LDF + cq + q];
       }
       r2_epilogue4<FMODE>(c, a, e, n0 + cq, Fs + e * LDF + cq, hf4, s2, z2);
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int m = m0 + lr, e2 = e0 + lq + q;
-        Hs[(lq + q) * LDH + lr] = (m < E && e2 < E) ? __ldg(Hb + (size_t)m * E + e2) : 0.f;
+        Hs[(lq + q) * LDH + lr] = (m < E && e2 < E) ? __ldg(Hb + (size_t)m * P->Ep + e2) : 0.f;
       }
       __syncthreads();
 #pragma unroll
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
     }
   }
 #endif
-  if (a.mode == MODE_SCORE) {
+  if (a.mode == MODE_SCORE || a.mode == MODE_NORM) {
     s2 = block_sum(s2, red);
     z2 = block_sum(z2, red);
     if (threadIdx.x == 0) {

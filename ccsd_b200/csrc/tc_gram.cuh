@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       tc::tc_fence_after_sync();
       for (int mt = 0; mt < mtiles; ++mt) {
         const int row = mt * 128 + q * 32 + lane;
-        float *Hrow = a.H + ((size_t)b * E + row) * E;
+        float *Hrow = a.H + ((size_t)b * E + row) * P->Ep;
         float *Prow = a.P0 + ((size_t)b * E + row) * PR0;
         for (int c0 = 0; c0 < ncols; c0 += 16) {
           float v[16];

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(XA_MAX_THREADS, XA_MIN_BLOCKS) xa_kernel(const
         // node branch, first Linear of multi_channel folded over the channel concat (attention.py:292):
         // hmc(o, i) += sum_f V_c(i, f) W1[c*nh + f, o]
         dense_fm(v, N4, nh, nullptr, 0, 0, W + mc.w[0] + (size_t)c * nh * mc_o1p, nullptr, mc_o1, hmc, 1, N4, N, ACT_NONE,
-                 c > 0);
+                 c > 0, /*first thread*/ (int)blockDim.x - 32);
         __syncthreads();
         for (int t = threadIdx.x; t < NT; t += blockDim.x) {
           float s = 0.f;
