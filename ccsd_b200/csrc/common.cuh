@@ -44,6 +44,7 @@ static inline float __uint2float_rn(uint32_t v) { return (float)v; }
 static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
 static inline float __shfl_sync(unsigned, float v, int) { return v; }
 #define CCSD_FAST_LOGF(v) logf(v)
+#define CCSD_FAST_RSQRTF(v) (1.0f / sqrtf(v))
 #define CCSD_FAST_SINCOSF(v, s, c) sincosf(v, s, c)
 #define CCSD_SMEM(name) float *name = ccsd_emu_smem
 typedef void *cudaStream_t;
@@ -67,6 +68,7 @@ template <class Fn> static inline void ccsd_emu_launch(dim3 grid, size_t smem_by
 #else
 #include <cuda_runtime.h>
 #define CCSD_FAST_LOGF(v) __logf(v)
+#define CCSD_FAST_RSQRTF(v) rsqrtf(v)
 #define CCSD_FAST_SINCOSF(v, s, c) __sincosf(v, s, c)
 #define CCSD_SMEM(name) extern __shared__ __align__(16) float name[]
 #define CCSD_LAUNCH(kern, grid, block, smem, stream, ...) \
@@ -128,23 +130,32 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// 23-bit uniform in (0, 1) from a random word without an int->float conversion: the top 23 bits become the
+// mantissa of a float in [1, 2); subtracting (1 - 2^-24) centres the 2^-23 grid inside (0, 1).
+__device__ __forceinline__ float u01(uint32_t r) {
+#ifdef CCSD_EMU
+  union { uint32_t u; float f; } c;
+  c.u = (r >> 9) | 0x3F800000u;
+  return c.f - 0.99999994f;
+#else
+  return __uint_as_float((r >> 9) | 0x3F800000u) - 0.99999994f;
+#endif
+}
+
 __device__ __forceinline__ void normal4(uint64_t seed, uint64_t sample, uint32_t draw_id, uint32_t group,
                                         float z[4]) {
   uint32_t r[4];
   philox4x32_10(group, draw_id, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
-  // uniforms in (0,1]: (r + 0.5) * 2^-32 keeps log() finite
-  const float u0 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u1 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = ((float)(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u3 = ((float)(r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  // Box-Muller with the SFU intrinsics (|err| ~1e-6 on a unit normal: irrelevant for noise, and 4x
-  // fewer instructions than the IEEE-accurate libm paths -- the draw is on the per-entry hot path)
-  const float ra = sqrtf(-2.0f * CCSD_FAST_LOGF(u0)), rb = sqrtf(-2.0f * CCSD_FAST_LOGF(u2));
+  // Box-Muller on the SFU: radius = sqrt(t) = t * rsqrt(t) with t = -2 ln u > 0, angle through the fast
+  // sin/cos (|err| ~1e-6 on a unit normal: irrelevant for noise).  The draw is on the per-entry hot path of
+  // every sampler pass, so its instruction count matters more than its last bits.
+  const float t0 = -2.0f * CCSD_FAST_LOGF(u01(r[0])), t2 = -2.0f * CCSD_FAST_LOGF(u01(r[2]));
+  const float ra = t0 * CCSD_FAST_RSQRTF(t0), rb = t2 * CCSD_FAST_RSQRTF(t2);
   float s, c;
-  CCSD_FAST_SINCOSF(6.283185307179586f * u1, &s, &c);
+  CCSD_FAST_SINCOSF(6.283185307179586f * u01(r[1]), &s, &c);
   z[0] = ra * c; z[1] = ra * s;
-  CCSD_FAST_SINCOSF(6.283185307179586f * u3, &s, &c);
+  CCSD_FAST_SINCOSF(6.283185307179586f * u01(r[3]), &s, &c);
   z[2] = rb * c; z[3] = rb * s;
 }
 

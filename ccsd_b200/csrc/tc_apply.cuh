@@ -22,8 +22,11 @@
 // accumulator, Philox noise and masks, and write the NEW state back into the staging tile in place;
 // the loader warps then copy the finished tile out with coalesced 16-byte stores.
 //
-// Warp roles (21 warps): 0-3 loaders (cp.async ring, bf16 split, copy-out), 4-19 epilogue (TMEM lane
-// quarter q = warp % 4; M tile and cell half from the warp index), 20 MMA issuer.
+// Warp roles (17 warps): 0-3 loaders (cp.async ring, bf16 split, copy-out), 4-15 epilogue (TMEM lane
+// quarter q = warp % 4; role = (warp - 4) / 4: M tile 0 cells 0-15 | M tile 0 cells 16-31 | M tile 1, where
+// the 16 edges of the quarter are processed by lane pairs (l, l + 16) taking 16 cells each, so every lane
+// of every epilogue warp has work), 16 MMA issuer.  The kernel is templated on the ScoreNetworkF entry
+// path AND the pass mode, so the per-entry code has no mode branches.
 #pragma once
 #include "r2_kernels.cuh"
 #include "tc_common.cuh"
@@ -31,7 +34,7 @@
 namespace ccsd {
 
 constexpr int TA_LOAD = 128;
-constexpr int TA_EPI = 512;
+constexpr int TA_EPI = 384;
 constexpr int TA_THREADS = TA_LOAD + TA_EPI + 32;
 constexpr int TA_TN = 32;                         // cells per tile
 constexpr int TA_NE = 192;                        // padded edge count
@@ -43,42 +46,51 @@ constexpr uint32_t TA_STAGE = TA_NE * 128u;       // 24576: 192 rows x 32 fp32
 constexpr uint32_t TA_BARS = TA_OPER + TA_NS * TA_STAGE;   // 147456
 constexpr uint32_t TA_FCS = TA_BARS + 256;        // [NS][32] cell flags
 constexpr uint32_t TA_RED = TA_FCS + TA_NS * 32 * 4;   // [2][16] warp partials
+constexpr int TA_MMAW = (TA_LOAD + TA_EPI) / 32;     // index of the MMA warp
 constexpr uint32_t TA_FW = TA_RED + 256;          // staged ScoreNetworkF weights (FMODE 2)
 constexpr size_t TA_SMEM = (size_t)TA_FW + 6144 + 1024 /*alignment slack*/;
 constexpr uint32_t TA_COL_D = 384;                // first accumulator column
 
 static inline int tc_apply_supported(int E, int K) { return E >= 8 && E <= TA_NE && K >= 8; }
 
+// Per-pass constants of the entry update, folded so that the affine ScoreNetworkF path is a handful of FMAs:
+//   score s = sc * o,  o = m * (a0 f + a1 hf + a2)  (FMODE 1)  ->  s = m * (k0 f + k1 hf + k2)
+struct R2Fold {
+  float k0, k1, k2;    // sc * aff (FMODE 1)
+  float sc;            // score scale
+  float cs, cn;        // Langevin step sizes (CORR)
+  float pa, pb, pc;    // predictor
+};
+
 // one entry (edge e, cell k): network -> score -> mode-specific value.  Returns the value that replaces
 // the entry in the staging tile (raw output, scaled score or new state).
-template <int FMODE>
-__device__ __forceinline__ float r2_entry(const R2Epi &c, const ApplyArgs &a, int e, int k, float f, float hf, float zraw,
-                                          float m, float cs, float cn, float &s2, float &z2) {
+template <int FMODE, int MODE>
+__device__ __forceinline__ float r2_entry(const R2Epi &c, const R2Fold &w, float f, float hf, float zraw, float m,
+                                          float &s2, float &z2, float &mu_out) {
   const DevPlan *P = c.P;
-  float o;
-  if (FMODE == 1) o = m * (c.aff0 * f + c.aff1 * hf + c.aff2);
-  else if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf, m);
-  else o = netf_entry(P->d.netf, P->W, f, hf, m);
-  if (a.mode == MODE_EVAL) return o;
-  const float s = c.co.score_scale * o;
+  float s;
+  if (FMODE == 1) {
+    s = m * (w.k0 * f + w.k1 * hf + w.k2);     // MODE_EVAL: the fold uses sc = 1
+  } else {
+    float o;
+    if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf, m);
+    else o = netf_entry(P->d.netf, P->W, f, hf, m);
+    s = w.sc * o;
+  }
+  if (MODE == MODE_EVAL) return s;
   const float z = zraw * m;
-  if (a.mode == MODE_SCORE || a.mode == MODE_NORM) {
+  if (MODE == MODE_SCORE || MODE == MODE_NORM) {
     s2 += s * s;
     z2 += z * z;
     return s;
   }
-  if (a.mode == MODE_CORR) return f + cs * s + cn * z;   // Langevin (solver.py:784-785)
-  const float mu = c.co.pa * f + c.co.pb * s;            // predictor (solver.py:283-300, 433-450)
-  const float v = mu + c.co.pc * z;
-  if (a.write_mean | (a.traj != nullptr)) {
-    const size_t g = ((size_t)c.b * c.E + e) * c.K + k;
-    if (a.write_mean) a.mean[g] = mu;
-    if (a.traj && c.b == 0) a.traj[(size_t)e * c.K + k] = a.denoise ? mu : v;
-  }
-  return v;
+  if (MODE == MODE_CORR) return f + w.cs * s + w.cn * z;   // Langevin (solver.py:784-785)
+  const float mu = w.pa * f + w.pb * s;                    // predictor (solver.py:283-300, 433-450)
+  mu_out = mu;
+  return mu + w.pc * z;
 }
 
-template <int FMODE>
+template <int FMODE, int MODE>
 __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a) {
   extern __shared__ uint8_t ta_smem_raw[];
   const ccsd_plan_desc_t &d = P->d;
@@ -118,7 +130,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     tc::mbar_init(h_ready, TA_EPI);
     tc::mbar_fence_init();
   }
-  if (warp == 20) tc::tmem_alloc(tslot, 512);
+  if (warp == TA_MMAW) tc::tmem_alloc(tslot, 512);
   if (FMODE == 2) netf_stage_w8(d.netf, P->W, fw);
   // operand rows that no edge fills stay zero for the whole kernel (their A columns are zero too, but
   // 0 * NaN from uninitialised shared memory would poison the accumulator)
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.r2) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     const int cu = threadIdx.x & 7, r0 = threadIdx.x >> 3;   // 16-byte chunk (4 cells) of rows r0 + 16 j
-    const bool writes = a.mode != MODE_NORM;
+    const bool writes = MODE != MODE_NORM;
     auto tile_of = [&](int g, int &b, int &k0) {
       const int si = g / ntile;
       b = (int)blockIdx.x + si * (int)gridDim.x;
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     }
     // drain: tiles [ntot - NS, ntot) are still in the ring (the loop copied out tile g + PD - NS)
     for (int g = ntot > TA_NS ? ntot - TA_NS : 0; g < ntot; ++g) copy_out(g);
-  } else if (warp == 20) {
+  } else if (warp == TA_MMAW) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = tc::make_idesc_bf16(128, TA_TN, /*A from TMEM*/ 0, /*B MN-major*/ 1);
     for (int g = 0; g < ntot; ++g) {
@@ -250,45 +262,61 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 4-19) =====================
-    const int ew = warp - 4;             // 0..15
+    // ===================== epilogue (warps 4-15) =====================
+    const int ew = warp - 4;             // 0..11
     const int q = ew & 3;                // TMEM lane quarter (= warp % 4)
-    const int mt = (ew >> 2) & 1;        // M tile
-    const int half = ew >> 3;            // cells [16 half, 16 half + 16) of the tile; e' half for the H fill
+    const int role = ew >> 2;            // 0: M tile 0, cells 0-15   1: M tile 0, cells 16-31   2: M tile 1
+    const int mt = role == 2 ? 1 : 0;
     const int et = threadIdx.x - TA_LOAD;
     const int Kg = P->Kp >> 2;
-    // the edge row this thread owns: M tile 0 holds edges 0..127 on lanes 0..127; M tile 1 holds edges
-    // 128 + 16 q + l on lanes 32 q + l, l < 16 (so that every lane quarter carries the same load)
-    int e = -1;
-    if (mt == 0) e = q * 32 + lane;
-    else if (lane < 16) e = 128 + q * 16 + lane;
+    // The edge row whose ENTRIES this thread processes, and its 16 cells of every tile.  M tile 0 holds
+    // edges 0..127 on lanes 0..127.  M tile 1 holds edge 128 + 16 q + l on lane 32 q + l for l < 16 (every
+    // lane quarter carries the same load); there lane l >= 16 processes cells 16-31 of lane (l - 16)'s row.
+    int e, chalf;
+    if (role < 2) { e = q * 32 + lane; chalf = role; }
+    else { e = 128 + q * 16 + (lane & 15); chalf = lane >> 4; }
     if (e >= E) e = -1;
+    // the A-operand row (TMEM lane 32 q + lane) this thread FILLS with H: the same edge, except that the
+    // upper lanes of M tile 1 hold no edge (zero rows)
+    const int efill = (role == 2 && lane >= 16) ? -1 : e;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float cs = 0.f, cn = 0.f;
-    if (a.mode == MODE_CORR) { cs = a.coef[4]; cn = a.coef[5]; }
     const int ei = e >= 0 ? P->edge_ij[2 * e] : 0, ej = e >= 0 ? P->edge_ij[2 * e + 1] : 0;
+    R2Fold w;
+    {
+      ccsd_objcoef_t co;
+      memset(&co, 0, sizeof co);
+      co.score_scale = 1.f;
+      if (MODE != MODE_EVAL) co = P->sched[a.nz.step * 3 + 2];
+      w.sc = co.score_scale;
+      w.k0 = w.sc * d.netf.aff[0]; w.k1 = w.sc * d.netf.aff[1]; w.k2 = w.sc * d.netf.aff[2];
+      w.cs = 0.f; w.cn = 0.f;
+      if (MODE == MODE_CORR) { w.cs = a.coef[4]; w.cn = a.coef[5]; }
+      w.pa = co.pa; w.pb = co.pb; w.pc = co.pc;
+    }
+    const uint32_t did = draw_id(2, a.nz.step, a.slot);
     for (int si = 0; si < nmine; ++si) {
       const int b = (int)blockIdx.x + si * (int)gridDim.x;
       const float *fl = a.flags + (size_t)b * N;
       R2Epi c;
       c.P = P; c.fl = fl; c.fw = fw; c.zm = 0ull;
       c.gs = (unsigned long long)(a.nz.sample_offset + b);
-      if (a.mode != MODE_EVAL) c.co = P->sched[a.nz.step * 3 + 2];
       c.b = b; c.E = E; c.K = K; c.Kg = Kg; c.f_nlin = P->f_nlin;
-      c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
       const float fe = e >= 0 ? fl[ei] * fl[ej] : 0.f;
+      const bool side = MODE == MODE_PRED && (a.write_mean || (a.traj != nullptr && b == 0));
       // ---- H of this sample -> TMEM (A operand).  Every MMA of the previous sample has completed: this
       // warp waited on t_full of its last tile. ----
       if (mt < mtiles) {
-        const float *Hrow = a.H + ((size_t)b * E + (e >= 0 ? e : 0)) * Ep;
-        for (int c16 = 0; c16 < 3; ++c16) {
-          const int kb = half * 96 + c16 * 32;          // first e' of this 32-element (16-column) group
+        const float *Hrow = a.H + ((size_t)b * E + (efill >= 0 ? efill : 0)) * Ep;
+        // roles 0 / 1 share the rows of M tile 0 (e' halves); role 2 fills both halves of M tile 1
+        const int h0 = role == 2 ? 0 : role, h1 = role == 2 ? 2 : role + 1;
+        for (int c16 = h0 * 3; c16 < h1 * 3; ++c16) {
+          const int kb = c16 * 32;                       // first e' of this 32-element (16-column) group
           uint32_t hw[16], lw[16];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             const int k = kb + 4 * j4;
-            if (e >= 0 && k < Ep) v = __ldg(reinterpret_cast<const float4 *>(Hrow + k));
+            if (efill >= 0 && k < Ep) v = __ldg(reinterpret_cast<const float4 *>(Hrow + k));
             if (k + 0 >= E) v.x = 0.f;
             if (k + 1 >= E) v.y = 0.f;
             if (k + 2 >= E) v.z = 0.f;
@@ -298,7 +326,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
             hw[2 * j4] = hi.x; hw[2 * j4 + 1] = hi.y;
             lw[2 * j4] = lo.x; lw[2 * j4 + 1] = lo.y;
           }
-          const uint32_t col = (uint32_t)(mt * 192 + half * 48 + c16 * 16);
+          const uint32_t col = (uint32_t)(mt * 192 + c16 * 16);
           tc::tmem_st16(tmem + lane_base + col, hw);
           tc::tmem_st16(tmem + lane_base + col + 96u, lw);
         }
@@ -313,80 +341,120 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         const int g = si * ntile + ct;
         const int slot = g & 1, stg = g % TA_NS;
         tc::mbar_wait(stage_full + 8 * stg, (uint32_t)(g / TA_NS) & 1u);   // staging tile + cell flags visible
-        tc::mbar_wait(t_full + 8 * slot, (uint32_t)(g >> 1) & 1u);   // accumulators complete
+        tc::mbar_wait(t_full + 8 * slot, (uint32_t)(g >> 1) & 1u);         // accumulators complete
         tc::tc_fence_after_sync();
         float v[16];
-        tc::tmem_ld16(tmem + lane_base + TA_COL_D + (uint32_t)(slot * 64 + mt * 32 + half * 16), v);
+        const uint32_t dcol = tmem + lane_base + TA_COL_D + (uint32_t)(slot * 64 + mt * 32);
+        if (role < 2) {
+          tc::tmem_ld16(dcol + (uint32_t)(role * 16), v);
+        } else {
+          uint32_t va[16], vb[16];
+          tc::tmem_ld16_nowait(dcol, va);
+          tc::tmem_ld16_nowait(dcol + 16u, vb);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t t = __shfl_sync(0xffffffffu, vb[j], lane & 15);
+            v[j] = __uint_as_float(lane < 16 ? va[j] : t);
+          }
+        }
         tc::tc_fence_before_sync();
         tc::mbar_arrive(d_empty + 8 * slot);                          // accumulator slot may be overwritten
         if (e >= 0) {
           uint8_t *row = gen + TA_OPER + (size_t)stg * TA_STAGE + (size_t)e * 128;
-          const float *fc = fcs + stg * TA_TN + half * 16;
-          const int kbase = ct * TA_TN + half * 16;
+          const float *fcp = fcs + stg * TA_TN + chalf * 16;
+          const int kbase = ct * TA_TN + chalf * 16;
+          const bool inside = kbase + 16 <= K;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const int k = kbase + 4 * c4;
-            float4 *cell = reinterpret_cast<float4 *>(row + (((half * 4 + c4) ^ (e & 7)) << 4));
+            float4 *cell = reinterpret_cast<float4 *>(row + (((chalf * 4 + c4) ^ (e & 7)) << 4));
             const float4 f4 = *cell;
+            const float4 fc4 = *reinterpret_cast<const float4 *>(fcp + 4 * c4);   // 0 for cells >= K
             const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+            const float mv[4] = {fe * fc4.x, fe * fc4.y, fe * fc4.z, fe * fc4.w};
             float z4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (a.mode != MODE_EVAL && k < K) {
+            if (MODE != MODE_EVAL) {
               if (Nb) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   if (k + i < K) z4[i] = Nb[(size_t)e * K + k + i];
               } else {
-                normal4(a.nz.seed, c.gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(e * Kg + (k >> 2)), z4);
+                normal4(a.nz.seed, c.gs, did, (uint32_t)(e * Kg + (k >> 2)), z4);
               }
             }
-            float o4[4];
+            float o4[4], mu4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              o4[i] = (k + i < K) ? r2_entry<FMODE>(c, a, e, k + i, fv[i], v[4 * c4 + i], z4[i], fe * fc[4 * c4 + i], cs, cn, s2, z2)
-                                  : 0.f;
-            if (a.mode != MODE_NORM) *cell = make_float4(o4[0], o4[1], o4[2], o4[3]);
+              o4[i] = r2_entry<FMODE, MODE>(c, w, fv[i], v[4 * c4 + i], z4[i], mv[i], s2, z2, mu4[i]);
+            if (MODE != MODE_NORM) *cell = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            if (MODE == MODE_PRED && side) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (inside || k + i < K) {
+                  if (a.write_mean) a.mean[((size_t)b * E + e) * K + k + i] = mu4[i];
+                  if (a.traj && b == 0) a.traj[(size_t)e * K + k + i] = a.denoise ? mu4[i] : o4[i];
+                }
+            }
           }
         }
         tc::mbar_arrive(epi_done + 8 * stg);                          // (release) tile may be copied out
       }
-      if (a.mode == MODE_SCORE || a.mode == MODE_NORM) {
-        // per-sample squared norms: reduce over the 16 epilogue warps (named barrier 1, 512 threads)
+      if (MODE == MODE_SCORE || MODE == MODE_NORM) {
+        // per-sample squared norms: reduce over the 12 epilogue warps (named barrier 1, 384 threads)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           z2 += __shfl_xor_sync(0xffffffffu, z2, o);
         }
         if (lane == 0) { red[ew] = s2; red[16 + ew] = z2; }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, 384;" ::: "memory");
         if (et == 0) {
           float ts = 0.f, tz = 0.f;
-          for (int w = 0; w < 16; ++w) { ts += red[w]; tz += red[16 + w]; }
+          for (int wv = 0; wv < 12; ++wv) { ts += red[wv]; tz += red[16 + wv]; }
           float *np = a.norm_part + ((size_t)(2 * d.B + b) * P->ntile_max) * 2;
           np[0] = ts; np[1] = tz;
           for (int t = 1; t < P->ntile_r2; ++t) { np[2 * t] = 0.f; np[2 * t + 1] = 0.f; }
         }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, 384;" ::: "memory");
       }
     }
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 20) tc::tmem_dealloc(tmem, 512);
+  if (warp == TA_MMAW) tc::tmem_dealloc(tmem, 512);
 }
 
-static inline int tc_apply_prepare() {
-  cudaError_t e = cudaFuncSetAttribute(tc_apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM);
-  return e == cudaSuccess ? 0 : -1;
+template <int FMODE, int MODE>
+static inline int tc_apply_launch_fm(const DevPlan *dP, int grid, const ApplyArgs &a, void *stream) {
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_apply_kernel<FMODE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  tc_apply_kernel<FMODE, MODE><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+template <int FMODE>
+static inline int tc_apply_launch_f(const DevPlan *dP, int grid, const ApplyArgs &a, void *stream) {
+  switch (a.mode) {
+    case MODE_EVAL: return tc_apply_launch_fm<FMODE, MODE_EVAL>(dP, grid, a, stream);
+    case MODE_SCORE: return tc_apply_launch_fm<FMODE, MODE_SCORE>(dP, grid, a, stream);
+    case MODE_PRED: return tc_apply_launch_fm<FMODE, MODE_PRED>(dP, grid, a, stream);
+    case MODE_NORM: return tc_apply_launch_fm<FMODE, MODE_NORM>(dP, grid, a, stream);
+    case MODE_CORR: return tc_apply_launch_fm<FMODE, MODE_CORR>(dP, grid, a, stream);
+  }
+  return -1;
+}
+
+static inline int tc_apply_prepare() { return 0; }   // attributes are set per instantiation at first launch
 
 static inline int tc_apply_launch(const DevPlan *dP, const DevPlan &hp, const ApplyArgs &a, void *stream) {
   const int grid = hp.d.B < 148 ? hp.d.B : 148;
-  if (hp.f_mode == 1) tc_apply_kernel<1><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a);
-  else if (hp.f_mode == 2) tc_apply_kernel<2><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a);
-  else tc_apply_kernel<0><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, stream);
+  if (hp.f_mode == 2) return tc_apply_launch_f<2>(dP, grid, a, stream);
+  return tc_apply_launch_f<0>(dP, grid, a, stream);
 }
 
 }  // namespace ccsd

@@ -37,12 +37,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.  The loop is two
+// instructions per failed try (try_wait itself suspends the thread for a hardware time slice), so waiting
+// warps do not take issue slots from the working ones; the bound is a try count, not a clock read.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity))
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz: a pipeline deadlock, not a wait
+    if (++tries > (1u << 28)) __trap();
 }
 
 // ---- proxy / tcgen05 fences ----
