@@ -131,6 +131,8 @@ def load():
     lib.ccsd_plan_get_profile.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     lib.ccsd_debug_gram.restype = C.c_int
     lib.ccsd_debug_gram.argtypes = [vp, vp, vp, vp, C.c_int, vp]
+    lib.ccsd_debug_apply_trace.restype = C.c_int
+    lib.ccsd_debug_apply_trace.argtypes = [vp, vp]
     lib.ccsd_last_error.restype = C.c_char_p
     lib.ccsd_version.restype = C.c_char_p
     if lib.ccsd_plan_desc_size() != C.sizeof(PlanDesc) or lib.ccsd_objcoef_size() != C.sizeof(ObjCoef):

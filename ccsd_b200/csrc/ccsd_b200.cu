@@ -69,6 +69,7 @@ struct ccsd_plan {
   float *H = nullptr, *P0 = nullptr, *P1 = nullptr, *norm_part = nullptr, *coef = nullptr;
   float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
   bool bound = false, inited = false;
+  long long *trace = nullptr;   // debug timeline buffer for the tensor-core apply kernel
   unsigned long long seed = 0;
   long long sample_offset = 0;
   size_t xa_smem = 0, apply_smem = 0;
@@ -561,6 +562,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     ApplyArgs q; memset(&q, 0, sizeof q);
     q.r2 = p->r2; q.H = p->H; q.flags = p->flags; q.mode = mode; q.slot = slot; q.denoise = d.denoise; q.nz = nz;
     q.norm_part = p->norm_part; q.coef = p->coef;
+    q.trace = mode == MODE_CORR ? p->trace : nullptr;   // debug timeline of the Langevin-correction pass
     q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
     if (mode == MODE_SCORE) q.out = p->sr2;
     else if (mode == MODE_CORR) q.out = p->r2;
@@ -690,6 +692,12 @@ int ccsd_quantize(const float *in, uint8_t *out, size_t n, float thr, int mol, v
 }
 
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }
+
+int ccsd_debug_apply_trace(ccsd_plan_t *p, long long *trace_dev) {
+  if (!p) return fail(CCSD_ERR_INVALID, "null plan");
+  p->trace = trace_dev;
+  return 0;
+}
 
 int ccsd_plan_info(const ccsd_plan_t *p, int what) {
   if (!p) return -1;

@@ -145,8 +145,12 @@ __device__ __forceinline__ float u01(uint32_t r) {
 __device__ __forceinline__ void normal4(uint64_t seed, uint64_t sample, uint32_t draw_id, uint32_t group,
                                         float z[4]) {
   uint32_t r[4];
+#ifdef CCSD_EXPERIMENT_NO_PHILOX
+  r[0] = group; r[1] = draw_id; r[2] = (uint32_t)sample; r[3] = (uint32_t)seed;   // timing experiment only
+#else
   philox4x32_10(group, draw_id, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
+#endif
   // Box-Muller on the SFU: radius = sqrt(t) = t * rsqrt(t) with t = -2 ln u > 0, angle through the fast
   // sin/cos (|err| ~1e-6 on a unit normal: irrelevant for noise).  The draw is on the per-entry hot path of
   // every sampler pass, so its instruction count matters more than its last bits.

@@ -276,6 +276,7 @@ struct ApplyArgs {
   float *traj;                   // PRED: sample 0 destination or nullptr
   int slot, denoise, write_mean;
   NoiseCtx nz;
+  long long *trace;              // debug: per-tile clock64 stamps of CTA 0 ([tile][16]) or nullptr
 };
 
 // Per-CTA epilogue context (everything the per-entry work needs), shared by the fp32 and the

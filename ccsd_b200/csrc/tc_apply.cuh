@@ -16,7 +16,7 @@
 //   bf16x3: D += Ahi.Bhi + Ahi.Blo + Alo.Bhi with fp32 accumulation (dropped term ~2^-18 relative).
 //
 // The SAME fp32 tile that feeds the operand conversion stays in a shared-memory staging ring
-// (cp.async, 4 stages x 24 KB, 16-byte chunks XOR-swizzled by the row so that both the row-wise loader
+// (cp.async, 6 stages x 24 KB, 16-byte chunks XOR-swizzled by the row so that both the row-wise loader
 // accesses and the column-wise epilogue accesses are conflict free).  The epilogue threads -- one per
 // edge row, i.e. per TMEM lane -- read their row's 16 cells from the staging tile, combine them with the
 // accumulator, Philox noise and masks, and write the NEW state back into the staging tile in place;
@@ -25,7 +25,8 @@
 // Warp roles (17 warps): 0-3 loaders (cp.async ring, bf16 split, copy-out), 4-15 epilogue (TMEM lane
 // quarter q = warp % 4; role = (warp - 4) / 4: M tile 0 cells 0-15 | M tile 0 cells 16-31 | M tile 1, where
 // the 16 edges of the quarter are processed by lane pairs (l, l + 16) taking 16 cells each, so every lane
-// of every epilogue warp has work), 16 MMA issuer.  The kernel is templated on the ScoreNetworkF entry
+// of every epilogue warp has work), 16-17 MMA issuers (one per M tile: the issue rate of one thread, not the
+// tensor pipe, bounds a 72-instruction tile).  The kernel is templated on the ScoreNetworkF entry
 // path AND the pass mode, so the per-entry code has no mode branches.
 #pragma once
 #include "r2_kernels.cuh"
@@ -33,13 +34,20 @@
 
 namespace ccsd {
 
-constexpr int TA_LOAD = 128;
+#ifndef TA_LOAD_THREADS
+#define TA_LOAD_THREADS 128
+#endif
+#ifndef TA_PREFETCH
+#define TA_PREFETCH 2
+#endif
+constexpr int TA_LOAD = TA_LOAD_THREADS;
+constexpr int TA_RSTEP = TA_LOAD / 8;              // rows covered by one sweep of the loader threads
 constexpr int TA_EPI = 384;
-constexpr int TA_THREADS = TA_LOAD + TA_EPI + 32;
+constexpr int TA_THREADS = TA_LOAD + TA_EPI + 64;   // + one MMA-issuing warp per M tile
 constexpr int TA_TN = 32;                         // cells per tile
 constexpr int TA_NE = 192;                        // padded edge count
-constexpr int TA_NS = 4;                          // staging stages
-constexpr int TA_PD = 2;                          // cp.async prefetch distance (tiles)
+constexpr int TA_NS = 6;                          // staging stages (the loaders only block on a tile 4 behind)
+constexpr int TA_PD = TA_PREFETCH;                          // cp.async prefetch distance (tiles)
 constexpr uint32_t TA_OPHALF = TA_NE * 128u;      // 24576: hi (or lo) operand rows, 64 cells (2 tile slots) x bf16
 constexpr uint32_t TA_OPER = 2u * TA_OPHALF;      // 49152
 constexpr uint32_t TA_STAGE = TA_NE * 128u;       // 24576: 192 rows x 32 fp32
@@ -90,6 +98,9 @@ __device__ __forceinline__ float r2_entry(const R2Epi &c, const R2Fold &w, float
   return mu + w.pc * z;
 }
 
+// debug timeline (ccsd_debug_apply_trace): stamp `slot` of tile g, CTA 0 only
+#define TA_STAMP(slot_, g_) do { if (a.trace && blockIdx.x == 0 && (g_) < 512) a.trace[(size_t)(g_) * 16 + (slot_)] = clock64(); } while (0)
+
 template <int FMODE, int MODE>
 __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a) {
   extern __shared__ uint8_t ta_smem_raw[];
@@ -119,8 +130,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(full + 8 * s, TA_LOAD);
-      tc::mbar_init(op_empty + 8 * s, 1);
-      tc::mbar_init(t_full + 8 * s, 1);
+      tc::mbar_init(op_empty + 8 * s, mtiles);   // one tcgen05.commit per MMA-issuing warp
+      tc::mbar_init(t_full + 8 * s, mtiles);
       tc::mbar_init(d_empty + 8 * s, TA_EPI);
     }
     for (int s = 0; s < TA_NS; ++s) {
@@ -144,12 +155,18 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int ntot = nmine * ntile;
 
-  if (warp < 4) {
+  if (warp < TA_LOAD / 32) {
     // ===================== loaders =====================
     const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.r2) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-    const int cu = threadIdx.x & 7, r0 = threadIdx.x >> 3;   // 16-byte chunk (4 cells) of rows r0 + 16 j
+    const int cu = threadIdx.x & 7, r0 = threadIdx.x >> 3;   // 16-byte chunk (4 cells) of rows r0 + RSTEP j
     const bool writes = MODE != MODE_NORM;
+    // rows advance by a multiple of 8, so the XOR swizzle term (r & 7) is a per-thread constant and every
+    // address below is base + j * stride
+    constexpr int NJ = TA_NE / TA_RSTEP;
+    constexpr uint32_t JSTR = TA_RSTEP * 128u;
+    const int nj = (E - r0 + TA_RSTEP - 1) / TA_RSTEP;          // rows of this thread (r0 < E: E >= 8... guarded below)
+    const uint32_t soff = (uint32_t)r0 * 128u + (uint32_t)((cu ^ (r0 & 7)) << 4);
     auto tile_of = [&](int g, int &b, int &k0) {
       const int si = g / ntile;
       b = (int)blockIdx.x + si * (int)gridDim.x;
@@ -159,43 +176,54 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       int b, k0;
       tile_of(g, b, k0);
       const float *Fb = a.r2 + (size_t)b * E * K;
-      const uint32_t st = sStage + (uint32_t)(g % TA_NS) * TA_STAGE;
+      const uint32_t st = sStage + (uint32_t)(g % TA_NS) * TA_STAGE + soff;
       const int k = k0 + 4 * cu;
-      for (int r = r0; r < E; r += 16) {
-        const uint32_t dst = st + (uint32_t)r * 128u + (uint32_t)((cu ^ (r & 7)) << 4);
-        const float *src = Fb + (size_t)r * K + k;
-        if (vec) {
-          const int nb = k + 4 <= K ? 16 : (k < K ? (K - k) * 4 : 0);
-          tc::cp_async16(dst, nb ? (const void *)src : (const void *)Fb, (uint32_t)nb);
-        } else {
+      const float *src = Fb + (size_t)r0 * K + k;
+      const size_t gstr = (size_t)TA_RSTEP * K;
+      if (vec) {
+        const int nb = k + 4 <= K ? 16 : (k < K ? (K - k) * 4 : 0);
+        if (nb == 0) src = Fb;
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) tc::cp_async16(st + (uint32_t)j * JSTR, nb ? (const void *)(src + j * gstr) : (const void *)Fb, (uint32_t)nb);
+      } else {
+        for (int j = 0; j < nj; ++j)
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            tc::cp_async4(dst + 4u * i, (k + i < K) ? (const void *)(src + i) : (const void *)Fb, (k + i < K) ? 4u : 0u);
-        }
+            tc::cp_async4(st + (uint32_t)j * JSTR + 4u * i, (k + i < K) ? (const void *)(src + j * gstr + i) : (const void *)Fb,
+                          (k + i < K) ? 4u : 0u);
       }
     };
     auto copy_out = [&](int g) {
-      tc::mbar_wait(epi_done + 8 * (g % TA_NS), (uint32_t)(g / TA_NS) & 1u);
+      tc::mbar_wait_relaxed(epi_done + 8 * (g % TA_NS), (uint32_t)(g / TA_NS) & 1u);
       if (!writes) return;
       int b, k0;
       tile_of(g, b, k0);
-      float *Ob = a.out + (size_t)b * E * K;
-      const uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE;
+      const uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE + soff;
       const int k = k0 + 4 * cu;
       if (k >= K) return;
-      for (int r = r0; r < E; r += 16) {
-        const float4 v = *reinterpret_cast<const float4 *>(st + (size_t)r * 128 + (size_t)((cu ^ (r & 7)) << 4));
-        float *dst = Ob + (size_t)r * K + k;
-        if (vec) {
-          __stcs(reinterpret_cast<float4 *>(dst), v);
-        } else {
+      float *dst = a.out + (size_t)b * E * K + (size_t)r0 * K + k;
+      const size_t gstr = (size_t)TA_RSTEP * K;
+      if (vec) {
+        for (int j0 = 0; j0 < nj; j0 += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (j0 + u < nj) v[u] = *reinterpret_cast<const float4 *>(st + (size_t)(j0 + u) * JSTR);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (j0 + u < nj) __stcs(reinterpret_cast<float4 *>(dst + (j0 + u) * gstr), v[u]);
+        }
+      } else {
+        for (int j = 0; j < nj; ++j) {
+          const float4 v = *reinterpret_cast<const float4 *>(st + (size_t)j * JSTR);
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (k + i < K) __stcs(dst + i, vv[i]);
+            if (k + i < K) __stcs(dst + j * gstr + i, vv[i]);
         }
       }
     };
+    (void)NJ;
     for (int t = 0; t < TA_PD; ++t) {
       if (t < ntot) issue(t);
       tc::cp_async_commit();
@@ -208,20 +236,30 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         issue(g + TA_PD);
       }
       tc::cp_async_commit();
+      if (threadIdx.x == 0) TA_STAMP(0, g);
       tc::cp_async_wait<TA_PD>();                                   // this thread's chunks of tile g have landed
+      if (threadIdx.x == 0) TA_STAMP(1, g);
       int b, k0;
       tile_of(g, b, k0);
       if (b != cur_b) { cur_b = b; zm = zero_mask_of(a.flags + (size_t)b * N, N); }
       if (g >= 2) tc::mbar_wait(op_empty + 8 * (g & 1), (uint32_t)(((g >> 1) & 1) ^ 1));
-      uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE;
-      const uint32_t slot4 = (uint32_t)(g & 1) * 4u;
-      for (int r = r0; r < E; r += 16) {
-        const float4 v = *reinterpret_cast<const float4 *>(st + (size_t)r * 128 + (size_t)((cu ^ (r & 7)) << 4));
-        uint2 hi, lo;
-        tc::split4(v, hi, lo);
-        const uint32_t off = (uint32_t)r * 128u + (((slot4 + (uint32_t)(cu >> 1)) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(cu & 1) * 8u;
-        *reinterpret_cast<uint2 *>(gen + off) = hi;
-        *reinterpret_cast<uint2 *>(gen + TA_OPHALF + off) = lo;
+      if (threadIdx.x == 0) TA_STAMP(2, g);
+      const uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE + soff;
+      uint8_t *op = gen + (uint32_t)r0 * 128u + ((((uint32_t)(g & 1) * 4u + (uint32_t)(cu >> 1)) ^ (uint32_t)(r0 & 7)) << 4) +
+                    (uint32_t)(cu & 1) * 8u;
+      for (int j0 = 0; j0 < nj; j0 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < nj) v[u] = *reinterpret_cast<const float4 *>(st + (size_t)(j0 + u) * JSTR);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < nj) {
+            uint2 hi, lo;
+            tc::split4(v[u], hi, lo);
+            *reinterpret_cast<uint2 *>(op + (size_t)(j0 + u) * JSTR) = hi;
+            *reinterpret_cast<uint2 *>(op + TA_OPHALF + (size_t)(j0 + u) * JSTR) = lo;
+          }
       }
       if (threadIdx.x < TA_TN) {
         const int k = k0 + (int)threadIdx.x;
@@ -230,40 +268,46 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(full + 8 * (g & 1));
       tc::mbar_arrive(stage_full + 8 * (g % TA_NS));
+      if (threadIdx.x == 0) TA_STAMP(3, g);
     }
     // drain: tiles [ntot - NS, ntot) are still in the ring (the loop copied out tile g + PD - NS)
     for (int g = ntot > TA_NS ? ntot - TA_NS : 0; g < ntot; ++g) copy_out(g);
-  } else if (warp == TA_MMAW) {
-    // ===================== MMA issuer =====================
+  } else if (warp >= TA_MMAW) {
+    // ===================== MMA issuers: warp TA_MMAW + mt drives M tile mt =====================
+    const int mt = warp - TA_MMAW;
     const uint32_t idesc = tc::make_idesc_bf16(128, TA_TN, /*A from TMEM*/ 0, /*B MN-major*/ 1);
-    for (int g = 0; g < ntot; ++g) {
-      const int slot = g & 1;
-      const int si = g / ntile;
-      if (g - si * ntile == 0) tc::mbar_wait(h_ready, (uint32_t)si & 1u);
-      tc::mbar_wait(full + 8 * slot, (uint32_t)(g >> 1) & 1u);
-      tc::mbar_wait(d_empty + 8 * slot, (uint32_t)(((g >> 1) & 1) ^ 1));
-      tc::tc_fence_after_sync();
-      if (lane == 0) {
-        for (int mt = 0; mt < mtiles; ++mt) {
+    if (mt < mtiles) {
+      for (int g = 0; g < ntot; ++g) {
+        const int slot = g & 1;
+        const int si = g / ntile;
+        if (g - si * ntile == 0) tc::mbar_wait(h_ready, (uint32_t)si & 1u);
+        tc::mbar_wait(full + 8 * slot, (uint32_t)(g >> 1) & 1u);
+        tc::mbar_wait(d_empty + 8 * slot, (uint32_t)(((g >> 1) & 1) ^ 1));
+        tc::tc_fence_after_sync();
+        if (lane == 0 && mt == 0) TA_STAMP(4, g);
+        if (lane == 0) {
+          // descriptors advance by 16 e' rows (2048 bytes = 128 descriptor units) per k step
+          uint64_t b_hi = tc::make_smem_desc(sOp + (uint32_t)slot * 64u, 8192, 1024);
+          uint64_t b_lo = tc::make_smem_desc(sOp + TA_OPHALF + (uint32_t)slot * 64u, 8192, 1024);
           const uint32_t dcol = tmem + TA_COL_D + (uint32_t)(slot * 64 + mt * 32);
-          const uint32_t a_hi = tmem + (uint32_t)(mt * 192), a_lo = a_hi + 96u;
+          uint32_t a_hi = tmem + (uint32_t)(mt * 192);
+#pragma unroll 1
           for (int k4 = 0; k4 < nk; ++k4) {
-            const uint32_t bo = (uint32_t)slot * 64u + (uint32_t)k4 * 2048u;   // 16 e' rows of 128 bytes
-            const uint64_t b_hi = tc::make_smem_desc(sOp + bo, 8192, 1024);
-            const uint64_t b_lo = tc::make_smem_desc(sOp + TA_OPHALF + bo, 8192, 1024);
-            tc::umma_bf16_ts(dcol, a_hi + (uint32_t)k4 * 8u, b_hi, idesc, k4 != 0);
-            tc::umma_bf16_ts(dcol, a_hi + (uint32_t)k4 * 8u, b_lo, idesc, 1);
-            tc::umma_bf16_ts(dcol, a_lo + (uint32_t)k4 * 8u, b_hi, idesc, 1);
+            tc::umma_bf16_ts_coll<1, 0>(dcol, a_hi, b_hi, idesc, k4 != 0);   // A_hi kept in the collector ...
+            tc::umma_bf16_ts_coll<0, 1>(dcol, a_hi, b_lo, idesc, 1);         // ... and reused
+            tc::umma_bf16_ts(dcol, a_hi + 96u, b_hi, idesc, 1);
+            a_hi += 8u; b_hi += 128u; b_lo += 128u;
           }
+          tc::umma_commit(op_empty + 8 * slot);   // operand slot may be refilled once these MMAs retire
+          tc::umma_commit(t_full + 8 * slot);     // accumulators complete
+          if (mt == 0) TA_STAMP(5, g);
         }
-        tc::umma_commit(op_empty + 8 * slot);   // operand slot may be refilled once these MMAs retire
-        tc::umma_commit(t_full + 8 * slot);     // accumulators complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 4-15) =====================
-    const int ew = warp - 4;             // 0..11
+    const int ew = warp - TA_LOAD / 32;   // 0..11
     const int q = ew & 3;                // TMEM lane quarter (= warp % 4)
     const int role = ew >> 2;            // 0: M tile 0, cells 0-15   1: M tile 0, cells 16-31   2: M tile 1
     const int mt = role == 2 ? 1 : 0;
@@ -340,9 +384,11 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       for (int ct = 0; ct < ntile; ++ct) {
         const int g = si * ntile + ct;
         const int slot = g & 1, stg = g % TA_NS;
-        tc::mbar_wait(stage_full + 8 * stg, (uint32_t)(g / TA_NS) & 1u);   // staging tile + cell flags visible
-        tc::mbar_wait(t_full + 8 * slot, (uint32_t)(g >> 1) & 1u);         // accumulators complete
+        tc::mbar_wait_relaxed(stage_full + 8 * stg, (uint32_t)(g / TA_NS) & 1u);   // staging tile + cell flags visible
+        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 6 : 10, g);
+        tc::mbar_wait_relaxed(t_full + 8 * slot, (uint32_t)(g >> 1) & 1u);         // accumulators complete
         tc::tc_fence_after_sync();
+        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 7 : 11, g);
         float v[16];
         const uint32_t dcol = tmem + lane_base + TA_COL_D + (uint32_t)(slot * 64 + mt * 32);
         if (role < 2) {
@@ -360,6 +406,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         }
         tc::tc_fence_before_sync();
         tc::mbar_arrive(d_empty + 8 * slot);                          // accumulator slot may be overwritten
+        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 8 : 12, g);
         if (e >= 0) {
           uint8_t *row = gen + TA_OPER + (size_t)stg * TA_STAGE + (size_t)e * 128;
           const float *fcp = fcs + stg * TA_TN + chalf * 16;
@@ -399,6 +446,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
           }
         }
         tc::mbar_arrive(epi_done + 8 * stg);                          // (release) tile may be copied out
+        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 9 : 13, g);
       }
       if (MODE == MODE_SCORE || MODE == MODE_NORM) {
         // per-sample squared norms: reduce over the 12 epilogue warps (named barrier 1, 384 threads)

@@ -30,10 +30,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
   return ok != 0;
 }
@@ -44,6 +44,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity))
     if (++tries > (1u << 28)) __trap();
+}
+
+// Same, for waiters that are NOT on the critical path (consumers that are usually early): back off with
+// nanosleep so that their polling does not compete for issue slots with the warps everybody waits for.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t tries = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(96);
+    if (++tries > (1u << 24)) __trap();
+  }
 }
 
 // ---- proxy / tcgen05 fences ----
@@ -98,6 +108,31 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with the A-operand collector hints: KEEP = 1 keeps this instruction's A fragment in the collector
+// buffer (.collector::a::fill), REUSE = 1 takes the fragment the previous instruction kept instead of
+// reading tensor memory again (.collector::a::lastuse).  The A read from TMEM (128 rows x 32 bytes), not the
+// math, paces a small-N MMA, so consecutive instructions that share A should share the read.
+template <int KEEP, int REUSE>
+__device__ __forceinline__ void umma_bf16_ts_coll(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  if (KEEP) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if (REUSE) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_bf16_ts(d_tmem, a_tmem, bdesc, idesc, accumulate);
+  }
 }
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -173,20 +208,18 @@ __device__ __forceinline__ void split8(const float x[8], uint4 &hi, uint4 &lo) {
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// 4 floats -> 4 bf16 hi (8 bytes) + 4 bf16 lo (8 bytes)
+// 4 floats -> 4 bf16 hi (8 bytes) + 4 bf16 lo (8 bytes).  hi is the TRUNCATED top half of the fp32 word (one
+// byte-permute packs two of them), the residual x - hi is exact in fp32 and is rounded to bf16 two at a time
+// (cvt.rn.bf16x2.f32): |x - hi - lo| <= 2^-17 |x|, in 12 instructions.
 __device__ __forceinline__ void split4(const float4 x, uint2 &hi, uint2 &lo) {
-  const float v[4] = {x.x, x.y, x.z, x.w};
-  uint32_t h[2], l[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  hi = make_uint2(h[0], h[1]);
-  lo = make_uint2(l[0], l[1]);
+  const uint32_t u0 = __float_as_uint(x.x), u1 = __float_as_uint(x.y), u2 = __float_as_uint(x.z), u3 = __float_as_uint(x.w);
+  hi.x = __byte_perm(u0, u1, 0x7632);   // (hi16(u1) << 16) | hi16(u0)
+  hi.y = __byte_perm(u2, u3, 0x7632);
+  const float r0 = x.x - __uint_as_float(u0 & 0xFFFF0000u), r1 = x.y - __uint_as_float(u1 & 0xFFFF0000u);
+  const float r2 = x.z - __uint_as_float(u2 & 0xFFFF0000u), r3 = x.w - __uint_as_float(u3 & 0xFFFF0000u);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(r0, r1), l23 = __floats2bfloat162_rn(r2, r3);
+  lo.x = *reinterpret_cast<const uint32_t *>(&l01);
+  lo.y = *reinterpret_cast<const uint32_t *>(&l23);
 }
 
 }  // namespace tc

@@ -210,6 +210,11 @@ int ccsd_plan_get_profile(ccsd_plan_t *plan, int max_records, char *names, int n
  * (use_tc = 0) or the tcgen05 kernel (use_tc = 1); outputs [B,E,E] and [B,E,PR0] (either may be NULL). */
 int ccsd_debug_gram(ccsd_plan_t *plan, const float *r2, float *H_out, float *P0_out, int use_tc, void *stream);
 
+/* Debug: device buffer of 512 x 16 int64 that receives clock64 stamps of the pipeline roles of CTA 0 of every
+ * sampler-step tensor-core apply pass (slots: 0 loader issue, 1 landed, 2 operand slot free, 3 full; 4 MMA
+ * start, 5 MMA issued; 6-9 / 10-13 epilogue warp 0 / 8: waiting, accumulator ready, loaded, done); NULL = off. */
+int ccsd_debug_apply_trace(ccsd_plan_t *plan, long long *trace_dev);
+
 const char *ccsd_last_error(void);
 const char *ccsd_version(void);
 

@@ -1,0 +1,30 @@
+"""Timeline of the tensor-core apply kernel's pipeline roles (CTA 0): python tools/apply_trace.py"""
+import sys, torch, numpy as np
+sys.path.insert(0, "/root/repo")
+from tests.helpers import Config
+from tests.parity_cases import make_engine
+from ccsd_b200 import _native as nat
+cfg = Config("community_small_cc"); B = 1024
+g = torch.Generator().manual_seed(0)
+n = torch.randint(10, 21, (B,), generator=g)
+flags = (torch.arange(20)[None, :] < n[:, None]).float()
+eng = make_engine(cfg, B, "cuda")
+eng.init(flags.cuda(), seed=1)
+eng.run(0, 2)
+tr = torch.zeros(512, 16, dtype=torch.int64, device="cuda")
+nat.check(eng.lib.ccsd_debug_apply_trace(eng.handle, tr.data_ptr()))
+eng.run(2, 3)   # the LAST apply pass of the step (PRED) leaves its stamps
+torch.cuda.synchronize()
+t = tr.cpu().numpy()
+t0 = t[0, 0]
+names = ["ld.issue", "ld.landed", "ld.opfree", "ld.full", "mma.start", "mma.issued", "e0.wait", "e0.acc", "e0.ld", "e0.done", "e8.wait", "e8.acc", "e8.ld", "e8.done"]
+print("tile " + " ".join(f"{n:>10s}" for n in names))
+for gidx in list(range(0, 12)) + list(range(30, 44)) + list(range(100, 108)):
+    print(f"{gidx:4d} " + " ".join(f"{(t[gidx, i] - t0):10d}" for i in range(14)))
+d = np.diff(t[:250, 9])
+print("epilogue(e0) tile period: mean", d.mean(), "median", np.median(d))
+for a_, b_, nm in [(0, 1, "cp.async wait"), (1, 2, "opfree wait"), (2, 3, "convert"), (4, 5, "mma issue"), (6, 7, "e0 wait acc"), (7, 8, "e0 tmem ld"), (8, 9, "e0 compute"), (10, 11, "e8 wait acc"), (12, 13, "e8 compute")]:
+    x = (t[2:250, b_] - t[2:250, a_])
+    print(f"{nm:14s} mean {x.mean():9.0f} median {np.median(x):9.0f}")
+x = t[2:250, 0][1:] - t[2:250, 3][:-1]
+print(f"{'ld full->next issue (copy-out + cp.async issue)':14s} mean {x.mean():9.0f}")
