@@ -237,7 +237,7 @@ def pack_netf(dst: nat.NetF, blob: Blob, model) -> None:
         Wf, bf = lin("final")
         A_all, c_all = np.concatenate(rows_A, 0), np.concatenate(rows_c, 0)
         coef = Wf @ A_all            # (1, 2)
-        gamma = float(Wf @ c_all + bf)
+        gamma = float((Wf @ c_all + bf).reshape(-1)[0])
         dst.affine = 1
         dst.aff[0], dst.aff[1], dst.aff[2] = float(coef[0, 0]), float(coef[0, 1]), gamma
 
