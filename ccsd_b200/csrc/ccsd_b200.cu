@@ -3,9 +3,11 @@
 //
 // Reference call structure being replaced: ccsd/src/solver.py:961-1003 / 1109-1174 (pc_sampler),
 // :1267-1371 / 1409-1561 (s4_solver).  Launch sequence per PC step with the Langevin corrector:
-//   corrector:  gram(F0) [proj1] xa(SCORE) apply(SCORE) coef update      -> (x1, adj1, F1)
-//   predictor:  gram(F1) [proj1] xa(PRED)  apply(PRED)                   -> (x2, adj2, F2)
+//   corrector:  gram(F0) [proj1] xa(SCORE) apply(NORM) coef update(x, adj) apply(CORR)   -> (x1, adj1, F1)
+//   predictor:  gram(F1) [proj1] xa(PRED)  apply(PRED)                                  -> (x2, adj2, F2)
 // and per S4 step:  gram [proj1] xa(SCORE) apply(SCORE) coef update(S4 chain).
+// "xa" is the x / adj network pipeline of xa_pipe.cuh (x_net, attn_channel + attn_finish per attention
+// layer, hodge, afinal).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,7 +16,7 @@
 #include <vector>
 
 #include "r2_kernels.cuh"
-#include "xa_kernel.cuh"
+#include "xa_pipe.cuh"
 #ifndef CCSD_EMU
 #include "tc_gram.cuh"
 #include "tc_apply.cuh"
@@ -56,7 +58,7 @@ struct ccsd_plan {
   DevPlan hp;  // host copy; device copy lives at the start of the workspace
   std::vector<ccsd_objcoef_t> sched;
   std::vector<unsigned long long> cell_mask;
-  std::vector<int> edge_ij;
+  std::vector<int> edge_ij, tri_ij;
   const float *weights = nullptr;
   size_t n_weights = 0;
   // workspace
@@ -67,12 +69,13 @@ struct ccsd_plan {
   float *mx = nullptr, *madj = nullptr, *mr2 = nullptr;
   float *sx = nullptr, *sadj = nullptr, *sr2 = nullptr;
   float *H = nullptr, *P0 = nullptr, *P1 = nullptr, *norm_part = nullptr, *coef = nullptr;
+  float *g_stack = nullptr, *g_att = nullptr, *g_hmc = nullptr, *g_x0 = nullptr, *g_x1 = nullptr;
   float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
   bool bound = false, inited = false;
   long long *trace = nullptr;   // debug timeline buffer for the tensor-core apply kernel
   unsigned long long seed = 0;
   long long sample_offset = 0;
-  size_t xa_smem = 0, apply_smem = 0;
+  size_t apply_smem = 0;
   int64_t launches = 0;
   int use_tc = 0, use_tc_apply = 0;
   // optional per-kernel timing (CUDA events on the launching stream)
@@ -103,6 +106,7 @@ static void prof_end(ccsd_plan *p, void *stream) {
 // ---------------------------------------------------------------------------------------------
 static int a4(int v) { return (v + 3) & ~3; }
 static int imax(int a, int b) { return a > b ? a : b; }
+static int imin(int a, int b) { return a < b ? a : b; }
 
 static int check_mlp(const ccsd_mlp_t &m, size_t nw, const char *name, int small) {
   if (m.nl < 1 || m.nl > CCSD_MAX_MLP) return fail(CCSD_ERR_UNSUPPORTED, std::string(name) + ": 1..4 linears supported");
@@ -202,17 +206,17 @@ static int validate(const ccsd_plan_desc_t &d, size_t nw) {
   return 0;
 }
 
-static void make_layout(const ccsd_plan_desc_t &d, XaLayout &L) {
+static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   memset(&L, 0, sizeof(L));
   const int N = d.N, F = d.F;
   const ccsd_netx_t &X = d.netx;
   const ccsd_neta_t &A = d.neta;
   const int N4 = a4(N), NT = N * (N + 1) / 2, ldp = a4(NT);
   L.N4 = N4; L.NT = NT; L.ldp = ldp;
-  L.T = NT >= 96 ? 128 : 64;
-  int o = 0;
-  auto take = [&](int n) { int r = o; o += a4(n); return r; };
-  int nh_max = 1, ad_max = 1, cin_max = 1, kin_max = F, mc_hid = 1, eh = 1, eh_bufs = 1, heads = imax(A.num_heads, 1);
+  const int T = NT >= 96 ? 128 : 64;
+  L.Tx = L.Tc = L.Tf = L.Th = L.Tm = T;
+  int nh_max = 1, ad_max = 1, cin_max = 1, kin_max = F, mc_hid = 1, mc_o1 = 1, eh = 1, eh_bufs = 1, nch_max = 1;
+  const int heads = imax(A.num_heads, 1);
   for (int l = 0; l < A.num_layers; ++l) {
     const ccsd_attn_layer_t &ly = A.layer[l];
     nh_max = imax(nh_max, ly.conv_out);
@@ -220,78 +224,78 @@ static void make_layout(const ccsd_plan_desc_t &d, XaLayout &L) {
     cin_max = imax(cin_max, ly.c_in);
     kin_max = imax(kin_max, ly.conv_in);
     mc_hid = imax(mc_hid, imax(ly.multi_channel.dhid, ly.multi_channel.dout));
+    mc_o1 = imax(mc_o1, ly.multi_channel.nl == 1 ? ly.multi_channel.dout : ly.multi_channel.dhid);
     if (ly.mlp.nl > 1) eh = imax(eh, ly.mlp.dhid);
     if (ly.mlp.nl > 2) eh_bufs = 2;
+    const int ds = imax(ly.attn_dim / heads, 1);   // torch.split: ceil(ad / (ad / heads)) chunks
+    nch_max = imax(nch_max, (ly.attn_dim + ds - 1) / ds);
   }
-  // torch.split: ceil(ad / (ad / heads)) chunks
-  int nch_max = 1;
-  for (int l = 0; l < A.num_layers; ++l) {
-    const int ad = A.layer[l].attn_dim, ds = imax(ad / heads, 1);
-    nch_max = imax(nch_max, (ad + ds - 1) / ds);
-  }
-  L.flags = take(N4);
-  L.dvec = take(N4);
-  L.pij = take(ldp);
-  L.an = take(N * N4);
-  L.x0 = take(F * N4);
-  L.xa = take(nh_max * N4);
-  L.xb = take(nh_max * N4);
-  L.sx = take(F * N4);
-  L.sadj = take(ldp);
-  L.red = take(40);
-  L.stack = take(imax(A.fdim, 1) * ldp);
-  L.scratch = o;
-  // ---- A-net layers (scratch-relative) ----
-  int s = 0;
-  auto stake = [&](int n) { int r = s; s += a4(n); return r; };
-  L.att = stake(cin_max * ldp);
-  L.ax = stake(kin_max * N4);
-  L.hmc = stake(mc_hid * N4);
-  L.hmc2 = stake(mc_hid * N4);
-  const int work = s;
-  L.q = stake(ad_max * N4);
-  L.k = stake(ad_max * N4);
-  L.v = stake(nh_max * N4);
-  L.atp = stake(nch_max * ldp);
-  const int s_attn = s;
-  s = work;
-  L.eh_a = stake(eh * ldp);
-  L.eh_b = eh_bufs == 2 ? stake(eh * ldp) : L.eh_a;
-  const int s_layers = imax(s_attn, s);
-  // ---- hodge, two layers (scratch-relative; the attention-layer buffers are dead by then) ----
-  int s_hodge = 0;
-  if (d.is_cc && A.is_cc && A.num_layers_h == 2) {
-    int h = 0;
-    auto htake = [&](int n) { int r = h; h += a4(n); return r; };
-    const int E = d.E;
-    L.lde = E | 1;
-    L.hq = htake(A.c_init * E * A.hodge[0].attn_dim);
-    L.hk = htake(A.c_init * E * A.hodge[0].attn_dim);
-    L.h1 = htake(A.hodge[0].c_out * E * L.lde);
-    L.hdeg = htake(A.hodge[0].c_out * E);
-    s_hodge = h;
-  }
-  int a_end = L.scratch + imax(s_layers, s_hodge);
-  // ---- X-net (absolute; from stack channel 1 on) ----
-  int xo = L.stack + ldp;
-  auto xtake = [&](int n) { int r = xo; xo += a4(n); return r; };
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += a4(n); return r; };
+  // ---- x_net_kernel ----
   int din_max = F;
   for (int k = 0; k < X.depth; ++k) din_max = imax(din_max, X.gcn[k].din);
-  L.xh_cat = xtake(imax(X.depth * X.nhid, 1) * N4);
-  L.xh_ax = xtake(din_max * N4);
-  L.xh_a = xtake(imax(X.fin.dhid, 1) * N4);
-  L.xh_b = X.fin.nl > 2 ? xtake(imax(X.fin.dhid, 1) * N4) : L.xh_a;
-  int total = imax(a_end, xo);
-  // ---- final per-edge MLP: as many rows per chunk as the scratch already paid for, at least 32 ----
-  const int fin_h = imax(A.fin.nl > 1 ? A.fin.dhid : 1, 1), fin_bufs = A.fin.nl > 2 ? 2 : 1;
-  int rows = ((total - L.scratch) / (fin_bufs * fin_h)) & ~3;
-  if (rows < 32) rows = 32;
-  if (rows > ldp) rows = ldp;
-  L.fin_rows = rows;
-  L.fh_a = 0;
-  L.fh_b = fin_bufs == 2 ? a4(fin_h * rows) : 0;
-  total = imax(total, L.scratch + fin_bufs * a4(fin_h * rows));
-  L.total = total;
+  o = 0;
+  L.x_flags = take(N4); L.x_dvec = take(N4);
+  L.x_adj = take(imax(A.c_init, 1) * ldp);
+  L.x_an = take(N * N4);
+  L.x_x0 = take(F * N4);
+  L.x_sx = take(F * N4);
+  L.x_red = take(40);
+  L.x_hcat = take(imax(X.depth * X.nhid, 1) * N4);
+  L.x_ax = take(din_max * N4);
+  L.x_ha = take(imax(X.fin.dhid, 1) * N4);
+  L.x_hb = X.fin.nl > 2 ? take(imax(X.fin.dhid, 1) * N4) : L.x_ha;
+  L.x_total = o;
+  // ---- attn_channel_kernel ----
+  o = 0;
+  L.c_dvec = take(N4);
+  L.c_adj = take(ldp);
+  L.c_an = take(N * N4);
+  L.c_xin = take(kin_max * N4);
+  L.c_ax = take(kin_max * N4);
+  L.c_q = take(ad_max * N4);
+  L.c_k = take(ad_max * N4);
+  L.c_v = take(nh_max * N4);
+  L.c_atp = take(nch_max * ldp);
+  L.c_total = o;
+  // ---- attn_finish_kernel ----
+  o = 0;
+  L.f_flags = take(N4);
+  L.f_hs = take(mc_hid * N4);
+  L.f_hs2 = take(mc_hid * N4);
+  L.f_eha = take(eh * ldp);
+  L.f_ehb = eh_bufs == 2 ? take(eh * ldp) : L.f_eha;
+  L.f_total = o;
+  // ---- hodge_kernel ----
+  o = 0;
+  L.h_flags = take(N4);
+  if (d.is_cc && A.is_cc && A.num_layers_h == 2) {
+    const int E = d.E;
+    L.lde = E | 1;
+    L.h_hq = take(A.c_init * E * A.hodge[0].attn_dim);
+    L.h_hk = take(A.c_init * E * A.hodge[0].attn_dim);
+    L.h_h1 = take(A.hodge[0].c_out * E * L.lde);
+    L.h_hdeg = take(A.hodge[0].c_out * E);
+  }
+  L.h_total = o;
+  // ---- afinal_kernel: 64-row chunks of node pairs ----
+  o = 0;
+  const int fin_h = imax(A.fin.nl > 1 ? A.fin.dhid : 1, 1);
+  L.m_rows = imin(64, ldp);
+  L.m_nchunk = (NT + L.m_rows - 1) / L.m_rows;
+  L.m_flags = take(N4);
+  L.m_out = take(L.m_rows);
+  L.m_red = take(40);
+  L.m_fa = take(fin_h * L.m_rows);
+  L.m_fb = A.fin.nl > 2 ? take(fin_h * L.m_rows) : L.m_fa;
+  L.m_total = o;
+  // ---- global scratch ----
+  L.g_stack = imax(A.fdim, 1) * ldp;
+  L.g_att = cin_max * ldp;
+  L.mc_o1_max = mc_o1;
+  L.g_hmc = cin_max * mc_o1 * N4;
+  L.g_x = imax(F, nh_max) * N4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,7 +315,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, tri, gstack, gatt, ghmc, gx0, gx1, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -323,6 +327,12 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.sched = take(p->sched.size() * sizeof(ccsd_objcoef_t));
   w.cells = take(imax(1, d.K) * sizeof(unsigned long long));
   w.edges = take(imax(1, d.E) * 2 * sizeof(int));
+  w.tri = take((size_t)p->hp.xp.ldp * sizeof(int));
+  w.gstack = take(B * (size_t)p->hp.xp.g_stack * 4);
+  w.gatt = take(B * (size_t)p->hp.xp.g_att * 4);
+  w.ghmc = take(B * (size_t)p->hp.xp.g_hmc * 4);
+  w.gx0 = take(B * (size_t)p->hp.xp.g_x * 4);
+  w.gx1 = take(B * (size_t)p->hp.xp.g_x * 4);
   w.flags = take(B * N * 4);
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
   w.mx = take(B * N * F * 4); w.madj = take(B * N * N * 4); w.mr2 = take(B * E * K * 4 + 16);
@@ -343,8 +353,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   ccsd_plan *p = new ccsd_plan();
   p->hp.d = *desc;
   const ccsd_plan_desc_t &d = p->hp.d;
-  make_layout(d, p->hp.xa);
-  p->xa_smem = (size_t)p->hp.xa.total * 4;
+  make_layout(d, p->hp.xp);
   p->weights = weights_dev;
   p->n_weights = n_weights;
   p->sched.assign(schedule_host, schedule_host + (size_t)d.n_diff_steps * 3);
@@ -354,7 +363,8 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.Kp = a4(d.K);
   p->hp.Ep = a4(d.E);
   p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
-  p->hp.ntile_max = imax(1, p->hp.ntile_r2);
+  p->hp.ntile_adj = p->hp.xp.m_nchunk;
+  p->hp.ntile_max = imax(imax(1, p->hp.ntile_r2), p->hp.ntile_adj);
   p->hp.f_mode = 0; p->hp.f_nlin = 0;
   if (d.is_cc && (d.nets & 4)) {
     const ccsd_netf_t &Fn = d.netf;
@@ -369,14 +379,23 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     else if (w8) { p->hp.f_mode = 2; p->hp.f_nlin = nlin; }
   }
   p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)p->hp.f_nlin * 72 + 48) * 4 : 0;
-  if (p->xa_smem > 227 * 1024 || p->apply_smem > 227 * 1024) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "graph tile does not fit shared memory (xa %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
-             p->xa_smem, p->apply_smem);
+  const XpLayout &XL = p->hp.xp;
+  const size_t xp_max = (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, XL.h_total)), XL.m_total) * 4;
+  if (xp_max > 227 * 1024 || p->apply_smem > 227 * 1024) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "graph tile does not fit shared memory (x/adj pipeline %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
+             xp_max, p->apply_smem);
     delete p;
     return fail(CCSD_ERR_UNSUPPORTED, buf);
   }
   // tables
+  {
+    const int N = d.N;
+    p->tri_ij.assign((size_t)XL.ldp, 0);
+    int t = 0;
+    for (int i = 0; i < N; ++i)
+      for (int j = i; j < N; ++j) p->tri_ij[t++] = (i << 8) | j;
+  }
   if (d.is_cc) {
     const int N = d.N;
     p->edge_ij.resize((size_t)d.E * 2);
@@ -407,11 +426,15 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
 #ifndef CCSD_EMU
   // the attribute is per function, not per plan: only ever raise it (several plans may coexist)
-  static size_t xa_attr = 0, apply_attr = 0;
+  static size_t xp_attr = 0, apply_attr = 0;
   cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-  if (p->xa_smem > xa_attr) {
-    e1 = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->xa_smem);
-    if (e1 == cudaSuccess) xa_attr = p->xa_smem;
+  if (xp_max > xp_attr) {
+    e1 = cudaFuncSetAttribute(x_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hodge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+    if (e1 == cudaSuccess) xp_attr = xp_max;
   }
   if (d.is_cc && p->apply_smem > apply_attr) {
     e2 = cudaFuncSetAttribute(apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
@@ -455,6 +478,9 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->sx = (float *)(ws + w.sx); p->sadj = (float *)(ws + w.sadj); p->sr2 = (float *)(ws + w.sr2);
   p->H = (float *)(ws + w.H); p->P0 = (float *)(ws + w.P0); p->P1 = (float *)(ws + w.P1);
   p->norm_part = (float *)(ws + w.norm); p->coef = (float *)(ws + w.coef);
+  p->g_stack = (float *)(ws + w.gstack); p->g_att = (float *)(ws + w.gatt); p->g_hmc = (float *)(ws + w.ghmc);
+  p->g_x0 = (float *)(ws + w.gx0); p->g_x1 = (float *)(ws + w.gx1);
+  p->hp.tri_ij = (const int *)(ws + w.tri);
   p->hp.W = p->weights;
   p->hp.sched = (const ccsd_objcoef_t *)(ws + w.sched);
   p->hp.cell_mask = (const unsigned long long *)(ws + w.cells);
@@ -465,6 +491,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
     if (int r = dev_copy(ws + w.cells, p->cell_mask.data(), p->cell_mask.size() * 8, stream)) return r;
   if (!p->edge_ij.empty())
     if (int r = dev_copy(ws + w.edges, p->edge_ij.data(), p->edge_ij.size() * 4, stream)) return r;
+  if (int r = dev_copy(ws + w.tri, p->tri_ij.data(), p->tri_ij.size() * 4, stream)) return r;
   p->bound = true;
   p->inited = false;
   return 0;
@@ -503,6 +530,51 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
     if (int r = dev_copy(p->mr2, p->r2, (size_t)d.B * d.E * d.K * 4, stream)) return r;
   p->inited = true;
   return dev_check("init_kernel");
+}
+
+// ScoreNetworkX / ScoreNetworkA(_CC) pipeline (xa_pipe.cuh) for the networks selected by a.which
+static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
+  const ccsd_plan_desc_t &d = p->hp.d;
+  const XpLayout &L = p->hp.xp;
+  const ccsd_neta_t &A = d.neta;
+  a.g_stack = p->g_stack; a.g_att = p->g_att; a.g_hmc = p->g_hmc; a.g_x0 = p->g_x0; a.g_x1 = p->g_x1;
+  PROF_BEGIN(p, "x_net_kernel", stream);
+  CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, stream, p->dP, a);
+  PROF_END(p, stream);
+  p->launches++;
+  if (!(a.which & 2)) return dev_check("x_net_kernel");
+  int ch_in = 0, ch_out = A.c_init;
+  const float *xin = p->g_x0;
+  float *xout = p->g_x1;
+  for (int l = 0; l < A.num_layers; ++l) {
+    const ccsd_attn_layer_t &ly = A.layer[l];
+    a.layer = l; a.ch_in = ch_in; a.ch_out = ch_out; a.g_xin = xin; a.g_xout = xout;
+    PROF_BEGIN(p, "attn_channel_kernel", stream);
+    CCSD_LAUNCH(attn_channel_kernel, dim3(ly.c_in, d.B, 1), L.Tc, (size_t)L.c_total * 4, stream, p->dP, a);
+    PROF_END(p, stream);
+    PROF_BEGIN(p, "attn_finish_kernel", stream);
+    CCSD_LAUNCH(attn_finish_kernel, dim3(d.B, 1, 1), L.Tf, (size_t)L.f_total * 4, stream, p->dP, a);
+    PROF_END(p, stream);
+    p->launches += 2;
+    ch_in = ch_out;
+    ch_out += ly.c_out;
+    const float *t = xout; xout = (float *)xin; xin = t;
+  }
+  int fd_have = ch_out;
+  if (A.is_cc) {
+    a.ch_in = ch_out;   // first hodge channel
+    PROF_BEGIN(p, "hodge_kernel", stream);
+    CCSD_LAUNCH(hodge_kernel, dim3(d.B, 1, 1), L.Th, (size_t)L.h_total * 4, stream, p->dP, a);
+    PROF_END(p, stream);
+    p->launches++;
+    fd_have += A.c_init + A.hodge[0].c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
+  }
+  a.ch_out = fd_have;   // channels the final MLP reads
+  PROF_BEGIN(p, "afinal_kernel", stream);
+  CCSD_LAUNCH(afinal_kernel, dim3(L.m_nchunk, d.B, 1), L.Tm, (size_t)L.m_total * 4, stream, p->dP, a);
+  PROF_END(p, stream);
+  p->launches++;
+  return dev_check("x/adj network pipeline");
 }
 
 static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
@@ -585,11 +657,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     a.noise_adj = nadj ? nadj + (size_t)slot * sa : nullptr;
     if (mode == MODE_SCORE) { a.out_x = p->sx; a.out_adj = p->sadj; }
     else { a.out_x = p->x; a.out_adj = p->adj; a.mean_x = p->mx; a.mean_adj = p->madj; a.traj_x = tx; a.traj_adj = ta; }
-    PROF_BEGIN(p, "xa_kernel", stream);
-    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), p->hp.xa.T, p->xa_smem, stream, p->dP, a);
-    PROF_END(p, stream);
-    p->launches++;
-    if (int r = dev_check("xa_kernel")) return r;
+    if (int r = launch_xa(p, a, stream)) return r;
     if (d.is_cc) return apply_pass(r2_mode, slot);
     return 0;
   };
@@ -669,9 +737,7 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
     a.x = x; a.adj = adj; a.flags = flags; a.P0 = p->P0; a.P1 = p->P1; a.mode = MODE_EVAL;
     a.which = which == CCSD_NET_X ? 1 : 2;
     a.out_x = out; a.out_adj = out;
-    CCSD_LAUNCH(xa_kernel, dim3(d.B, 1, 1), p->hp.xa.T, p->xa_smem, stream, p->dP, a);
-    p->launches++;
-    return dev_check("xa_kernel");
+    return launch_xa(p, a, stream);
   }
   if (which == CCSD_NET_RANK2) {
     if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
@@ -702,13 +768,18 @@ int ccsd_debug_apply_trace(ccsd_plan_t *p, long long *trace_dev) {
 int ccsd_plan_info(const ccsd_plan_t *p, int what) {
   if (!p) return -1;
   switch (what) {
-    case 0: return (int)p->xa_smem;
-    case 1: return p->hp.xa.T;
+    case 0: return imax(imax(imax(p->hp.xp.x_total, p->hp.xp.c_total), imax(p->hp.xp.f_total, p->hp.xp.h_total)), p->hp.xp.m_total) * 4;
+    case 1: return p->hp.xp.Tc;
     case 2: return (int)p->apply_smem;
     case 3: return p->use_tc;
     case 4: return p->use_tc_apply;
     case 5: return p->hp.f_mode;
-    case 6: return p->hp.xa.fin_rows;
+    case 6: return p->hp.xp.m_rows;
+    case 7: return p->hp.xp.x_total * 4;
+    case 8: return p->hp.xp.c_total * 4;
+    case 9: return p->hp.xp.f_total * 4;
+    case 10: return p->hp.xp.h_total * 4;
+    case 11: return p->hp.xp.m_total * 4;
     default: return -1;
   }
 }

@@ -1,0 +1,528 @@
+// xa_pipe.cuh -- ScoreNetworkX and ScoreNetworkA / ScoreNetworkA_CC as a pipeline of small kernels with
+// (graph x channel) grid parallelism, plus the x / adj sampler epilogues.
+//
+// Reference: ScoreNetwork_X.py:102-133, ScoreNetwork_A.py:505-541, ScoreNetwork_A_CC.py:275-332,
+// attention.py:84-132,270-304, hodge_attention.py:80-129,290-325, layers.py:115-158.
+//
+// Why a pipeline: a graph is tiny (N <= 64), every phase of the networks has O(100) independent work
+// items, and an attention layer is a chain of ~6 such phases PER CHANNEL.  One CTA per graph running the
+// whole network keeps few warps per SM (the channel stack needs ~75 KB of shared memory) and spends its
+// time in barrier bubbles (measured: 37 k cycles per channel for ~1.5 k cycles of FMAs).  Here the unit of
+// work is small and there are many of them:
+//   x_net_kernel          one CTA per graph            ScoreNetworkX + x epilogue; adjacency powers
+//   attn_channel_kernel   one CTA per (graph, channel) GCN Q/K/V, attention scores, V's share of the node MLP
+//   attn_finish_kernel    one CTA per graph            node MLP -> next node features; per-edge MLP -> next channels
+//   hodge_kernel          one CTA per graph            hodge branch of ScoreNetworkA_CC (reduced form)
+//   afinal_kernel         one CTA per (row chunk, graph) final per-edge MLP + adj epilogue
+// Each CTA needs 15-45 KB of shared memory, so 5-12 of them share an SM and hide each other's barriers.
+// Intermediates (channel stack, attention maps, node features: ~45 KB per graph) travel through global
+// memory and stay in the 126 MB L2 for the batch sizes of interest.
+//
+// Every adjacency-shaped tensor is stored as its upper triangle (N(N+1)/2 pairs, "tri" index): the
+// adjacency state is symmetric and so is everything derived from it (powers, symmetrised attention,
+// M + M^T), which also halves the per-edge MLP work.
+//
+// Hodge branch (ScoreNetworkA_CC): the Hodge-dual adjacency built by adj_to_hodgedual
+// (cc_utils.py:1503-1538) is diagonal and hodgedual_to_adj (cc_utils.py:1541-1588) reads only
+// diagonals back, so layer 0 is a per-edge row scaling of the projections rank2 @ W_{q,k}
+// (computed by the Gram kernel as P0) and the last hodge layer only needs diag(attention); its
+// value branch is dead.  With two hodge layers the first layer's E x E attention output is
+// materialised in shared memory and the second layer aggregates the projections P1 of the first
+// layer's value output with it.
+#pragma once
+#include "prims.cuh"
+
+namespace ccsd {
+
+struct XaArgs {
+  const float *x, *adj, *flags;  // [B,N,F] [B,N,N] [B,N]
+  const float *P0, *P1;          // hodge projections [B,E,PR0] [B,E,PR1] (CC only)
+  int mode;                      // MODE_EVAL / MODE_SCORE / MODE_PRED
+  int which;                     // bit0: evaluate X net, bit1: evaluate A net
+  float *out_x, *out_adj;        // EVAL: raw net output; SCORE: scaled score; PRED: new state
+  float *mean_x, *mean_adj;      // PRED: means
+  float *norm_part;              // SCORE: [3][B][ntile_max][2]
+  const float *noise_x, *noise_adj;  // raw normals for this draw ([B,...]) or nullptr (Philox)
+  float *traj_x, *traj_adj;      // PRED: destination for sample 0 of this shard (or nullptr)
+  int slot;                      // draw slot within the step
+  int denoise;
+  NoiseCtx nz;
+  // pipeline scratch in global memory (per graph strides in XpLayout)
+  float *g_stack, *g_att, *g_hmc, *g_x0, *g_x1;
+  // per-launch (attention layers)
+  int layer, ch_in, ch_out;
+  const float *g_xin;            // node features read by this layer  [kin x N4] per graph
+  float *g_xout;                 // node features written by this layer
+};
+
+// =============================================================================================
+// x_net_kernel: ScoreNetworkX, x epilogue, adjacency powers + feature-major x for the A pipeline
+// =============================================================================================
+__global__ void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.x;
+  const int N = d.N, F = d.F, N4 = L.N4, NT = L.NT, ldp = L.ldp;
+  const float *W = P->W;
+  float *flags = sm + L.x_flags, *dvec = sm + L.x_dvec, *adj = sm + L.x_adj, *an = sm + L.x_an, *x0 = sm + L.x_x0;
+  float *sx = sm + L.x_sx, *red = sm + L.x_red;
+
+  for (int i = threadIdx.x; i < N4; i += blockDim.x) flags[i] = i < N ? a.flags[(size_t)b * N + i] : 0.f;
+  for (int p = threadIdx.x; p < F * N4; p += blockDim.x) {
+    const int f = p / N4, i = p - f * N4;
+    x0[p] = i < N ? a.x[((size_t)b * N + i) * F + f] : 0.f;
+  }
+  for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+    const int ij = P->tri_ij[t];
+    adj[t] = a.adj[(size_t)b * N * N + (ij >> 8) * N + (ij & 255)];
+  }
+  __syncthreads();
+
+  if (a.which & 2) {
+    // pow_tensor (graph_utils.py:274-292): A^c = A^(c-1) . A, symmetric; channels 0..c_init-1 of the stack
+    const int c0 = d.neta.c_init;
+    for (int c = 1; c < c0; ++c) {
+      for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+        const int ij = P->tri_ij[t], i = ij >> 8, j = ij & 255;
+        float s = 0.f;
+        for (int k = 0; k < N; ++k) s += adj[(c - 1) * ldp + tri_index_any(i, k, N)] * adj[tri_index_any(k, j, N)];
+        adj[c * ldp + t] = s;
+      }
+      __syncthreads();
+    }
+    float *gs = a.g_stack + (size_t)b * L.g_stack;
+    for (int p = threadIdx.x; p < c0 * ldp; p += blockDim.x) gs[p] = (p % ldp) < NT ? adj[p] : 0.f;
+    float *gx = a.g_x0 + (size_t)b * L.g_x;
+    for (int p = threadIdx.x; p < F * N4; p += blockDim.x) gx[p] = x0[p];
+  }
+  if (!(a.which & 1)) return;
+
+  // ---- ScoreNetworkX ----
+  const ccsd_netx_t &X = d.netx;
+  float *hcat = sm + L.x_hcat, *ax = sm + L.x_ax, *hA = sm + L.x_ha, *hB = sm + L.x_hb;
+  gcn_norm_tri(adj, N, N4, dvec, an);
+  const float *in = x0;
+  int din = F, row = 0;
+  for (int k = 0; k < X.depth; ++k) {
+    const ccsd_gcn_t &g = X.gcn[k];
+    gcn_aggregate_fm(an, N, N4, in, din, ax);
+    __syncthreads();
+    dense_fm(ax, N4, din, nullptr, 0, 0, W + g.w, W + g.b, g.dout, hcat + row * N4, 1, N4, N, ACT_TANH);
+    __syncthreads();
+    in = hcat + row * N4;
+    din = g.dout;
+    row += g.dout;
+  }
+  mlp_fm(X.fin, W, x0, N4, F, hcat, N4, row, N, hA, hB, N4, sx, 1, N4, ACT_ELU, ACT_NONE);
+  for (int p = threadIdx.x; p < F * N4; p += blockDim.x) {
+    const int i = p % N4;
+    if (i < N) sx[p] *= flags[i];
+  }
+  __syncthreads();
+
+  // ---- x epilogue ----
+  const size_t gxo = (size_t)b * N * F;
+  if (a.mode == MODE_EVAL) {
+    for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
+      const int i = p / F, f = p - i * F;
+      a.out_x[gxo + p] = sx[f * N4 + i];
+    }
+    return;
+  }
+  const ccsd_objcoef_t cx = P->sched[a.nz.step * 3 + 0];
+  const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
+  if (a.mode == MODE_SCORE) {
+    // scaled score + per-sample squared norms of score and (masked) noise (solver.py:693-699, 1299-1305)
+    float s2 = 0.f, z2 = 0.f;
+    for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
+      const int i = p / F, f = p - i * F;
+      const float s = cx.score_scale * sx[f * N4 + i];
+      a.out_x[gxo + p] = s;
+      const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, a.nz.step, a.slot), p)) * flags[i];
+      s2 += s * s;
+      z2 += z * z;
+    }
+    s2 = block_sum(s2, red);
+    z2 = block_sum(z2, red);
+    if (threadIdx.x == 0) {
+      float *np = a.norm_part + ((size_t)(0 * d.B + b) * P->ntile_max) * 2;
+      np[0] = s2; np[1] = z2;
+    }
+    return;
+  }
+  // MODE_PRED: mean = pa*obj + pb*score ; new = mean + pc*z   (solver.py:230-244, 386-398; sde.py:200-235)
+  for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
+    const int i = p / F, f = p - i * F;
+    const float s = cx.score_scale * sx[f * N4 + i];
+    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, a.nz.step, a.slot), p)) * flags[i];
+    const float m = cx.pa * x0[f * N4 + i] + cx.pb * s;
+    const float v = m + cx.pc * z;
+    a.out_x[gxo + p] = v;
+    a.mean_x[gxo + p] = m;
+    if (a.traj_x && b == 0) a.traj_x[p] = a.denoise ? m : v;
+  }
+}
+
+// =============================================================================================
+// attn_channel_kernel: Attention.forward of ONE channel of one graph (attention.py:84-132)
+// =============================================================================================
+__global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const ccsd_neta_t &A = d.neta;
+  const ccsd_attn_layer_t &ly = A.layer[a.layer];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int N = d.N, N4 = L.N4, NT = L.NT, ldp = L.ldp;
+  const float *W = P->W;
+  float *dvec = sm + L.c_dvec, *adjc = sm + L.c_adj, *an = sm + L.c_an, *xin = sm + L.c_xin, *ax = sm + L.c_ax;
+  float *q = sm + L.c_q, *kf = sm + L.c_k, *v = sm + L.c_v, *atp = sm + L.c_atp;
+  const int kin = ly.conv_in, ad = ly.attn_dim, nh = ly.conv_out;
+  const float scale = 1.0f / sqrtf((float)nh);  // / sqrt(out_dim)  (attention.py:125)
+
+  const float *gadj = a.g_stack + (size_t)b * L.g_stack + (size_t)(a.ch_in + c) * ldp;
+  for (int t = threadIdx.x; t < ldp; t += blockDim.x) adjc[t] = gadj[t];
+  const float *gx = a.g_xin + (size_t)b * L.g_x;
+  for (int p = threadIdx.x; p < kin * N4; p += blockDim.x) xin[p] = gx[p];
+  __syncthreads();
+  gcn_norm_tri(adjc, N, N4, dvec, an);
+  gcn_aggregate_fm(an, N, N4, xin, kin, ax);
+  __syncthreads();
+  {
+    // Q | K | V = (A x) W_{q,k,v} + b as one item space (same input tile, three weight matrices)
+    const int ngrp = N4 >> 2;
+    const int nq = (round_up(ad, 8) >> 3) * ngrp, nv = (round_up(nh, 8) >> 3) * ngrp;
+    for (int it = threadIdx.x; it < 2 * nq + nv; it += blockDim.x) {
+      const int w = it < nq ? 0 : (it < 2 * nq ? 1 : 2);
+      const int li = it - (w == 0 ? 0 : (w == 1 ? nq : 2 * nq));
+      const ccsd_gcn_t &g = w == 0 ? ly.q[c] : (w == 1 ? ly.k[c] : ly.v[c]);
+      float *dst = w == 0 ? q : (w == 1 ? kf : v);
+      const int O = g.dout, Opad = round_up(O, 8);
+      const int chunk = li / ngrp, r0 = (li - chunk * ngrp) << 2, oc = chunk << 3;
+      float acc[4][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float bv = __ldg(W + g.b + oc + j);
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) acc[rr][j] = bv;
+      }
+      dense_tile(acc, ax, N4, kin, nullptr, 0, 0, W + g.w, Opad, r0, oc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (oc + j < O) {
+          // padded node rows are written too (finite values: the attention blocks read them)
+          float *o = dst + (oc + j) * N4 + r0;
+          o[0] = acc[0][j]; o[1] = acc[1][j]; o[2] = acc[2][j]; o[3] = acc[3][j];
+        }
+    }
+  }
+  __syncthreads();
+  attn_scores_blk(q, kf, N, N4, ad, A.num_heads, scale, atp, ldp);
+  {
+    // V's share of the first Linear of multi_channel, which is linear in the channel concat
+    // (attention.py:292): hmc_c(o, i) = sum_f V_c(i, f) W1[c*nh + f, o]; the finish kernel sums over c
+    const ccsd_mlp_t &mc = ly.multi_channel;
+    const int o1 = mc.nl == 1 ? mc.dout : mc.dhid, o1p = round_up(o1, 8);
+    float *gh = a.g_hmc + (size_t)b * L.g_hmc + (size_t)c * L.mc_o1_max * N4;
+    dense_fm(v, N4, nh, nullptr, 0, 0, W + mc.w[0] + (size_t)c * nh * o1p, nullptr, o1, gh, 1, N4, N, ACT_NONE, false,
+             (int)blockDim.x - 32);
+  }
+  __syncthreads();
+  {
+    const int ds = ad / A.num_heads, nch = (ad + ds - 1) / ds;
+    float *ga = a.g_att + (size_t)b * L.g_att + (size_t)c * ldp;
+    for (int t = threadIdx.x; t < ldp; t += blockDim.x) {
+      float s = 0.f;
+      if (t < NT)
+        for (int h = 0; h < nch; ++h) s += atp[h * ldp + t];
+      ga[t] = s;
+    }
+  }
+}
+
+// =============================================================================================
+// attn_finish_kernel: the rest of AttentionLayer.forward (attention.py:292-302) for one graph
+// =============================================================================================
+__global__ void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const ccsd_attn_layer_t &ly = d.neta.layer[a.layer];
+  const int b = blockIdx.x;
+  const int N = d.N, N4 = L.N4, NT = L.NT, ldp = L.ldp;
+  const float *W = P->W;
+  float *flags = sm + L.f_flags, *hs = sm + L.f_hs, *hs2 = sm + L.f_hs2, *ehA = sm + L.f_eha, *ehB = sm + L.f_ehb;
+  const int nh = ly.conv_out;
+  const ccsd_mlp_t &mc = ly.multi_channel;
+  const int o1 = mc.nl == 1 ? mc.dout : mc.dhid;
+
+  for (int i = threadIdx.x; i < N4; i += blockDim.x) flags[i] = i < N ? a.flags[(size_t)b * N + i] : 0.f;
+  // node branch: x_out = tanh(mask_x(MLP(cat V)))  (attention.py:292-293)
+  {
+    const float *gh = a.g_hmc + (size_t)b * L.g_hmc;
+    for (int p = threadIdx.x; p < o1 * N4; p += blockDim.x) {
+      const int o = p / N4, i = p - o * N4;
+      float s = 0.f;
+      if (i < N) {
+        s = __ldg(W + mc.b[0] + o);
+        for (int c = 0; c < ly.c_in; ++c) s += gh[(size_t)c * L.mc_o1_max * N4 + p];
+        if (mc.nl > 1) s = fast_elu(s);
+      }
+      hs[p] = s;
+    }
+    __syncthreads();
+    float *cur = hs, *oth = hs2;
+    for (int li = 1; li < mc.nl; ++li) {
+      const bool last = li == mc.nl - 1;
+      const int O = last ? mc.dout : mc.dhid;
+      dense_fm(cur, N4, li == 1 ? o1 : mc.dhid, nullptr, 0, 0, W + mc.w[li], W + mc.b[li], O, oth, 1, N4, N,
+               last ? ACT_NONE : ACT_ELU);
+      __syncthreads();
+      float *t = cur; cur = oth; oth = t;
+    }
+    float *gx = a.g_xout + (size_t)b * L.g_x;
+    for (int p = threadIdx.x; p < nh * N4; p += blockDim.x) {
+      const int i = p % N4;
+      gx[p] = i < N ? fast_tanh(cur[p] * flags[i]) : 0.f;
+    }
+  }
+  // edge branch: M = MLP(cat[A_1..A_c, adj_1..adj_c]) ; adj_out = mask_adjs(M + M^T) = 2 M mask (M symmetric)
+  float *gs = a.g_stack + (size_t)b * L.g_stack;
+  const float *ga = a.g_att + (size_t)b * L.g_att;
+  mlp_fm(ly.mlp, W, ga, ldp, ly.c_in, gs + (size_t)a.ch_in * ldp, ldp, ly.c_in, NT, ehA, ehB, ldp, gs + (size_t)a.ch_out * ldp,
+         1, ldp, ACT_ELU, ACT_NONE);   // ends with __syncthreads: this CTA's global writes are visible to it
+  for (int p = threadIdx.x; p < ly.c_out * ldp; p += blockDim.x) {
+    const int c = p / ldp, t = p - c * ldp;
+    float *pl = gs + (size_t)(a.ch_out + c) * ldp + t;
+    if (t < NT) {
+      const int ij = P->tri_ij[t];
+      *pl = 2.0f * *pl * flags[ij >> 8] * flags[ij & 255];
+    } else {
+      *pl = 0.f;
+    }
+  }
+}
+
+// =============================================================================================
+// hodge_kernel: hodge branch of ScoreNetworkA_CC on the channel stack in global memory
+// =============================================================================================
+__device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, int ad, int heads, float scale) {
+  const int ds = ad / heads;
+  const int nch = (ad + ds - 1) / ds;
+  float s = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    const int d0 = c * ds, d1 = (d0 + ds < ad) ? d0 + ds : ad;
+    float a = 0.f;
+    for (int dd = d0; dd < d1; ++dd) a += q[dd] * k[dd];
+    s += tanhf(a * scale);
+  }
+  return s / (float)nch;
+}
+
+__global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const ccsd_neta_t &A = d.neta;
+  const int b = blockIdx.x;
+  const int N = d.N, E = d.E, N4 = L.N4, ldp = L.ldp, NT = L.NT;
+  const float *W = P->W;
+  float *flags = sm + L.h_flags;
+  float *stack = a.g_stack + (size_t)b * L.g_stack;
+  const int ch_hodge0 = a.ch_in;   // first hodge channel of the stack
+  const float scale = 1.0f / sqrtf((float)d.K);  // HodgeAttention out_dim = K (hodge_attention.py:236-239)
+  const int c0 = A.c_init;
+  const ccsd_hodge_layer_t &h0 = A.hodge[0];
+  const int ad0 = h0.attn_dim;
+  const int PR0 = P->PR0;
+  const float *P0 = a.P0 + (size_t)b * E * PR0;
+
+  for (int i = threadIdx.x; i < N4; i += blockDim.x) flags[i] = i < N ? a.flags[(size_t)b * N + i] : 0.f;
+  // channels [ch_hodge0, ch_hodge0 + c0): hodgedual_to_adj(adj_to_hodgedual(adjc)) = adjc with zero diagonal;
+  // the hodge output channels start as zero (diagonals stay zero, off-diagonals are filled per edge)
+  {
+    const int nout = h0.c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
+    for (int p = threadIdx.x; p < (c0 + nout) * ldp; p += blockDim.x) {
+      const int c = p / ldp, t = p - c * ldp;
+      float v = 0.f;
+      if (c < c0 && t < NT) {
+        const int ij = P->tri_ij[t];
+        if ((ij >> 8) != (ij & 255)) v = stack[c * ldp + t];
+      }
+      stack[(ch_hodge0 + c) * ldp + t] = v;
+    }
+  }
+  __syncthreads();
+
+  if (A.num_layers_h == 1) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+      const int t = tri_index(i, j, N);
+      const float fe = flags[i] * flags[j];
+      float att[CCSD_MAX_CH], q[SMALL_MAX], k[SMALL_MAX], out[SMALL_MAX];
+      for (int c = 0; c < c0; ++c) {
+        const float av = stack[c * ldp + t];
+        const float dg = 1.0f / sqrtf(fmaxf(av, 1.f));
+        const float nrm = dg * av * dg;
+        const float *pq = P0 + (size_t)e * PR0 + h0.proj_row + (c * 2 + 0) * ad0;
+        const float *pk = pq + ad0;
+        for (int dd = 0; dd < ad0; ++dd) {
+          q[dd] = nrm * pq[dd] + __ldg(W + h0.bq[c] + dd);
+          k[dd] = nrm * pk[dd] + __ldg(W + h0.bk[c] + dd);
+        }
+        att[c] = hodge_diag_att(q, k, ad0, A.num_heads_h, scale);
+      }
+      small_mlp(h0.mlp_attention, W, att, out, ACT_ELU);
+      for (int c = 0; c < h0.c_out; ++c) stack[(ch_hodge0 + c0 + c) * ldp + t] = 2.0f * tanhf(fe * fe * out[c]);
+    }
+    return;
+  }
+
+  // ---- two hodge layers ----
+  const ccsd_hodge_layer_t &h1 = A.hodge[1];
+  const int c1 = h0.c_out, ad1 = h1.attn_dim, PR1 = P->PR1, lde = L.lde;
+  float *hq = sm + L.h_hq, *hk = sm + L.h_hk, *H1 = sm + L.h_h1, *hdeg = sm + L.h_hdeg;
+  const float *P1 = a.P1 + (size_t)b * E * PR1;
+  // layer-0 Q, K for every edge and channel
+  for (int p = threadIdx.x; p < c0 * E; p += blockDim.x) {
+    const int c = p / E, e = p - c * E;
+    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+    const float av = stack[c * ldp + tri_index(i, j, N)];
+    const float dg = 1.0f / sqrtf(fmaxf(av, 1.f));
+    const float nrm = dg * av * dg;
+    const float *pq = P0 + (size_t)e * PR0 + h0.proj_row + (c * 2 + 0) * ad0;
+    const float *pk = pq + ad0;
+    for (int dd = 0; dd < ad0; ++dd) {
+      hq[(c * E + e) * ad0 + dd] = nrm * pq[dd] + __ldg(W + h0.bq[c] + dd);
+      hk[(c * E + e) * ad0 + dd] = nrm * pk[dd] + __ldg(W + h0.bk[c] + dd);
+    }
+  }
+  __syncthreads();
+  // layer-0 output  H1[c'][e][e'] = 2 tanh(fe fe' MLP_att(A_.[e,e'])),  A symmetric
+  for (int p = threadIdx.x; p < E * (E + 1) / 2; p += blockDim.x) {
+    int e = 0, rem = p;
+    while (rem >= E - e) { rem -= E - e; ++e; }
+    const int e2 = e + rem;
+    const float fe = flags[P->edge_ij[2 * e]] * flags[P->edge_ij[2 * e + 1]];
+    const float fe2 = flags[P->edge_ij[2 * e2]] * flags[P->edge_ij[2 * e2 + 1]];
+    float att[CCSD_MAX_CH], out[SMALL_MAX];
+    for (int c = 0; c < c0; ++c) {
+      const float s1 = hodge_diag_att(hq + (c * E + e) * ad0, hk + (c * E + e2) * ad0, ad0, A.num_heads_h, scale);
+      const float s2 = hodge_diag_att(hq + (c * E + e2) * ad0, hk + (c * E + e) * ad0, ad0, A.num_heads_h, scale);
+      att[c] = 0.5f * (s1 + s2);
+    }
+    small_mlp(h0.mlp_attention, W, att, out, ACT_ELU);
+    for (int c = 0; c < c1; ++c) {
+      const float v = 2.0f * tanhf(fe * fe2 * out[c]);
+      H1[(c * E + e) * lde + e2] = v;
+      H1[(c * E + e2) * lde + e] = v;
+    }
+  }
+  __syncthreads();
+  // diag of layer-0 output -> stack ; DenseHCNConv degrees of layer 1 (hodge_layers.py:186)
+  for (int p = threadIdx.x; p < c1 * E; p += blockDim.x) {
+    const int c = p / E, e = p - c * E;
+    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+    const float *row = H1 + (c * E + e) * lde;
+    float s = 0.f;
+    for (int e2 = 0; e2 < E; ++e2) s += row[e2];
+    hdeg[c * E + e] = 1.0f / sqrtf(fmaxf(s, 1.f));
+    stack[(ch_hodge0 + c0 + c) * ldp + tri_index(i, j, N)] = row[e];
+  }
+  __syncthreads();
+  // layer 1 (last): only diag(attention) is read back (cc_utils.py:1571)
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+    const float fe = flags[i] * flags[j];
+    float att[CCSD_MAX_CH], q[SMALL_MAX], k[SMALL_MAX], out[SMALL_MAX];
+    for (int c = 0; c < c1; ++c) {
+      for (int dd = 0; dd < ad1; ++dd) { q[dd] = 0.f; k[dd] = 0.f; }
+      const float *row = H1 + (c * E + e) * lde;
+      const float de = hdeg[c * E + e];
+      for (int e2 = 0; e2 < E; ++e2) {
+        const float w = de * row[e2] * hdeg[c * E + e2];
+        const float *pq = P1 + (size_t)e2 * PR1 + h1.proj_row + (c * 2 + 0) * ad1;
+        const float *pk = pq + ad1;
+        for (int dd = 0; dd < ad1; ++dd) { q[dd] += w * pq[dd]; k[dd] += w * pk[dd]; }
+      }
+      for (int dd = 0; dd < ad1; ++dd) {
+        q[dd] += __ldg(W + h1.bq[c] + dd);
+        k[dd] += __ldg(W + h1.bk[c] + dd);
+      }
+      att[c] = hodge_diag_att(q, k, ad1, A.num_heads_h, scale);
+    }
+    small_mlp(h1.mlp_attention, W, att, out, ACT_ELU);
+    for (int c = 0; c < h1.c_out; ++c)
+      stack[(ch_hodge0 + c0 + c1 + c) * ldp + tri_index(i, j, N)] = 2.0f * tanhf(fe * fe * out[c]);
+  }
+}
+
+// =============================================================================================
+// afinal_kernel: final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) on a chunk of node
+// pairs + the adjacency sampler epilogue
+// =============================================================================================
+__global__ void __launch_bounds__(128) afinal_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const ccsd_neta_t &A = d.neta;
+  const int b = blockIdx.y;
+  const int N = d.N, NP = N * N, NT = L.NT, ldp = L.ldp, RC = L.m_rows;
+  const int r0 = blockIdx.x * RC;
+  const int R = (NT - r0 < RC) ? NT - r0 : RC;
+  float *flags = sm + L.m_flags, *fA = sm + L.m_fa, *fB = sm + L.m_fb, *so = sm + L.m_out, *red = sm + L.m_red;
+  const float *gs = a.g_stack + (size_t)b * L.g_stack;
+  for (int i = threadIdx.x; i < L.N4; i += blockDim.x) flags[i] = i < N ? a.flags[(size_t)b * N + i] : 0.f;
+  mlp_fm(A.fin, P->W, gs + r0, ldp, a.ch_out /* = channels in the stack */, nullptr, 0, 0, R, fA, fB, RC, so, 1, 0, ACT_ELU,
+         ACT_NONE);
+  const size_t ga = (size_t)b * NP;
+  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 1];
+  const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
+  float s2 = 0.f, z2 = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const int ij = P->tri_ij[r0 + r], i = ij >> 8, j = ij & 255;
+    // (1 - I) mask and mask_adjs
+    const float o = (i == j) ? 0.f : so[r] * flags[i] * flags[j];
+    if (a.mode == MODE_EVAL) {
+      a.out_adj[ga + i * N + j] = o;
+      a.out_adj[ga + j * N + i] = o;
+      continue;
+    }
+    const float s = ca.score_scale * o;
+    float z = 0.f;
+    if (i != j) {
+      const int q = i * N + j;
+      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, a.nz.step, a.slot), q)) * flags[i] * flags[j];
+    }
+    if (a.mode == MODE_SCORE) {
+      a.out_adj[ga + i * N + j] = s;
+      if (i != j) {
+        a.out_adj[ga + j * N + i] = s;
+        s2 += 2.f * s * s;
+        z2 += 2.f * z * z;
+      }
+    } else {
+      const float m = ca.pa * a.adj[ga + i * N + j] + ca.pb * s;
+      const float v = m + ca.pc * z;
+      a.out_adj[ga + i * N + j] = v;
+      a.mean_adj[ga + i * N + j] = m;
+      if (a.traj_adj && b == 0) a.traj_adj[i * N + j] = a.denoise ? m : v;
+      if (i != j) {
+        a.out_adj[ga + j * N + i] = v;
+        a.mean_adj[ga + j * N + i] = m;
+        if (a.traj_adj && b == 0) a.traj_adj[j * N + i] = a.denoise ? m : v;
+      }
+    }
+  }
+  if (a.mode == MODE_SCORE) {
+    s2 = block_sum(s2, red);
+    z2 = block_sum(z2, red);
+    if (threadIdx.x == 0) {
+      float *np = a.norm_part + ((size_t)(1 * d.B + b) * P->ntile_max + blockIdx.x) * 2;
+      np[0] = s2; np[1] = z2;
+    }
+  }
+}
+
+}  // namespace ccsd

@@ -231,7 +231,8 @@ class Engine:
         return [(raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]
 
     def info(self) -> dict:
-        names = ("xa_smem_bytes", "xa_threads", "apply_smem_bytes", "tc_gram", "tc_apply", "f_mode", "fin_rows")
+        names = ("xa_smem_bytes", "xa_threads", "apply_smem_bytes", "tc_gram", "tc_apply", "f_mode", "fin_rows",
+                 "smem_x_net", "smem_attn_channel", "smem_attn_finish", "smem_hodge", "smem_afinal")
         return {n: int(self.lib.ccsd_plan_info(self.handle, i)) for i, n in enumerate(names)}
 
     @property
