@@ -258,6 +258,16 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   L.c_k = take(ad_max * N4);
   L.c_v = take(nh_max * N4);
   L.c_atp = take(nch_max * ldp);
+  {
+    int wmax = 0;
+    for (int l = 0; l < A.num_layers; ++l) {
+      const ccsd_attn_layer_t &ly = A.layer[l];
+      const int o1 = ly.multi_channel.nl == 1 ? ly.multi_channel.dout : ly.multi_channel.dhid;
+      const int r8a = (ly.attn_dim + 7) / 8 * 8, r8n = (ly.conv_out + 7) / 8 * 8, r8o = (o1 + 7) / 8 * 8;
+      wmax = imax(wmax, ly.conv_in * (2 * r8a + r8n) + ly.conv_out * r8o);
+    }
+    L.c_w = take(wmax);
+  }
   L.c_total = o;
   // ---- attn_finish_kernel ----
   o = 0;

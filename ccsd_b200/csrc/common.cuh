@@ -77,6 +77,25 @@ template <class Fn> static inline void ccsd_emu_launch(dim3 grid, size_t smem_by
 
 namespace ccsd {
 
+// Block-cooperative global -> shared copy of n floats (n % 4 == 0, both 16-byte aligned) that does not
+// block: cp.async on the device (complete after stage_wait()), a plain loop in the host emulation.
+__device__ __forceinline__ void stage_async(float *dst_smem, const float *__restrict__ src, int n) {
+#ifdef CCSD_EMU
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst_smem[i] = src[i];
+#else
+  const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 4u * i), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+// This thread's staged copies have landed (a __syncthreads makes every thread's visible to the block).
+__device__ __forceinline__ void stage_wait() {
+#ifndef CCSD_EMU
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_TANH = 2 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {

@@ -60,15 +60,22 @@ __device__ __forceinline__ void tile_fma(float acc[4][8], const float4 a, const 
 struct TileOps {   // operands of two consecutive k-steps
   float4 a0, a1, w00, w01, w10, w11;
 };
+// WSM: the weights were staged in shared memory (plain loads) instead of global memory (read-only path)
+template <bool WSM>
+__device__ __forceinline__ float4 ldw4(const float *p) {
+  return WSM ? *reinterpret_cast<const float4 *>(p) : __ldg(reinterpret_cast<const float4 *>(p));
+}
+template <bool WSM>
 __device__ __forceinline__ void tile_load2(TileOps &t, const float *in, int ld, const float *__restrict__ wp, int Opad) {
   t.a0 = ld4(in); t.a1 = ld4(in + ld);
-  t.w00 = __ldg(reinterpret_cast<const float4 *>(wp)); t.w01 = __ldg(reinterpret_cast<const float4 *>(wp + 4));
-  t.w10 = __ldg(reinterpret_cast<const float4 *>(wp + Opad)); t.w11 = __ldg(reinterpret_cast<const float4 *>(wp + Opad + 4));
+  t.w00 = ldw4<WSM>(wp); t.w01 = ldw4<WSM>(wp + 4);
+  t.w10 = ldw4<WSM>(wp + Opad); t.w11 = ldw4<WSM>(wp + Opad + 4);
 }
 
 // Software pipelined: the six loads of k-steps (k+2, k+3) are issued before the 64 FMAs of (k, k+1), so a
 // weight load that misses L1 (the weights are shared by every CTA and live in L2) is covered by this warp's
 // own FMAs plus the other resident warps'.
+template <bool WSM = false>
 __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, int ld1, int K1, const float *in2, int ld2,
                                            int K2, const float *__restrict__ W, int Opad, int r0, int oc) {
   const float *wp = W + oc;
@@ -79,10 +86,10 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
     const int npair = K >> 1;
     if (npair > 0) {
       TileOps cur, nxt;
-      tile_load2(cur, in, ld, wp, Opad);
+      tile_load2<WSM>(cur, in, ld, wp, Opad);
 #pragma unroll 1
       for (int p = 1; p < npair; ++p) {
-        tile_load2(nxt, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
+        tile_load2<WSM>(nxt, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
         tile_fma(acc, cur.a0, cur.w00, cur.w01);
         tile_fma(acc, cur.a1, cur.w10, cur.w11);
         cur = nxt;
@@ -93,7 +100,7 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
     if (K & 1) {
       const int k = K - 1;
       const float4 a0 = ld4(in + k * ld);
-      const float4 w00 = __ldg(reinterpret_cast<const float4 *>(wp + k * Opad)), w01 = __ldg(reinterpret_cast<const float4 *>(wp + k * Opad + 4));
+      const float4 w00 = ldw4<WSM>(wp + k * Opad), w01 = ldw4<WSM>(wp + k * Opad + 4);
       tile_fma(acc, a0, w00, w01);
     }
     wp += K * Opad;
@@ -103,6 +110,7 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
 // out(r, o) = act(bias[o] + sum_k in(k, r) W[k, o]),  r < R, o < O, stored at out[r*sro + o*soo].
 // bias may be nullptr.  When `accum` the previous out(r, o) is added (and act / bias are the caller's
 // business): used to fold a Linear over a channel-concatenated input channel by channel.
+template <bool WSM = false>
 __device__ __forceinline__ void dense_fm(const float *in1, int ld1, int K1, const float *in2, int ld2, int K2,
                                          const float *__restrict__ W, const float *__restrict__ bias, int O,
                                          float *out, int sro, int soo, int R, int act, bool accum = false,
@@ -122,7 +130,7 @@ __device__ __forceinline__ void dense_fm(const float *in1, int ld1, int K1, cons
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) acc[rr][j] = bv;
     }
-    dense_tile(acc, in1, ld1, K1, in2, ld2, K2, W, Opad, r0, oc);
+    dense_tile<WSM>(acc, in1, ld1, K1, in2, ld2, K2, W, Opad, r0, oc);
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int r = r0 + rr;

@@ -193,33 +193,28 @@ __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
-// ---- fp32 -> (hi, lo) bf16 split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x| ----
-__device__ __forceinline__ void split8(const float x[8], uint4 &hi, uint4 &lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// 4 floats -> 4 bf16 hi (8 bytes) + 4 bf16 lo (8 bytes).  hi is the TRUNCATED top half of the fp32 word (one
-// byte-permute packs two of them), the residual x - hi is exact in fp32 and is rounded to bf16 two at a time
-// (cvt.rn.bf16x2.f32): |x - hi - lo| <= 2^-17 |x|, in 12 instructions.
+// 4 floats -> 4 bf16 hi (8 bytes) + 4 bf16 lo (8 bytes), both round-to-nearest, two values per
+// cvt.rn.bf16x2.f32; the hi halves are expanded back to fp32 with a shift / mask so that the residual
+// x - hi is exact: |x - hi - lo| <= 2^-17 |x|, |lo| <= 2^-8 |x| (the dropped lo.lo product term is 2^-16),
+// in 12 instructions.
 __device__ __forceinline__ void split4(const float4 x, uint2 &hi, uint2 &lo) {
-  const uint32_t u0 = __float_as_uint(x.x), u1 = __float_as_uint(x.y), u2 = __float_as_uint(x.z), u3 = __float_as_uint(x.w);
-  hi.x = __byte_perm(u0, u1, 0x7632);   // (hi16(u1) << 16) | hi16(u0)
-  hi.y = __byte_perm(u2, u3, 0x7632);
-  const float r0 = x.x - __uint_as_float(u0 & 0xFFFF0000u), r1 = x.y - __uint_as_float(u1 & 0xFFFF0000u);
-  const float r2 = x.z - __uint_as_float(u2 & 0xFFFF0000u), r3 = x.w - __uint_as_float(u3 & 0xFFFF0000u);
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+  hi.x = *reinterpret_cast<const uint32_t *>(&h01);
+  hi.y = *reinterpret_cast<const uint32_t *>(&h23);
+  const float r0 = x.x - __uint_as_float(hi.x << 16), r1 = x.y - __uint_as_float(hi.x & 0xFFFF0000u);
+  const float r2 = x.z - __uint_as_float(hi.y << 16), r3 = x.w - __uint_as_float(hi.y & 0xFFFF0000u);
   const __nv_bfloat162 l01 = __floats2bfloat162_rn(r0, r1), l23 = __floats2bfloat162_rn(r2, r3);
   lo.x = *reinterpret_cast<const uint32_t *>(&l01);
   lo.y = *reinterpret_cast<const uint32_t *>(&l23);
+}
+
+// 8 floats -> 8 bf16 hi (16 bytes) + 8 bf16 lo (16 bytes)
+__device__ __forceinline__ void split8(const float x[8], uint4 &hi, uint4 &lo) {
+  uint2 h0, l0, h1, l1;
+  split4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
+  split4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
+  hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
 }  // namespace tc

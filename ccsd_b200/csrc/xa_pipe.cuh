@@ -32,6 +32,13 @@
 #pragma once
 #include "prims.cuh"
 
+#ifndef XP_MINB_C
+#define XP_MINB_C 1
+#endif
+#ifndef XP_MINB_M
+#define XP_MINB_M 1
+#endif
+
 namespace ccsd {
 
 struct XaArgs {
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__ 
 // =============================================================================================
 // attn_channel_kernel: Attention.forward of ONE channel of one graph (attention.py:84-132)
 // =============================================================================================
-__global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+__global__ void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -181,6 +188,16 @@ __global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__rest
   const int kin = ly.conv_in, ad = ly.attn_dim, nh = ly.conv_out;
   const float scale = 1.0f / sqrtf((float)nh);  // / sqrt(out_dim)  (attention.py:125)
 
+  // this channel's weights (Q, K, V transforms and V's slice of the node MLP) stream into shared memory
+  // while the normalisation and aggregation phases run
+  const ccsd_mlp_t &mc = ly.multi_channel;
+  const int o1 = mc.nl == 1 ? mc.dout : mc.dhid, o1p = round_up(o1, 8);
+  const int adp8 = round_up(ad, 8), nhp8 = round_up(nh, 8);
+  float *wq = sm + L.c_w, *wk = wq + kin * adp8, *wv = wk + kin * adp8, *w1 = wv + kin * nhp8;
+  stage_async(wq, W + ly.q[c].w, kin * adp8);
+  stage_async(wk, W + ly.k[c].w, kin * adp8);
+  stage_async(wv, W + ly.v[c].w, kin * nhp8);
+  stage_async(w1, W + mc.w[0] + (size_t)c * nh * o1p, nh * o1p);
   const float *gadj = a.g_stack + (size_t)b * L.g_stack + (size_t)(a.ch_in + c) * ldp;
   for (int t = threadIdx.x; t < ldp; t += blockDim.x) adjc[t] = gadj[t];
   const float *gx = a.g_xin + (size_t)b * L.g_x;
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__rest
   __syncthreads();
   gcn_norm_tri(adjc, N, N4, dvec, an);
   gcn_aggregate_fm(an, N, N4, xin, kin, ax);
+  stage_wait();
   __syncthreads();
   {
     // Q | K | V = (A x) W_{q,k,v} + b as one item space (same input tile, three weight matrices)
@@ -198,6 +216,7 @@ __global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__rest
       const int li = it - (w == 0 ? 0 : (w == 1 ? nq : 2 * nq));
       const ccsd_gcn_t &g = w == 0 ? ly.q[c] : (w == 1 ? ly.k[c] : ly.v[c]);
       float *dst = w == 0 ? q : (w == 1 ? kf : v);
+      const float *ws = w == 0 ? wq : (w == 1 ? wk : wv);
       const int O = g.dout, Opad = round_up(O, 8);
       const int chunk = li / ngrp, r0 = (li - chunk * ngrp) << 2, oc = chunk << 3;
       float acc[4][8];
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__rest
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) acc[rr][j] = bv;
       }
-      dense_tile(acc, ax, N4, kin, nullptr, 0, 0, W + g.w, Opad, r0, oc);
+      dense_tile<true>(acc, ax, N4, kin, nullptr, 0, 0, ws, Opad, r0, oc);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (oc + j < O) {
@@ -222,11 +241,8 @@ __global__ void __launch_bounds__(128) attn_channel_kernel(const DevPlan *__rest
   {
     // V's share of the first Linear of multi_channel, which is linear in the channel concat
     // (attention.py:292): hmc_c(o, i) = sum_f V_c(i, f) W1[c*nh + f, o]; the finish kernel sums over c
-    const ccsd_mlp_t &mc = ly.multi_channel;
-    const int o1 = mc.nl == 1 ? mc.dout : mc.dhid, o1p = round_up(o1, 8);
     float *gh = a.g_hmc + (size_t)b * L.g_hmc + (size_t)c * L.mc_o1_max * N4;
-    dense_fm(v, N4, nh, nullptr, 0, 0, W + mc.w[0] + (size_t)c * nh * o1p, nullptr, o1, gh, 1, N4, N, ACT_NONE, false,
-             (int)blockDim.x - 32);
+    dense_fm<true>(v, N4, nh, nullptr, 0, 0, w1, nullptr, o1, gh, 1, N4, N, ACT_NONE, false, (int)blockDim.x - 32);
   }
   __syncthreads();
   {
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
 // afinal_kernel: final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) on a chunk of node
 // pairs + the adjacency sampler epilogue
 // =============================================================================================
-__global__ void __launch_bounds__(128) afinal_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+__global__ void __launch_bounds__(128, XP_MINB_M) afinal_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
