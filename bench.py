@@ -121,15 +121,32 @@ def xa_flops(meta):
     return fl
 
 
-def kernel_alg_flops(meta, B, pr0):
+def kernel_alg_work(meta, B, pr0):
+    """Algorithmic work per launch of every kernel: (flops, hbm_bytes).  FLOPs are dense-matmul 2mnk only
+    (SURVEY 8d); bytes are the compulsory traffic of the rank-2 state (4 E K per sample per read or write)."""
     N, F, E, K, _, _ = dims(meta)
-    out = {"xa_kernel": B * xa_flops(meta)}
+    x_fl, a_fl = xa_flops_split(meta)
+    out = {"x_net_kernel": (B * x_fl, 0), "xa_pipeline": (B * (x_fl + a_fl), 0)}
     if meta["is_cc"]:
-        out["gram_kernel"] = B * 2 * E * (E + pr0) * K
-        out["tc_gram_kernel"] = out["gram_kernel"]
-        out["apply_kernel"] = B * 2 * E * E * K
-        out["tc_apply_kernel"] = out["apply_kernel"]
+        st = 4 * E * K * B
+        out["gram_kernel"] = out["tc_gram_kernel"] = (B * 2 * E * (E + pr0) * K, st)
+        # apply passes: read the state once; CORR / PRED / SCORE / EVAL also write it once (NORM does not)
+        out["apply_kernel"] = out["tc_apply_kernel"] = (B * 2 * E * E * K, 2 * st)
+        out["tc_apply_kernel:norm"] = (B * 2 * E * E * K, st)
     return out
+
+
+def xa_flops_split(meta):
+    tot = xa_flops(meta)
+    N, F, E, K, _, _ = dims(meta)
+    px = meta["params"]["x"]
+    fl, din = 0, F
+    for _ in range(px["depth"]):
+        fl += 2 * N * din * px["nhid"] + 2 * N * N * px["nhid"]
+        din = px["nhid"]
+    fd = F + px["depth"] * px["nhid"]
+    fl += mlp_flops(N, [fd, 2 * fd, 2 * fd, F])
+    return fl, tot - fl
 
 
 # ---- clocks -----------------------------------------------------------------------------------
@@ -372,15 +389,42 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         if not pk.exists():
             src = "fallback (B200_PROFILING.md)"
-        alg = kernel_alg_flops(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
+        work = kernel_alg_work(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
+        peak_hbm = peaks.get("hbm_gbs", 6650.0)
+        XA = ("x_net_kernel", "attn_channel_kernel", "attn_finish_kernel", "hodge_kernel", "afinal_kernel")
+        kern = {}
+        for k_, v in prof_summary.items():
+            ms_l = v[0] / v[1]
+            fl, by = work.get(k_, (0, 0))
+            kern[k_] = {"ms_per_launch": ms_l, "launches": v[1], "share": v[0] / tot,
+                        "alg_tflops": fl / (ms_l * 1e-3) / 1e12, "alg_gbs": by / (ms_l * 1e-3) / 1e9}
+        # the x / adj network pipeline as ONE unit of work (its five kernels implement one score evaluation)
+        xa_ms = sum(prof_summary[k_][0] for k_ in XA if k_ in prof_summary)
+        n_eval = prof_summary.get("x_net_kernel", [0, 0])[1]
+        if n_eval:
+            kern["xa_pipeline"] = {"ms_per_launch": xa_ms / n_eval, "launches": n_eval, "share": xa_ms / tot,
+                                   "alg_tflops": work["xa_pipeline"][0] / (xa_ms / n_eval * 1e-3) / 1e12, "alg_gbs": 0.0,
+                                   "kernels": [k_ for k_ in XA if k_ in prof_summary]}
+        dom = max((k_ for k_ in prof_summary), key=lambda k_: prof_summary[k_][0])
         avg_ms = prof_summary[dom][0] / prof_summary[dom][1]
-        ach = alg.get(dom, 0) / (avg_ms * 1e-3) / 1e12
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_source": src, "avg_launch_ms": avg_ms,
-                    "share_of_step": prof_summary[dom][0] / tot,
-                    "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / tot,
-                                     "alg_tflops": alg.get(k_, 0) / (v[0] / v[1] * 1e-3) / 1e12}
-                                for k_, v in prof_summary.items()}}
+        fl, by = work.get(dom, (0, 0))
+        traffic = None
+        tf = ROOT / "profiles" / "ncu_traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(wname, {}).get(dom)
+        if by:   # a kernel that streams the rank-2 state: HBM roofline
+            if dom == "tc_apply_kernel" and sampler == "PC" and sh["corrector"] == "Langevin":
+                by = (work["tc_apply_kernel:norm"][1] + 2 * work["tc_apply_kernel"][1]) / 3.0   # NORM, CORR, PRED passes
+            ach = by / (avg_ms * 1e-3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
+                        "traffic": traffic, "peak_source": src.replace("sustained", "hbm_gbs"), "avg_launch_ms": avg_ms,
+                        "algorithmic_bytes_per_launch": by}
+        else:
+            ach = fl / (avg_ms * 1e-3) / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                        "traffic": traffic, "peak_source": src, "avg_launch_ms": avg_ms}
+        roofline["share_of_step"] = prof_summary[dom][0] / tot
+        roofline["kernels"] = kern
         del eng2
 
     if rank == 0:

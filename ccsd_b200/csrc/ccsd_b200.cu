@@ -214,7 +214,12 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   const int N4 = a4(N), NT = N * (N + 1) / 2, ldp = a4(NT);
   L.N4 = N4; L.NT = NT; L.ldp = ldp;
   const int T = NT >= 96 ? 128 : 64;
-  L.Tx = L.Tc = L.Tf = L.Th = L.Tm = T;
+  L.Tx = L.Th = L.Tm = T;
+  L.Tc = L.Tf = 64;   // measured on B200 (community_small_CC): 64 threads beat 32 and 128 for the per-channel CTAs
+  // tuning overrides (experiments): threads per CTA of the individual pipeline kernels
+  auto envi = [](const char *nm, int dflt) { const char *e = getenv(nm); return e ? atoi(e) : dflt; };
+  L.Tx = envi("CCSD_XP_TX", L.Tx); L.Tc = envi("CCSD_XP_TC", L.Tc); L.Tf = envi("CCSD_XP_TF", L.Tf);
+  L.Tm = envi("CCSD_XP_TM", L.Tm);
   int nh_max = 1, ad_max = 1, cin_max = 1, kin_max = F, mc_hid = 1, mc_o1 = 1, eh = 1, eh_bufs = 1, nch_max = 1;
   const int heads = imax(A.num_heads, 1);
   for (int l = 0; l < A.num_layers; ++l) {
