@@ -26,11 +26,16 @@
 // quarter q = warp % 4; role = (warp - 4) / 4: M tile 0 cells 0-15 | M tile 0 cells 16-31 | M tile 1, where
 // the 16 edges of the quarter are processed by lane pairs (l, l + 16) taking 16 cells each, so every lane
 // of every epilogue warp has work), 16-17 MMA issuers (one per M tile: the issue rate of one thread, not the
-// tensor pipe, bounds a 72-instruction tile).  The kernel is templated on the ScoreNetworkF entry
+// tensor pipe, bounds a 72-instruction tile), 18 TMA warp.  When the state's row pitch allows it (K % 4 == 0)
+// the fp32 tiles move by TMA: one elected thread issues a 2-D tensor load per tile into the staging ring
+// (SWIZZLE_128B is exactly the ring's chunk-XOR layout; cells past K are zero-filled) and a tensor store of
+// every finished tile (clipped at K), so the loader warps only convert operands.  Otherwise the loader
+// warps move the tiles themselves with cp.async and coalesced stores.  The kernel is templated on the ScoreNetworkF entry
 // path AND the pass mode, so the per-entry code has no mode branches.
 #pragma once
 #include "r2_kernels.cuh"
 #include "tc_common.cuh"
+#include <cuda.h>   // CUtensorMap
 
 namespace ccsd {
 
@@ -43,7 +48,7 @@ namespace ccsd {
 constexpr int TA_LOAD = TA_LOAD_THREADS;
 constexpr int TA_RSTEP = TA_LOAD / 8;              // rows covered by one sweep of the loader threads
 constexpr int TA_EPI = 384;
-constexpr int TA_THREADS = TA_LOAD + TA_EPI + 64;   // + one MMA-issuing warp per M tile
+constexpr int TA_THREADS = TA_LOAD + TA_EPI + 96;   // + one MMA-issuing warp per M tile + the TMA warp
 constexpr int TA_TN = 32;                         // cells per tile
 constexpr int TA_NE = 192;                        // padded edge count
 constexpr int TA_NS = 6;                          // staging stages (the loaders only block on a tile 4 behind)
@@ -102,7 +107,9 @@ __device__ __forceinline__ float r2_entry(const R2Epi &c, const R2Fold &w, float
 #define TA_STAMP(slot_, g_) do { if (a.trace && blockIdx.x == 0 && (g_) < 512) a.trace[(size_t)(g_) * 16 + (slot_)] = clock64(); } while (0)
 
 template <int FMODE, int MODE>
-__global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a) {
+__global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a,
+                                                                 const __grid_constant__ CUtensorMap tm_in,
+                                                                 const __grid_constant__ CUtensorMap tm_out, int use_tma) {
   extern __shared__ uint8_t ta_smem_raw[];
   const ccsd_plan_desc_t &d = P->d;
   const int N = d.N, E = d.E, K = d.K, B = d.B, Ep = P->Ep;
@@ -121,8 +128,9 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   // warp only; the epilogue learns that a STAGING tile is complete from stage_full (4-deep), whose next
   // phase needs the stage to have been copied out, i.e. every epilogue thread to be done with it.
   const uint32_t full = bars, op_empty = bars + 16, t_full = bars + 32, d_empty = bars + 48, epi_done = bars + 64,
-                 stage_full = epi_done + 8 * TA_NS, h_ready = stage_full + 8 * TA_NS, tslot = h_ready + 8;
-  uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen + TA_BARS + 64 + 16 * TA_NS + 8);
+                 stage_full = epi_done + 8 * TA_NS, tma_full = stage_full + 8 * TA_NS, h_ready = tma_full + 8 * TA_NS,
+                 tslot = h_ready + 8;
+  uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen + TA_BARS + 64 + 24 * TA_NS + 8);
   float *fcs = reinterpret_cast<float *>(gen + TA_FCS);
   float *red = reinterpret_cast<float *>(gen + TA_RED);
   float *fw = reinterpret_cast<float *>(gen + TA_FW);
@@ -137,6 +145,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     for (int s = 0; s < TA_NS; ++s) {
       tc::mbar_init(epi_done + 8 * s, TA_EPI);
       tc::mbar_init(stage_full + 8 * s, TA_LOAD);
+      tc::mbar_init(tma_full + 8 * s, 1);
     }
     tc::mbar_init(h_ready, TA_EPI);
     tc::mbar_fence_init();
@@ -224,20 +233,26 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       }
     };
     (void)NJ;
-    for (int t = 0; t < TA_PD; ++t) {
-      if (t < ntot) issue(t);
-      tc::cp_async_commit();
-    }
+    if (!use_tma)
+      for (int t = 0; t < TA_PD; ++t) {
+        if (t < ntot) issue(t);
+        tc::cp_async_commit();
+      }
     int cur_b = -1;
     unsigned long long zm = 0ull;
     for (int g = 0; g < ntot; ++g) {
-      if (g + TA_PD < ntot) {
-        if (g + TA_PD - TA_NS >= 0) copy_out(g + TA_PD - TA_NS);   // frees the stage tile g + PD lands in
-        issue(g + TA_PD);
+      if (use_tma) {
+        if (threadIdx.x == 0) TA_STAMP(0, g);
+        tc::mbar_wait(tma_full + 8 * (g % TA_NS), (uint32_t)(g / TA_NS) & 1u);   // the tensor load of tile g has landed
+      } else {
+        if (g + TA_PD < ntot) {
+          if (g + TA_PD - TA_NS >= 0) copy_out(g + TA_PD - TA_NS);   // frees the stage tile g + PD lands in
+          issue(g + TA_PD);
+        }
+        tc::cp_async_commit();
+        if (threadIdx.x == 0) TA_STAMP(0, g);
+        tc::cp_async_wait<TA_PD>();                                   // this thread's chunks of tile g have landed
       }
-      tc::cp_async_commit();
-      if (threadIdx.x == 0) TA_STAMP(0, g);
-      tc::cp_async_wait<TA_PD>();                                   // this thread's chunks of tile g have landed
       if (threadIdx.x == 0) TA_STAMP(1, g);
       int b, k0;
       tile_of(g, b, k0);
@@ -271,10 +286,44 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       if (threadIdx.x == 0) TA_STAMP(3, g);
     }
     // drain: tiles [ntot - NS, ntot) are still in the ring (the loop copied out tile g + PD - NS)
-    for (int g = ntot > TA_NS ? ntot - TA_NS : 0; g < ntot; ++g) copy_out(g);
+    if (!use_tma)
+      for (int g = ntot > TA_NS ? ntot - TA_NS : 0; g < ntot; ++g) copy_out(g);
+  } else if (warp == TA_MMAW + 2) {
+    // ===================== TMA warp: tensor loads into / tensor stores out of the staging ring =====================
+    if (use_tma && lane == 0) {
+      const bool writes = MODE != MODE_NORM;
+      const uint32_t tile_bytes = (uint32_t)E * 128u;
+      auto coords = [&](int g, int &col, int &row) {
+        const int si = g / ntile;
+        row = ((int)blockIdx.x + si * (int)gridDim.x) * E;
+        col = (g - si * ntile) * TA_TN;
+      };
+      auto store = [&](int g) {   // tile g is final in its stage once every epilogue thread arrived (after a proxy fence)
+        tc::mbar_wait(epi_done + 8 * (g % TA_NS), (uint32_t)(g / TA_NS) & 1u);
+        if (writes) {
+          int col, row;
+          coords(g, col, row);
+          tc::tma_store_2d(&tm_out, col, row, sStage + (uint32_t)(g % TA_NS) * TA_STAGE);
+        }
+        tc::bulk_commit();
+      };
+      for (int g = 0; g < ntot; ++g) {
+        // Stage g % NS held tile g - NS.  Its store is issued one iteration EARLY (with tile g - NS + 1 ... see
+        // below), so that by now only its shared-memory read has to have finished, not its issue.
+        if (g >= TA_NS - 1) store(g - (TA_NS - 1));
+        if (g >= TA_NS) tc::bulk_wait_read<1>();   // every store but the newest has read its stage: tile g - NS is out
+        int col, row;
+        coords(g, col, row);
+        tc::mbar_arrive_expect_tx(tma_full + 8 * (g % TA_NS), tile_bytes);
+        tc::tma_load_2d(sStage + (uint32_t)(g % TA_NS) * TA_STAGE, &tm_in, col, row, tma_full + 8 * (g % TA_NS));
+      }
+      for (int g = ntot > TA_NS - 1 ? ntot - (TA_NS - 1) : 0; g < ntot; ++g) store(g);
+      tc::bulk_wait<0>();   // the stores must have completed before the CTA exits
+    }
   } else if (warp >= TA_MMAW) {
     // ===================== MMA issuers: warp TA_MMAW + mt drives M tile mt =====================
-    const int mt = warp - TA_MMAW;
+    const int mt = warp - TA_MMAW;   // 0 or 1 (the TMA warp, TA_MMAW + 2, is handled above)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy of the TMEM base
     const uint32_t idesc = tc::make_idesc_bf16(128, TA_TN, /*A from TMEM*/ 0, /*B MN-major*/ 1);
     if (mt < mtiles) {
       for (int g = 0; g < ntot; ++g) {
@@ -285,12 +334,12 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         tc::mbar_wait(d_empty + 8 * slot, (uint32_t)(((g >> 1) & 1) ^ 1));
         tc::tc_fence_after_sync();
         if (lane == 0 && mt == 0) TA_STAMP(4, g);
-        if (lane == 0) {
+        if (tc::elect_one()) {
           // descriptors advance by 16 e' rows (2048 bytes = 128 descriptor units) per k step
           uint64_t b_hi = tc::make_smem_desc(sOp + (uint32_t)slot * 64u, 8192, 1024);
           uint64_t b_lo = tc::make_smem_desc(sOp + TA_OPHALF + (uint32_t)slot * 64u, 8192, 1024);
-          const uint32_t dcol = tmem + TA_COL_D + (uint32_t)(slot * 64 + mt * 32);
-          uint32_t a_hi = tmem + (uint32_t)(mt * 192);
+          const uint32_t dcol = tmem_u + TA_COL_D + (uint32_t)(slot * 64 + mt * 32);
+          uint32_t a_hi = tmem_u + (uint32_t)(mt * 192);
 #pragma unroll 1
           for (int k4 = 0; k4 < nk; ++k4) {
             tc::umma_bf16_ts_coll<1, 0>(dcol, a_hi, b_hi, idesc, k4 != 0);   // A_hi kept in the collector ...
@@ -300,7 +349,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
           }
           tc::umma_commit(op_empty + 8 * slot);   // operand slot may be refilled once these MMAs retire
           tc::umma_commit(t_full + 8 * slot);     // accumulators complete
-          if (mt == 0) TA_STAMP(5, g);
+          if (mt == 0) TA_STAMP(5, g);   // (stamped by the elected lane)
         }
         __syncwarp();
       }
@@ -445,6 +494,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
             }
           }
         }
+        if (MODE != MODE_NORM) tc::fence_proxy_async_smem();          // generic writes -> visible to the TMA store
         tc::mbar_arrive(epi_done + 8 * stg);                          // (release) tile may be copied out
         if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 9 : 13, g);
       }
@@ -473,36 +523,72 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   if (warp == TA_MMAW) tc::tmem_dealloc(tmem, 512);
 }
 
+struct TcApplyMaps {   // host side: tensor maps of the state read and the state / score written, or use_tma = 0
+  CUtensorMap in, out;
+  int use_tma;
+};
+
 template <int FMODE, int MODE>
-static inline int tc_apply_launch_fm(const DevPlan *dP, int grid, const ApplyArgs &a, void *stream) {
+static inline int tc_apply_launch_fm(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream) {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_apply_kernel<FMODE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM) != cudaSuccess)
       return -1;
     attr_set = true;
   }
-  tc_apply_kernel<FMODE, MODE><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a);
+  tc_apply_kernel<FMODE, MODE><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a, m.in, m.out, m.use_tma);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 template <int FMODE>
-static inline int tc_apply_launch_f(const DevPlan *dP, int grid, const ApplyArgs &a, void *stream) {
+static inline int tc_apply_launch_f(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream) {
   switch (a.mode) {
-    case MODE_EVAL: return tc_apply_launch_fm<FMODE, MODE_EVAL>(dP, grid, a, stream);
-    case MODE_SCORE: return tc_apply_launch_fm<FMODE, MODE_SCORE>(dP, grid, a, stream);
-    case MODE_PRED: return tc_apply_launch_fm<FMODE, MODE_PRED>(dP, grid, a, stream);
-    case MODE_NORM: return tc_apply_launch_fm<FMODE, MODE_NORM>(dP, grid, a, stream);
-    case MODE_CORR: return tc_apply_launch_fm<FMODE, MODE_CORR>(dP, grid, a, stream);
+    case MODE_EVAL: return tc_apply_launch_fm<FMODE, MODE_EVAL>(dP, grid, a, m, stream);
+    case MODE_SCORE: return tc_apply_launch_fm<FMODE, MODE_SCORE>(dP, grid, a, m, stream);
+    case MODE_PRED: return tc_apply_launch_fm<FMODE, MODE_PRED>(dP, grid, a, m, stream);
+    case MODE_NORM: return tc_apply_launch_fm<FMODE, MODE_NORM>(dP, grid, a, m, stream);
+    case MODE_CORR: return tc_apply_launch_fm<FMODE, MODE_CORR>(dP, grid, a, m, stream);
   }
   return -1;
+}
+
+// 2-D tensor map of a [B*E rows][K cols] fp32 tensor with a box of E rows x 32 columns, SWIZZLE_128B.
+// Returns 0 on success; fails (-> cp.async path) when the pitch or the base is not 16-byte aligned.
+static inline int tc_apply_make_map(CUtensorMap *m, const float *base, int B, int E, int K) {
+  if ((K & 3) || (reinterpret_cast<uintptr_t>(base) & 15) || E > 256) return -1;
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return -1;
+    fn = (EncodeFn)p;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)B * E};
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TA_TN, (cuuint32_t)E};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0 : -1;
 }
 
 static inline int tc_apply_prepare() { return 0; }   // attributes are set per instantiation at first launch
 
 static inline int tc_apply_launch(const DevPlan *dP, const DevPlan &hp, const ApplyArgs &a, void *stream) {
   const int grid = hp.d.B < 148 ? hp.d.B : 148;
-  if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, stream);
-  if (hp.f_mode == 2) return tc_apply_launch_f<2>(dP, grid, a, stream);
-  return tc_apply_launch_f<0>(dP, grid, a, stream);
+  TcApplyMaps m;
+  memset(&m, 0, sizeof m);
+  m.use_tma = 0;
+  static const bool no_tma = getenv("CCSD_B200_NO_TMA") != nullptr;   // A/B switch for tests and profiling
+  if (!no_tma && tc_apply_make_map(&m.in, a.r2, hp.d.B, hp.d.E, hp.d.K) == 0 &&
+      (a.mode == MODE_NORM || tc_apply_make_map(&m.out, a.out, hp.d.B, hp.d.E, hp.d.K) == 0))
+    m.use_tma = 1;
+  if (a.mode == MODE_NORM) m.out = m.in;
+  if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, m, stream);
+  if (hp.f_mode == 2) return tc_apply_launch_f<2>(dP, grid, a, m, stream);
+  return tc_apply_launch_f<0>(dP, grid, a, m, stream);
 }
 
 }  // namespace ccsd

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   } else if (warp == TG_PROD_WARPS + 4) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = tc::make_idesc_bf16(128, ncols, 0, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy (uniform-register MMA operands)
     uint32_t it = 0, tile = 0;
     for (int b = blockIdx.x; b < B; b += gridDim.x, ++tile) {
       tc::mbar_wait(tempty, (tile & 1) ^ 1);   // epilogue has drained the previous accumulators
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
         const uint32_t ph = (it / TG_STAGES) & 1;
         tc::mbar_wait(full0 + 8 * s, ph);
         tc::tc_fence_after_sync();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint32_t sb = base + (uint32_t)s * TG_STAGE;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
             for (int mt = 0; mt < mtiles; ++mt) {
               const uint64_t a_hi = tc::make_smem_desc(sb + (uint32_t)mt * 16384u + ko, 0, 1024);
               const uint64_t a_lo = tc::make_smem_desc(sb + TG_HALF + (uint32_t)mt * 16384u + ko, 0, 1024);
-              const uint32_t dcol = tmem + (uint32_t)(mt * ncols);
+              const uint32_t dcol = tmem_u + (uint32_t)(mt * ncols);
               tc::umma_bf16(dcol, a_hi, b_hi, idesc, (kb | k4) != 0);
               tc::umma_bf16(dcol, a_hi, b_lo, idesc, 1);
               tc::umma_bf16(dcol, a_lo, b_hi, idesc, 1);
