@@ -69,6 +69,7 @@ struct ccsd_plan {
   float *mx = nullptr, *madj = nullptr, *mr2 = nullptr;
   float *sx = nullptr, *sadj = nullptr, *sr2 = nullptr;
   float *H = nullptr, *P0 = nullptr, *P1 = nullptr, *norm_part = nullptr, *coef = nullptr;
+  unsigned long long *zmask = nullptr, *zmask_eval = nullptr;
   float *g_stack = nullptr, *g_att = nullptr, *g_hmc = nullptr, *g_x0 = nullptr, *g_x1 = nullptr;
   float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
   bool bound = false, inited = false;
@@ -330,7 +331,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, tri, gstack, gatt, ghmc, gx0, gx1, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -342,6 +343,8 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.sched = take(p->sched.size() * sizeof(ccsd_objcoef_t));
   w.cells = take(imax(1, d.K) * sizeof(unsigned long long));
   w.edges = take(imax(1, d.E) * 2 * sizeof(int));
+  w.zmask = take(B * 8);
+  w.zmask_eval = take(B * 8);
   w.tri = take((size_t)p->hp.xp.ldp * sizeof(int));
   w.gstack = take(B * (size_t)p->hp.xp.g_stack * 4);
   w.gatt = take(B * (size_t)p->hp.xp.g_att * 4);
@@ -381,6 +384,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.ntile_adj = p->hp.xp.m_nchunk;
   p->hp.ntile_max = imax(imax(1, p->hp.ntile_r2), p->hp.ntile_adj);
   p->hp.f_mode = 0; p->hp.f_nlin = 0;
+  p->hp.ap_group = d.is_cc ? imax(1, imin(8, 192 / imax(d.E, 1))) : 1;
   if (d.is_cc && (d.nets & 4)) {
     const ccsd_netf_t &Fn = d.netf;
     bool w8 = Fn.fin.nl == 1 && Fn.fdim <= 40;
@@ -496,6 +500,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->g_stack = (float *)(ws + w.gstack); p->g_att = (float *)(ws + w.gatt); p->g_hmc = (float *)(ws + w.ghmc);
   p->g_x0 = (float *)(ws + w.gx0); p->g_x1 = (float *)(ws + w.gx1);
   p->hp.tri_ij = (const int *)(ws + w.tri);
+  p->zmask = (unsigned long long *)(ws + w.zmask); p->zmask_eval = (unsigned long long *)(ws + w.zmask_eval);
   p->hp.W = p->weights;
   p->hp.sched = (const ccsd_objcoef_t *)(ws + w.sched);
   p->hp.cell_mask = (const unsigned long long *)(ws + w.cells);
@@ -532,6 +537,7 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
   const ccsd_plan_desc_t &d = p->hp.d;
   if (int r = dev_copy(p->flags, flags_dev, (size_t)d.B * d.N * 4, stream)) return r;
   p->seed = seed; p->sample_offset = sample_offset;
+  CCSD_LAUNCH(zmask_kernel, dim3(grid_for(d.B), 1, 1), 256, 0, stream, p->flags, p->zmask, d.B, d.N);
   InitArgs a;
   a.flags = p->flags; a.px = px; a.padj = padj; a.pr2 = pr2; a.x = p->x; a.adj = p->adj; a.r2 = p->r2;
   a.nz.seed = seed; a.nz.sample_offset = sample_offset; a.nz.step = -1;
@@ -648,7 +654,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
   auto apply_pass = [&](int mode, int slot) -> int {
     ApplyArgs q; memset(&q, 0, sizeof q);
     q.r2 = p->r2; q.H = p->H; q.flags = p->flags; q.mode = mode; q.slot = slot; q.denoise = d.denoise; q.nz = nz;
-    q.norm_part = p->norm_part; q.coef = p->coef;
+    q.norm_part = p->norm_part; q.coef = p->coef; q.zmask = p->zmask;
     q.trace = mode == MODE_CORR ? p->trace : nullptr;   // debug timeline of the Langevin-correction pass
     q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
     if (mode == MODE_SCORE) q.out = p->sr2;
@@ -756,8 +762,9 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
   }
   if (which == CCSD_NET_RANK2) {
     if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
+    CCSD_LAUNCH(zmask_kernel, dim3(grid_for(d.B), 1, 1), 256, 0, stream, flags, p->zmask_eval, d.B, d.N);
     ApplyArgs q; memset(&q, 0, sizeof q);
-    q.r2 = r2; q.H = p->H; q.flags = flags; q.mode = MODE_EVAL; q.out = out;
+    q.r2 = r2; q.H = p->H; q.flags = flags; q.mode = MODE_EVAL; q.out = out; q.zmask = p->zmask_eval;
     launch_apply(p, q, stream);
     p->launches++;
     return dev_check("apply_kernel");

@@ -52,6 +52,7 @@ struct DevPlan {
   int ntile_max;                  // stride of the per-object norm partials
   int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled
   int f_nlin;                     // number of Linears staged for f_mode 2
+  int ap_group;                   // tensor-core apply kernel: samples per work group (min(8, 192 / E))
 };
 
 // modes of the score kernels

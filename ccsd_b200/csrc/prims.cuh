@@ -75,6 +75,9 @@ __device__ __forceinline__ void tile_load2(TileOps &t, const float *in, int ld, 
 // Software pipelined: the six loads of k-steps (k+2, k+3) are issued before the 64 FMAs of (k, k+1), so a
 // weight load that misses L1 (the weights are shared by every CTA and live in L2) is covered by this warp's
 // own FMAs plus the other resident warps'.
+#ifndef CCSD_DENSE_PIPE
+#define CCSD_DENSE_PIPE 1
+#endif
 template <bool WSM = false>
 __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, int ld1, int K1, const float *in2, int ld2,
                                            int K2, const float *__restrict__ W, int Opad, int r0, int oc) {
@@ -84,6 +87,7 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
     const float *in = (seg ? in2 : in1) + r0;
     const int ld = seg ? ld2 : ld1, K = seg ? K2 : K1;
     const int npair = K >> 1;
+#if CCSD_DENSE_PIPE
     if (npair > 0) {
       TileOps cur, nxt;
       tile_load2<WSM>(cur, in, ld, wp, Opad);
@@ -97,6 +101,16 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
       tile_fma(acc, cur.a0, cur.w00, cur.w01);
       tile_fma(acc, cur.a1, cur.w10, cur.w11);
     }
+#else
+    // lean variant (fewer registers -> more resident CTAs): no software pipelining, latency hidden by other warps
+#pragma unroll 1
+    for (int p = 0; p < npair; ++p) {
+      TileOps cur;
+      tile_load2<WSM>(cur, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
+      tile_fma(acc, cur.a0, cur.w00, cur.w01);
+      tile_fma(acc, cur.a1, cur.w10, cur.w11);
+    }
+#endif
     if (K & 1) {
       const int k = K - 1;
       const float4 a0 = ld4(in + k * ld);

@@ -277,6 +277,7 @@ struct ApplyArgs {
   int slot, denoise, write_mean;
   NoiseCtx nz;
   long long *trace;              // debug: per-tile clock64 stamps of CTA 0 ([tile][16]) or nullptr
+  const unsigned long long *zmask;   // [B] zero-flag node masks of the samples (zmask_kernel)
 };
 
 // Per-CTA epilogue context (everything the per-entry work needs), shared by the fp32 and the
@@ -628,6 +629,13 @@ __global__ void __launch_bounds__(256) update_kernel(const DevPlan *__restrict__
       }
     }
   }
+}
+
+// zero-flag node mask of every sample (bit n set <=> flags[b][n] == 0): a cell is masked iff it shares a bit
+__global__ void __launch_bounds__(256) zmask_kernel(const float *__restrict__ flags, unsigned long long *__restrict__ zmask,
+                                                    int B, int N) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x)
+    zmask[b] = zero_mask_of(flags + (size_t)b * N, N);
 }
 
 // quantize / quantize_mol (graph_utils.py:181-213)

@@ -22,6 +22,11 @@
 // accumulator, Philox noise and masks, and write the NEW state back into the staging tile in place;
 // the loader warps then copy the finished tile out with coalesced 16-byte stores.
 //
+// Small complexes: when E <= 96 several consecutive samples form one work group (G = min(8, 192 / E) samples,
+// G * E edge rows): their rows are contiguous in the state, so the F tile is simply taller, and H becomes
+// block diagonal in tensor memory.  Every per-row quantity (flags, Philox key, norm partial) follows the
+// row's own sample.
+//
 // Warp roles (17 warps): 0-3 loaders (cp.async ring, bf16 split, copy-out), 4-15 epilogue (TMEM lane
 // quarter q = warp % 4; role = (warp - 4) / 4: M tile 0 cells 0-15 | M tile 0 cells 16-31 | M tile 1, where
 // the 16 edges of the quarter are processed by lane pairs (l, l + 16) taking 16 cells each, so every lane
@@ -57,10 +62,11 @@ constexpr uint32_t TA_OPHALF = TA_NE * 128u;      // 24576: hi (or lo) operand r
 constexpr uint32_t TA_OPER = 2u * TA_OPHALF;      // 49152
 constexpr uint32_t TA_STAGE = TA_NE * 128u;       // 24576: 192 rows x 32 fp32
 constexpr uint32_t TA_BARS = TA_OPER + TA_NS * TA_STAGE;   // 147456
-constexpr uint32_t TA_FCS = TA_BARS + 256;        // [NS][32] cell flags
-constexpr uint32_t TA_RED = TA_FCS + TA_NS * 32 * 4;   // [2][16] warp partials
+constexpr int TA_GMAX = 8;                        // samples per work group (E <= 24)
+constexpr uint32_t TA_FCS = TA_BARS + 256;        // [NS][GMAX][32] cell flags
+constexpr uint32_t TA_RED = TA_FCS + TA_NS * TA_GMAX * 32 * 4;   // [2 cell halves][192 rows][2] norm partials
 constexpr int TA_MMAW = (TA_LOAD + TA_EPI) / 32;     // index of the MMA warp
-constexpr uint32_t TA_FW = TA_RED + 256;          // staged ScoreNetworkF weights (FMODE 2)
+constexpr uint32_t TA_FW = TA_RED + 2 * TA_NE * 2 * 4;   // staged ScoreNetworkF weights (FMODE 2)
 constexpr size_t TA_SMEM = (size_t)TA_FW + 6144 + 1024 /*alignment slack*/;
 constexpr uint32_t TA_COL_D = 384;                // first accumulator column
 
@@ -114,8 +120,11 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   const ccsd_plan_desc_t &d = P->d;
   const int N = d.N, E = d.E, K = d.K, B = d.B, Ep = P->Ep;
   const int ntile = (K + TA_TN - 1) / TA_TN;
-  const int nk = (E + 15) >> 4;                 // 16-wide k steps over e'
-  const int mtiles = E > 128 ? 2 : 1;
+  const int G = P->ap_group;                    // samples per work group
+  const int EB = G * E;                         // edge rows of a full group (<= 192)
+  const int ngroups = (B + G - 1) / G;
+  const int nk = (EB + 15) >> 4;                // 16-wide k steps over e'
+  const int mtiles = EB > 128 ? 2 : 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const uint32_t raw = tc::smem_u32(ta_smem_raw);
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tslot_gen;
-  const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nmine = (ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // groups of this CTA
   const int ntot = nmine * ntile;
 
   if (warp < TA_LOAD / 32) {
@@ -174,56 +183,64 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     // address below is base + j * stride
     constexpr int NJ = TA_NE / TA_RSTEP;
     constexpr uint32_t JSTR = TA_RSTEP * 128u;
-    const int nj = (E - r0 + TA_RSTEP - 1) / TA_RSTEP;          // rows of this thread (r0 < E: E >= 8... guarded below)
+    const int nj = (EB - r0 + TA_RSTEP - 1) / TA_RSTEP;         // rows of this thread in a full group
     const uint32_t soff = (uint32_t)r0 * 128u + (uint32_t)((cu ^ (r0 & 7)) << 4);
-    auto tile_of = [&](int g, int &b, int &k0) {
+    // tile g -> first sample b of its group, rows Eg of the group that exist (the last group may be short), first cell
+    auto tile_of = [&](int g, int &b, int &Eg, int &k0) {
       const int si = g / ntile;
-      b = (int)blockIdx.x + si * (int)gridDim.x;
+      b = ((int)blockIdx.x + si * (int)gridDim.x) * G;
+      Eg = (B - b < G ? B - b : G) * E;
       k0 = (g - si * ntile) * TA_TN;
     };
     auto issue = [&](int g) {
-      int b, k0;
-      tile_of(g, b, k0);
+      int b, Eg, k0;
+      tile_of(g, b, Eg, k0);
       const float *Fb = a.r2 + (size_t)b * E * K;
       const uint32_t st = sStage + (uint32_t)(g % TA_NS) * TA_STAGE + soff;
       const int k = k0 + 4 * cu;
       const float *src = Fb + (size_t)r0 * K + k;
       const size_t gstr = (size_t)TA_RSTEP * K;
+      // rows past the group's last sample (short last group) are zero-filled (src-size 0)
       if (vec) {
         const int nb = k + 4 <= K ? 16 : (k < K ? (K - k) * 4 : 0);
         if (nb == 0) src = Fb;
 #pragma unroll 4
-        for (int j = 0; j < nj; ++j) tc::cp_async16(st + (uint32_t)j * JSTR, nb ? (const void *)(src + j * gstr) : (const void *)Fb, (uint32_t)nb);
+        for (int j = 0; j < nj; ++j) {
+          const bool ok = nb && r0 + j * TA_RSTEP < Eg;
+          tc::cp_async16(st + (uint32_t)j * JSTR, ok ? (const void *)(src + j * gstr) : (const void *)a.r2, ok ? (uint32_t)nb : 0u);
+        }
       } else {
         for (int j = 0; j < nj; ++j)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            tc::cp_async4(st + (uint32_t)j * JSTR + 4u * i, (k + i < K) ? (const void *)(src + j * gstr + i) : (const void *)Fb,
-                          (k + i < K) ? 4u : 0u);
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = k + i < K && r0 + j * TA_RSTEP < Eg;
+            tc::cp_async4(st + (uint32_t)j * JSTR + 4u * i, ok ? (const void *)(src + j * gstr + i) : (const void *)a.r2, ok ? 4u : 0u);
+          }
       }
     };
     auto copy_out = [&](int g) {
       tc::mbar_wait_relaxed(epi_done + 8 * (g % TA_NS), (uint32_t)(g / TA_NS) & 1u);
       if (!writes) return;
-      int b, k0;
-      tile_of(g, b, k0);
+      int b, Eg, k0;
+      tile_of(g, b, Eg, k0);
       const uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE + soff;
       const int k = k0 + 4 * cu;
       if (k >= K) return;
+      const int njw = Eg > r0 ? (Eg - r0 + TA_RSTEP - 1) / TA_RSTEP : 0;   // rows of this thread that exist
       float *dst = a.out + (size_t)b * E * K + (size_t)r0 * K + k;
       const size_t gstr = (size_t)TA_RSTEP * K;
       if (vec) {
-        for (int j0 = 0; j0 < nj; j0 += 4) {
+        for (int j0 = 0; j0 < njw; j0 += 4) {
           float4 v[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (j0 + u < nj) v[u] = *reinterpret_cast<const float4 *>(st + (size_t)(j0 + u) * JSTR);
+            if (j0 + u < njw) v[u] = *reinterpret_cast<const float4 *>(st + (size_t)(j0 + u) * JSTR);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (j0 + u < nj) __stcs(reinterpret_cast<float4 *>(dst + (j0 + u) * gstr), v[u]);
+            if (j0 + u < njw) __stcs(reinterpret_cast<float4 *>(dst + (j0 + u) * gstr), v[u]);
         }
       } else {
-        for (int j = 0; j < nj; ++j) {
+        for (int j = 0; j < njw; ++j) {
           const float4 v = *reinterpret_cast<const float4 *>(st + (size_t)j * JSTR);
           const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -238,8 +255,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         if (t < ntot) issue(t);
         tc::cp_async_commit();
       }
-    int cur_b = -1;
-    unsigned long long zm = 0ull;
+
     for (int g = 0; g < ntot; ++g) {
       if (use_tma) {
         if (threadIdx.x == 0) TA_STAMP(0, g);
@@ -254,9 +270,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         tc::cp_async_wait<TA_PD>();                                   // this thread's chunks of tile g have landed
       }
       if (threadIdx.x == 0) TA_STAMP(1, g);
-      int b, k0;
-      tile_of(g, b, k0);
-      if (b != cur_b) { cur_b = b; zm = zero_mask_of(a.flags + (size_t)b * N, N); }
+      int b, Eg, k0;
+      tile_of(g, b, Eg, k0);
       if (g >= 2) tc::mbar_wait(op_empty + 8 * (g & 1), (uint32_t)(((g >> 1) & 1) ^ 1));
       if (threadIdx.x == 0) TA_STAMP(2, g);
       const uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE + soff;
@@ -276,9 +291,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
             *reinterpret_cast<uint2 *>(op + TA_OPHALF + (size_t)(j0 + u) * JSTR) = lo;
           }
       }
-      if (threadIdx.x < TA_TN) {
-        const int k = k0 + (int)threadIdx.x;
-        fcs[(g % TA_NS) * TA_TN + threadIdx.x] = (k < K && !(P->cell_mask[k] & zm)) ? 1.f : 0.f;
+      for (int t = threadIdx.x; t < G * TA_TN; t += TA_LOAD) {   // cell flags of every sample of the group
+        const int sg = t >> 5, k = k0 + (t & 31);
+        const bool on = b + sg < B && k < K && !(P->cell_mask[k] & a.zmask[b + sg]);
+        fcs[((g % TA_NS) * TA_GMAX + sg) * TA_TN + (t & 31)] = on ? 1.f : 0.f;
       }
       tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(full + 8 * (g & 1));
@@ -292,10 +308,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     // ===================== TMA warp: tensor loads into / tensor stores out of the staging ring =====================
     if (use_tma && lane == 0) {
       const bool writes = MODE != MODE_NORM;
-      const uint32_t tile_bytes = (uint32_t)E * 128u;
+      const uint32_t tile_bytes = (uint32_t)EB * 128u;   // the box is EB rows; rows past the tensor are zero-filled / clipped
       auto coords = [&](int g, int &col, int &row) {
         const int si = g / ntile;
-        row = ((int)blockIdx.x + si * (int)gridDim.x) * E;
+        row = ((int)blockIdx.x + si * (int)gridDim.x) * EB;
         col = (g - si * ntile) * TA_TN;
       };
       auto store = [&](int g) {   // tile g is final in its stage once every epilogue thread arrived (after a proxy fence)
@@ -365,13 +381,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     // The edge row whose ENTRIES this thread processes, and its 16 cells of every tile.  M tile 0 holds
     // edges 0..127 on lanes 0..127.  M tile 1 holds edge 128 + 16 q + l on lane 32 q + l for l < 16 (every
     // lane quarter carries the same load); there lane l >= 16 processes cells 16-31 of lane (l - 16)'s row.
-    int e, chalf;
-    if (role < 2) { e = q * 32 + lane; chalf = role; }
-    else { e = 128 + q * 16 + (lane & 15); chalf = lane >> 4; }
-    if (e >= E) e = -1;
-    // the A-operand row (TMEM lane 32 q + lane) this thread FILLS with H: the same edge, except that the
+    int er, chalf;   // edge ROW of the group (sample-in-group * E + edge), cell half
+    if (role < 2) { er = q * 32 + lane; chalf = role; }
+    else { er = 128 + q * 16 + (lane & 15); chalf = lane >> 4; }
+    if (er >= EB) er = -1;
+    const int sg = er >= 0 ? er / E : 0;          // sample within the group
+    const int e = er >= 0 ? er - sg * E : -1;     // edge of that sample
+    // the A-operand row (TMEM lane 32 q + lane) this thread FILLS with H: the same row, except that the
     // upper lanes of M tile 1 hold no edge (zero rows)
-    const int efill = (role == 2 && lane >= 16) ? -1 : e;
+    const bool fills = er >= 0 && !(role == 2 && lane >= 16);
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int ei = e >= 0 ? P->edge_ij[2 * e] : 0, ej = e >= 0 ? P->edge_ij[2 * e + 1] : 0;
     R2Fold w;
@@ -388,32 +406,47 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     }
     const uint32_t did = draw_id(2, a.nz.step, a.slot);
     for (int si = 0; si < nmine; ++si) {
-      const int b = (int)blockIdx.x + si * (int)gridDim.x;
-      const float *fl = a.flags + (size_t)b * N;
+      const int b0 = ((int)blockIdx.x + si * (int)gridDim.x) * G;   // first sample of the group
+      const int gsz = B - b0 < G ? B - b0 : G;
+      const int b = b0 + sg;                                         // this thread's sample
+      const bool live = er >= 0 && sg < gsz;
+      const float *fl = a.flags + (size_t)(live ? b : b0) * N;
       R2Epi c;
       c.P = P; c.fl = fl; c.fw = fw; c.zm = 0ull;
       c.gs = (unsigned long long)(a.nz.sample_offset + b);
       c.b = b; c.E = E; c.K = K; c.Kg = Kg; c.f_nlin = P->f_nlin;
-      const float fe = e >= 0 ? fl[ei] * fl[ej] : 0.f;
+      const float fe = live ? fl[ei] * fl[ej] : 0.f;
       const bool side = MODE == MODE_PRED && (a.write_mean || (a.traj != nullptr && b == 0));
       // ---- H of this sample -> TMEM (A operand).  Every MMA of the previous sample has completed: this
       // warp waited on t_full of its last tile. ----
       if (mt < mtiles) {
-        const float *Hrow = a.H + ((size_t)b * E + (efill >= 0 ? efill : 0)) * Ep;
+        // row er of the block-diagonal operand: H of the row's sample in columns [sg E, sg E + E), zeros elsewhere
+        const bool frow = fills && sg < gsz;
+        const float *Hrow = a.H + ((size_t)(frow ? b : b0) * E + (frow ? e : 0)) * Ep;
+        const int c_lo = sg * E;
         // roles 0 / 1 share the rows of M tile 0 (e' halves); role 2 fills both halves of M tile 1
         const int h0 = role == 2 ? 0 : role, h1 = role == 2 ? 2 : role + 1;
         for (int c16 = h0 * 3; c16 < h1 * 3; ++c16) {
-          const int kb = c16 * 32;                       // first e' of this 32-element (16-column) group
+          const int kb = c16 * 32;                       // first e' column of this 32-element (16-column) group
           uint32_t hw[16], lw[16];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int k = kb + 4 * j4;
-            if (efill >= 0 && k < Ep) v = __ldg(reinterpret_cast<const float4 *>(Hrow + k));
-            if (k + 0 >= E) v.x = 0.f;
-            if (k + 1 >= E) v.y = 0.f;
-            if (k + 2 >= E) v.z = 0.f;
-            if (k + 3 >= E) v.w = 0.f;
+            const int k = kb + 4 * j4 - c_lo;             // column inside the sample's own H
+            if (frow) {
+              if (G == 1) {
+                if (k < Ep) v = __ldg(reinterpret_cast<const float4 *>(Hrow + k));
+                if (k + 0 >= E) v.x = 0.f;
+                if (k + 1 >= E) v.y = 0.f;
+                if (k + 2 >= E) v.z = 0.f;
+                if (k + 3 >= E) v.w = 0.f;
+              } else {
+                if (k + 0 >= 0 && k + 0 < E) v.x = __ldg(Hrow + k + 0);
+                if (k + 1 >= 0 && k + 1 < E) v.y = __ldg(Hrow + k + 1);
+                if (k + 2 >= 0 && k + 2 < E) v.z = __ldg(Hrow + k + 2);
+                if (k + 3 >= 0 && k + 3 < E) v.w = __ldg(Hrow + k + 3);
+              }
+            }
             uint2 hi, lo;
             tc::split4(v, hi, lo);
             hw[2 * j4] = hi.x; hw[2 * j4 + 1] = hi.y;
@@ -429,7 +462,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       tc::mbar_arrive(h_ready);
 
       float s2 = 0.f, z2 = 0.f;
-      const float *Nb = a.noise ? a.noise + (size_t)b * E * K : nullptr;
+      const float *Nb = a.noise ? a.noise + (size_t)(live ? b : b0) * E * K : nullptr;
       for (int ct = 0; ct < ntile; ++ct) {
         const int g = si * ntile + ct;
         const int slot = g & 1, stg = g % TA_NS;
@@ -456,15 +489,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         tc::tc_fence_before_sync();
         tc::mbar_arrive(d_empty + 8 * slot);                          // accumulator slot may be overwritten
         if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 8 : 12, g);
-        if (e >= 0) {
-          uint8_t *row = gen + TA_OPER + (size_t)stg * TA_STAGE + (size_t)e * 128;
-          const float *fcp = fcs + stg * TA_TN + chalf * 16;
+        if (live) {
+          uint8_t *row = gen + TA_OPER + (size_t)stg * TA_STAGE + (size_t)er * 128;
+          const float *fcp = fcs + (stg * TA_GMAX + sg) * TA_TN + chalf * 16;
           const int kbase = ct * TA_TN + chalf * 16;
           const bool inside = kbase + 16 <= K;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const int k = kbase + 4 * c4;
-            float4 *cell = reinterpret_cast<float4 *>(row + (((chalf * 4 + c4) ^ (e & 7)) << 4));
+            float4 *cell = reinterpret_cast<float4 *>(row + (((chalf * 4 + c4) ^ (er & 7)) << 4));
             const float4 f4 = *cell;
             const float4 fc4 = *reinterpret_cast<const float4 *>(fcp + 4 * c4);   // 0 for cells >= K
             const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
@@ -499,18 +532,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 9 : 13, g);
       }
       if (MODE == MODE_SCORE || MODE == MODE_NORM) {
-        // per-sample squared norms: reduce over the 12 epilogue warps (named barrier 1, 384 threads)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          z2 += __shfl_xor_sync(0xffffffffu, z2, o);
-        }
-        if (lane == 0) { red[ew] = s2; red[16 + ew] = z2; }
+        // per-sample squared norms: every (cell half, row) partial goes to shared memory, then one thread per
+        // sample of the group sums its rows in a fixed order (bit-reproducible); named barrier 1, 384 threads
+        if (er >= 0) { red[(chalf * TA_NE + er) * 2] = live ? s2 : 0.f; red[(chalf * TA_NE + er) * 2 + 1] = live ? z2 : 0.f; }
         asm volatile("bar.sync 1, 384;" ::: "memory");
-        if (et == 0) {
+        if (et < gsz) {
           float ts = 0.f, tz = 0.f;
-          for (int wv = 0; wv < 12; ++wv) { ts += red[wv]; tz += red[16 + wv]; }
-          float *np = a.norm_part + ((size_t)(2 * d.B + b) * P->ntile_max) * 2;
+          for (int h = 0; h < 2; ++h)
+            for (int r = et * E; r < et * E + E; ++r) { ts += red[(h * TA_NE + r) * 2]; tz += red[(h * TA_NE + r) * 2 + 1]; }
+          float *np = a.norm_part + ((size_t)(2 * d.B + b0 + et) * P->ntile_max) * 2;
           np[0] = ts; np[1] = tz;
           for (int t = 1; t < P->ntile_r2; ++t) { np[2 * t] = 0.f; np[2 * t + 1] = 0.f; }
         }
@@ -553,8 +583,8 @@ static inline int tc_apply_launch_f(const DevPlan *dP, int grid, const ApplyArgs
 
 // 2-D tensor map of a [B*E rows][K cols] fp32 tensor with a box of E rows x 32 columns, SWIZZLE_128B.
 // Returns 0 on success; fails (-> cp.async path) when the pitch or the base is not 16-byte aligned.
-static inline int tc_apply_make_map(CUtensorMap *m, const float *base, int B, int E, int K) {
-  if ((K & 3) || (reinterpret_cast<uintptr_t>(base) & 15) || E > 256) return -1;
+static inline int tc_apply_make_map(CUtensorMap *m, const float *base, int B, int E, int K, int box_rows) {
+  if ((K & 3) || (reinterpret_cast<uintptr_t>(base) & 15) || box_rows > 256) return -1;
   typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -567,7 +597,7 @@ static inline int tc_apply_make_map(CUtensorMap *m, const float *base, int B, in
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)B * E};
   const cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)TA_TN, (cuuint32_t)E};
+  const cuuint32_t box[2] = {(cuuint32_t)TA_TN, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
@@ -577,13 +607,15 @@ static inline int tc_apply_make_map(CUtensorMap *m, const float *base, int B, in
 static inline int tc_apply_prepare() { return 0; }   // attributes are set per instantiation at first launch
 
 static inline int tc_apply_launch(const DevPlan *dP, const DevPlan &hp, const ApplyArgs &a, void *stream) {
-  const int grid = hp.d.B < 148 ? hp.d.B : 148;
+  const int ngroups = (hp.d.B + hp.ap_group - 1) / hp.ap_group;
+  const int grid = ngroups < 148 ? ngroups : 148;
+  const int box_rows = hp.ap_group * hp.d.E;
   TcApplyMaps m;
   memset(&m, 0, sizeof m);
   m.use_tma = 0;
   static const bool no_tma = getenv("CCSD_B200_NO_TMA") != nullptr;   // A/B switch for tests and profiling
-  if (!no_tma && tc_apply_make_map(&m.in, a.r2, hp.d.B, hp.d.E, hp.d.K) == 0 &&
-      (a.mode == MODE_NORM || tc_apply_make_map(&m.out, a.out, hp.d.B, hp.d.E, hp.d.K) == 0))
+  if (!no_tma && tc_apply_make_map(&m.in, a.r2, hp.d.B, hp.d.E, hp.d.K, box_rows) == 0 &&
+      (a.mode == MODE_NORM || tc_apply_make_map(&m.out, a.out, hp.d.B, hp.d.E, hp.d.K, box_rows) == 0))
     m.use_tma = 1;
   if (a.mode == MODE_NORM) m.out = m.in;
   if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, m, stream);
