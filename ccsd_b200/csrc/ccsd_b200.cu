@@ -376,8 +376,23 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->n_weights = n_weights;
   p->sched.assign(schedule_host, schedule_host + (size_t)d.n_diff_steps * 3);
   const bool hodge = d.is_cc && (d.nets & 2) && d.neta.is_cc;
-  p->hp.PR0 = hodge ? d.neta.n_proj_rows[0] : 0;
+  p->hp.PR0h = hodge ? d.neta.n_proj_rows[0] : 0;
+  p->hp.PR0 = p->hp.PR0h;
   p->hp.PR1 = (hodge && d.neta.num_layers_h == 2) ? d.neta.n_proj_rows[1] : 0;
+  p->hp.p1_fold = 0;
+  if (p->hp.PR1 > 0 && d.neta.hodge[0].mlp_value.nl == 1 && d.neta.hodge[0].mlp_value.dout == 1 &&
+      p->hp.PR0h + p->hp.PR1 <= 64) {
+    // the second hodge layer's projections become extra Gram columns (xa_pipe.cuh, hodge_kernel)
+    p->hp.p1_fold = 1;
+    p->hp.PR0 = p->hp.PR0h + p->hp.PR1;
+    p->hp.PR1 = 0;
+  }
+  if (p->hp.p1_fold) {   // shared memory of hodge_kernel for the folded projections
+    XpLayout &XL2 = p->hp.xp;
+    const int n1 = d.neta.n_proj_rows[1];
+    XL2.h_p1 = XL2.h_total; XL2.h_total += a4(d.E * n1);
+    XL2.h_u = XL2.h_total; XL2.h_total += a4(n1);
+  }
   p->hp.Kp = a4(d.K);
   p->hp.Ep = a4(d.E);
   p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
@@ -582,6 +597,16 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     const float *t = xout; xout = (float *)xin; xin = t;
   }
   int fd_have = ch_out;
+  if (A.is_cc && p->hp.PR1 > 0) {
+    // projections of hodge layer 1 (value MLP with a non-linearity: not foldable into the Gram product)
+    Proj1Args q; q.r2 = a.r2; q.flags = a.flags; q.g_stack = p->g_stack; q.g_stack_stride = L.g_stack; q.ldp = L.ldp;
+    q.P1 = p->P1;
+    q.epc = imax(1, imin(8, (48 * 1024) / (p->hp.Kp * 4)));
+    PROF_BEGIN(p, "proj1_kernel", stream);
+    CCSD_LAUNCH(proj1_kernel, dim3((d.E + q.epc - 1) / q.epc, d.B, 1), 128, (size_t)q.epc * p->hp.Kp * 4, stream, p->dP, q);
+    PROF_END(p, stream);
+    p->launches++;
+  }
   if (A.is_cc) {
     a.ch_in = ch_out;   // first hodge channel
     PROF_BEGIN(p, "hodge_kernel", stream);
@@ -628,13 +653,6 @@ static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, con
     PROF_END(p, stream);
     p->launches++;
   }
-  if (p->hp.PR1 > 0) {
-    Proj1Args q; q.r2 = r2; q.adj = adj; q.flags = flags; q.P1 = p->P1;
-    PROF_BEGIN(p, "proj1_kernel", stream);
-    CCSD_LAUNCH(proj1_kernel, dim3(d.E, d.B, 1), 128, (2 * 64 + 16 + p->hp.Kp + 4) * 4, stream, p->dP, q);
-    PROF_END(p, stream);
-    p->launches++;
-  }
   return dev_check("rank2 pre-pass");
 }
 
@@ -671,7 +689,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     if (d.is_cc)
       if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
     XaArgs a; memset(&a, 0, sizeof a);
-    a.x = p->x; a.adj = p->adj; a.flags = p->flags; a.P0 = p->P0; a.P1 = p->P1;
+    a.x = p->x; a.adj = p->adj; a.flags = p->flags; a.P0 = p->P0; a.P1 = p->P1; a.r2 = p->r2;
     a.mode = mode; a.which = 3; a.slot = slot; a.denoise = d.denoise; a.nz = nz;
     a.norm_part = p->norm_part;
     a.noise_x = nx ? nx + (size_t)slot * sx : nullptr;
@@ -755,7 +773,7 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
     if (which == CCSD_NET_ADJ && d.is_cc)
       if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
     XaArgs a; memset(&a, 0, sizeof a);
-    a.x = x; a.adj = adj; a.flags = flags; a.P0 = p->P0; a.P1 = p->P1; a.mode = MODE_EVAL;
+    a.x = x; a.adj = adj; a.flags = flags; a.P0 = p->P0; a.P1 = p->P1; a.r2 = r2; a.mode = MODE_EVAL;
     a.which = which == CCSD_NET_X ? 1 : 2;
     a.out_x = out; a.out_adj = out;
     return launch_xa(p, a, stream);
@@ -797,6 +815,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
     case 4: return p->use_tc_apply;
     case 5: return p->hp.f_mode;
     case 6: return p->hp.xp.m_rows;
+    case 12: return p->hp.PR0;
     case 7: return p->hp.xp.x_total * 4;
     case 8: return p->hp.xp.c_total * 4;
     case 9: return p->hp.xp.f_total * 4;

@@ -25,7 +25,7 @@ struct XpLayout {
   // attn_finish_kernel
   int f_flags, f_hs, f_hs2 /*[mc_hid x N4]*/, f_eha, f_ehb /*[hid x ldp]*/, f_total;
   // hodge_kernel (two hodge layers: hq, hk [c0 x E x ad0], h1 [c1 x E x lde], hdeg [c1 x E])
-  int h_flags, h_hq, h_hk, h_h1, lde, h_hdeg, h_total;
+  int h_flags, h_hq, h_hk, h_h1, lde, h_hdeg, h_p1 /*[E x n1] folded projections*/, h_u /*[n1]*/, h_total;
   // afinal_kernel
   int m_flags, m_fa, m_fb /*[dhid x m_rows]*/, m_out /*[m_rows]*/, m_red, m_rows, m_nchunk, m_total;
   // global scratch, floats per graph
@@ -44,7 +44,10 @@ struct DevPlan {
   const unsigned long long *cell_mask;  // [K] bit n set <=> node n in cell
   const int *edge_ij;             // [E][2]
   const int *tri_ij;              // [N(N+1)/2] (i << 8) | j of every node pair i <= j, row-major upper triangle
-  int PR0, PR1;                   // projection rows of hodge layer 0 / 1
+  int PR0, PR1;                   // columns of the Gram projection output P0 (row pitch) / of the P1 buffer
+  int PR0h;                       // projection rows of hodge layer 0 proper (P0 columns [0, PR0h))
+  int p1_fold;                    // hodge layer 0's value MLP is one Linear: its layer-1 projections are Gram
+                                  // columns [PR0h, PR0) of F itself, rescaled per edge inside hodge_kernel
   int Kp;                         // K rounded up to 4 (Philox groups per rank-2 row = Kp/4)
   int Ep;                         // E rounded up to 4: row pitch of the H buffer [B][E][Ep]
   int ntile_r2;                   // apply-kernel column tiles per sample

@@ -121,54 +121,44 @@ __global__ void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P
 
 // ---------------------------------------------------------------------------------------------
 struct Proj1Args {
-  const float *r2, *adj, *flags;  // [B,E,K] [B,N,N] [B,N]
+  const float *r2, *flags;        // [B,E,K] [B,N]
+  const float *g_stack;           // channel stack of the x/adj pipeline: channels [0, c_init) = adjacency powers (tri storage)
+  int g_stack_stride, ldp;
   float *P1;                      // [B,E,PR1]
+  int epc;                        // edges per CTA
 };
 
+// One CTA per (block of `epc` edges, sample): the value output rank2' of hodge layer 0 for those edge rows
+// (an element-wise function of F, see the file header) goes to shared memory, then every warp takes
+// projection rows r and accumulates the epc dot products with ONE pass over the weight row, so the weights
+// (PR1 x K floats, shared by all CTAs through L2) are read once per edge block instead of once per edge.
 __global__ void __launch_bounds__(128) proj1_kernel(const DevPlan *__restrict__ P, Proj1Args a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const ccsd_neta_t &A = d.neta;
-  const int N = d.N, E = d.E, K = d.K, PR0 = P->PR0, PR1 = P->PR1, Kw = P->Kp;
-  const int e = blockIdx.x, b = blockIdx.y;
-  const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
-  const float *adj = a.adj + (size_t)b * N * N;
+  const int N = d.N, E = d.E, K = d.K, PR0 = P->PR0h, PR1 = P->PR1, Kw = P->Kp;
+  const int e0 = blockIdx.x * a.epc, b = blockIdx.y;
+  const int ne = (E - e0 < a.epc) ? E - e0 : a.epc;
   const float *fl = a.flags + (size_t)b * N;
-  float *vrow = sm;            // [2][N] ping-pong: row i of A^c
-  float *ac = sm + 2 * 64;     // [c0]
-  float *r2v = sm + 2 * 64 + 16;  // [Kw]
+  const float *stack = a.g_stack + (size_t)b * a.g_stack_stride;
+  float *r2v = sm;                 // [epc][Kw]
   const int c0 = A.c_init;
-  // a_c[e] = (A^c)[i][j]
-  for (int n = threadIdx.x; n < N; n += blockDim.x) vrow[n] = adj[i * N + n];
-  __syncthreads();
-  if (threadIdx.x == 0) ac[0] = vrow[j];
-  for (int c = 1; c < c0; ++c) {
-    const float *src = vrow + ((c - 1) & 1) * 64;
-    float *dst = vrow + (c & 1) * 64;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-      float s = 0.f;
-      for (int k = 0; k < N; ++k) s += src[k] * adj[k * N + n];
-      dst[n] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) ac[c] = dst[j];
-  }
-  __syncthreads();
   const unsigned long long zm = zero_mask_of(fl, N);
-  const float fe = fl[i] * fl[j];
-  const float *Fr = a.r2 + ((size_t)b * E + e) * K;
   const ccsd_hodge_layer_t &h0 = A.hodge[0];
-  for (int k = threadIdx.x; k < Kw; k += blockDim.x) {
+  for (int p = threadIdx.x; p < ne * Kw; p += blockDim.x) {
+    const int le = p / Kw, k = p - le * Kw, e = e0 + le;
     float v = 0.f;
     if (k < K) {
+      const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+      const int t = i * N - (i * (i - 1)) / 2 + (j - i);   // tri index, i < j
       float in[CCSD_MAX_CH], out[SMALL_MAX];
-      const float f = Fr[k];
-      for (int c = 0; c < c0; ++c) in[c] = ac[c] * f;  // V_c = diag(a_c) rank2  (hodge_attention.py:107)
+      const float f = a.r2[((size_t)b * E + e) * K + k];
+      for (int c = 0; c < c0; ++c) in[c] = stack[c * a.ldp + t] * f;  // V_c = diag(a_c) rank2  (hodge_attention.py:107)
       small_mlp(h0.mlp_value, P->W, in, out, ACT_ELU);
       const float fc = (P->cell_mask[k] & zm) ? 0.f : 1.f;
-      v = out[0] * fe * fc;  // mask_rank2 (hodge_attention.py:323)
+      v = out[0] * fl[i] * fl[j] * fc;  // mask_rank2 (hodge_attention.py:323)
     }
-    r2v[k] = v;
+    r2v[p] = v;
   }
   __syncthreads();
 #ifdef CCSD_EMU
@@ -178,13 +168,21 @@ __global__ void __launch_bounds__(128) proj1_kernel(const DevPlan *__restrict__ 
 #endif
   const float *Wp = P->W + A.proj_w + (size_t)PR0 * Kw;  // rows of hodge layer 1
   for (int r = warp; r < PR1; r += nwarp) {
-    float s = 0.f;
-    for (int k = lane; k < K; k += nlane) s += r2v[k] * __ldg(Wp + (size_t)r * Kw + k);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < K; k += nlane) {
+      const float w = __ldg(Wp + (size_t)r * Kw + k);
+#pragma unroll
+      for (int le = 0; le < 8; ++le)
+        if (le < ne) s[le] += r2v[le * Kw + k] * w;
+    }
+#pragma unroll
+    for (int le = 0; le < 8; ++le) {
 #ifndef CCSD_EMU
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      for (int o = 16; o > 0; o >>= 1) s[le] += __shfl_xor_sync(0xffffffffu, s[le], o);
 #endif
-    if (lane == 0) a.P1[((size_t)b * E + e) * PR1 + r] = s;
+      if (lane == 0 && le < ne) a.P1[((size_t)b * E + e0 + le) * PR1 + r] = s[le];
+    }
   }
 }
 

@@ -42,7 +42,7 @@ static inline int tc_gram_wp0(int E) { return (E + 7) & ~7; }
 static inline int tc_gram_ncols(int E, int PR0) { return (tc_gram_wp0(E) + PR0 + 15) & ~15; }
 static inline int tc_gram_supported(int E, int K, int PR0) {
   (void)K;
-  return E >= 8 && E <= 192 && PR0 <= 32 && tc_gram_ncols(E, PR0) <= 256;
+  return E >= 8 && E <= 192 && PR0 <= 64 && tc_gram_ncols(E, PR0) <= 256;
 }
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *__restrict__ P, TcGramArgs a) {

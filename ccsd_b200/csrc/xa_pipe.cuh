@@ -44,6 +44,7 @@ namespace ccsd {
 struct XaArgs {
   const float *x, *adj, *flags;  // [B,N,F] [B,N,N] [B,N]
   const float *P0, *P1;          // hodge projections [B,E,PR0] [B,E,PR1] (CC only)
+  const float *r2;               // rank-2 state [B,E,K] (CC only: proj1_kernel reads it)
   int mode;                      // MODE_EVAL / MODE_SCORE / MODE_PRED
   int which;                     // bit0: evaluate X net, bit1: evaluate A net
   float *out_x, *out_adj;        // EVAL: raw net output; SCORE: scaled score; PRED: new state
@@ -397,9 +398,39 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
 
   // ---- two hodge layers ----
   const ccsd_hodge_layer_t &h1 = A.hodge[1];
-  const int c1 = h0.c_out, ad1 = h1.attn_dim, PR1 = P->PR1, lde = L.lde;
+  const int c1 = h0.c_out, ad1 = h1.attn_dim, lde = L.lde;
   float *hq = sm + L.h_hq, *hk = sm + L.h_hk, *H1 = sm + L.h_h1, *hdeg = sm + L.h_hdeg;
+  int PR1 = P->PR1;
   const float *P1 = a.P1 + (size_t)b * E * PR1;
+  if (P->p1_fold) {
+    // Layer 0's value MLP is one Linear, so its output is rank2' = mask (alpha_e F + beta) with
+    // alpha_e = sum_c w_c (A^c)_ij, and the layer-1 projections are
+    //   P1[e, r] = alpha_e (F Wp1^T)[e, r] + beta fe_e u[r],   u[r] = sum_k fc_k Wp1[r, k]
+    // where F Wp1^T are Gram columns [PR0h, PR0) of P0 (F is masked, so fe fc F = F).
+    PR1 = A.n_proj_rows[1];
+    float *p1s = sm + L.h_p1, *u = sm + L.h_u;
+    const int Kw = P->Kp, K = d.K;
+    const unsigned long long zm = zero_mask_of(flags, N);
+    const float *Wp = W + A.proj_w + (size_t)P->PR0h * Kw;
+    for (int r = threadIdx.x; r < PR1; r += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k)
+        if (!(P->cell_mask[k] & zm)) s += __ldg(Wp + (size_t)r * Kw + k);
+      u[r] = s;
+    }
+    __syncthreads();
+    const ccsd_mlp_t &mv = h0.mlp_value;
+    const float beta = __ldg(W + mv.b[0]);
+    for (int p = threadIdx.x; p < E * PR1; p += blockDim.x) {
+      const int e = p / PR1, r = p - e * PR1;
+      const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+      float alpha = 0.f;
+      for (int c = 0; c < c0; ++c) alpha += __ldg(W + mv.w[0] + c * 8) * stack[c * ldp + tri_index(i, j, N)];
+      p1s[p] = alpha * P0[(size_t)e * PR0 + P->PR0h + r] + beta * flags[i] * flags[j] * u[r];
+    }
+    __syncthreads();
+    P1 = p1s;
+  }
   // layer-0 Q, K for every edge and channel
   for (int p = threadIdx.x; p < c0 * E; p += blockDim.x) {
     const int c = p / E, e = p - c * E;

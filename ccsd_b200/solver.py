@@ -210,7 +210,7 @@ class Engine:
         """(H, P0) of `rank2` through the fp32 FMA or the tcgen05 Gram kernel (test seam)."""
         d = self.desc
         r2 = self._dev(rank2)
-        pr0 = d.neta.n_proj_rows[0] if (d.nets & 2 and d.neta.is_cc) else 0
+        pr0 = int(self.lib.ccsd_plan_info(self.handle, 12))   # Gram projection columns (hodge layer 0 [+ folded layer 1])
         H = torch.empty(d.B, d.E, d.E, dtype=torch.float32, device=self.device)
         P0 = torch.empty(d.B, d.E, max(pr0, 1), dtype=torch.float32, device=self.device)
         nat.check(self.lib.ccsd_debug_gram(self.handle, _ptr(r2), _ptr(H), _ptr(P0) if pr0 else None, int(use_tc),
