@@ -402,15 +402,16 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.ap_group = d.is_cc ? imax(1, imin(8, 192 / imax(d.E, 1))) : 1;
   if (d.is_cc && (d.nets & 4)) {
     const ccsd_netf_t &Fn = d.netf;
-    bool w8 = Fn.fin.nl == 1 && Fn.fdim <= 40;
+    bool w8 = Fn.fin.nl == 1 && Fn.fdim <= 40, w4 = true;
     int nlin = 0;
     for (int l = 0; l < Fn.num_layers; ++l) {
       const ccsd_mlp_t &M = Fn.layer[l];
       if (M.din > 8 || M.dout > 8 || (M.nl > 1 && M.dhid > 8)) w8 = false;
+      if (M.din > 4 || M.dout > 4 || (M.nl > 1 && M.dhid > 4)) w4 = false;
       nlin += M.nl;
     }
     if (Fn.affine) p->hp.f_mode = 1;
-    else if (w8) { p->hp.f_mode = 2; p->hp.f_nlin = nlin; }
+    else if (w8) { p->hp.f_mode = w4 ? 3 : 2; p->hp.f_nlin = nlin; }   // 3: four entries at a time (tensor-core apply kernel)
   }
   p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)p->hp.f_nlin * 72 + 48) * 4 : 0;
   const XpLayout &XL = p->hp.xp;
@@ -603,7 +604,7 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     q.P1 = p->P1;
     q.epc = imax(1, imin(8, (48 * 1024) / (p->hp.Kp * 4)));
     PROF_BEGIN(p, "proj1_kernel", stream);
-    CCSD_LAUNCH(proj1_kernel, dim3((d.E + q.epc - 1) / q.epc, d.B, 1), 128, (size_t)q.epc * p->hp.Kp * 4, stream, p->dP, q);
+    CCSD_LAUNCH(proj1_kernel, dim3((d.E + q.epc - 1) / q.epc, d.B, 1), 128, ((size_t)q.epc * p->hp.Kp + 2 * 72 + 8) * 4, stream, p->dP, q);
     PROF_END(p, stream);
     p->launches++;
   }
@@ -629,7 +630,7 @@ static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
 #endif
   const dim3 grid(p->hp.ntile_r2, p->hp.d.B, 1);
   if (p->hp.f_mode == 1) CCSD_LAUNCH(apply_kernel<1>, grid, 256, p->apply_smem, stream, p->dP, q);
-  else if (p->hp.f_mode == 2) CCSD_LAUNCH(apply_kernel<2>, grid, 256, p->apply_smem, stream, p->dP, q);
+  else if (p->hp.f_mode >= 2) CCSD_LAUNCH(apply_kernel<2>, grid, 256, p->apply_smem, stream, p->dP, q);
   else CCSD_LAUNCH(apply_kernel<0>, grid, 256, p->apply_smem, stream, p->dP, q);
 }
 

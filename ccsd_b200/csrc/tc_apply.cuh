@@ -85,14 +85,15 @@ struct R2Fold {
 // the entry in the staging tile (raw output, scaled score or new state).
 template <int FMODE, int MODE>
 __device__ __forceinline__ float r2_entry(const R2Epi &c, const R2Fold &w, float f, float hf, float zraw, float m,
-                                          float &s2, float &z2, float &mu_out) {
+                                          float &s2, float &z2, float &mu_out, float o_pre) {
   const DevPlan *P = c.P;
   float s;
   if (FMODE == 1) {
     s = m * (w.k0 * f + w.k1 * hf + w.k2);     // MODE_EVAL: the fold uses sc = 1
   } else {
     float o;
-    if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf, m);
+    if (FMODE == 3) o = o_pre;                 // network evaluated four entries at a time by the caller
+    else if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf, m);
     else o = netf_entry(P->d.netf, P->W, f, hf, m);
     s = w.sc * o;
   }
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     tc::mbar_fence_init();
   }
   if (warp == TA_MMAW) tc::tmem_alloc(tslot, 512);
-  if (FMODE == 2) netf_stage_w8(d.netf, P->W, fw);
+  if (FMODE == 2 || FMODE == 3) netf_stage_w8(d.netf, P->W, fw);
   // operand rows that no edge fills stay zero for the whole kernel (their A columns are zero too, but
   // 0 * NaN from uninitialised shared memory would poison the accumulator)
   for (uint32_t o = threadIdx.x * 16u; o < TA_OPER; o += TA_THREADS * 16u)
@@ -512,10 +513,11 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
                 normal4(a.nz.seed, c.gs, did, (uint32_t)(e * Kg + (k >> 2)), z4);
               }
             }
-            float o4[4], mu4[4];
+            float o4[4], mu4[4], pre[4] = {0.f, 0.f, 0.f, 0.f};
+            if (FMODE == 3) netf_entry_w4x4(d.netf, fw, c.f_nlin, fv, v + 4 * c4, mv, pre);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              o4[i] = r2_entry<FMODE, MODE>(c, w, fv[i], v[4 * c4 + i], z4[i], mv[i], s2, z2, mu4[i]);
+              o4[i] = r2_entry<FMODE, MODE>(c, w, fv[i], v[4 * c4 + i], z4[i], mv[i], s2, z2, mu4[i], pre[i]);
             if (MODE != MODE_NORM) *cell = make_float4(o4[0], o4[1], o4[2], o4[3]);
             if (MODE == MODE_PRED && side) {
 #pragma unroll
@@ -620,6 +622,7 @@ static inline int tc_apply_launch(const DevPlan *dP, const DevPlan &hp, const Ap
   if (a.mode == MODE_NORM) m.out = m.in;
   if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, m, stream);
   if (hp.f_mode == 2) return tc_apply_launch_f<2>(dP, grid, a, m, stream);
+  if (hp.f_mode == 3) return tc_apply_launch_f<3>(dP, grid, a, m, stream);
   return tc_apply_launch_f<0>(dP, grid, a, m, stream);
 }
 

@@ -197,7 +197,7 @@ int64_t ccsd_plan_launch_count(const ccsd_plan_t *plan);
 
 /* Introspection for tests / DESIGN.md tables: what = 0 xa-kernel dynamic shared memory (bytes), 1 xa-kernel
  * threads per CTA, 2 fp32 apply-kernel shared memory, 3 / 4 whether the tcgen05 Gram / apply kernels are
- * selected, 5 ScoreNetworkF entry path (0 generic, 1 affine fold, 2 <= 8-wide unrolled), 6 final-MLP row chunk. */
+ * selected, 5 ScoreNetworkF entry path (0 generic, 1 affine fold, 2 <= 8-wide unrolled, 3 <= 4-wide, four entries at a time), 6 final-MLP row chunk. */
 int ccsd_plan_info(const ccsd_plan_t *plan, int what);
 
 /* Per-kernel device timing for bench.py's roofline: when on, every launch of ccsd_plan_step /
