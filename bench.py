@@ -391,7 +391,7 @@ def main():
             src = "fallback (B200_PROFILING.md)"
         work = kernel_alg_work(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
         peak_hbm = peaks.get("hbm_gbs", 6650.0)
-        XA = ("x_net_kernel", "attn_channel_kernel", "attn_finish_kernel", "hodge_kernel", "afinal_kernel")
+        XA = ("x_net_kernel", "attn_channel_kernel", "attn_finish_kernel", "proj1_kernel", "hodge_kernel", "afinal_kernel", "tc_afinal_kernel")
         kern = {}
         for k_, v in prof_summary.items():
             ms_l = v[0] / v[1]

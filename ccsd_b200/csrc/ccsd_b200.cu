@@ -20,6 +20,7 @@
 #ifndef CCSD_EMU
 #include "tc_gram.cuh"
 #include "tc_apply.cuh"
+#include "tc_afinal.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -78,7 +79,7 @@ struct ccsd_plan {
   long long sample_offset = 0;
   size_t apply_smem = 0;
   int64_t launches = 0;
-  int use_tc = 0, use_tc_apply = 0;
+  int use_tc = 0, use_tc_apply = 0, use_tc_fin = 0;
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
   struct ProfRec { const char *name; void *e0, *e1; };
@@ -483,7 +484,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
   p->use_tc_apply = (d.is_cc && (d.nets & 4)) ? tc_apply_supported(d.E, d.K) : 0;
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = 0;  // A/B switch for tests and profiling
+  p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = 0;  // A/B switch for tests and profiling
+  if (p->use_tc_fin) p->hp.ntile_adj = (p->hp.xp.NT + 127) / 128;   // norm partial slots = 128-row tiles per graph
   if (p->use_tc_apply) {
     if (int r = tc_apply_prepare()) { delete p; return fail(CCSD_ERR_CUDA, "tc_apply_prepare failed"); }
   }
@@ -617,6 +620,15 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     fd_have += A.c_init + A.hodge[0].c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
   }
   a.ch_out = fd_have;   // channels the final MLP reads
+#ifndef CCSD_EMU
+  if (p->use_tc_fin) {
+    PROF_BEGIN(p, "tc_afinal_kernel", stream);
+    if (tc_afinal_launch(p->dP, p->hp, a, fd_have, stream)) return fail(CCSD_ERR_CUDA, "tc_afinal launch failed");
+    PROF_END(p, stream);
+    p->launches++;
+    return dev_check("x/adj network pipeline");
+  }
+#endif
   PROF_BEGIN(p, "afinal_kernel", stream);
   CCSD_LAUNCH(afinal_kernel, dim3(L.m_nchunk, d.B, 1), L.Tm, (size_t)L.m_total * 4, stream, p->dP, a);
   PROF_END(p, stream);
@@ -817,6 +829,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
     case 5: return p->hp.f_mode;
     case 6: return p->hp.xp.m_rows;
     case 12: return p->hp.PR0;
+    case 13: return p->use_tc_fin;
     case 7: return p->hp.xp.x_total * 4;
     case 8: return p->hp.xp.c_total * 4;
     case 9: return p->hp.xp.f_total * 4;

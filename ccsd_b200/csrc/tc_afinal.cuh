@@ -1,0 +1,302 @@
+// tc_afinal.cuh -- final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) as a fused tcgen05 MLP,
+// plus the adjacency sampler epilogue.  Replaces afinal_kernel when the MLP is 3 Linears with one output
+// (every shipped checkpoint) and fits: fd <= 64 channels, hidden width <= 128.
+//
+//   rows    = node pairs (i <= j) of one graph, 128 per tile (the channel stack [fd][ldp] of the x/adj pipeline
+//             is feature-major, i.e. an MN-major A operand as it lies in memory)
+//   layer 1 : D1[128 x H] = X[128 x fd] . W1          A, B MN-major bf16 hi/lo in shared memory
+//   layer 2 : D2[128 x H] = elu(D1 + b1) . W2          A K-major (written by the epilogue threads, one row
+//                                                      each), B MN-major
+//   layer 3 : out = elu(D2 + b2) . w3 + b3             H FMAs per row in the epilogue
+// bf16x3 (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM) keeps the 1e-4 parity bar.  W1 / W2 are converted
+// once per CTA and stay resident (<= 96 KB); a persistent CTA walks tiles (graph, row block).
+#pragma once
+#include "xa_pipe.cuh"
+#include "tc_common.cuh"
+
+namespace ccsd {
+
+constexpr int TF_THREADS = 160;   // 4 epilogue / loader warps (one TMEM lane quarter each) + 1 MMA warp
+
+struct TcFinLayout {   // byte offsets from the 1024-aligned base; *_half = distance hi -> lo
+  int K1p, Hp;         // fd rounded up to 16, hidden width rounded up to 16
+  uint32_t w1, w1_half, w2, w2_half, a1, a1_half, a2, a2_half, vec, bars, total;
+};
+
+static inline int tc_afinal_supported(const ccsd_neta_t &A, int fd_have) {
+  return A.fin.nl == 3 && A.fin.dout == 1 && fd_have >= 1 && fd_have <= 64 && A.fin.dhid >= 8 && A.fin.dhid <= 128;
+}
+static inline TcFinLayout tc_afinal_layout(int fd, int dhid) {
+  TcFinLayout L;
+  L.K1p = (fd + 15) & ~15;
+  L.Hp = (dhid + 15) & ~15;
+  uint32_t o = 0;
+  L.w1_half = 2u * L.K1p * 128u; L.w1 = o; o += 2 * L.w1_half;     // [2 n-blocks][K1p k-rows][128 B]
+  L.w2_half = 2u * L.Hp * 128u;  L.w2 = o; o += 2 * L.w2_half;     // [2 n-blocks][Hp k-rows][128 B]
+  L.a1_half = 2u * L.K1p * 128u; L.a1 = o; o += 2 * L.a1_half;     // [2 m-blocks][K1p k-rows][128 B]
+  L.a2_half = 2u * 16384u;       L.a2 = o; o += 2 * L.a2_half;     // [2 k-blocks][128 rows][128 B]
+  L.vec = o; o += 3 * 128 * 4 + 256;                               // b1, b2, w3 (+ b3, reduction scratch)
+  L.bars = o; o += 64;
+  L.total = o + 1024;
+  return L;
+}
+
+struct TcFinArgs {
+  XaArgs x;
+  TcFinLayout L;
+  int fd;              // channels in the stack
+  int ntg;             // tiles per graph
+};
+
+__global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan *__restrict__ P, TcFinArgs ta) {
+  extern __shared__ uint8_t tf_smem_raw[];
+  const XaArgs &a = ta.x;
+  const TcFinLayout &TL = ta.L;
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const ccsd_mlp_t &fin = d.neta.fin;
+  const int N = d.N, NP = N * N, NT = L.NT, ldp = L.ldp, fd = ta.fd, dh = fin.dhid;
+  const int K1p = TL.K1p, Hp = TL.Hp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float *W = P->W;
+
+  const uint32_t raw = tc::smem_u32(tf_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen = tf_smem_raw + (base - raw);
+  const uint32_t bar = base + TL.bars, tslot = bar + 8;
+  uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen + TL.bars + 8);
+  float *vb1 = reinterpret_cast<float *>(gen + TL.vec), *vb2 = vb1 + 128, *vw3 = vb2 + 128, *red = vw3 + 128;
+
+  if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+  if (warp == 4) tc::tmem_alloc(tslot, 256);
+  // ---- zero the operand buffers, then convert the weights (resident for the whole kernel) ----
+  for (uint32_t o = threadIdx.x * 16u; o < TL.vec; o += TF_THREADS * 16u) *reinterpret_cast<uint4 *>(gen + o) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 128; i += TF_THREADS) {
+    vb1[i] = i < dh ? __ldg(W + fin.b[0] + i) : 0.f;
+    vb2[i] = i < dh ? __ldg(W + fin.b[1] + i) : 0.f;
+    vw3[i] = i < dh ? __ldg(W + fin.w[2] + i * 8) : 0.f;   // (in, out_pad = 8), output 0
+  }
+  __syncthreads();
+  {
+    // Linear l: (in = k, out_pad) row-major -> MN-major B operand: (n, k) at (n/64)*blk + k*128 + (((n%64)/8) ^ (k%8))*16 + (n%8)*2
+    const int opad = round_up(dh, 8);
+    for (int l = 0; l < 2; ++l) {
+      const int Kin = l == 0 ? fd : dh;
+      const uint32_t blk = (uint32_t)(l == 0 ? K1p : Hp) * 128u, dst = l == 0 ? TL.w1 : TL.w2, half = l == 0 ? TL.w1_half : TL.w2_half;
+      const int nchunk = opad >> 3;
+      for (int t = threadIdx.x; t < Kin * nchunk; t += TF_THREADS) {
+        const int k = t / nchunk, nc = t - k * nchunk, n0 = nc << 3;
+        const float *src = W + fin.w[l] + (size_t)k * opad + n0;
+        float x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = n0 + q < dh ? __ldg(src + q) : 0.f;
+        uint4 hi, lo;
+        tc::split8(x, hi, lo);
+        const uint32_t off = dst + (uint32_t)(n0 >> 6) * blk + (uint32_t)k * 128u + (uint32_t)((((n0 & 63) >> 3) ^ (k & 7)) << 4);
+        *reinterpret_cast<uint4 *>(gen + off) = hi;
+        *reinterpret_cast<uint4 *>(gen + off + half) = lo;
+      }
+    }
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tslot_gen;
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t id1 = tc::make_idesc_bf16(128, Hp, /*A MN-major*/ 1, /*B MN-major*/ 1);
+  const uint32_t id2 = tc::make_idesc_bf16(128, Hp, /*A K-major*/ 0, /*B MN-major*/ 1);
+  const float b3 = __ldg(W + fin.b[2]);
+  uint32_t phase = 0;
+  const int ntiles = d.B * ta.ntg;
+
+  for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
+    const int b = w / ta.ntg, tt = w - b * ta.ntg, t0 = tt * 128;
+    const float *gs = a.g_stack + (size_t)b * L.g_stack;
+    // ---- X tile -> A1 (MN-major): chunk = 8 consecutive rows of one channel ----
+    if (warp < 4) {
+      for (int t = threadIdx.x; t < fd * 16; t += 128) {
+        const int k = t >> 4, mc = t & 15, m0 = mc << 3;
+        const float *src = gs + (size_t)k * ldp + t0 + m0;
+        float x[8];
+        if (t0 + m0 + 8 <= ldp) {
+          const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
+          x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = t0 + m0 + q < ldp ? src[q] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (t0 + m0 + q >= NT) x[q] = 0.f;
+        uint4 hi, lo;
+        tc::split8(x, hi, lo);
+        const uint32_t off = TL.a1 + (uint32_t)(m0 >> 6) * ((uint32_t)K1p * 128u) + (uint32_t)k * 128u +
+                             (uint32_t)((((m0 & 63) >> 3) ^ (k & 7)) << 4);
+        *reinterpret_cast<uint4 *>(gen + off) = hi;
+        *reinterpret_cast<uint4 *>(gen + off + TL.a1_half) = lo;
+      }
+      tc::fence_proxy_async_smem();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    // ---- layer 1 MMAs ----
+    if (warp == 4) {
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t blk = (uint32_t)K1p * 128u;
+        for (int k4 = 0; k4 < K1p / 16; ++k4) {
+          const uint64_t a_hi = tc::make_smem_desc(base + TL.a1 + (uint32_t)k4 * 2048u, blk, 1024);
+          const uint64_t a_lo = tc::make_smem_desc(base + TL.a1 + TL.a1_half + (uint32_t)k4 * 2048u, blk, 1024);
+          const uint64_t b_hi = tc::make_smem_desc(base + TL.w1 + (uint32_t)k4 * 2048u, blk, 1024);
+          const uint64_t b_lo = tc::make_smem_desc(base + TL.w1 + TL.w1_half + (uint32_t)k4 * 2048u, blk, 1024);
+          tc::umma_bf16(tmem_u, a_hi, b_hi, id1, k4 != 0);
+          tc::umma_bf16(tmem_u, a_hi, b_lo, id1, 1);
+          tc::umma_bf16(tmem_u, a_lo, b_hi, id1, 1);
+        }
+        tc::umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc::tc_fence_after_sync();
+    // ---- epilogue 1: elu(D1 + b1) -> A2 (K-major, one row per thread) ----
+    if (warp < 4) {
+      const int r = threadIdx.x;
+      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < Hp; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float x[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = c0 + h8 * 8 + q;
+            x[q] = c < dh ? fast_elu(v[h8 * 8 + q] + vb1[c]) : 0.f;
+          }
+          uint4 hi, lo;
+          tc::split8(x, hi, lo);
+          const int c = c0 + h8 * 8;
+          const uint32_t off = TL.a2 + (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u + (uint32_t)((((c & 63) >> 3) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4 *>(gen + off) = hi;
+          *reinterpret_cast<uint4 *>(gen + off + TL.a2_half) = lo;
+        }
+      }
+      tc::fence_proxy_async_smem();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    // ---- layer 2 MMAs ----
+    if (warp == 4) {
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t blk = (uint32_t)Hp * 128u;
+        for (int k4 = 0; k4 < Hp / 16; ++k4) {
+          const uint32_t ao = (uint32_t)(k4 >> 2) * 16384u + (uint32_t)(k4 & 3) * 32u;   // 64-wide k block, 32 bytes per step
+          const uint64_t a_hi = tc::make_smem_desc(base + TL.a2 + ao, 0, 1024);
+          const uint64_t a_lo = tc::make_smem_desc(base + TL.a2 + TL.a2_half + ao, 0, 1024);
+          const uint64_t b_hi = tc::make_smem_desc(base + TL.w2 + (uint32_t)k4 * 2048u, blk, 1024);
+          const uint64_t b_lo = tc::make_smem_desc(base + TL.w2 + TL.w2_half + (uint32_t)k4 * 2048u, blk, 1024);
+          tc::umma_bf16(tmem_u + 128u, a_hi, b_hi, id2, k4 != 0);
+          tc::umma_bf16(tmem_u + 128u, a_hi, b_lo, id2, 1);
+          tc::umma_bf16(tmem_u + 128u, a_lo, b_hi, id2, 1);
+        }
+        tc::umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc::tc_fence_after_sync();
+    // ---- epilogue 2: out = elu(D2 + b2) . w3 + b3, masks, adjacency sampler epilogue ----
+    float s2 = 0.f, z2 = 0.f;
+    if (warp < 4) {
+      const int r = threadIdx.x, t = t0 + r;
+      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + 128u;
+      float acc = b3;
+      for (int c0 = 0; c0 < Hp; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc += fast_elu(v[q] + vb2[c0 + q]) * vw3[c0 + q];   // vw3 = 0 past dh
+      }
+      if (t < NT) {
+        const int ij = P->tri_ij[t], i = ij >> 8, j = ij & 255;
+        const float fi = a.flags[(size_t)b * N + i], fj = a.flags[(size_t)b * N + j];
+        const float o = (i == j) ? 0.f : acc * fi * fj;   // (1 - I) mask and mask_adjs
+        const size_t ga = (size_t)b * NP;
+        if (a.mode == MODE_EVAL) {
+          a.out_adj[ga + i * N + j] = o;
+          a.out_adj[ga + j * N + i] = o;
+        } else {
+          const ccsd_objcoef_t ca = P->sched[a.nz.step * 3 + 1];
+          const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
+          const float s = ca.score_scale * o;
+          float z = 0.f;
+          if (i != j) {
+            const int q = i * N + j;
+            z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, a.nz.step, a.slot), q)) * fi * fj;
+          }
+          if (a.mode == MODE_SCORE) {
+            a.out_adj[ga + i * N + j] = s;
+            if (i != j) {
+              a.out_adj[ga + j * N + i] = s;
+              s2 = 2.f * s * s;
+              z2 = 2.f * z * z;
+            }
+          } else {
+            const float m = ca.pa * a.adj[ga + i * N + j] + ca.pb * s;
+            const float v = m + ca.pc * z;
+            a.out_adj[ga + i * N + j] = v;
+            a.mean_adj[ga + i * N + j] = m;
+            if (a.traj_adj && b == 0) a.traj_adj[i * N + j] = a.denoise ? m : v;
+            if (i != j) {
+              a.out_adj[ga + j * N + i] = v;
+              a.mean_adj[ga + j * N + i] = m;
+              if (a.traj_adj && b == 0) a.traj_adj[j * N + i] = a.denoise ? m : v;
+            }
+          }
+        }
+      }
+    }
+    if (a.mode == MODE_SCORE) {
+      // per-tile norm partial (fixed order): warps 0-3 reduce, thread 0 sums the four warp values
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+      }
+      if (lane == 0 && warp < 4) { red[warp] = s2; red[8 + warp] = z2; }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();   // every thread is done with D1 / D2 / A1 / A2 of this tile
+    if (a.mode == MODE_SCORE && threadIdx.x == 0) {
+      float *np = a.norm_part + ((size_t)(1 * d.B + b) * P->ntile_max + tt) * 2;
+      np[0] = red[0] + red[1] + red[2] + red[3];
+      np[1] = red[8] + red[9] + red[10] + red[11];
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 256);
+}
+
+static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const XaArgs &a, int fd, void *stream) {
+  TcFinArgs ta;
+  ta.x = a;
+  ta.L = tc_afinal_layout(fd, hp.d.neta.fin.dhid);
+  ta.fd = fd;
+  ta.ntg = (hp.xp.NT + 127) / 128;
+  static size_t attr = 0;
+  if (ta.L.total > attr) {
+    if (cudaFuncSetAttribute(tc_afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ta.L.total) != cudaSuccess) return -1;
+    attr = ta.L.total;
+  }
+  const int ntiles = hp.d.B * ta.ntg;
+  tc_afinal_kernel<<<ntiles < 148 ? ntiles : 148, TF_THREADS, ta.L.total, (cudaStream_t)stream>>>(dP, ta);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace ccsd
