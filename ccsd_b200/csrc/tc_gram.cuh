@@ -23,7 +23,12 @@
 
 namespace ccsd {
 
-constexpr int TG_PROD_WARPS = 8;
+#ifndef TG_PRODUCER_WARPS
+#define TG_PRODUCER_WARPS 16
+#endif
+constexpr int TG_PROD_WARPS = TG_PRODUCER_WARPS;   // two groups of TG_PROD_WARPS / 2 warps fill alternate k-blocks
+constexpr int TG_GRP = TG_PROD_WARPS * 16;          // threads per producer group
+constexpr int TG_RSTEP = TG_GRP / 8;               // rows covered by one sweep of a group
 constexpr int TG_PROD = TG_PROD_WARPS * 32;
 constexpr int TG_THREADS = TG_PROD + 128 + 32;   // producers, 4 epilogue warps, 1 MMA warp
 constexpr int TG_STAGES = 3;
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
-      tc::mbar_init(full0 + 8 * s, 128);      // every thread of the producer group that fills it
+      tc::mbar_init(full0 + 8 * s, TG_GRP);   // every thread of the producer group that fills it
       tc::mbar_init(empty0 + 8 * s, 1);   // tcgen05.commit
     }
     tc::mbar_init(tfull, 1);
@@ -86,8 +91,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
     // strides and the 24 loads of a k-block are independent.
     const float *Wp = P->W + d.neta.proj_w;
     const bool vec = (K & 3) == 0;
-    constexpr int NT = 12;                      // 16 * 12 = 192 rows of F per k-block (E <= 192)
-    const int grp = warp >> 2, tg = threadIdx.x & 127;
+    constexpr int NT = 192 / TG_RSTEP;          // RSTEP * NT = 192 rows of F per k-block (E <= 192)
+    const int grp = warp / (TG_PROD_WARPS / 2), tg = threadIdx.x - grp * TG_GRP;
     const int c = tg & 7, r0 = tg >> 3;
     const uint32_t off0 = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
     const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -102,8 +107,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       float x[NT][8];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        if (r0 + 16 * j < E) {
-          const float *sj = src + (size_t)(16 * j) * K;
+        if (r0 + TG_RSTEP * j < E) {
+          const float *sj = src + (size_t)(TG_RSTEP * j) * K;
           if (fast) {
             const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sj));
             const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sj + 4));
@@ -121,15 +126,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       uint8_t *st = gen_base + (size_t)s * TG_STAGE;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        if (r0 + 16 * j < E) {
+        if (r0 + TG_RSTEP * j < E) {
           uint4 hi, lo;
           tc::split8(x[j], hi, lo);
-          *reinterpret_cast<uint4 *>(st + off0 + j * 2048u) = hi;
-          *reinterpret_cast<uint4 *>(st + TG_HALF + off0 + j * 2048u) = lo;
+          *reinterpret_cast<uint4 *>(st + off0 + j * (TG_RSTEP * 128u)) = hi;
+          *reinterpret_cast<uint4 *>(st + TG_HALF + off0 + j * (TG_RSTEP * 128u)) = lo;
         }
       }
       // projection rows of the weight blob (zero padded to Kw, L1/L2 resident)
-      for (int rw = r0; rw < PR0; rw += 16) {
+      for (int rw = r0; rw < PR0; rw += TG_RSTEP) {
         const float *sw = Wp + (size_t)rw * Kw + k;
         float y[8];
         if (k + 8 <= Kw) {
@@ -195,7 +200,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       tc::tc_fence_after_sync();
       for (int mt = 0; mt < mtiles; ++mt) {
         const int row = mt * 128 + q * 32 + lane;
-        float *Hrow = a.H + ((size_t)b * E + row) * P->Ep;
+        // H is symmetric: lane `row` holds H[row][c0 .. c0+15]; it is stored as H[c0+j][row], so that for
+        // every j the 32 lanes of the warp write 32 CONSECUTIVE floats (one coalesced 128-byte store)
+        // instead of 32 rows 760 bytes apart.
+        float *Hcol = a.H + (size_t)b * E * P->Ep + row;
         float *Prow = a.P0 + ((size_t)b * E + row) * PR0;
         for (int c0 = 0; c0 < ncols; c0 += 16) {
           float v[16];
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = c0 + j;
-              if (col < E) Hrow[col] = (mask_diag && col == row) ? 0.f : v[j];
+              if (col < E) Hcol[(size_t)col * P->Ep] = (mask_diag && col == row) ? 0.f : v[j];
               else if (col >= wp0 && col - wp0 < PR0) Prow[col - wp0] = v[j];
             }
           }
