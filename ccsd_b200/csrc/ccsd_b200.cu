@@ -273,7 +273,11 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
       const int r8a = (ly.attn_dim + 7) / 8 * 8, r8n = (ly.conv_out + 7) / 8 * 8, r8o = (o1 + 7) / 8 * 8;
       wmax = imax(wmax, ly.conv_in * (2 * r8a + r8n) + ly.conv_out * r8o);
     }
+#if XP_STAGE_W
     L.c_w = take(wmax);
+#else
+    L.c_w = o; (void)wmax;
+#endif
   }
   L.c_total = o;
   // ---- attn_finish_kernel ----

@@ -89,17 +89,30 @@ __device__ __forceinline__ void dense_tile(float acc[4][8], const float *in1, in
     const int npair = K >> 1;
 #if CCSD_DENSE_PIPE
     if (npair > 0) {
-      TileOps cur, nxt;
-      tile_load2<WSM>(cur, in, ld, wp, Opad);
+      // two operand sets used alternately (no register copies): the loads of pair p+1 are in flight during
+      // the 64 FMAs of pair p
+      TileOps A, B;
+      tile_load2<WSM>(A, in, ld, wp, Opad);
+      int p = 1;
 #pragma unroll 1
-      for (int p = 1; p < npair; ++p) {
-        tile_load2<WSM>(nxt, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
-        tile_fma(acc, cur.a0, cur.w00, cur.w01);
-        tile_fma(acc, cur.a1, cur.w10, cur.w11);
-        cur = nxt;
+      for (; p + 1 < npair; p += 2) {
+        tile_load2<WSM>(B, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
+        tile_fma(acc, A.a0, A.w00, A.w01);
+        tile_fma(acc, A.a1, A.w10, A.w11);
+        tile_load2<WSM>(A, in + 2 * (p + 1) * ld, ld, wp + 2 * (p + 1) * Opad, Opad);
+        tile_fma(acc, B.a0, B.w00, B.w01);
+        tile_fma(acc, B.a1, B.w10, B.w11);
       }
-      tile_fma(acc, cur.a0, cur.w00, cur.w01);
-      tile_fma(acc, cur.a1, cur.w10, cur.w11);
+      if (p < npair) {
+        tile_load2<WSM>(B, in + 2 * p * ld, ld, wp + 2 * p * Opad, Opad);
+        tile_fma(acc, A.a0, A.w00, A.w01);
+        tile_fma(acc, A.a1, A.w10, A.w11);
+        tile_fma(acc, B.a0, B.w00, B.w01);
+        tile_fma(acc, B.a1, B.w10, B.w11);
+      } else {
+        tile_fma(acc, A.a0, A.w00, A.w01);
+        tile_fma(acc, A.a1, A.w10, A.w11);
+      }
     }
 #else
     // lean variant (fewer registers -> more resident CTAs): no software pipelining, latency hidden by other warps

@@ -35,6 +35,9 @@
 #ifndef XP_MINB_C
 #define XP_MINB_C 1
 #endif
+#ifndef XP_STAGE_W
+#define XP_STAGE_W 1   // stage the channel's Q/K/V/W1 weights in shared memory (0: read them through L1/L2)
+#endif
 #ifndef XP_MINB_M
 #define XP_MINB_M 1
 #endif
@@ -195,10 +198,15 @@ __global__ void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevP
   const int o1 = mc.nl == 1 ? mc.dout : mc.dhid, o1p = round_up(o1, 8);
   const int adp8 = round_up(ad, 8), nhp8 = round_up(nh, 8);
   float *wq = sm + L.c_w, *wk = wq + kin * adp8, *wv = wk + kin * adp8, *w1 = wv + kin * nhp8;
+#if XP_STAGE_W
   stage_async(wq, W + ly.q[c].w, kin * adp8);
   stage_async(wk, W + ly.k[c].w, kin * adp8);
   stage_async(wv, W + ly.v[c].w, kin * nhp8);
   stage_async(w1, W + mc.w[0] + (size_t)c * nh * o1p, nh * o1p);
+#else
+  wq = const_cast<float *>(W + ly.q[c].w); wk = const_cast<float *>(W + ly.k[c].w); wv = const_cast<float *>(W + ly.v[c].w);
+  w1 = const_cast<float *>(W + mc.w[0] + (size_t)c * nh * o1p);
+#endif
   const float *gadj = a.g_stack + (size_t)b * L.g_stack + (size_t)(a.ch_in + c) * ldp;
   for (int t = threadIdx.x; t < ldp; t += blockDim.x) adjc[t] = gadj[t];
   const float *gx = a.g_xin + (size_t)b * L.g_x;
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevP
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) acc[rr][j] = bv;
       }
-      dense_tile<true>(acc, ax, N4, kin, nullptr, 0, 0, ws, Opad, r0, oc);
+      dense_tile<XP_STAGE_W != 0>(acc, ax, N4, kin, nullptr, 0, 0, ws, Opad, r0, oc);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (oc + j < O) {
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevP
     // V's share of the first Linear of multi_channel, which is linear in the channel concat
     // (attention.py:292): hmc_c(o, i) = sum_f V_c(i, f) W1[c*nh + f, o]; the finish kernel sums over c
     float *gh = a.g_hmc + (size_t)b * L.g_hmc + (size_t)c * L.mc_o1_max * N4;
-    dense_fm<true>(v, N4, nh, nullptr, 0, 0, w1, nullptr, o1, gh, 1, N4, N, ACT_NONE, false, (int)blockDim.x - 32);
+    dense_fm<XP_STAGE_W != 0>(v, N4, nh, nullptr, 0, 0, w1, nullptr, o1, gh, 1, N4, N, ACT_NONE, false, (int)blockDim.x - 32);
   }
   __syncthreads();
   {
