@@ -12,11 +12,18 @@ SCORE_TOL = 1e-4  # BASELINE.json north_star: per-step score outputs within 1e-4
 
 
 def make_engine(cfg: Config, B: int, device: str, sampler="PC", predictor="Euler", corrector="Langevin", snr=None,
-                scale_eps=None, denoise=True):
+                scale_eps=None, denoise=True, probability_flow=False, sdes=None):
     sh = cfg.shipped
-    return Engine(cfg.holders, cfg.sdes(), cfg.shapes(B), sampler=sampler, predictor=predictor, corrector=corrector,
+    return Engine(cfg.holders, sdes or cfg.sdes(), cfg.shapes(B), sampler=sampler, predictor=predictor, corrector=corrector,
                   snr=sh["snr"] if snr is None else snr, scale_eps=sh["scale_eps"] if scale_eps is None else scale_eps,
-                  n_steps=1, denoise=denoise, eps=1e-4, device=device, d_min=cfg.d_min, d_max=cfg.d_max)
+                  n_steps=1, denoise=denoise, eps=1e-4, device=device, d_min=cfg.d_min, d_max=cfg.d_max,
+                  probability_flow=probability_flow)
+
+
+def sdes_of_kind(cfg: Config, kind: str):
+    """The config's SDEs with their type replaced (subVP has no shipped checkpoint; the networks do not care)."""
+    s = cfg.meta["sde"]
+    return [O.make_sde(kind, s[k]["beta_min"], s[k]["beta_max"], s[k]["num_scales"]) for k in cfg.keys]
 
 
 def score_parity(name: str, B: int, device: str, seed: int = 1):
@@ -35,7 +42,7 @@ def score_parity(name: str, B: int, device: str, seed: int = 1):
 
 
 def sampler_parity(name: str, sampler: str, predictor: str, corrector: str, B: int, steps: int, device: str,
-                   seed: int = 5, denoise: bool = True):
+                   seed: int = 5, denoise: bool = True, probability_flow: bool = False, sde_kind: str = None):
     """`steps` sampler iterations on the real schedule with an injected noise stream.  Returns per
     object (rel err of the returned tensor, rel err of the raw state, quantised agreement)."""
     cfg = Config(name)
@@ -45,12 +52,14 @@ def sampler_parity(name: str, sampler: str, predictor: str, corrector: str, B: i
     rec = []
     kw = dict(snr=sh["snr"], scale_eps=sh["scale_eps"], denoise=denoise, eps=1e-4, d_min=cfg.d_min, d_max=cfg.d_max,
               noise=src, max_steps=steps, record=rec)
+    sdes = sdes_of_kind(cfg, sde_kind) if sde_kind else cfg.sdes()
     if sampler == "S4":
-        res, _ = O.s4_solver(cfg.oracle_models, cfg.sdes(), cfg.shapes(B), flags, **kw)
+        res, _ = O.s4_solver(cfg.oracle_models, sdes, cfg.shapes(B), flags, **kw)
     else:
-        res, _ = O.pc_sampler(cfg.oracle_models, cfg.sdes(), cfg.shapes(B), flags, predictor=predictor,
-                              corrector=corrector, n_steps=1, **kw)
-    eng = make_engine(cfg, B, device, sampler, predictor, corrector, denoise=denoise)
+        res, _ = O.pc_sampler(cfg.oracle_models, sdes, cfg.shapes(B), flags, predictor=predictor,
+                              corrector=corrector, n_steps=1, probability_flow=probability_flow, **kw)
+    eng = make_engine(cfg, B, device, sampler, predictor, corrector, denoise=denoise, probability_flow=probability_flow,
+                      sdes=sdes)
     inj = InjectedNoise.from_flat_log(src.log, len(cfg.keys), eng.n_draws, steps)
     eng.init(flags, prior=inj.prior)
     for i in range(steps):

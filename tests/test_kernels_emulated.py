@@ -47,3 +47,15 @@ def test_sampler_not_denoised():
     res = sampler_parity("qm9_cc", "PC", "Reverse", "Langevin", B=2, steps=2, device="cpu", denoise=False)
     for k, (e_ret, e_state, _) in res.items():
         assert e_ret < 1e-4 and e_state < 1e-4
+
+
+@pytest.mark.parametrize("pred,corr,pf,kind", [
+    ("Reverse", "Langevin", False, "subVP"),   # subVP: std without the square root, Euler-type discretize (sde.py:746, 93-111)
+    ("Euler", "Langevin", False, "subVP"),
+    ("Reverse", "None", True, "VP"),           # probability flow: half score term, no diffusion (sde.py:204-235)
+    ("Euler", "Langevin", True, "VE"),
+])
+def test_sampler_sde_variants(pred, corr, pf, kind):
+    res = sampler_parity("qm9_cc", "PC", pred, corr, B=2, steps=2, device="cpu", probability_flow=pf, sde_kind=kind)
+    for k, (e_ret, e_state, agree) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4, (pred, corr, pf, kind, k, e_ret, e_state)
