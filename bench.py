@@ -37,6 +37,8 @@ WORKLOADS = {
     "qm9_cc": ("qm9_cc", 10000, 2500),
     "enzymes_small_cc": ("enzymes_small_cc", 4096, 64),
     "community_small": ("community_small", 128, 128),
+    "ego_small": ("ego_small", 128, 128),
+    "ego_small_cc": ("ego_small_cc", 128, 32),
     "qm9": ("qm9", 1024, 1024),
 }
 

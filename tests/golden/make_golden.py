@@ -44,6 +44,9 @@ CONFIGS = {
     "qm9_cc": ("QM9/ccsd_qm9_CC", ("Reverse", "Langevin", 0.2, 0.7), 3),
     "community_small_cc": ("community_small_CC/ccsd_community_small_CC", ("Euler", "Langevin", 0.05, 0.7), 2),
     "enzymes_small_cc": ("ENZYMES_small_CC/ccsd_enzymes_small_CC", ("S4", "None", 0.15, 0.7), 2),
+    # config/sample_ego_small_CC.yaml: Euler predictor, no corrector (snr / scale_eps unused)
+    "ego_small_cc": ("ego_small_CC/ccsd_ego_small_CC", ("Euler", "None", 0.0, 0.0), 2),
+    "ego_small": ("ego_small/gdss_ego_small", ("Euler", "None", 0.0, 0.0), 3),
 }
 
 

@@ -16,7 +16,7 @@ def test_emulation_build_is_flagged():
     assert b"EMULATION" in nat.load().ccsd_version()
 
 
-@pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1)])
+@pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1), ("ego_small", 2)])
 def test_scores(name, B):
     for k, e in score_parity(name, B, "cpu").items():
         assert e < SCORE_TOL, (name, k, e)

@@ -21,7 +21,7 @@ def test_product_library_is_loaded():
 
 
 @pytest.mark.parametrize("name,B", [("qm9", 64), ("community_small", 16), ("qm9_cc", 16), ("enzymes_small_cc", 8),
-                                    ("community_small_cc", 4)])
+                                    ("community_small_cc", 4), ("ego_small", 8), ("ego_small_cc", 2)])
 def test_score_parity(name, B):
     """per-step score outputs within 1e-4 relative of the fp32 reference path (north_star)."""
     errs = score_parity(name, B, DEV)
@@ -29,7 +29,8 @@ def test_score_parity(name, B):
         assert e < SCORE_TOL, (name, k, e)
 
 
-@pytest.mark.parametrize("name", ["qm9", "community_small", "qm9_cc", "community_small_cc", "enzymes_small_cc"])
+@pytest.mark.parametrize("name", ["qm9", "community_small", "ego_small", "qm9_cc", "community_small_cc", "enzymes_small_cc",
+                                  "ego_small_cc"])
 def test_scores_against_committed_reference_outputs(name):
     """The same inputs the unmodified reference was run on (tests/golden/io_<cfg>.npz)."""
     cfg = Config(name)
@@ -60,6 +61,9 @@ def test_scores_against_committed_reference_outputs(name):
     ("enzymes_small_cc", "S4", "None", "None", 4, 3),
     ("enzymes_small_cc", "PC", "Reverse", "Langevin", 4, 2),
     ("community_small_cc", "PC", "Euler", "Langevin", 2, 2),
+    ("ego_small", "PC", "Euler", "None", 8, 3),
+    ("ego_small_cc", "PC", "Euler", "None", 2, 2),
+    ("ego_small_cc", "PC", "Reverse", "Langevin", 2, 2),
 ])
 def test_sampler_steps_with_injected_noise(name, sampler, pred, corr, B, steps):
     res = sampler_parity(name, sampler, pred, corr, B, steps, DEV)
