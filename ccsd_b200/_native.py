@@ -2,9 +2,10 @@
 
 The product library is ``ccsd_b200/_lib/libccsd_b200.so`` (built in-tree by ``ccsd_b200.build``
 for sm_100a).  There is no CPU implementation: if the library is missing, or torch sees no CUDA
-device, every entry point of the package raises.  (``CCSD_B200_LIB`` may point at another build of
-the same ABI; the CPU test-suite uses that to drive the host-emulation build of the kernels in
-``tests/_emu`` -- test infrastructure, see ccsd_b200/csrc/common.cuh.)
+device, every entry point of the package raises.  ``CCSD_B200_LIB`` may point at another CUDA build of
+the same ABI (A/B experiments).  The host-emulation build of the kernels (``tests/_emu``, test
+infrastructure, see ccsd_b200/csrc/common.cuh) is refused unless the test-suite itself asked for it
+with ``enable_test_emulation()`` -- no environment variable turns the package into a CPU path.
 """
 from __future__ import annotations
 
@@ -75,9 +76,20 @@ class PlanDesc(C.Structure):
 
 
 _LIB = None
+_TEST_EMULATION = None   # path of the host-emulation build, set only by enable_test_emulation()
+
+
+def enable_test_emulation(path) -> None:
+    """TEST-SUITE ONLY (tests/conftest.py, tests/test_shard_gloo.py workers): drive the host-emulation build
+    of the kernels so that `pytest -m "not gpu"` can check index arithmetic and packing without a GPU."""
+    global _TEST_EMULATION, _LIB
+    _TEST_EMULATION = Path(path)
+    _LIB = None
 
 
 def lib_path() -> Path:
+    if _TEST_EMULATION is not None:
+        return _TEST_EMULATION
     env = os.environ.get("CCSD_B200_LIB")
     if env:
         return Path(env)
@@ -135,6 +147,11 @@ def load():
     lib.ccsd_debug_apply_trace.argtypes = [vp, vp]
     lib.ccsd_last_error.restype = C.c_char_p
     lib.ccsd_version.restype = C.c_char_p
+    if b"EMULATION" in lib.ccsd_version() and _TEST_EMULATION is None:
+        raise RuntimeError(
+            f"ccsd_b200: {p} is the host-emulation build of the kernels (test infrastructure); the package has no "
+            "CPU path. Build the CUDA library with `python -m ccsd_b200.build`."
+        )
     if lib.ccsd_plan_desc_size() != C.sizeof(PlanDesc) or lib.ccsd_objcoef_size() != C.sizeof(ObjCoef):
         raise RuntimeError("ccsd_b200: ABI mismatch between ccsd_b200/_native.py and the shared library")
     _LIB = lib

@@ -2,7 +2,8 @@
 
 * ``-m "not gpu"``: runs here without a GPU.  Kernel code is exercised through the host-emulation
   build (tests/_emu/libccsd_b200_emu.so, one thread per block -- see ccsd_b200/csrc/common.cuh);
-  it is built on demand and selected via CCSD_B200_LIB *only* when torch sees no CUDA device.
+  it is built on demand and selected through ccsd_b200._native.enable_test_emulation() *only* when torch
+  sees no CUDA device (no environment variable makes the product package load it).
 * ``-m gpu``: parity tests proper, on a B200, through the product library and the C ABI.
 """
 import os
@@ -17,10 +18,13 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 HAS_CUDA = torch.cuda.is_available()
-if not HAS_CUDA and "CCSD_B200_LIB" not in os.environ:
+if not HAS_CUDA:
+    from ccsd_b200 import _native as _nat
     from ccsd_b200 import build as _build
 
-    os.environ["CCSD_B200_LIB"] = str(_build.build_emu())
+    _EMU = str(_build.build_emu())
+    os.environ["CCSD_B200_TEST_EMU"] = _EMU     # for spawned worker processes of the test-suite (they call the hook too)
+    _nat.enable_test_emulation(_EMU)
 
 
 def pytest_configure(config):

@@ -33,3 +33,19 @@ def test_emulation_library_exports_the_same_surface():
     lib = ctypes.CDLL(str(build.build_emu()))
     for name in _declared():
         assert hasattr(lib, name), name
+
+
+def test_emulation_build_is_refused_outside_the_test_hook(monkeypatch):
+    """No environment variable turns the package into a CPU path: pointing CCSD_B200_LIB at the emulation
+    build raises unless the test-suite's own hook enabled it."""
+    import pytest
+    from ccsd_b200 import _native as nat
+
+    saved = (nat._TEST_EMULATION, nat._LIB)
+    try:
+        nat._TEST_EMULATION, nat._LIB = None, None
+        monkeypatch.setenv("CCSD_B200_LIB", str(build.build_emu()))
+        with pytest.raises(RuntimeError, match="host-emulation"):
+            nat.load()
+    finally:
+        nat._TEST_EMULATION, nat._LIB = saved

@@ -38,6 +38,9 @@ def _maker(cfg, corrector):
 
 
 def _worker(rank, world, port, corrector, out):
+    from ccsd_b200 import _native as nat
+
+    nat.enable_test_emulation(os.environ["CCSD_B200_TEST_EMU"])   # spawned process: conftest did not run here
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = Config("qm9_cc")
