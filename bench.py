@@ -38,6 +38,8 @@ WORKLOADS = {
     "enzymes_small_cc": ("enzymes_small_cc", 4096, 64),
     "community_small": ("community_small", 128, 128),
     "ego_small": ("ego_small", 128, 128),
+    "qm9_base_cc": ("qm9_base_cc", 10000, 2500),
+    "community_small_base_cc": ("community_small_base_cc", 1024, 32),
     "ego_small_cc": ("ego_small_cc", 128, 32),
     "qm9": ("qm9", 1024, 1024),
 }

@@ -47,11 +47,19 @@ class HodgeLayer(C.Structure):
     ]
 
 
+class HBaseLayer(C.Structure):
+    _fields_ = [
+        ("c_in", i32), ("c_out", i32), ("hid", i32),
+        ("w1", i32 * MAX_CH), ("b1", i32 * MAX_CH), ("w2", i32 * MAX_CH), ("b2", i32 * MAX_CH), ("mlp_hodge", Mlp),
+    ]
+
+
 class NetA(C.Structure):
     _fields_ = [
         ("is_cc", i32), ("num_layers", i32), ("c_init", i32), ("num_heads", i32), ("fdim", i32),
         ("layer", AttnLayer * MAX_LAYERS), ("num_layers_h", i32), ("num_heads_h", i32),
-        ("n_proj_rows", i32 * MAX_HODGE), ("proj_w", i32), ("hodge", HodgeLayer * MAX_HODGE), ("fin", Mlp),
+        ("n_proj_rows", i32 * MAX_HODGE), ("proj_w", i32), ("hodge", HodgeLayer * MAX_HODGE),
+        ("base_cc", i32), ("hbase", HBaseLayer * MAX_HODGE), ("fin", Mlp),
     ]
 
 

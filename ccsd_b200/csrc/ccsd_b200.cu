@@ -169,7 +169,25 @@ static int validate(const ccsd_plan_desc_t &d, size_t nw) {
     ch += ly.c_out; cin = ly.c_out; kin = ly.conv_out;
   }
   if (A.is_cc && !d.is_cc) return fail(CCSD_ERR_INVALID, "ScoreNetworkA_CC needs a combinatorial-complex plan (is_cc)");
-  if (A.is_cc) {
+  if (A.is_cc && A.base_cc) {
+    if (A.num_layers_h < 1 || A.num_layers_h > CCSD_MAX_HODGE_LAYERS)
+      return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA_Base_CC: num_layers_h must be 1 or 2");
+    int hin = A.c_init;
+    for (int l = 0; l < A.num_layers_h; ++l) {
+      const ccsd_hbase_layer_t &h = A.hbase[l];
+      if (h.c_in != hin || h.c_in > CCSD_MAX_CH || h.c_out > CCSD_MAX_CH || h.hid < 1 || h.hid > (l == 0 ? SMALL_MAX : 8))
+        return fail(CCSD_ERR_UNSUPPORTED, "HodgeBaselineLayer: channels <= 8, hidden width <= 32 (first layer) / 8 (second layer)");
+      if (int r = check_mlp(h.mlp_hodge, nw, "mlp_hodge", 1)) return r;
+      if (h.mlp_hodge.din != h.c_in) return fail(CCSD_ERR_INVALID, "HodgeBaselineLayer: mlp_hodge input width mismatch");
+      const int hp = (h.hid + 7) / 8 * 8;
+      for (int c = 0; c < h.c_in; ++c)
+        if (h.w1[c] < 0 || h.w2[c] < 0 || h.b1[c] < 0 || h.b2[c] < 0 || (size_t)h.w1[c] + (size_t)d.E * hp > nw ||
+            (size_t)h.w2[c] + (size_t)d.E * hp > nw || (size_t)h.b2[c] + d.E > nw)
+          return fail(CCSD_ERR_INVALID, "HodgeBaselineLayer: weight offsets out of range");
+      ch += h.c_out; hin = h.c_out;
+    }
+    ch += A.c_init;
+  } else if (A.is_cc) {
     if (A.num_layers_h < 1 || A.num_layers_h > CCSD_MAX_HODGE_LAYERS)
       return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA_CC: num_layers_h must be 1 or 2 (the dense H @ rank2 value path of deeper stacks is not implemented)");
     int hin = A.c_init;
@@ -300,6 +318,14 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
     L.h_hdeg = take(A.hodge[0].c_out * E);
   }
   L.h_total = o;
+  // ---- hodge_base_kernel ----
+  o = L.h_flags + a4(N4);
+  if (d.is_cc && A.is_cc && A.base_cc) {
+    L.hb_u0 = take(A.c_init * d.E * ((A.hbase[0].hid + 7) / 8 * 8));
+    L.hb_fe = take(d.E);
+    L.hb_tri = take(d.E);
+  }
+  L.hb_total = o;
   // ---- afinal_kernel: 64-row chunks of node pairs ----
   o = 0;
   const int fin_h = imax(A.fin.nl > 1 ? A.fin.dhid : 1, 1);
@@ -380,7 +406,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->weights = weights_dev;
   p->n_weights = n_weights;
   p->sched.assign(schedule_host, schedule_host + (size_t)d.n_diff_steps * 3);
-  const bool hodge = d.is_cc && (d.nets & 2) && d.neta.is_cc;
+  const bool hodge = d.is_cc && (d.nets & 2) && d.neta.is_cc && !d.neta.base_cc;   // the baseline network has no rank-2 projections
   p->hp.PR0h = hodge ? d.neta.n_proj_rows[0] : 0;
   p->hp.PR0 = p->hp.PR0h;
   p->hp.PR1 = (hodge && d.neta.num_layers_h == 2) ? d.neta.n_proj_rows[1] : 0;
@@ -420,7 +446,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
   p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)p->hp.f_nlin * 72 + 48) * 4 : 0;
   const XpLayout &XL = p->hp.xp;
-  const size_t xp_max = (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, XL.h_total)), XL.m_total) * 4;
+  const size_t xp_max = (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, imax(XL.h_total, XL.hb_total))), XL.m_total) * 4;
   if (xp_max > 227 * 1024 || p->apply_smem > 227 * 1024) {
     char buf[200];
     snprintf(buf, sizeof buf, "graph tile does not fit shared memory (x/adj pipeline %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
@@ -473,6 +499,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hodge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hodge_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) xp_attr = xp_max;
   }
@@ -605,7 +632,15 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     const float *t = xout; xout = (float *)xin; xin = t;
   }
   int fd_have = ch_out;
-  if (A.is_cc && p->hp.PR1 > 0) {
+  if (A.is_cc && A.base_cc) {
+    a.ch_in = ch_out;   // first hodge channel
+    PROF_BEGIN(p, "hodge_base_kernel", stream);
+    CCSD_LAUNCH(hodge_base_kernel, dim3(d.B, 1, 1), L.Th, (size_t)L.hb_total * 4, stream, p->dP, a);
+    PROF_END(p, stream);
+    p->launches++;
+    fd_have += A.c_init + A.hbase[0].c_out + (A.num_layers_h == 2 ? A.hbase[1].c_out : 0);
+  }
+  if (A.is_cc && !A.base_cc && p->hp.PR1 > 0) {
     // projections of hodge layer 1 (value MLP with a non-linearity: not foldable into the Gram product)
     Proj1Args q; q.r2 = a.r2; q.flags = a.flags; q.g_stack = p->g_stack; q.g_stack_stride = L.g_stack; q.ldp = L.ldp;
     q.P1 = p->P1;
@@ -615,7 +650,7 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     PROF_END(p, stream);
     p->launches++;
   }
-  if (A.is_cc) {
+  if (A.is_cc && !A.base_cc) {
     a.ch_in = ch_out;   // first hodge channel
     PROF_BEGIN(p, "hodge_kernel", stream);
     CCSD_LAUNCH(hodge_kernel, dim3(d.B, 1, 1), L.Th, (size_t)L.h_total * 4, stream, p->dP, a);

@@ -514,6 +514,117 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
 }
 
 // =============================================================================================
+// hodge_base_kernel: hodge branch of ScoreNetworkA_Base_CC (ScoreNetwork_A_Base_CC.py:296-312,
+// hodge_layers.py:202-416) on the channel stack in global memory.
+//
+// The hodge-adjacency chain of the baseline network does not depend on rank2 at all: BaselineBlock's
+// hodge output is sym(tanh(MLP(hodge_adj))) and only the rank-2 outputs (never read by the adjacency score)
+// use rank2.  Layer 0 sees the diagonal Hodge dual diag(a_c), so its block c is
+//     M_c[e, e'] = tanh(b2_c[e'] + W2_c[e', :] . u_c[e]),   u_c[e] = elu(W1_c[:, e] a_c[e] + b1_c)
+// i.e. `hid` MACs per entry: the E x E layer-0 output is recomputed on the fly (never stored) while the thread
+// that owns row e accumulates the first Linear of every layer-1 block over e'.  Only the DIAGONALS of the
+// layer outputs reach the final MLP (hodgedual_to_adj, cc_utils.py:1571).
+// =============================================================================================
+__global__ void __launch_bounds__(128) hodge_base_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const ccsd_neta_t &A = d.neta;
+  const int b = blockIdx.x;
+  const int N = d.N, E = d.E, N4 = L.N4, ldp = L.ldp, NT = L.NT;
+  const float *W = P->W;
+  float *flags = sm + L.h_flags, *u0 = sm + L.hb_u0, *fes = sm + L.hb_fe, *tix = sm + L.hb_tri;
+  float *stack = a.g_stack + (size_t)b * L.g_stack;
+  const int ch_h0 = a.ch_in;                       // first hodge channel of the stack
+  const ccsd_hbase_layer_t &h0 = A.hbase[0], &h1 = A.hbase[1];
+  const int c0 = A.c_init, hid0 = h0.hid, hp0 = round_up(hid0, 8), c1 = h0.c_out;
+  const int Lh = A.num_layers_h;
+
+  for (int i = threadIdx.x; i < N4; i += blockDim.x) flags[i] = i < N ? a.flags[(size_t)b * N + i] : 0.f;
+  // channels [ch_h0, ch_h0 + c0): adjc with zero diagonal; hodge output channels start as zero
+  {
+    const int nout = h0.c_out + (Lh == 2 ? h1.c_out : 0);
+    for (int p = threadIdx.x; p < (c0 + nout) * ldp; p += blockDim.x) {
+      const int c = p / ldp, t = p - c * ldp;
+      float v = 0.f;
+      if (c < c0 && t < NT) {
+        const int ij = P->tri_ij[t];
+        if ((ij >> 8) != (ij & 255)) v = stack[c * ldp + t];
+      }
+      stack[(ch_h0 + c) * ldp + t] = v;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+    fes[e] = flags[i] * flags[j];
+    reinterpret_cast<int *>(tix)[e] = tri_index(i, j, N);
+  }
+  __syncthreads();
+  // u0[c][e][h] = elu(W1_c[e][h] a_c[e] + b1_c[h])
+  for (int p = threadIdx.x; p < c0 * E * hp0; p += blockDim.x) {
+    const int c = p / (E * hp0), r = p - c * E * hp0, e = r / hp0, h = r - e * hp0;
+    float v = 0.f;
+    if (h < hid0) {
+      const float ac = stack[c * ldp + reinterpret_cast<const int *>(tix)[e]];
+      v = fast_elu(__ldg(W + h0.w1[c] + e * hp0 + h) * ac + __ldg(W + h0.b1[c] + h));
+    }
+    u0[p] = v;
+  }
+  __syncthreads();
+
+  const int hid1 = Lh == 2 ? h1.hid : 0;   // <= 8 (validated): hid_pad = 8, so acc[c][0..8) covers a whole padded row
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float fe = fes[e];
+    const int te = reinterpret_cast<const int *>(tix)[e];
+    float acc[CCSD_MAX_CH][8];   // first Linear of the layer-1 blocks: acc[c][h] = sum_e2 W1'_c[e2][h] O0_c[e, e2]
+#pragma unroll
+    for (int c = 0; c < CCSD_MAX_CH; ++c)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) acc[c][h] = 0.f;
+    for (int e2 = (Lh == 1 ? e : 0); e2 < (Lh == 1 ? e + 1 : E); ++e2) {   // one hodge layer: only its diagonal
+      // layer 0, entry (e, e2): symmetrised block outputs -> mlp_hodge -> mask -> tanh -> + transpose
+      float S[CCSD_MAX_CH], Y[SMALL_MAX];
+      for (int c = 0; c < c0; ++c) {
+        const float *ue = u0 + ((size_t)c * E + e) * hp0, *ue2 = u0 + ((size_t)c * E + e2) * hp0;
+        const float *w2a = W + h0.w2[c] + (size_t)e2 * hp0, *w2b = W + h0.w2[c] + (size_t)e * hp0;
+        float m1 = __ldg(W + h0.b2[c] + e2), m2 = __ldg(W + h0.b2[c] + e);
+        for (int h = 0; h < hid0; ++h) { m1 += __ldg(w2a + h) * ue[h]; m2 += __ldg(w2b + h) * ue2[h]; }
+        S[c] = 0.5f * (fast_tanh(m1) + fast_tanh(m2));
+      }
+      small_mlp(h0.mlp_hodge, W, S, Y, ACT_ELU);
+      const float fm = fe * fes[e2];
+#pragma unroll
+      for (int c = 0; c < CCSD_MAX_CH; ++c)
+        if (c < c1) {
+          const float o = 2.0f * fast_tanh(fm * Y[c]);
+          if (e2 == e) stack[(ch_h0 + c0 + c) * ldp + te] = o;
+          if (Lh == 2) {
+            const float *w1 = W + h1.w1[c] + (size_t)e2 * 8;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) acc[c][h] += __ldg(w1 + h) * o;   // padded columns hold zeros
+          }
+        }
+    }
+    if (Lh == 2) {
+      // layer 1: only the diagonal entry (e, e) of every block and of the layer output is needed
+      float Sd[CCSD_MAX_CH], Y[SMALL_MAX];
+#pragma unroll
+      for (int c = 0; c < CCSD_MAX_CH; ++c)
+        if (c < c1) {
+          float m = __ldg(W + h1.b2[c] + e);
+#pragma unroll
+          for (int h = 0; h < 8; ++h)
+            if (h < hid1) m += __ldg(W + h1.w2[c] + (size_t)e * 8 + h) * fast_elu(acc[c][h] + __ldg(W + h1.b1[c] + h));
+          Sd[c] = fast_tanh(m);
+        }
+      small_mlp(h1.mlp_hodge, W, Sd, Y, ACT_ELU);
+      for (int c = 0; c < h1.c_out; ++c) stack[(ch_h0 + c0 + c1 + c) * ldp + te] = 2.0f * fast_tanh(fe * fe * Y[c]);
+    }
+  }
+}
+
+// =============================================================================================
 // afinal_kernel: final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) on a chunk of node
 // pairs + the adjacency sampler epilogue
 // =============================================================================================

@@ -105,6 +105,28 @@ class HodgeAdjAttentionLayer(nn.Module):
         self.mlp_attention = MLP(num_linears, input_dim, self.hidden_dim, conv_output_dim, use_bn)
 
 
+class BaselineBlock(nn.Module):
+    """hodge_layers.py:202-245."""
+
+    def __init__(self, in_dim: int, hidden_dim: int, out_dim: int) -> None:
+        super().__init__()
+        self.mlp_layer = MLP(2, in_dim, hidden_dim, out_dim, False)
+
+
+class HodgeBaselineLayer(nn.Module):
+    """hodge_layers.py:287-357."""
+
+    def __init__(self, num_linears, input_dim, hidden_dim, conv_output_dim, N, d_min, d_max, use_bn=False) -> None:
+        super().__init__()
+        from .packer import rank2_dim
+
+        E = rank2_dim(N, d_min, d_max)[0]
+        self.layers = nn.ModuleList(BaselineBlock(E, hidden_dim, E) for _ in range(input_dim))
+        self.hidden_dim_mlp = 2 * max(input_dim, conv_output_dim)
+        self.mlp_rank2 = MLP(num_linears, input_dim, self.hidden_dim_mlp, 1, use_bn)
+        self.mlp_hodge = MLP(num_linears, input_dim, self.hidden_dim_mlp, conv_output_dim, use_bn)
+
+
 class HodgeNetworkLayer(nn.Module):
     """hodge_layers.py:17-63."""
 
@@ -234,6 +256,38 @@ class ScoreNetworkA_CC(ScoreNetworkA):
         return self._score(x, adj, rank2, flags)
 
 
+class ScoreNetworkA_Base_CC(ScoreNetworkA):
+    """ScoreNetwork_A_Base_CC.py:24-323."""
+
+    def __init__(self, max_feat_num, max_node_num, d_min, d_max, nhid, nhid_h, num_layers, num_layers_h, num_linears,
+                 num_linears_h, c_init, c_hid, c_hid_h, c_final, c_final_h, adim, hidden_h, num_heads=4, conv="GCN",
+                 use_bn=False, is_cc=True) -> None:
+        if not is_cc:
+            raise ValueError("ScoreNetworkA_Base_CC is only for combinatorial complexes")
+        nn.Module.__init__(self)
+        self.max_feat_num, self.max_node_num, self.N, self.d_min, self.d_max = max_feat_num, max_node_num, max_node_num, d_min, d_max
+        self.nhid, self.nhid_h, self.num_layers, self.num_layers_h = nhid, nhid_h, num_layers, num_layers_h
+        self.num_linears, self.num_linears_h = num_linears, num_linears_h
+        self.c_init, self.c_hid, self.c_hid_h, self.c_final, self.c_final_h = c_init, c_hid, c_hid_h, c_final, c_final_h
+        self.adim, self.hidden_h, self.num_heads = adim, hidden_h, num_heads
+        self.conv, self.use_bn, self.is_cc = conv, use_bn, is_cc
+        self.layers = nn.ModuleList(self._trunk())
+        hl = []
+        for k in range(num_layers_h):
+            if k == 0:
+                hl.append(HodgeBaselineLayer(num_linears_h, c_init, nhid_h, c_hid_h, max_node_num, d_min, d_max, use_bn))
+            elif k == num_layers_h - 1:
+                hl.append(HodgeBaselineLayer(num_linears_h, c_hid_h, hidden_h, c_final_h, max_node_num, d_min, d_max, use_bn))
+            else:
+                hl.append(HodgeBaselineLayer(num_linears_h, c_hid_h, hidden_h, c_hid_h, max_node_num, d_min, d_max, use_bn))
+        self.layers_hodge = nn.ModuleList(hl)
+        self.fdim = c_hid * (num_layers - 1) + c_final + c_init + c_hid_h * (num_layers_h - 1) + c_final_h + c_init
+        self.final = MLP(3, self.fdim, 2 * self.fdim, 1, use_bn)
+
+    def forward(self, x, adj, rank2, flags=None):
+        return self._score(x, adj, rank2, flags)
+
+
 class ScoreNetworkF(_ScoreNet):
     """ScoreNetwork_F.py:24-217."""
 
@@ -263,8 +317,8 @@ def load_model(params: dict) -> nn.Module:
     p = dict(params)
     model_type = p.pop("model_type", None)
     table = {"ScoreNetworkX": ScoreNetworkX, "ScoreNetworkA": ScoreNetworkA, "ScoreNetworkA_CC": ScoreNetworkA_CC,
-             "ScoreNetworkF": ScoreNetworkF}
-    if model_type in ("ScoreNetworkX_GMH", "ScoreNetworkA_Base_CC"):
+             "ScoreNetworkA_Base_CC": ScoreNetworkA_Base_CC, "ScoreNetworkF": ScoreNetworkF}
+    if model_type in ("ScoreNetworkX_GMH",):
         raise NotImplementedError(f"{model_type} is not on the accelerated path yet (SURVEY.md 8f)")
     if model_type not in table:
         raise ValueError(

@@ -140,7 +140,8 @@ def pack_neta(dst: nat.NetA, blob: Blob, model, K: int) -> None:
         raise NotImplementedError(f"ScoreNetworkA num_layers {L} not in 1..{nat.MAX_LAYERS}")
     dst.num_layers = L
     dst.num_heads = int(m.num_heads)
-    dst.is_cc = 1 if kind == "ScoreNetworkA_CC" else 0
+    dst.is_cc = 1 if kind in ("ScoreNetworkA_CC", "ScoreNetworkA_Base_CC") else 0
+    dst.base_cc = 1 if kind == "ScoreNetworkA_Base_CC" else 0
     fdim = 0
     for l in range(L):
         ly = dst.layer[l]
@@ -159,7 +160,37 @@ def pack_neta(dst: nat.NetA, blob: Blob, model, K: int) -> None:
             dst.c_init = c_in
             fdim += c_in
         fdim += ly.c_out
-    if dst.is_cc:
+    if dst.base_cc:
+        # ScoreNetworkA_Base_CC: HodgeBaselineLayers (hodge_layers.py:287-416).  Their rank-2 outputs never reach the
+        # adjacency score (ScoreNetwork_A_Base_CC.py:296-312 reads only the hodge adjacencies), so mlp_rank2 is not packed.
+        Lh = _count(sd, "layers_hodge")
+        if Lh < 1 or Lh > nat.MAX_HODGE:
+            raise NotImplementedError(f"ScoreNetworkA_Base_CC num_layers_h = {Lh}: only 1 or 2 hodge layers are implemented")
+        dst.num_layers_h = Lh
+        for l in range(Lh):
+            h = dst.hbase[l]
+            c_in = _count(sd, f"layers_hodge.{l}.layers")
+            if c_in > nat.MAX_CH:
+                raise NotImplementedError("more than 8 hodge channels")
+            for c in range(c_in):
+                pre = f"layers_hodge.{l}.layers.{c}.mlp_layer.linears"
+                if f"{pre}.2.weight" in sd:
+                    raise NotImplementedError("BaselineBlock MLP with more than 2 Linears")
+                w1, b1 = sd[f"{pre}.0.weight"], sd[f"{pre}.0.bias"]       # (hid, E), (hid)
+                w2, b2 = sd[f"{pre}.1.weight"], sd[f"{pre}.1.bias"]       # (E, hid), (E)
+                hid = w1.shape[0]
+                if hid > 32:
+                    raise NotImplementedError("BaselineBlock hidden width > 32")
+                h.w1[c], h.b1[c] = blob.add_in_out(w1.T, b1)
+                w2p = np.zeros((w2.shape[0], _r8(hid)), np.float32)
+                w2p[:, :hid] = w2
+                h.w2[c], h.b2[c] = blob.add(w2p), blob.add(b2)
+                h.hid = hid
+            _fill_mlp(h.mlp_hodge, blob, sd, f"layers_hodge.{l}.mlp_hodge")
+            h.c_in, h.c_out = c_in, h.mlp_hodge.dout
+            fdim += h.c_out
+        fdim += dst.c_init
+    elif dst.is_cc:
         if getattr(m, "conv_hodge", "HCN") != "HCN":
             raise NotImplementedError("conv_hodge == 'MLP' is not implemented (no shipped config uses it)")
         Lh = _count(sd, "layers_hodge")

@@ -86,7 +86,18 @@ typedef struct {
   ccsd_mlp_t mlp_attention, mlp_value;
 } ccsd_hodge_layer_t;
 
-/* ScoreNetworkA (ScoreNetwork_A.py:370-541) / ScoreNetworkA_CC (ScoreNetwork_A_CC.py:24-332) */
+/* HodgeBaselineLayer (hodge_layers.py:287-416) of ScoreNetworkA_Base_CC.  BaselineBlock c (hodge_layers.py:202-284)
+ * is a row-wise MLP E -> hid -> E on the Hodge adjacency: its first Linear is stored (E, hid_pad) row-major
+ * (input-major, like every other Linear), its second Linear (hid -> E) as (E, hid_pad) row-major BY OUTPUT ROW,
+ * bias b2 with E entries. */
+typedef struct {
+  int32_t c_in, c_out, hid;
+  int32_t w1[CCSD_MAX_CH], b1[CCSD_MAX_CH], w2[CCSD_MAX_CH], b2[CCSD_MAX_CH];
+  ccsd_mlp_t mlp_hodge;
+} ccsd_hbase_layer_t;
+
+/* ScoreNetworkA (ScoreNetwork_A.py:370-541) / ScoreNetworkA_CC (ScoreNetwork_A_CC.py:24-332) /
+ * ScoreNetworkA_Base_CC (ScoreNetwork_A_Base_CC.py:24-323: is_cc = 1, base_cc = 1, hbase[] instead of hodge[]) */
 typedef struct {
   int32_t is_cc;
   int32_t num_layers, c_init, num_heads, fdim;
@@ -95,6 +106,8 @@ typedef struct {
   int32_t n_proj_rows[CCSD_MAX_HODGE_LAYERS]; /* projection rows per hodge layer */
   int32_t proj_w;                              /* blob offset of [sum rows x K_pad] */
   ccsd_hodge_layer_t hodge[CCSD_MAX_HODGE_LAYERS];
+  int32_t base_cc;
+  ccsd_hbase_layer_t hbase[CCSD_MAX_HODGE_LAYERS];
   ccsd_mlp_t fin;
 } ccsd_neta_t;
 

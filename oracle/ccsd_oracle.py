@@ -343,6 +343,45 @@ def score_network_a_cc(sd: SD, hp: dict, x: Tensor, adj: Tensor, rank2: Tensor, 
     return mask_adjs(score, flags)
 
 
+def baseline_block(sd: SD, hodge_adj: Tensor, rank2: Tensor) -> Tuple[Tensor, Tensor]:
+    """BaselineBlock.forward: row-wise 2-layer MLP (E -> hidden -> E, elu) on the Hodge adjacency, tanh;
+    rank2_out = that @ rank2, hodge_out = its symmetrisation.  hodge_layers.py:261-284."""
+    h = torch.tanh(mlp(_sub(sd, "mlp_layer"), hodge_adj))
+    return torch.bmm(h, rank2), (h + h.transpose(-1, -2)) / 2
+
+
+def hodge_baseline_layer(sd: SD, hodge_adj: Tensor, rank2: Tensor, flags: Optional[Tensor], N: int, d_min: int,
+                         d_max: int) -> Tuple[Tensor, Tensor]:
+    """HodgeBaselineLayer.forward.  hodge_layers.py:380-416."""
+    r2s, hs = [], []
+    for k in range(hodge_adj.shape[1]):
+        r, h = baseline_block(_sub(sd, f"layers.{k}"), hodge_adj[:, k], rank2)
+        r2s.append(r.unsqueeze(-1))
+        hs.append(h.unsqueeze(-1))
+    out = mask_hodge_adjs(mlp(_sub(sd, "mlp_hodge"), torch.cat(hs, dim=-1)).permute(0, 3, 1, 2), flags)
+    out = torch.tanh(out)
+    out = out + out.transpose(-1, -2)
+    r2 = mask_rank2(mlp(_sub(sd, "mlp_rank2"), torch.cat(r2s, dim=-1)).squeeze(-1), N, d_min, d_max, flags)
+    return out, r2
+
+
+def score_network_a_base_cc(sd: SD, hp: dict, x: Tensor, adj: Tensor, rank2: Tensor, flags: Optional[Tensor]) -> Tensor:
+    """ScoreNetworkA_Base_CC.forward.  ScoreNetwork_A_Base_CC.py:266-323."""
+    N = adj.shape[-1]
+    adj_list = _adj_trunk(sd, hp, x, adj, flags)
+    hodge = adj_to_hodgedual(adj_list[0])
+    hodge_list = [hodge]
+    r2 = rank2
+    for k in range(hp["num_layers_h"]):
+        hodge, r2 = hodge_baseline_layer(_sub(sd, f"layers_hodge.{k}"), hodge, r2, flags, N, hp["d_min"], hp["d_max"])
+        hodge_list.append(hodge)
+    adjs = torch.cat(adj_list, dim=1).permute(0, 2, 3, 1)
+    hadj = hodgedual_to_adj(torch.cat(hodge_list, dim=1)).permute(0, 2, 3, 1)
+    score = mlp(_sub(sd, "final"), torch.cat([adjs, hadj], dim=-1)).squeeze(-1)
+    score = score * (1.0 - torch.eye(N)).unsqueeze(0)
+    return mask_adjs(score, flags)
+
+
 def score_network_f(sd: SD, hp: dict, rank2: Tensor, flags: Optional[Tensor]) -> Tensor:
     """ScoreNetworkF.forward (ignores x and adj).  ScoreNetwork_F.py:175-217."""
     N, d_min, d_max = hp["max_node_num"], hp["d_min"], hp["d_max"]
@@ -375,6 +414,9 @@ class Model:
         if self.kind == "ScoreNetworkA_CC":
             x, adj, rank2, flags = args
             return score_network_a_cc(self.sd, self.hp, x, adj, rank2, flags)
+        if self.kind == "ScoreNetworkA_Base_CC":
+            x, adj, rank2, flags = args
+            return score_network_a_base_cc(self.sd, self.hp, x, adj, rank2, flags)
         if self.kind == "ScoreNetworkF":
             x, adj, rank2, flags = args
             return score_network_f(self.sd, self.hp, rank2, flags)

@@ -47,6 +47,9 @@ CONFIGS = {
     # config/sample_ego_small_CC.yaml: Euler predictor, no corrector (snr / scale_eps unused)
     "ego_small_cc": ("ego_small_CC/ccsd_ego_small_CC", ("Euler", "None", 0.0, 0.0), 2),
     "ego_small": ("ego_small/gdss_ego_small", ("Euler", "None", 0.0, 0.0), 3),
+    # ScoreNetworkA_Base_CC checkpoints (config/sample_*_Base_CC.yaml)
+    "qm9_base_cc": ("QM9/ccsd_qm9_Base_CC", ("Reverse", "Langevin", 0.2, 0.7), 3),
+    "community_small_base_cc": ("community_small_CC/ccsd_community_small_Base_CC", ("Euler", "Langevin", 0.05, 0.7), 2),
 }
 
 

@@ -16,7 +16,8 @@ def test_emulation_build_is_flagged():
     assert b"EMULATION" in nat.load().ccsd_version()
 
 
-@pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1), ("ego_small", 2)])
+@pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1), ("ego_small", 2),
+                                    ("qm9_base_cc", 2), ("community_small_base_cc", 1)])
 def test_scores(name, B):
     for k, e in score_parity(name, B, "cpu").items():
         assert e < SCORE_TOL, (name, k, e)
@@ -35,6 +36,7 @@ def test_scores_community_small_cc():
     ("qm9_cc", "PC", "Euler", "Langevin"),
     ("qm9_cc", "S4", "None", "None"),
     ("enzymes_small_cc", "S4", "None", "None"),
+    ("qm9_base_cc", "PC", "Reverse", "Langevin"),
 ])
 def test_sampler_steps(name, sampler, pred, corr):
     res = sampler_parity(name, sampler, pred, corr, B=2, steps=2, device="cpu")

@@ -21,7 +21,8 @@ def test_product_library_is_loaded():
 
 
 @pytest.mark.parametrize("name,B", [("qm9", 64), ("community_small", 16), ("qm9_cc", 16), ("enzymes_small_cc", 8),
-                                    ("community_small_cc", 4), ("ego_small", 8), ("ego_small_cc", 2)])
+                                    ("community_small_cc", 4), ("ego_small", 8), ("ego_small_cc", 2),
+                                    ("qm9_base_cc", 16), ("community_small_base_cc", 4)])
 def test_score_parity(name, B):
     """per-step score outputs within 1e-4 relative of the fp32 reference path (north_star)."""
     errs = score_parity(name, B, DEV)
@@ -30,7 +31,7 @@ def test_score_parity(name, B):
 
 
 @pytest.mark.parametrize("name", ["qm9", "community_small", "ego_small", "qm9_cc", "community_small_cc", "enzymes_small_cc",
-                                  "ego_small_cc"])
+                                  "ego_small_cc", "qm9_base_cc", "community_small_base_cc"])
 def test_scores_against_committed_reference_outputs(name):
     """The same inputs the unmodified reference was run on (tests/golden/io_<cfg>.npz)."""
     cfg = Config(name)
@@ -62,6 +63,8 @@ def test_scores_against_committed_reference_outputs(name):
     ("enzymes_small_cc", "PC", "Reverse", "Langevin", 4, 2),
     ("community_small_cc", "PC", "Euler", "Langevin", 2, 2),
     ("ego_small", "PC", "Euler", "None", 8, 3),
+    ("qm9_base_cc", "PC", "Reverse", "Langevin", 8, 3),
+    ("community_small_base_cc", "PC", "Euler", "Langevin", 2, 2),
     ("ego_small_cc", "PC", "Euler", "None", 2, 2),
     ("ego_small_cc", "PC", "Reverse", "Langevin", 2, 2),
 ])
