@@ -41,6 +41,10 @@ WORKLOADS = {
     "qm9_base_cc": ("qm9_base_cc", 10000, 2500),
     "community_small_base_cc": ("community_small_base_cc", 1024, 32),
     "ego_small_cc": ("ego_small_cc", 128, 32),
+    "ego_small_cc_v2": ("ego_small_cc_v2", 128, 32),
+    "enzymes_small_base_cc": ("enzymes_small_base_cc", 4096, 64),
+    "zinc250k": ("zinc250k", 10000, 2500),
+    "enzymes_small": ("enzymes_small", 64, 64),
     "qm9": ("qm9", 1024, 1024),
 }
 

@@ -433,7 +433,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.ap_group = d.is_cc ? imax(1, imin(8, 192 / imax(d.E, 1))) : 1;
   if (d.is_cc && (d.nets & 4)) {
     const ccsd_netf_t &Fn = d.netf;
-    bool w8 = Fn.fin.nl == 1 && Fn.fdim <= 40, w4 = true;
+    bool w8 = Fn.fdim <= 40, w4 = true;
     int nlin = 0;
     for (int l = 0; l < Fn.num_layers; ++l) {
       const ccsd_mlp_t &M = Fn.layer[l];
@@ -442,9 +442,12 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
       nlin += M.nl;
     }
     if (Fn.affine) p->hp.f_mode = 1;
-    else if (w8) { p->hp.f_mode = w4 ? 3 : 2; p->hp.f_nlin = nlin; }   // 3: four entries at a time (tensor-core apply kernel)
+    else if (w8 && Fn.fin.nl == 1) { p->hp.f_mode = w4 ? 3 : 2; p->hp.f_nlin = nlin; }   // 3: four entries at a time (tensor-core apply kernel)
+    else if (w8 && Fn.fin.nl == 2 && Fn.num_layers <= NETF_F2_MAXL && netf_stage_floats(Fn, nlin, 4) <= 2048) {
+      p->hp.f_mode = 4; p->hp.f_nlin = nlin;                                             // two-Linear final MLP (Base_CC checkpoints)
+    }
   }
-  p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)p->hp.f_nlin * 72 + 48) * 4 : 0;
+  p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)netf_stage_floats(d.netf, p->hp.f_nlin, p->hp.f_mode) + 4) * 4 : 0;
   const XpLayout &XL = p->hp.xp;
   const size_t xp_max = (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, imax(XL.h_total, XL.hb_total))), XL.m_total) * 4;
   if (xp_max > 227 * 1024 || p->apply_smem > 227 * 1024) {
@@ -507,6 +510,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     e2 = cudaFuncSetAttribute(apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
     if (e2 == cudaSuccess) apply_attr = p->apply_smem;
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -681,6 +685,7 @@ static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
 #endif
   const dim3 grid(p->hp.ntile_r2, p->hp.d.B, 1);
   if (p->hp.f_mode == 1) CCSD_LAUNCH(apply_kernel<1>, grid, 256, p->apply_smem, stream, p->dP, q);
+  else if (p->hp.f_mode == 4) CCSD_LAUNCH(apply_kernel<4>, grid, 256, p->apply_smem, stream, p->dP, q);
   else if (p->hp.f_mode >= 2) CCSD_LAUNCH(apply_kernel<2>, grid, 256, p->apply_smem, stream, p->dP, q);
   else CCSD_LAUNCH(apply_kernel<0>, grid, 256, p->apply_smem, stream, p->dP, q);
 }

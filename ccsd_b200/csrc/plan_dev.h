@@ -55,7 +55,7 @@ struct DevPlan {
   int ntile_r2;                   // apply-kernel column tiles per sample
   int ntile_adj;                  // afinal-kernel row chunks per sample (norm partial slots of the adjacency)
   int ntile_max;                  // stride of the per-object norm partials
-  int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled
+  int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled, 3 <=4-wide x4 entries, 4 <=8-wide + 2-Linear final
   int f_nlin;                     // number of Linears staged for f_mode 2
   int ap_group;                   // tensor-core apply kernel: samples per work group (min(8, 192 / E))
 };

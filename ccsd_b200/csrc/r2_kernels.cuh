@@ -372,6 +372,100 @@ __device__ __forceinline__ void netf_stage_w8(const ccsd_netf_t &Fn, const float
   }
 }
 
+// f_mode 4: layers at most 8 wide (staged 8x8 blocks as above, at most 3 of them) and a TWO-Linear final MLP
+// (num_layers_mlp == 2: the Base_CC checkpoints).  The final MLP's first Linear is staged per hidden unit h
+// as a row of NETF_F2_LD floats over the statically indexed register inputs:
+//   [0] f, [1] H f, [2 + 8 l + o] output o of layer l (zero weight past dout), [26] b1[h], [27] w2[h]
+// followed by b2; every thread of a warp reads the same row (shared-memory broadcast).
+constexpr int NETF_F2_LD = 28;
+constexpr int NETF_F2_MAXL = 3;
+__device__ __forceinline__ float netf_entry_w8f2(const ccsd_netf_t &Fn, const float *fw, int nlin, float f, float hf,
+                                                 float m) {
+  float lay[NETF_F2_MAXL][8];
+  float cur[8] = {f, hf, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int li = 0;
+#pragma unroll
+  for (int l = 0; l < NETF_F2_MAXL; ++l) {
+    if (l < Fn.num_layers) {
+      const int nl = Fn.layer[l].nl;
+      for (int i = 0; i < nl; ++i, ++li) {
+        const float *Wm = fw + li * 72;
+        float t[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) t[o] = Wm[64 + o];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int o = 0; o < 8; ++o) t[o] += cur[k] * Wm[k * 8 + o];
+        if (i == nl - 1) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) cur[o] = t[o] * m;
+        } else {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) cur[o] = fast_elu(t[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) lay[l][o] = (l < Fn.num_layers) ? cur[o] : 0.f;
+  }
+  const float *wf = fw + nlin * 72;
+  const int dh = Fn.fin.dhid;
+  float acc = wf[dh * NETF_F2_LD];
+  for (int h = 0; h < dh; ++h) {
+    const float *r = wf + h * NETF_F2_LD;
+    float t = r[26] + r[0] * f + r[1] * hf;
+#pragma unroll
+    for (int l = 0; l < NETF_F2_MAXL; ++l)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) t += r[2 + 8 * l + o] * lay[l][o];
+    acc += r[27] * fast_elu(t);
+  }
+  return acc * m;
+}
+
+// staged size in floats of the f_mode 2/3 (final = 1 Linear) and f_mode 4 layouts
+static inline int netf_stage_floats(const ccsd_netf_t &Fn, int nlin, int f_mode) {
+  return nlin * 72 + (f_mode == 4 ? Fn.fin.dhid * NETF_F2_LD + 4 : 44);
+}
+
+__device__ __forceinline__ void netf_stage_w8f2(const ccsd_netf_t &Fn, const float *__restrict__ W, float *fw) {
+  int li = 0;
+  for (int l = 0; l < Fn.num_layers; ++l) {
+    const ccsd_mlp_t &M = Fn.layer[l];
+    for (int i = 0; i < M.nl; ++i, ++li) {
+      const int din = (i == 0) ? M.din : M.dhid;
+      for (int p = threadIdx.x; p < 72; p += blockDim.x) {
+        float v;
+        if (p < 64) v = (p / 8 < din) ? __ldg(W + M.w[i] + p) : 0.f;
+        else v = __ldg(W + M.b[i] + (p - 64));
+        fw[li * 72 + p] = v;
+      }
+    }
+  }
+  float *wf = fw + li * 72;
+  const ccsd_mlp_t &Fm = Fn.fin;
+  const int dh = Fm.dhid, hp = (dh + 7) / 8 * 8;    // first Linear stored (fdim, hp); second (dh, 8) with out = 1
+  for (int p = threadIdx.x; p < dh * NETF_F2_LD; p += blockDim.x) {
+    const int h = p / NETF_F2_LD, c = p - h * NETF_F2_LD;
+    float v = 0.f;
+    if (c == 26) v = __ldg(W + Fm.b[0] + h);
+    else if (c == 27) v = __ldg(W + Fm.w[1] + h * 8);
+    else if (c < 2) v = __ldg(W + Fm.w[0] + c * hp + h);
+    else {
+      // input row of lst = [f, hf, layer 0 outputs, layer 1 outputs, ...]
+      const int l = (c - 2) >> 3, o = (c - 2) & 7;
+      if (l < Fn.num_layers && o < Fn.layer[l].dout) {
+        int row = 2;
+        for (int q = 0; q < l; ++q) row += Fn.layer[q].dout;
+        v = __ldg(W + Fm.w[0] + (size_t)(row + o) * hp + h);
+      }
+    }
+    wf[p] = v;
+  }
+  if (threadIdx.x == 0) wf[dh * NETF_F2_LD] = __ldg(W + Fm.b[1]);
+}
+
 struct ApplyArgs {
   const float *r2, *H, *flags;   // [B,E,K] [B,E,E] [B,N]
   int mode;
@@ -429,6 +523,7 @@ __device__ __forceinline__ void r2_epilogue4(const R2Epi &c, const ApplyArgs &a,
       float o;
       if (FMODE == 1) o = m * (c.aff0 * f + c.aff1 * hf4[q] + c.aff2);
       else if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf4[q], m);
+      else if (FMODE == 4) o = netf_entry_w8f2(P->d.netf, c.fw, c.f_nlin, f, hf4[q], m);
       else o = netf_entry(P->d.netf, P->W, f, hf4[q], m);
       const size_t g = g0 + q;
       if (a.mode == MODE_EVAL) {
@@ -469,6 +564,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
   float *red = Hs + 16 * LDH;             // [40]
   float *fw = red + 40;                   // staged ScoreNetworkF weights (f_mode 2)
   if (FMODE == 2) netf_stage_w8(d.netf, P->W, fw);
+  if (FMODE == 4) netf_stage_w8f2(d.netf, P->W, fw);
   R2Epi c;
   c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
   c.gs = (unsigned long long)(a.nz.sample_offset + b);

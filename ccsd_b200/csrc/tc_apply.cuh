@@ -67,7 +67,8 @@ constexpr uint32_t TA_FCS = TA_BARS + 256;        // [NS][GMAX][32] cell flags
 constexpr uint32_t TA_RED = TA_FCS + TA_NS * TA_GMAX * 32 * 4;   // [2 cell halves][192 rows][2] norm partials
 constexpr int TA_MMAW = (TA_LOAD + TA_EPI) / 32;     // index of the MMA warp
 constexpr uint32_t TA_FW = TA_RED + 2 * TA_NE * 2 * 4;   // staged ScoreNetworkF weights (FMODE 2)
-constexpr size_t TA_SMEM = (size_t)TA_FW + 6144 + 1024 /*alignment slack*/;
+constexpr int TA_FW_FLOATS = 2048;
+constexpr size_t TA_SMEM = (size_t)TA_FW + TA_FW_FLOATS * 4 + 1024 /*alignment slack*/;
 constexpr uint32_t TA_COL_D = 384;                // first accumulator column
 
 static inline int tc_apply_supported(int E, int K) { return E >= 8 && E <= TA_NE && K >= 8; }
@@ -94,6 +95,7 @@ __device__ __forceinline__ float r2_entry(const R2Epi &c, const R2Fold &w, float
     float o;
     if (FMODE == 3) o = o_pre;                 // network evaluated four entries at a time by the caller
     else if (FMODE == 2) o = netf_entry_w8(P->d.netf, c.fw, c.f_nlin, f, hf, m);
+    else if (FMODE == 4) o = netf_entry_w8f2(P->d.netf, c.fw, c.f_nlin, f, hf, m);
     else o = netf_entry(P->d.netf, P->W, f, hf, m);
     s = w.sc * o;
   }
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   }
   if (warp == TA_MMAW) tc::tmem_alloc(tslot, 512);
   if (FMODE == 2 || FMODE == 3) netf_stage_w8(d.netf, P->W, fw);
+  if (FMODE == 4) netf_stage_w8f2(d.netf, P->W, fw);
   // operand rows that no edge fills stay zero for the whole kernel (their A columns are zero too, but
   // 0 * NaN from uninitialised shared memory would poison the accumulator)
   for (uint32_t o = threadIdx.x * 16u; o < TA_OPER; o += TA_THREADS * 16u)
@@ -623,6 +626,7 @@ static inline int tc_apply_launch(const DevPlan *dP, const DevPlan &hp, const Ap
   if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, m, stream);
   if (hp.f_mode == 2) return tc_apply_launch_f<2>(dP, grid, a, m, stream);
   if (hp.f_mode == 3) return tc_apply_launch_f<3>(dP, grid, a, m, stream);
+  if (hp.f_mode == 4) return tc_apply_launch_f<4>(dP, grid, a, m, stream);
   return tc_apply_launch_f<0>(dP, grid, a, m, stream);
 }
 

@@ -50,6 +50,11 @@ CONFIGS = {
     # ScoreNetworkA_Base_CC checkpoints (config/sample_*_Base_CC.yaml)
     "qm9_base_cc": ("QM9/ccsd_qm9_Base_CC", ("Reverse", "Langevin", 0.2, 0.7), 3),
     "community_small_base_cc": ("community_small_CC/ccsd_community_small_Base_CC", ("Euler", "Langevin", 0.05, 0.7), 2),
+    "enzymes_small_base_cc": ("ENZYMES_small_CC/ccsd_enzymes_small_Base_CC", ("S4", "None", 0.15, 0.7), 2),
+    "ego_small_cc_v2": ("ego_small_CC/ccsd_ego_small_CC_v2", ("Euler", "None", 0.0, 0.0), 2),
+    # graph-only checkpoints of the remaining datasets
+    "zinc250k": ("ZINC250k/gdss_zinc250k", ("Reverse", "Langevin", 0.2, 0.9), 3),
+    "enzymes_small": ("ENZYMES_small/gdss_enzymes_small_retrained", ("S4", "None", 0.15, 0.7), 3),
 }
 
 

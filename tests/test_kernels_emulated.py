@@ -17,7 +17,8 @@ def test_emulation_build_is_flagged():
 
 
 @pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1), ("ego_small", 2),
-                                    ("qm9_base_cc", 2), ("community_small_base_cc", 1)])
+                                    ("qm9_base_cc", 2), ("community_small_base_cc", 1),
+                                    ("enzymes_small_base_cc", 1), ("zinc250k", 1), ("enzymes_small", 2)])
 def test_scores(name, B):
     for k, e in score_parity(name, B, "cpu").items():
         assert e < SCORE_TOL, (name, k, e)
@@ -37,6 +38,7 @@ def test_scores_community_small_cc():
     ("qm9_cc", "S4", "None", "None"),
     ("enzymes_small_cc", "S4", "None", "None"),
     ("qm9_base_cc", "PC", "Reverse", "Langevin"),
+    ("enzymes_small", "S4", "None", "None"),
 ])
 def test_sampler_steps(name, sampler, pred, corr):
     res = sampler_parity(name, sampler, pred, corr, B=2, steps=2, device="cpu")
