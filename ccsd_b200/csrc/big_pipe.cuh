@@ -1,0 +1,416 @@
+// big_pipe.cuh -- ScoreNetworkX and ScoreNetworkA for LARGE graphs (max_node_num > 64: grid N = 361,
+// ENZYMES N = 125), graph-only configs.  Same reference functions as xa_pipe.cuh (ScoreNetwork_X.py:102-133,
+// ScoreNetwork_A.py:505-541, attention.py:84-132,270-304, layers.py:115-158, graph_utils.py:274-292), other
+// shape regime: one graph no longer fits a CTA's shared memory (54 adjacency channels x 361^2 = 28 MB), so
+// every phase is tiled over (row chunk | channel | graph) CTAs and the channel stack lives in HBM / L2 as
+// full N x Np planes (Np = N rounded up to 8).
+//
+// All the contractions are expressed through the feature-major register-tile primitive dense_fm (prims.cuh):
+//   out(r, o) = sum_k in(k, r) W[k, o]
+//   * A^c = A^(c-1) A        in(k, r) = A^(c-1)[k][r] (symmetric), W = A            (pow_tensor)
+//   * x W_{q|k|v}            in = node features, feature-major [kin][Np]            (DenseGCNConv transform)
+//   * A^ (x W)               in(k, r) = adj_c[k][r] (symmetric), W = the scaled transform Y, node-major
+//                            (DenseGCNConv aggregation; the unit diagonal of A^ is a rank-one fix-up)
+//   * the per-edge MLPs      in = channel planes (plane stride = N Np), rows = 64-pair segments of one row
+// Symmetry: every adjacency-shaped tensor is symmetric, so the per-pair kernels only visit the 64-column
+// segments of row i that reach the diagonal (j0 + 63 >= i) and write (i, j) and (j, i).
+//
+// Launch sequence of one evaluation (host: launch_xa_big):
+//   prep -> pow (c_init - 1) -> deg -> [X net: depth x (xw, agg) -> xfin]
+//        -> L x (xw, agg, attn, node, edge, deg) -> final
+#pragma once
+#include "xa_pipe.cuh"
+
+namespace ccsd {
+
+constexpr int BIG_RC = 32;     // node rows per CTA of the row-chunk kernels
+constexpr int BIG_SEG = 64;    // node pairs (columns of one row) per CTA of the per-pair kernels
+
+struct BigArgs {
+  XaArgs a;
+  float *base;        // scratch [B][big.g_total]
+  int layer;          // attention layer
+  int ch_in, ch_out;  // first input / output plane of the stack
+  const float *xin;   // node features read  (feature-major [kin][Np], per-graph stride big.g_xf)
+  float *xout;        // node features written
+  int c;              // pow: plane to produce
+  int xmode;          // 0: attention layer `layer`, 1: GCN layer `gk` of ScoreNetworkX
+  int gk, in_row, out_row;   // X net: GCN layer, first input / output row of the feature concat HC
+  int nch;            // deg: number of planes starting at ch_in
+};
+
+__device__ __forceinline__ float *big_ptr(const DevPlan *P, const BigArgs &g, int b, int off) {
+  return g.base + (size_t)b * P->xp.big_total + off;
+}
+
+// plane 0 of the stack <- adj; node features (feature-major) <- x, also rows [0, F) of the X net's concat
+__global__ void __launch_bounds__(256) big_prep_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.y, N = d.N, F = d.F, Np = L.big_Np;
+  float *S = big_ptr(P, g, b, L.big_S), *xf = big_ptr(P, g, b, L.big_XF0), *hc = big_ptr(P, g, b, L.big_HC);
+  const int tot = N * Np + F * Np;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < tot; p += gridDim.x * blockDim.x) {
+    if (p < N * Np) {
+      const int i = p / Np, j = p - i * Np;
+      S[p] = j < N ? g.a.adj[((size_t)b * N + i) * N + j] : 0.f;
+    } else {
+      const int q = p - N * Np, f = q / Np, i = q - f * Np;
+      const float v = i < N ? g.a.x[((size_t)b * N + i) * F + f] : 0.f;
+      xf[q] = v;
+      hc[q] = v;
+    }
+  }
+}
+
+// pow_tensor (graph_utils.py:274-292): plane c = plane (c-1) . plane 0
+__global__ void __launch_bounds__(128) big_pow_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, N = P->d.N, Np = L.big_Np, PS = L.big_PS;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  float *S = big_ptr(P, g, b, L.big_S);
+  dense_fm(S + (size_t)(g.c - 1) * PS + i0, Np, N, nullptr, 0, 0, S, nullptr, N, S + (size_t)g.c * PS + (size_t)i0 * Np, Np, 1, R,
+           ACT_NONE);
+}
+
+// DenseGCNConv degrees (layers.py:139-146): d_i = clamp(sum_j A^_ij, 1)^-1/2 with the unit diagonal of A^
+__global__ void __launch_bounds__(128) big_deg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, c = blockIdx.y, N = P->d.N, Np = L.big_Np;
+  const float *pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_in + c) * L.big_PS;
+  float *dv = big_ptr(P, g, b, L.big_DV) + c * Np;
+  const int i1 = (blockIdx.x + 1) * 128 < N ? (blockIdx.x + 1) * 128 : N;
+  for (int i = blockIdx.x * 128 + threadIdx.x; i < i1; i += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s += (j == i) ? 1.f : pl[(size_t)j * Np + i];   // column i = row i (symmetric), coalesced
+    dv[i] = 1.0f / sqrtf(fmaxf(s, 1.f));
+  }
+}
+
+// Y = diag(d) (x W): the feature transforms of one channel's Q | K | V convolutions (xmode 0) or of one GCN
+// layer of ScoreNetworkX (xmode 1), node-major, pre-scaled by d_j for the aggregation
+__global__ void __launch_bounds__(128) big_xw_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const float *W = P->W;
+  const float *dv = big_ptr(P, g, b, L.big_DV) + c * Np;
+  if (g.xmode == 0) {
+    const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+    const int kin = ly.conv_in, ad = ly.attn_dim, nh = ly.conv_out, adp = round_up(ad, 8), nhp = round_up(nh, 8), w2 = 2 * adp;
+    const float *xin = g.xin + (size_t)b * L.big_total;
+    float *yqk = big_ptr(P, g, b, L.big_YQK) + (size_t)c * N * w2, *yv = big_ptr(P, g, b, L.big_YV) + (size_t)c * N * nhp;
+    dense_fm(xin + i0, Np, kin, nullptr, 0, 0, W + ly.q[c].w, nullptr, ad, yqk + (size_t)i0 * w2, w2, 1, R, ACT_NONE);
+    dense_fm(xin + i0, Np, kin, nullptr, 0, 0, W + ly.k[c].w, nullptr, ad, yqk + (size_t)i0 * w2 + adp, w2, 1, R, ACT_NONE);
+    dense_fm(xin + i0, Np, kin, nullptr, 0, 0, W + ly.v[c].w, nullptr, nh, yv + (size_t)i0 * nhp, nhp, 1, R, ACT_NONE);
+    __syncthreads();
+    for (int p = threadIdx.x; p < R * (w2 + nhp); p += blockDim.x) {
+      const int r = p / (w2 + nhp), o = p - r * (w2 + nhp), i = i0 + r;
+      float *y = o < w2 ? yqk + (size_t)i * w2 + o : yv + (size_t)i * nhp + (o - w2);
+      const int oo = o < w2 ? (o < adp ? o : o - adp) : o - w2;
+      *y = (oo < (o < w2 ? ad : nh)) ? *y * dv[i] : 0.f;
+    }
+  } else {
+    const ccsd_gcn_t &gc = d.netx.gcn[g.gk];
+    const int dout = gc.dout, dp = round_up(dout, 8);
+    const float *in = big_ptr(P, g, b, L.big_HC) + (size_t)g.in_row * Np;
+    float *y = big_ptr(P, g, b, L.big_YV);
+    dense_fm(in + i0, Np, gc.din, nullptr, 0, 0, W + gc.w, nullptr, dout, y + (size_t)i0 * dp, dp, 1, R, ACT_NONE);
+    __syncthreads();
+    for (int p = threadIdx.x; p < R * dp; p += blockDim.x) {
+      const int r = p / dp, o = p - r * dp, i = i0 + r;
+      float *yy = y + (size_t)i * dp + o;
+      *yy = o < dout ? *yy * dv[i] : 0.f;
+    }
+  }
+}
+
+// T = diag(d) A^ Y + bias: the aggregation of DenseGCNConv (layers.py:147-156).  A^ = plane with a unit
+// diagonal: sum_j a_ij y_j over the stored plane plus the rank-one fix-up (1 - a_ii) y_i.
+// xmode 0: Q | K rows -> TQK (feature-major [2 adp][Np]), V -> TV ([c nh + o][Np]);  xmode 1: tanh -> HC rows.
+__global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const float *W = P->W;
+  const float *dv = big_ptr(P, g, b, L.big_DV) + c * Np;
+  if (g.xmode == 0) {
+    const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+    const int ad = ly.attn_dim, nh = ly.conv_out, adp = round_up(ad, 8), nhp = round_up(nh, 8), w2 = 2 * adp;
+    const float *pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_in + c) * L.big_PS;
+    const float *yqk = big_ptr(P, g, b, L.big_YQK) + (size_t)c * N * w2, *yv = big_ptr(P, g, b, L.big_YV) + (size_t)c * N * nhp;
+    float *tqk = big_ptr(P, g, b, L.big_TQK) + (size_t)c * w2 * Np, *tv = big_ptr(P, g, b, L.big_TV) + (size_t)c * nh * Np;
+    dense_fm(pl + i0, Np, N, nullptr, 0, 0, yqk, nullptr, w2, tqk + i0, 1, Np, R, ACT_NONE);
+    dense_fm(pl + i0, Np, N, nullptr, 0, 0, yv, nullptr, nh, tv + i0, 1, Np, R, ACT_NONE);
+    __syncthreads();
+    for (int p = threadIdx.x; p < R * (w2 + nh); p += blockDim.x) {
+      const int o = p / R, r = p - o * R, i = i0 + r;
+      const float fix = 1.f - pl[(size_t)i * Np + i];
+      if (o < w2) {
+        const int oo = o < adp ? o : o - adp;
+        if (oo < ad) {
+          const float bias = __ldg(W + (o < adp ? ly.q[c].b : ly.k[c].b) + oo);
+          tqk[(size_t)o * Np + i] = dv[i] * (tqk[(size_t)o * Np + i] + fix * yqk[(size_t)i * w2 + o]) + bias;
+        }
+      } else {
+        const int oo = o - w2;
+        tv[(size_t)oo * Np + i] = dv[i] * (tv[(size_t)oo * Np + i] + fix * yv[(size_t)i * nhp + oo]) + __ldg(W + ly.v[c].b + oo);
+      }
+    }
+  } else {
+    const ccsd_gcn_t &gc = d.netx.gcn[g.gk];
+    const int dout = gc.dout, dp = round_up(dout, 8);
+    const float *pl = big_ptr(P, g, b, L.big_S);
+    const float *y = big_ptr(P, g, b, L.big_YV);
+    float *out = big_ptr(P, g, b, L.big_HC) + (size_t)g.out_row * Np;
+    dense_fm(pl + i0, Np, N, nullptr, 0, 0, y, nullptr, dout, out + i0, 1, Np, R, ACT_NONE);
+    __syncthreads();
+    for (int p = threadIdx.x; p < R * dout; p += blockDim.x) {
+      const int o = p / R, r = p - o * R, i = i0 + r;
+      const float fix = 1.f - pl[(size_t)i * Np + i];
+      out[(size_t)o * Np + i] = fast_tanh(dv[i] * (out[(size_t)o * Np + i] + fix * y[(size_t)i * dp + o]) + __ldg(W + gc.b + o));
+    }
+  }
+}
+
+// Attention scores of one channel (attention.py:111-130): heads = chunks of ds = ad / heads features
+// (torch.split), att(i, j) = mean_h 0.5 (tanh(q_i.k_j s) + tanh(q_j.k_i s)).  Item = 4x4 node block I <= J.
+__global__ void __launch_bounds__(128) big_attn_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
+  const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+  const int ad = ly.attn_dim, adp = round_up(ad, 8), heads = d.neta.num_heads;
+  const int ds = ad / heads, nch = (ad + ds - 1) / ds;
+  const float inv = 0.5f / (float)nch, scale = 1.0f / sqrtf((float)ly.conv_out);
+  const float *Q = big_ptr(P, g, b, L.big_TQK) + (size_t)c * 2 * adp * Np, *Kf = Q + (size_t)adp * Np;
+  float *att = big_ptr(P, g, b, L.big_ATT) + (size_t)c * L.big_PS;
+  const int nb = (N + 3) >> 2, nblk = nb * (nb + 1) / 2;
+  const int it1 = (blockIdx.x + 1) * 128 < nblk ? (blockIdx.x + 1) * 128 : nblk;
+  for (int it = blockIdx.x * 128 + threadIdx.x; it < it1; it += blockDim.x) {
+    // row-major upper triangle of nb x nb blocks: rows before I hold I nb - I (I - 1) / 2 blocks
+    int I = (int)(((float)(2 * nb + 1) - sqrtf((float)(2 * nb + 1) * (float)(2 * nb + 1) - 8.f * (float)it)) * 0.5f);
+    if (I < 0) I = 0;
+    if (I > nb - 1) I = nb - 1;
+    while (I > 0 && I * nb - I * (I - 1) / 2 > it) --I;
+    while ((I + 1) * nb - (I + 1) * I / 2 <= it) ++I;
+    const int J = I + (it - (I * nb - I * (I - 1) / 2));
+    const int i0 = I << 2, j0 = J << 2;
+    float sum[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) sum[u][v] = 0.f;
+    for (int h = 0; h < nch; ++h) {
+      float qa[4][4], qb[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { qa[u][v] = 0.f; qb[u][v] = 0.f; }
+      const int d0 = h * ds, d1 = (d0 + ds < ad) ? d0 + ds : ad;
+      for (int dd = d0; dd < d1; ++dd) {
+        const float4 qi = ld4(Q + (size_t)dd * Np + i0), kj = ld4(Kf + (size_t)dd * Np + j0);
+        const float4 qj = ld4(Q + (size_t)dd * Np + j0), ki = ld4(Kf + (size_t)dd * Np + i0);
+        const float qiv[4] = {qi.x, qi.y, qi.z, qi.w}, kjv[4] = {kj.x, kj.y, kj.z, kj.w};
+        const float qjv[4] = {qj.x, qj.y, qj.z, qj.w}, kiv[4] = {ki.x, ki.y, ki.z, ki.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) { qa[u][v] += qiv[u] * kjv[v]; qb[u][v] += qjv[v] * kiv[u]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) sum[u][v] += fast_tanh(qa[u][v] * scale) + fast_tanh(qb[u][v] * scale);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = i0 + u, j = j0 + v;
+        if (i <= j && j < N) {
+          const float o = inv * sum[u][v];
+          att[(size_t)i * Np + j] = o;
+          att[(size_t)j * Np + i] = o;
+        }
+      }
+  }
+}
+
+// node branch of AttentionLayer (attention.py:292-293): x_out = tanh(mask_x(MLP(cat_c V_c)))
+__global__ void __launch_bounds__(128) big_node_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, N = d.N, Np = L.big_Np;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+  const ccsd_mlp_t &mc = ly.multi_channel;
+  const int nh = ly.conv_out, hid = mc.nl > 1 ? mc.dhid : 1;
+  float *so = sm, *hA = sm + round_up(nh, 4) * BIG_RC, *hB = mc.nl > 2 ? hA + hid * BIG_RC : hA;
+  const float *tv = big_ptr(P, g, b, L.big_TV);
+  mlp_fm(mc, P->W, tv + i0, Np, ly.c_in * nh, nullptr, 0, 0, R, hA, hB, BIG_RC, so, 1, BIG_RC, ACT_ELU, ACT_NONE);
+  float *xo = g.xout + (size_t)b * L.big_total;
+  for (int p = threadIdx.x; p < nh * R; p += blockDim.x) {
+    const int o = p / R, r = p - o * R, i = i0 + r;
+    xo[(size_t)o * Np + i] = fast_tanh(so[o * BIG_RC + r] * g.a.flags[(size_t)b * N + i]);
+  }
+}
+
+// segment of row i that this CTA of a per-pair kernel owns; false when it lies wholly below the diagonal
+__device__ __forceinline__ bool big_segment(const DevPlan *P, int &i, int &j0, int &R) {
+  const int nseg = P->xp.big_nseg, N = P->d.N;
+  i = blockIdx.x / nseg;
+  j0 = (blockIdx.x - i * nseg) * BIG_SEG;
+  R = (N - j0 < BIG_SEG) ? N - j0 : BIG_SEG;
+  return j0 + BIG_SEG > i;
+}
+
+// edge branch of AttentionLayer (attention.py:295-303): M = MLP([att_1..att_c, adj_1..adj_c]),
+// adj_out = mask_adjs(M + M^T) = 2 M mask (M is symmetric because its inputs are)
+__global__ void __launch_bounds__(128) big_edge_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, N = d.N, Np = L.big_Np, PS = L.big_PS;
+  int i, j0, R;
+  if (!big_segment(P, i, j0, R)) return;
+  const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+  const ccsd_mlp_t &m = ly.mlp;
+  const int hid = m.nl > 1 ? m.dhid : 1;
+  float *so = sm, *hA = sm + ly.c_out * BIG_SEG, *hB = m.nl > 2 ? hA + hid * BIG_SEG : hA;
+  float *S = big_ptr(P, g, b, L.big_S);
+  const float *att = big_ptr(P, g, b, L.big_ATT);
+  const size_t t0 = (size_t)i * Np + j0;
+  mlp_fm(m, P->W, att + t0, PS, ly.c_in, S + (size_t)g.ch_in * PS + t0, PS, ly.c_in, R, hA, hB, BIG_SEG, so, 1, BIG_SEG, ACT_ELU,
+         ACT_NONE);
+  const float fi = g.a.flags[(size_t)b * N + i];
+  for (int p = threadIdx.x; p < ly.c_out * R; p += blockDim.x) {
+    const int o = p / R, r = p - o * R, j = j0 + r;
+    if (j < i) continue;
+    const float v = 2.0f * so[o * BIG_SEG + r] * fi * g.a.flags[(size_t)b * N + j];
+    float *pl = S + (size_t)(g.ch_out + o) * PS;
+    pl[(size_t)i * Np + j] = v;
+    pl[(size_t)j * Np + i] = v;
+  }
+}
+
+// final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) + the adjacency sampler epilogue
+// (same arithmetic as afinal_kernel)
+__global__ void __launch_bounds__(128) big_final_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const XaArgs &a = g.a;
+  const int b = blockIdx.z, N = d.N, Np = L.big_Np, PS = L.big_PS;
+  int i, j0, R;
+  float *np = a.norm_part + ((size_t)(1 * d.B + b) * P->ntile_max + blockIdx.x) * 2;
+  if (!big_segment(P, i, j0, R)) {
+    if (a.mode == MODE_SCORE && threadIdx.x == 0) { np[0] = 0.f; np[1] = 0.f; }
+    return;
+  }
+  const ccsd_mlp_t &m = d.neta.fin;
+  const int hid = m.nl > 1 ? m.dhid : 1;
+  float *so = sm, *red = sm + BIG_SEG, *hA = red + 40, *hB = m.nl > 2 ? hA + hid * BIG_SEG : hA;
+  const float *S = big_ptr(P, g, b, L.big_S);
+  mlp_fm(m, P->W, S + (size_t)i * Np + j0, PS, g.ch_out /* planes in the stack */, nullptr, 0, 0, R, hA, hB, BIG_SEG, so, 1, 0,
+         ACT_ELU, ACT_NONE);
+  const size_t ga = (size_t)b * N * N;
+  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 1];
+  const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
+  const float fi = a.flags[(size_t)b * N + i];
+  float s2 = 0.f, z2 = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const int j = j0 + r;
+    if (j < i) continue;
+    const float fij = fi * a.flags[(size_t)b * N + j];
+    const float o = (i == j) ? 0.f : so[r] * fij;   // (1 - I) mask and mask_adjs
+    if (a.mode == MODE_EVAL) {
+      a.out_adj[ga + (size_t)i * N + j] = o;
+      a.out_adj[ga + (size_t)j * N + i] = o;
+      continue;
+    }
+    const float s = ca.score_scale * o;
+    float z = 0.f;
+    if (i != j) {
+      const int q = i * N + j;
+      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, a.nz.step, a.slot), q)) * fij;
+    }
+    if (a.mode == MODE_SCORE) {
+      a.out_adj[ga + (size_t)i * N + j] = s;
+      if (i != j) {
+        a.out_adj[ga + (size_t)j * N + i] = s;
+        s2 += 2.f * s * s;
+        z2 += 2.f * z * z;
+      }
+    } else {
+      const float mu = ca.pa * a.adj[ga + (size_t)i * N + j] + ca.pb * s;
+      const float v = mu + ca.pc * z;
+      a.out_adj[ga + (size_t)i * N + j] = v;
+      a.mean_adj[ga + (size_t)i * N + j] = mu;
+      if (a.traj_adj && b == 0) a.traj_adj[(size_t)i * N + j] = a.denoise ? mu : v;
+      if (i != j) {
+        a.out_adj[ga + (size_t)j * N + i] = v;
+        a.mean_adj[ga + (size_t)j * N + i] = mu;
+        if (a.traj_adj && b == 0) a.traj_adj[(size_t)j * N + i] = a.denoise ? mu : v;
+      }
+    }
+  }
+  if (a.mode == MODE_SCORE) {
+    s2 = block_sum(s2, red);
+    z2 = block_sum(z2, red);
+    if (threadIdx.x == 0) { np[0] = s2; np[1] = z2; }
+  }
+}
+
+// final MLP of ScoreNetworkX over a row chunk (ScoreNetwork_X.py:127-133) + the x sampler epilogue
+// (same arithmetic as x_net_kernel)
+__global__ void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const XaArgs &a = g.a;
+  const int b = blockIdx.z, N = d.N, F = d.F, Np = L.big_Np;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const ccsd_netx_t &X = d.netx;
+  const ccsd_mlp_t &m = X.fin;
+  const int hid = m.nl > 1 ? m.dhid : 1;
+  float *so = sm, *red = sm + round_up(F, 4) * BIG_RC, *hA = red + 40, *hB = m.nl > 2 ? hA + hid * BIG_RC : hA;
+  const float *hc = big_ptr(P, g, b, L.big_HC);
+  mlp_fm(m, P->W, hc + i0, Np, X.fdim, nullptr, 0, 0, R, hA, hB, BIG_RC, so, 1, BIG_RC, ACT_ELU, ACT_NONE);
+  const size_t gxo = (size_t)b * N * F;
+  const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 0];
+  const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
+  float s2 = 0.f, z2 = 0.f;
+  for (int q = threadIdx.x; q < R * F; q += blockDim.x) {
+    const int r = q / F, f = q - r * F, i = i0 + r, p = i * F + f;
+    const float fl = a.flags[(size_t)b * N + i];
+    const float o = so[f * BIG_RC + r] * fl;   // mask_x
+    if (a.mode == MODE_EVAL) { a.out_x[gxo + p] = o; continue; }
+    const float s = cx.score_scale * o;
+    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, a.nz.step, a.slot), p)) * fl;
+    if (a.mode == MODE_SCORE) {
+      a.out_x[gxo + p] = s;
+      s2 += s * s;
+      z2 += z * z;
+    } else {
+      const float mu = cx.pa * a.x[gxo + p] + cx.pb * s;
+      const float v = mu + cx.pc * z;
+      a.out_x[gxo + p] = v;
+      a.mean_x[gxo + p] = mu;
+      if (a.traj_x && b == 0) a.traj_x[p] = a.denoise ? mu : v;
+    }
+  }
+  if (a.mode == MODE_SCORE) {
+    s2 = block_sum(s2, red);
+    z2 = block_sum(z2, red);
+    if (threadIdx.x == 0) {
+      float *np = a.norm_part + ((size_t)(0 * d.B + b) * P->ntile_max + blockIdx.x) * 2;
+      np[0] = s2; np[1] = z2;
+    }
+  }
+}
+
+}  // namespace ccsd

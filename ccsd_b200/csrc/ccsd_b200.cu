@@ -17,6 +17,7 @@
 
 #include "r2_kernels.cuh"
 #include "xa_pipe.cuh"
+#include "big_pipe.cuh"
 #ifndef CCSD_EMU
 #include "tc_gram.cuh"
 #include "tc_apply.cuh"
@@ -72,6 +73,7 @@ struct ccsd_plan {
   float *H = nullptr, *P0 = nullptr, *P1 = nullptr, *norm_part = nullptr, *coef = nullptr;
   unsigned long long *zmask = nullptr, *zmask_eval = nullptr;
   float *g_stack = nullptr, *g_att = nullptr, *g_hmc = nullptr, *g_x0 = nullptr, *g_x1 = nullptr;
+  float *g_big = nullptr;       // scratch of the large-graph pipeline [B][xp.big_total]
   float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
   bool bound = false, inited = false;
   long long *trace = nullptr;   // debug timeline buffer for the tensor-core apply kernel
@@ -132,7 +134,9 @@ static int check_gcn(const ccsd_gcn_t &g, size_t nw, const char *name) {
 
 static int validate(const ccsd_plan_desc_t &d, size_t nw) {
   if (d.B < 1 || d.N < 2 || d.F < 1) return fail(CCSD_ERR_INVALID, "B, N, F must be positive (N >= 2)");
-  if (d.N > 64) return fail(CCSD_ERR_UNSUPPORTED, "max_node_num > 64 is not supported by the per-graph-tile kernels yet");
+  if (d.N > 64 && d.is_cc)
+    return fail(CCSD_ERR_UNSUPPORTED, "max_node_num > 64 is only supported for graph-only plans (the large-graph pipeline has no hodge branch)");
+  if (d.N > 1024) return fail(CCSD_ERR_UNSUPPORTED, "max_node_num > 1024 is not supported");
   if (d.sampler != CCSD_SAMPLER_PC && d.sampler != CCSD_SAMPLER_S4) return fail(CCSD_ERR_INVALID, "unknown sampler");
   if (d.n_lang_steps != 1) return fail(CCSD_ERR_UNSUPPORTED, "Langevin n_steps != 1 is not implemented");
   if (d.n_diff_steps < 1) return fail(CCSD_ERR_INVALID, "n_diff_steps must be >= 1");
@@ -343,6 +347,48 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   L.mc_o1_max = mc_o1;
   L.g_hmc = cin_max * mc_o1 * N4;
   L.g_x = imax(F, nh_max) * N4;
+  // ---- large-graph pipeline (big_pipe.cuh) ----
+  {
+    static const bool force_big = getenv("CCSD_B200_FORCE_BIG") != nullptr;   // A/B switch for tests: small graphs through the large-graph kernels
+    L.big = (!d.is_cc && (N > 64 || force_big)) ? 1 : 0;
+  }
+  if (L.big) {
+    const int Np = (N + 7) / 8 * 8;
+    L.big_Np = Np; L.big_PS = N * Np;
+    L.big_nrc = (N + BIG_RC - 1) / BIG_RC;
+    L.big_nseg = (N + BIG_SEG - 1) / BIG_SEG;
+    int adp_max = 8, nhp_max = 8, cout_max = 1, sm_node = 0, sm_edge = 0;
+    for (int l = 0; l < A.num_layers; ++l) {
+      const ccsd_attn_layer_t &ly = A.layer[l];
+      adp_max = imax(adp_max, (ly.attn_dim + 7) / 8 * 8);
+      nhp_max = imax(nhp_max, (ly.conv_out + 7) / 8 * 8);
+      cout_max = imax(cout_max, ly.c_out);
+      const ccsd_mlp_t &mc = ly.multi_channel, &me = ly.mlp;
+      sm_node = imax(sm_node, a4(ly.conv_out) * BIG_RC + (mc.nl > 1 ? mc.dhid : 1) * BIG_RC * (mc.nl > 2 ? 2 : 1));
+      sm_edge = imax(sm_edge, ly.c_out * BIG_SEG + (me.nl > 1 ? me.dhid : 1) * BIG_SEG * (me.nl > 2 ? 2 : 1));
+    }
+    int xdp = 8;
+    for (int k = 0; k < X.depth; ++k) xdp = imax(xdp, (X.gcn[k].dout + 7) / 8 * 8);
+    L.big_sm_node = sm_node + 8; L.big_sm_edge = sm_edge + 8;
+    L.big_sm_fin = BIG_SEG + 40 + (A.fin.nl > 1 ? A.fin.dhid : 1) * BIG_SEG * (A.fin.nl > 2 ? 2 : 1) + 8;
+    L.big_sm_xfin = a4(F) * BIG_RC + 40 + (X.fin.nl > 1 ? X.fin.dhid : 1) * BIG_RC * (X.fin.nl > 2 ? 2 : 1) + 8;
+    int ob = 0;
+    auto tk = [&](long long n) { int r = ob; ob += (int)((n + 7) / 8 * 8); return r; };
+    const int cm = imax(cin_max, imax(A.c_init, 1));
+    L.big_S = tk((long long)imax(A.fdim, 1) * L.big_PS);
+    L.big_ATT = tk((long long)cm * L.big_PS);
+    L.big_YQK = tk((long long)cm * N * 2 * adp_max);
+    L.big_YV = tk((long long)imax(cm * N * nhp_max, N * xdp));
+    L.big_TQK = tk((long long)cm * 2 * adp_max * Np);
+    L.big_TV = tk((long long)cm * nhp_max * Np);
+    L.big_XF0 = tk((long long)imax(kin_max, nh_max) * Np);
+    L.big_XF1 = tk((long long)imax(kin_max, nh_max) * Np);
+    L.big_DV = tk((long long)cm * Np);
+    L.big_HC = tk((long long)imax(X.fdim, F) * Np);
+    L.big_total = ob;
+    // the per-graph-tile scratch is not used
+    L.g_stack = L.g_att = L.g_hmc = L.g_x = 8;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -362,7 +408,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -382,6 +428,7 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.ghmc = take(B * (size_t)p->hp.xp.g_hmc * 4);
   w.gx0 = take(B * (size_t)p->hp.xp.g_x * 4);
   w.gx1 = take(B * (size_t)p->hp.xp.g_x * 4);
+  w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
   w.mx = take(B * N * F * 4); w.madj = take(B * N * N * 4); w.mr2 = take(B * E * K * 4 + 16);
@@ -428,7 +475,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.Ep = a4(d.E);
   p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
   p->hp.ntile_adj = p->hp.xp.m_nchunk;
-  p->hp.ntile_max = imax(imax(1, p->hp.ntile_r2), p->hp.ntile_adj);
+  p->hp.ntile_x = 1;
+  if (p->hp.xp.big) { p->hp.ntile_adj = d.N * p->hp.xp.big_nseg; p->hp.ntile_x = p->hp.xp.big_nrc; }
+  p->hp.ntile_max = imax(imax(imax(1, p->hp.ntile_r2), p->hp.ntile_adj), p->hp.ntile_x);
   p->hp.f_mode = 0; p->hp.f_nlin = 0;
   p->hp.ap_group = d.is_cc ? imax(1, imin(8, 192 / imax(d.E, 1))) : 1;
   if (d.is_cc && (d.nets & 4)) {
@@ -449,7 +498,8 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
   p->apply_smem = d.is_cc ? ((size_t)d.E * (APPLY_TN + 4) + 16 * 68 + 40 + (size_t)netf_stage_floats(d.netf, p->hp.f_nlin, p->hp.f_mode) + 4) * 4 : 0;
   const XpLayout &XL = p->hp.xp;
-  const size_t xp_max = (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, imax(XL.h_total, XL.hb_total))), XL.m_total) * 4;
+  const size_t xp_max = XL.big ? (size_t)imax(imax(XL.big_sm_node, XL.big_sm_edge), imax(XL.big_sm_fin, XL.big_sm_xfin)) * 4
+                               : (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, imax(XL.h_total, XL.hb_total))), XL.m_total) * 4;
   if (xp_max > 227 * 1024 || p->apply_smem > 227 * 1024) {
     char buf[200];
     snprintf(buf, sizeof buf, "graph tile does not fit shared memory (x/adj pipeline %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
@@ -462,8 +512,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     const int N = d.N;
     p->tri_ij.assign((size_t)XL.ldp, 0);
     int t = 0;
-    for (int i = 0; i < N; ++i)
-      for (int j = i; j < N; ++j) p->tri_ij[t++] = (i << 8) | j;
+    if (N <= 255)   // (i << 8) | j packing; the large-graph pipeline does not use the table
+      for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) p->tri_ij[t++] = (i << 8) | j;
   }
   if (d.is_cc) {
     const int N = d.N;
@@ -495,9 +546,17 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
 #ifndef CCSD_EMU
   // the attribute is per function, not per plan: only ever raise it (several plans may coexist)
-  static size_t xp_attr = 0, apply_attr = 0;
+  static size_t xp_attr = 0, apply_attr = 0, big_attr = 0;
   cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-  if (xp_max > xp_attr) {
+  if (XL.big) {
+    if (xp_max > big_attr) {
+      e1 = cudaFuncSetAttribute(big_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(big_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(big_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(big_xfin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
+      if (e1 == cudaSuccess) big_attr = xp_max;
+    }
+  } else if (xp_max > xp_attr) {
     e1 = cudaFuncSetAttribute(x_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
@@ -519,7 +578,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
   p->use_tc_apply = (d.is_cc && (d.nets & 4)) ? tc_apply_supported(d.E, d.K) : 0;
-  p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
+  p->use_tc_fin = ((d.nets & 2) && !XL.big) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = 0;  // A/B switch for tests and profiling
   if (p->use_tc_fin) p->hp.ntile_adj = (p->hp.xp.NT + 127) / 128;   // norm partial slots = 128-row tiles per graph
   if (p->use_tc_apply) {
@@ -553,6 +612,16 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->norm_part = (float *)(ws + w.norm); p->coef = (float *)(ws + w.coef);
   p->g_stack = (float *)(ws + w.gstack); p->g_att = (float *)(ws + w.gatt); p->g_hmc = (float *)(ws + w.ghmc);
   p->g_x0 = (float *)(ws + w.gx0); p->g_x1 = (float *)(ws + w.gx1);
+  p->g_big = (float *)(ws + w.gbig);
+  if (p->hp.xp.big) {
+    // pad columns / rows of the planes are read as don't-care operands: make them finite once
+    const size_t nb = (size_t)p->hp.d.B * p->hp.xp.big_total * 4;
+#ifdef CCSD_EMU
+    memset(p->g_big, 0, nb);
+#else
+    if (cudaMemsetAsync(p->g_big, 0, nb, (cudaStream_t)stream) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaMemsetAsync (large-graph scratch)");
+#endif
+  }
   p->hp.tri_ij = (const int *)(ws + w.tri);
   p->zmask = (unsigned long long *)(ws + w.zmask); p->zmask_eval = (unsigned long long *)(ws + w.zmask_eval);
   p->hp.W = p->weights;
@@ -607,8 +676,58 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
   return dev_check("init_kernel");
 }
 
+// Large-graph pipeline (big_pipe.cuh): same contract as launch_xa
+static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
+  const ccsd_plan_desc_t &d = p->hp.d;
+  const XpLayout &L = p->hp.xp;
+  const ccsd_neta_t &A = d.neta;
+  const ccsd_netx_t &X = d.netx;
+  BigArgs g; memset(&g, 0, sizeof g);
+  g.a = a; g.base = p->g_big;
+  const int B = d.B, nrc = L.big_nrc;
+#define BIG_LAUNCH(kern, grid, thr, smem) do { PROF_BEGIN(p, #kern, stream); CCSD_LAUNCH(kern, grid, thr, smem, stream, p->dP, g); PROF_END(p, stream); p->launches++; } while (0)
+  BIG_LAUNCH(big_prep_kernel, dim3(imin(148 * 2, (d.N * L.big_Np + 255) / 256), B, 1), 256, 0);
+  const int c0 = (a.which & 2) ? A.c_init : 1;
+  for (int c = 1; c < c0; ++c) { g.c = c; BIG_LAUNCH(big_pow_kernel, dim3(nrc, 1, B), 128, 0); }
+  g.ch_in = 0; g.nch = c0;
+  BIG_LAUNCH(big_deg_kernel, dim3((d.N + 127) / 128, c0, B), 128, 0);
+  if (a.which & 1) {
+    g.xmode = 1;
+    int in_row = 0, out_row = d.F;
+    for (int k = 0; k < X.depth; ++k) {
+      g.gk = k; g.in_row = in_row; g.out_row = out_row;
+      BIG_LAUNCH(big_xw_kernel, dim3(nrc, 1, B), 128, 0);
+      BIG_LAUNCH(big_agg_kernel, dim3(nrc, 1, B), 128, 0);
+      in_row = out_row; out_row += X.gcn[k].dout;
+    }
+    BIG_LAUNCH(big_xfin_kernel, dim3(nrc, 1, B), 128, (size_t)L.big_sm_xfin * 4);
+  }
+  if (!(a.which & 2)) return dev_check("large-graph x network");
+  g.xmode = 0;
+  int ch_in = 0, ch_out = A.c_init;
+  float *xf0 = p->g_big + L.big_XF0, *xf1 = p->g_big + L.big_XF1;
+  for (int l = 0; l < A.num_layers; ++l) {
+    const ccsd_attn_layer_t &ly = A.layer[l];
+    g.layer = l; g.ch_in = ch_in; g.ch_out = ch_out; g.xin = xf0; g.xout = xf1;
+    if (l > 0) { g.nch = ly.c_in; BIG_LAUNCH(big_deg_kernel, dim3((d.N + 127) / 128, ly.c_in, B), 128, 0); }
+    BIG_LAUNCH(big_xw_kernel, dim3(nrc, ly.c_in, B), 128, 0);
+    BIG_LAUNCH(big_agg_kernel, dim3(nrc, ly.c_in, B), 128, 0);
+    const int nb = (d.N + 3) / 4, nblk = nb * (nb + 1) / 2;
+    BIG_LAUNCH(big_attn_kernel, dim3((nblk + 127) / 128, ly.c_in, B), 128, 0);
+    BIG_LAUNCH(big_node_kernel, dim3(nrc, 1, B), 128, (size_t)L.big_sm_node * 4);
+    BIG_LAUNCH(big_edge_kernel, dim3(d.N * L.big_nseg, 1, B), 128, (size_t)L.big_sm_edge * 4);
+    ch_in = ch_out; ch_out += ly.c_out;
+    float *t = xf0; xf0 = xf1; xf1 = t;
+  }
+  g.ch_out = ch_out;   // planes the final MLP reads
+  BIG_LAUNCH(big_final_kernel, dim3(d.N * L.big_nseg, 1, B), 128, (size_t)L.big_sm_fin * 4);
+#undef BIG_LAUNCH
+  return dev_check("large-graph x/adj network pipeline");
+}
+
 // ScoreNetworkX / ScoreNetworkA(_CC) pipeline (xa_pipe.cuh) for the networks selected by a.which
 static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
+  if (p->hp.xp.big) return launch_xa_big(p, a, stream);
   const ccsd_plan_desc_t &d = p->hp.d;
   const XpLayout &L = p->hp.xp;
   const ccsd_neta_t &A = d.neta;

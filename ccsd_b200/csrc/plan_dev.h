@@ -36,6 +36,15 @@ struct XpLayout {
   int g_hmc;           // [c_in x mc_o1_max x N4]  per-channel shares of the node MLP's first Linear
   int g_x;             // [max(F, nhid) x N4]      node features (ping-pong)
   int mc_o1_max;
+  // large-graph pipeline (big_pipe.cuh, max_node_num > 64): full N x Np planes in global memory
+  int big;                      // 1: the plan runs the large-graph pipeline
+  int big_Np, big_PS;           // N rounded up to 8; plane stride N * Np
+  int big_nrc, big_nseg;        // row chunks per graph (BIG_RC rows); 64-column segments per row
+  int big_total;                // floats of scratch per graph; offsets inside:
+  int big_S /*[fdimA][N][Np]*/, big_ATT /*[c][N][Np]*/, big_YQK /*[c][N][2 adp]*/, big_YV /*[c][N][nhp]*/,
+      big_TQK /*[c][2 adp][Np]*/, big_TV /*[c nh][Np]*/, big_XF0, big_XF1 /*[kmax][Np]*/, big_DV /*[c][Np]*/,
+      big_HC /*[fdimX][Np]*/;
+  int big_sm_node, big_sm_edge, big_sm_fin, big_sm_xfin;   // dynamic shared memory (floats) of the MLP kernels
 };
 
 struct DevPlan {
@@ -54,6 +63,7 @@ struct DevPlan {
   int Ep;                         // E rounded up to 4: row pitch of the H buffer [B][E][Ep]
   int ntile_r2;                   // apply-kernel column tiles per sample
   int ntile_adj;                  // afinal-kernel row chunks per sample (norm partial slots of the adjacency)
+  int ntile_x;                    // norm partial slots of x (1 on the per-graph-tile path)
   int ntile_max;                  // stride of the per-object norm partials
   int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled, 3 <=4-wide x4 entries, 4 <=8-wide + 2-Linear final
   int f_nlin;                     // number of Linears staged for f_mode 2

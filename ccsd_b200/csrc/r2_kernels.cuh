@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ P
   const ccsd_plan_desc_t &d = P->d;
   const int nobj = d.is_cc ? 3 : 2;
   for (int obj = 0; obj < nobj; ++obj) {
-    const int nt = (obj == 2) ? P->ntile_r2 : (obj == 1 ? P->ntile_adj : 1);
+    const int nt = (obj == 2) ? P->ntile_r2 : (obj == 1 ? P->ntile_adj : P->ntile_x);
     float gs = 0.f, zs = 0.f;
     for (int b = threadIdx.x; b < d.B; b += blockDim.x) {
       const float *np = a.norm_part + ((size_t)(obj * d.B + b) * P->ntile_max) * 2;

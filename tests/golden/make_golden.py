@@ -55,6 +55,9 @@ CONFIGS = {
     # graph-only checkpoints of the remaining datasets
     "zinc250k": ("ZINC250k/gdss_zinc250k", ("Reverse", "Langevin", 0.2, 0.9), 3),
     "enzymes_small": ("ENZYMES_small/gdss_enzymes_small_retrained", ("S4", "None", 0.15, 0.7), 3),
+    # large graphs (N > 64): no sample_*.yaml is shipped for them; GDSS's sampler settings
+    "enzymes": ("ENZYMES/gdss_enzymes", ("Reverse", "Langevin", 0.1, 0.7), 2),
+    "grid": ("grid/gdss_grid", ("Reverse", "Langevin", 0.1, 0.7), 1),
 }
 
 

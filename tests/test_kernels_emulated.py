@@ -18,7 +18,8 @@ def test_emulation_build_is_flagged():
 
 @pytest.mark.parametrize("name,B", [("qm9", 3), ("qm9_cc", 2), ("community_small", 2), ("enzymes_small_cc", 1), ("ego_small", 2),
                                     ("qm9_base_cc", 2), ("community_small_base_cc", 1),
-                                    ("enzymes_small_base_cc", 1), ("zinc250k", 1), ("enzymes_small", 2)])
+                                    ("enzymes_small_base_cc", 1), ("zinc250k", 1), ("enzymes_small", 2),
+                                    ("enzymes", 1), ("grid", 1)])   # N = 125, 361: the large-graph pipeline (big_pipe.cuh)
 def test_scores(name, B):
     for k, e in score_parity(name, B, "cpu").items():
         assert e < SCORE_TOL, (name, k, e)
@@ -39,6 +40,7 @@ def test_scores_community_small_cc():
     ("enzymes_small_cc", "S4", "None", "None"),
     ("qm9_base_cc", "PC", "Reverse", "Langevin"),
     ("enzymes_small", "S4", "None", "None"),
+    ("enzymes", "PC", "Reverse", "Langevin"),
 ])
 def test_sampler_steps(name, sampler, pred, corr):
     res = sampler_parity(name, sampler, pred, corr, B=2, steps=2, device="cpu")
@@ -63,3 +65,28 @@ def test_sampler_sde_variants(pred, corr, pf, kind):
     res = sampler_parity("qm9_cc", "PC", pred, corr, B=2, steps=2, device="cpu", probability_flow=pf, sde_kind=kind)
     for k, (e_ret, e_state, agree) in res.items():
         assert e_ret < 1e-4 and e_state < 1e-4, (pred, corr, pf, kind, k, e_ret, e_state)
+
+
+def test_large_graph_pipeline_on_small_graphs():
+    """CCSD_B200_FORCE_BIG routes graph-only plans with N <= 64 through the large-graph kernels (big_pipe.cuh): same
+    checkpoints, same oracle, same bar -- and the two pipelines must agree with each other."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, '.')\n"
+        "import tests.conftest\n"
+        "from tests.parity_cases import score_parity, sampler_parity\n"
+        "for n, B in (('qm9', 3), ('community_small', 2), ('zinc250k', 1)):\n"
+        "    for k, e in score_parity(n, B, 'cpu').items():\n"
+        "        assert e < 1e-4, (n, k, e)\n"
+        "for args in (('qm9', 'PC', 'Reverse', 'Langevin', 3, 2), ('community_small', 'PC', 'Euler', 'Langevin', 2, 2),\n"
+        "             ('enzymes_small', 'S4', 'None', 'None', 2, 2)):\n"
+        "    for k, v in sampler_parity(*args, 'cpu').items():\n"
+        "        assert v[0] < 1e-4 and v[1] < 1e-4 and v[2] >= 0.999, (args, k, v)\n"
+        "from ccsd_b200 import _native as nat\n"
+        "print('ok')\n")
+    env = dict(os.environ, CCSD_B200_FORCE_BIG="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]), env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
