@@ -139,6 +139,16 @@ def kernel_alg_work(meta, B, pr0):
     x_fl, a_fl = xa_flops_split(meta)
     out = {"x_net_kernel": (B * x_fl, 0), "xa_pipeline": (B * (x_fl + a_fl), 0),
            "big_final_kernel": (B * xa_flops.final, 0), "afinal_kernel": (B * xa_flops.final, 0), "tc_afinal_kernel": (B * xa_flops.final, 0)}
+    # large-graph pipeline: the aggregation GEMMs A^ (x W) of all GCN convolutions, averaged over its launches per evaluation
+    px, pa = meta["params"]["x"], meta["params"]["adj"]
+    L_, c0, ch, cf, nh, ad = (pa[k] for k in ("num_layers", "c_init", "c_hid", "c_final", "nhid", "adim"))
+    agg = px["depth"] * 2 * N * N * px["nhid"]
+    cin = c0
+    for l in range(L_):
+        a_ = nh if l == 0 else ad
+        agg += cin * 2 * N * N * (2 * a_ + nh)
+        cin = ch if l < L_ - 1 or L_ == 1 else cf
+    out["big_agg_kernel"] = (B * agg / (px["depth"] + L_), 0)
     if meta["is_cc"]:
         st = 4 * E * K * B
         out["gram_kernel"] = out["tc_gram_kernel"] = (B * 2 * E * (E + pr0) * K, st)

@@ -87,90 +87,105 @@ __global__ void __launch_bounds__(128) big_deg_kernel(const DevPlan *__restrict_
   }
 }
 
-// Y = diag(d) (x W): the feature transforms of one channel's Q | K | V convolutions (xmode 0) or of one GCN
-// layer of ScoreNetworkX (xmode 1), node-major, pre-scaled by d_j for the aggregation
+// Y = diag(d) (x W): the feature transforms of one channel's Q | K | V convolutions (xmode 0, one node-major
+// buffer [N][2 adp + nhp]) or of one GCN layer of ScoreNetworkX (xmode 1), pre-scaled by d_j for the aggregation.
+// One pass: item = (8 output columns, 4 rows); the item picks its weight matrix and scales its own tile.
 __global__ void __launch_bounds__(128) big_xw_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
-  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC, ngrp = (R + 3) >> 2;
   const float *W = P->W;
   const float *dv = big_ptr(P, g, b, L.big_DV) + c * Np;
-  if (g.xmode == 0) {
-    const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
-    const int kin = ly.conv_in, ad = ly.attn_dim, nh = ly.conv_out, adp = round_up(ad, 8), nhp = round_up(nh, 8), w2 = 2 * adp;
-    const float *xin = g.xin + (size_t)b * L.big_total;
-    float *yqk = big_ptr(P, g, b, L.big_YQK) + (size_t)c * N * w2, *yv = big_ptr(P, g, b, L.big_YV) + (size_t)c * N * nhp;
-    dense_fm(xin + i0, Np, kin, nullptr, 0, 0, W + ly.q[c].w, nullptr, ad, yqk + (size_t)i0 * w2, w2, 1, R, ACT_NONE);
-    dense_fm(xin + i0, Np, kin, nullptr, 0, 0, W + ly.k[c].w, nullptr, ad, yqk + (size_t)i0 * w2 + adp, w2, 1, R, ACT_NONE);
-    dense_fm(xin + i0, Np, kin, nullptr, 0, 0, W + ly.v[c].w, nullptr, nh, yv + (size_t)i0 * nhp, nhp, 1, R, ACT_NONE);
-    __syncthreads();
-    for (int p = threadIdx.x; p < R * (w2 + nhp); p += blockDim.x) {
-      const int r = p / (w2 + nhp), o = p - r * (w2 + nhp), i = i0 + r;
-      float *y = o < w2 ? yqk + (size_t)i * w2 + o : yv + (size_t)i * nhp + (o - w2);
-      const int oo = o < w2 ? (o < adp ? o : o - adp) : o - w2;
-      *y = (oo < (o < w2 ? ad : nh)) ? *y * dv[i] : 0.f;
-    }
-  } else {
-    const ccsd_gcn_t &gc = d.netx.gcn[g.gk];
-    const int dout = gc.dout, dp = round_up(dout, 8);
-    const float *in = big_ptr(P, g, b, L.big_HC) + (size_t)g.in_row * Np;
-    float *y = big_ptr(P, g, b, L.big_YV);
-    dense_fm(in + i0, Np, gc.din, nullptr, 0, 0, W + gc.w, nullptr, dout, y + (size_t)i0 * dp, dp, 1, R, ACT_NONE);
-    __syncthreads();
-    for (int p = threadIdx.x; p < R * dp; p += blockDim.x) {
-      const int r = p / dp, o = p - r * dp, i = i0 + r;
-      float *yy = y + (size_t)i * dp + o;
-      *yy = o < dout ? *yy * dv[i] : 0.f;
+  const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+  const ccsd_gcn_t &gc = d.netx.gcn[g.gk];
+  const int ad = ly.attn_dim, nh = ly.conv_out, adp = round_up(ad, 8), nhp = round_up(nh, 8), w2 = 2 * adp;
+  const int YW = g.xmode == 0 ? w2 + nhp : round_up(gc.dout, 8);
+  const int kin = g.xmode == 0 ? ly.conv_in : gc.din;
+  const float *in = g.xmode == 0 ? g.xin + (size_t)b * L.big_total : big_ptr(P, g, b, L.big_HC) + (size_t)g.in_row * Np;
+  float *y = big_ptr(P, g, b, L.big_Y) + (g.xmode == 0 ? (size_t)c * N * YW : 0);
+  for (int it = threadIdx.x; it < (YW >> 3) * ngrp; it += blockDim.x) {
+    const int cc = it / ngrp, r0 = i0 + ((it - cc * ngrp) << 2), o0 = cc << 3;
+    const float *Wm;
+    int Opad, oc, valid;
+    if (g.xmode == 1) { Wm = W + gc.w; Opad = YW; oc = o0; valid = gc.dout - oc; }
+    else if (o0 < adp) { Wm = W + ly.q[c].w; Opad = adp; oc = o0; valid = ad - oc; }
+    else if (o0 < w2) { Wm = W + ly.k[c].w; Opad = adp; oc = o0 - adp; valid = ad - oc; }
+    else { Wm = W + ly.v[c].w; Opad = nhp; oc = o0 - w2; valid = nh - oc; }
+    float acc[4][8];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[rr][j] = 0.f;
+    dense_tile(acc, in, Np, kin, nullptr, 0, 0, Wm, Opad, r0, oc);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int i = r0 + rr;
+      if (i < N) {
+        const float di = dv[i];
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = j < valid ? acc[rr][j] * di : 0.f;
+        float4 *dst = reinterpret_cast<float4 *>(y + (size_t)i * YW + o0);
+        dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      }
     }
   }
 }
 
 // T = diag(d) A^ Y + bias: the aggregation of DenseGCNConv (layers.py:147-156).  A^ = plane with a unit
-// diagonal: sum_j a_ij y_j over the stored plane plus the rank-one fix-up (1 - a_ii) y_i.
+// diagonal: sum_j a_ij y_j over the stored plane plus the rank-one fix-up (1 - a_ii) y_i, applied by the item
+// that owns the tile (no second pass).
 // xmode 0: Q | K rows -> TQK (feature-major [2 adp][Np]), V -> TV ([c nh + o][Np]);  xmode 1: tanh -> HC rows.
 __global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
-  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC, ngrp = (R + 3) >> 2;
   const float *W = P->W;
   const float *dv = big_ptr(P, g, b, L.big_DV) + c * Np;
-  if (g.xmode == 0) {
-    const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
-    const int ad = ly.attn_dim, nh = ly.conv_out, adp = round_up(ad, 8), nhp = round_up(nh, 8), w2 = 2 * adp;
-    const float *pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_in + c) * L.big_PS;
-    const float *yqk = big_ptr(P, g, b, L.big_YQK) + (size_t)c * N * w2, *yv = big_ptr(P, g, b, L.big_YV) + (size_t)c * N * nhp;
-    float *tqk = big_ptr(P, g, b, L.big_TQK) + (size_t)c * w2 * Np, *tv = big_ptr(P, g, b, L.big_TV) + (size_t)c * nh * Np;
-    dense_fm(pl + i0, Np, N, nullptr, 0, 0, yqk, nullptr, w2, tqk + i0, 1, Np, R, ACT_NONE);
-    dense_fm(pl + i0, Np, N, nullptr, 0, 0, yv, nullptr, nh, tv + i0, 1, Np, R, ACT_NONE);
-    __syncthreads();
-    for (int p = threadIdx.x; p < R * (w2 + nh); p += blockDim.x) {
-      const int o = p / R, r = p - o * R, i = i0 + r;
-      const float fix = 1.f - pl[(size_t)i * Np + i];
-      if (o < w2) {
+  const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+  const ccsd_gcn_t &gc = d.netx.gcn[g.gk];
+  const int ad = ly.attn_dim, nh = ly.conv_out, adp = round_up(ad, 8), nhp = round_up(nh, 8), w2 = 2 * adp;
+  const int YW = g.xmode == 0 ? w2 + nhp : round_up(gc.dout, 8);
+  const float *pl = big_ptr(P, g, b, L.big_S) + (g.xmode == 0 ? (size_t)(g.ch_in + c) * L.big_PS : 0);
+  const float *y = big_ptr(P, g, b, L.big_Y) + (g.xmode == 0 ? (size_t)c * N * YW : 0);
+  float *tqk = big_ptr(P, g, b, L.big_TQK) + (size_t)c * w2 * Np, *tv = big_ptr(P, g, b, L.big_TV) + (size_t)c * nh * Np;
+  float *hc = big_ptr(P, g, b, L.big_HC) + (size_t)g.out_row * Np;
+  for (int it = threadIdx.x; it < (YW >> 3) * ngrp; it += blockDim.x) {
+    const int cc = it / ngrp, r0 = i0 + ((it - cc * ngrp) << 2), o0 = cc << 3;
+    float acc[4][8];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[rr][j] = 0.f;
+    dense_tile(acc, pl, Np, N, nullptr, 0, 0, y, YW, r0, o0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = o0 + j;
+      float *dst;
+      float bias;
+      int act = ACT_NONE;
+      if (g.xmode == 1) {
+        if (o >= gc.dout) continue;
+        dst = hc + (size_t)o * Np; bias = __ldg(W + gc.b + o); act = ACT_TANH;
+      } else if (o < w2) {
         const int oo = o < adp ? o : o - adp;
-        if (oo < ad) {
-          const float bias = __ldg(W + (o < adp ? ly.q[c].b : ly.k[c].b) + oo);
-          tqk[(size_t)o * Np + i] = dv[i] * (tqk[(size_t)o * Np + i] + fix * yqk[(size_t)i * w2 + o]) + bias;
-        }
+        if (oo >= ad) continue;
+        dst = tqk + (size_t)o * Np; bias = __ldg(W + (o < adp ? ly.q[c].b : ly.k[c].b) + oo);
       } else {
-        const int oo = o - w2;
-        tv[(size_t)oo * Np + i] = dv[i] * (tv[(size_t)oo * Np + i] + fix * yv[(size_t)i * nhp + oo]) + __ldg(W + ly.v[c].b + oo);
+        if (o - w2 >= nh) continue;
+        dst = tv + (size_t)(o - w2) * Np; bias = __ldg(W + ly.v[c].b + (o - w2));
       }
-    }
-  } else {
-    const ccsd_gcn_t &gc = d.netx.gcn[g.gk];
-    const int dout = gc.dout, dp = round_up(dout, 8);
-    const float *pl = big_ptr(P, g, b, L.big_S);
-    const float *y = big_ptr(P, g, b, L.big_YV);
-    float *out = big_ptr(P, g, b, L.big_HC) + (size_t)g.out_row * Np;
-    dense_fm(pl + i0, Np, N, nullptr, 0, 0, y, nullptr, dout, out + i0, 1, Np, R, ACT_NONE);
-    __syncthreads();
-    for (int p = threadIdx.x; p < R * dout; p += blockDim.x) {
-      const int o = p / R, r = p - o * R, i = i0 + r;
-      const float fix = 1.f - pl[(size_t)i * Np + i];
-      out[(size_t)o * Np + i] = fast_tanh(dv[i] * (out[(size_t)o * Np + i] + fix * y[(size_t)i * dp + o]) + __ldg(W + gc.b + o));
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = r0 + rr;
+        if (i < N) {
+          const float fix = 1.f - pl[(size_t)i * Np + i];
+          dst[i] = act_fast(dv[i] * (acc[rr][j] + fix * y[(size_t)i * YW + o]) + bias, act);
+        }
+      }
     }
   }
 }

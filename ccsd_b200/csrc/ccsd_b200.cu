@@ -377,8 +377,8 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
     const int cm = imax(cin_max, imax(A.c_init, 1));
     L.big_S = tk((long long)imax(A.fdim, 1) * L.big_PS);
     L.big_ATT = tk((long long)cm * L.big_PS);
-    L.big_YQK = tk((long long)cm * N * 2 * adp_max);
-    L.big_YV = tk((long long)imax(cm * N * nhp_max, N * xdp));
+    L.big_Y = tk((long long)imax(cm * N * (2 * adp_max + nhp_max), N * xdp));
+    L.big_T_xw = imin(128, ((2 * adp_max + nhp_max) / 8 * (BIG_RC / 4) + 31) / 32 * 32);
     L.big_TQK = tk((long long)cm * 2 * adp_max * Np);
     L.big_TV = tk((long long)cm * nhp_max * Np);
     L.big_XF0 = tk((long long)imax(kin_max, nh_max) * Np);
@@ -578,9 +578,12 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
   p->use_tc_apply = (d.is_cc && (d.nets & 4)) ? tc_apply_supported(d.E, d.K) : 0;
-  p->use_tc_fin = ((d.nets & 2) && !XL.big) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
+  p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = 0;  // A/B switch for tests and profiling
-  if (p->use_tc_fin) p->hp.ntile_adj = (p->hp.xp.NT + 127) / 128;   // norm partial slots = 128-row tiles per graph
+  if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
+    p->hp.ntile_adj = XL.big ? d.N * ((d.N + 127) / 128) : (p->hp.xp.NT + 127) / 128;
+    p->hp.ntile_max = imax(p->hp.ntile_max, p->hp.ntile_adj);
+  }
   if (p->use_tc_apply) {
     if (int r = tc_apply_prepare()) { delete p; return fail(CCSD_ERR_CUDA, "tc_apply_prepare failed"); }
   }
@@ -685,10 +688,15 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
   BigArgs g; memset(&g, 0, sizeof g);
   g.a = a; g.base = p->g_big;
   const int B = d.B, nrc = L.big_nrc;
+  // threads per CTA (<= 128, the kernels' launch bound); environment overrides are tuning experiments
+  static const auto envt = [](const char *nm, int dflt) { const char *e = getenv(nm); const int v = e ? atoi(e) : dflt; return v >= 32 && v <= 128 ? v / 32 * 32 : dflt; };
+  static const int T_pow = envt("CCSD_BIG_T_POW", 128), T_xw = envt("CCSD_BIG_T_XW", 0), T_agg = envt("CCSD_BIG_T_AGG", 0),
+                   T_node = envt("CCSD_BIG_T_NODE", 64), T_edge = envt("CCSD_BIG_T_EDGE", 32), T_fin = envt("CCSD_BIG_T_FIN", 128),
+                   T_xfin = envt("CCSD_BIG_T_XFIN", 128);
 #define BIG_LAUNCH(kern, grid, thr, smem) do { PROF_BEGIN(p, #kern, stream); CCSD_LAUNCH(kern, grid, thr, smem, stream, p->dP, g); PROF_END(p, stream); p->launches++; } while (0)
   BIG_LAUNCH(big_prep_kernel, dim3(imin(148 * 2, (d.N * L.big_Np + 255) / 256), B, 1), 256, 0);
   const int c0 = (a.which & 2) ? A.c_init : 1;
-  for (int c = 1; c < c0; ++c) { g.c = c; BIG_LAUNCH(big_pow_kernel, dim3(nrc, 1, B), 128, 0); }
+  for (int c = 1; c < c0; ++c) { g.c = c; BIG_LAUNCH(big_pow_kernel, dim3(nrc, 1, B), T_pow, 0); }
   g.ch_in = 0; g.nch = c0;
   BIG_LAUNCH(big_deg_kernel, dim3((d.N + 127) / 128, c0, B), 128, 0);
   if (a.which & 1) {
@@ -696,11 +704,11 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
     int in_row = 0, out_row = d.F;
     for (int k = 0; k < X.depth; ++k) {
       g.gk = k; g.in_row = in_row; g.out_row = out_row;
-      BIG_LAUNCH(big_xw_kernel, dim3(nrc, 1, B), 128, 0);
-      BIG_LAUNCH(big_agg_kernel, dim3(nrc, 1, B), 128, 0);
+      BIG_LAUNCH(big_xw_kernel, dim3(nrc, 1, B), 32, 0);    // 4 x 8 items (nhid <= 32)
+      BIG_LAUNCH(big_agg_kernel, dim3(nrc, 1, B), 32, 0);
       in_row = out_row; out_row += X.gcn[k].dout;
     }
-    BIG_LAUNCH(big_xfin_kernel, dim3(nrc, 1, B), 128, (size_t)L.big_sm_xfin * 4);
+    BIG_LAUNCH(big_xfin_kernel, dim3(nrc, 1, B), T_xfin, (size_t)L.big_sm_xfin * 4);
   }
   if (!(a.which & 2)) return dev_check("large-graph x network");
   g.xmode = 0;
@@ -710,17 +718,28 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
     const ccsd_attn_layer_t &ly = A.layer[l];
     g.layer = l; g.ch_in = ch_in; g.ch_out = ch_out; g.xin = xf0; g.xout = xf1;
     if (l > 0) { g.nch = ly.c_in; BIG_LAUNCH(big_deg_kernel, dim3((d.N + 127) / 128, ly.c_in, B), 128, 0); }
-    BIG_LAUNCH(big_xw_kernel, dim3(nrc, ly.c_in, B), 128, 0);
-    BIG_LAUNCH(big_agg_kernel, dim3(nrc, ly.c_in, B), 128, 0);
+    BIG_LAUNCH(big_xw_kernel, dim3(nrc, ly.c_in, B), T_xw ? T_xw : L.big_T_xw, 0);
+    BIG_LAUNCH(big_agg_kernel, dim3(nrc, ly.c_in, B), T_agg ? T_agg : L.big_T_xw, 0);
     const int nb = (d.N + 3) / 4, nblk = nb * (nb + 1) / 2;
     BIG_LAUNCH(big_attn_kernel, dim3((nblk + 127) / 128, ly.c_in, B), 128, 0);
-    BIG_LAUNCH(big_node_kernel, dim3(nrc, 1, B), 128, (size_t)L.big_sm_node * 4);
-    BIG_LAUNCH(big_edge_kernel, dim3(d.N * L.big_nseg, 1, B), 128, (size_t)L.big_sm_edge * 4);
+    BIG_LAUNCH(big_node_kernel, dim3(nrc, 1, B), T_node, (size_t)L.big_sm_node * 4);
+    BIG_LAUNCH(big_edge_kernel, dim3(d.N * L.big_nseg, 1, B), T_edge, (size_t)L.big_sm_edge * 4);
     ch_in = ch_out; ch_out += ly.c_out;
     float *t = xf0; xf0 = xf1; xf1 = t;
   }
   g.ch_out = ch_out;   // planes the final MLP reads
-  BIG_LAUNCH(big_final_kernel, dim3(d.N * L.big_nseg, 1, B), 128, (size_t)L.big_sm_fin * 4);
+#ifndef CCSD_EMU
+  if (p->use_tc_fin) {
+    XaArgs af = a;
+    af.g_stack = p->g_big + L.big_S;
+    PROF_BEGIN(p, "tc_afinal_kernel", stream);
+    if (tc_afinal_launch(p->dP, p->hp, af, ch_out, stream)) return fail(CCSD_ERR_CUDA, "tc_afinal launch failed");
+    PROF_END(p, stream);
+    p->launches++;
+    return dev_check("large-graph x/adj network pipeline");
+  }
+#endif
+  BIG_LAUNCH(big_final_kernel, dim3(d.N * L.big_nseg, 1, B), T_fin, (size_t)L.big_sm_fin * 4);
 #undef BIG_LAUNCH
   return dev_check("large-graph x/adj network pipeline");
 }

@@ -41,9 +41,10 @@ struct XpLayout {
   int big_Np, big_PS;           // N rounded up to 8; plane stride N * Np
   int big_nrc, big_nseg;        // row chunks per graph (BIG_RC rows); 64-column segments per row
   int big_total;                // floats of scratch per graph; offsets inside:
-  int big_S /*[fdimA][N][Np]*/, big_ATT /*[c][N][Np]*/, big_YQK /*[c][N][2 adp]*/, big_YV /*[c][N][nhp]*/,
+  int big_S /*[fdimA][N][Np]*/, big_ATT /*[c][N][Np]*/, big_Y /*[c][N][2 adp + nhp]*/,
       big_TQK /*[c][2 adp][Np]*/, big_TV /*[c nh][Np]*/, big_XF0, big_XF1 /*[kmax][Np]*/, big_DV /*[c][Np]*/,
       big_HC /*[fdimX][Np]*/;
+  int big_T_xw;                 // threads per CTA of the xw / agg kernels (= items per CTA, <= 128)
   int big_sm_node, big_sm_edge, big_sm_fin, big_sm_xfin;   // dynamic shared memory (floats) of the MLP kernels
 };
 

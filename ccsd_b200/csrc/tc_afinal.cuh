@@ -16,7 +16,9 @@
 
 namespace ccsd {
 
-constexpr int TF_THREADS = 160;   // 4 epilogue / loader warps (one TMEM lane quarter each) + 1 MMA warp
+constexpr int TF_EPI = 256;       // 8 epilogue / loader warps: TMEM lane quarter = warp % 4, column half = warp / 4
+constexpr int TF_THREADS = TF_EPI + 32;   // + 1 MMA warp
+constexpr int TF_MMAW = TF_EPI / 32;
 
 struct TcFinLayout {   // byte offsets from the 1024-aligned base; *_half = distance hi -> lo
   int K1p, Hp;         // fd rounded up to 16, hidden width rounded up to 16
@@ -35,7 +37,7 @@ static inline TcFinLayout tc_afinal_layout(int fd, int dhid) {
   L.w2_half = 2u * L.Hp * 128u;  L.w2 = o; o += 2 * L.w2_half;     // [2 n-blocks][Hp k-rows][128 B]
   L.a1_half = 2u * L.K1p * 128u; L.a1 = o; o += 2 * L.a1_half;     // [2 m-blocks][K1p k-rows][128 B]
   L.a2_half = 2u * 16384u;       L.a2 = o; o += 2 * L.a2_half;     // [2 k-blocks][128 rows][128 B]
-  L.vec = o; o += 3 * 128 * 4 + 256;                               // b1, b2, w3 (+ b3, reduction scratch)
+  L.vec = o; o += 3 * 128 * 4 + 256 + 512;                         // b1, b2, w3, reduction scratch, [128] partial dot products
   L.bars = o; o += 64;
   L.total = o + 1024;
   return L;
@@ -46,6 +48,12 @@ struct TcFinArgs {
   TcFinLayout L;
   int fd;              // channels in the stack
   int ntg;             // tiles per graph
+  // geometry of the channel stack: per-graph-tile pipeline = triangle rows [fd][ldp]; large-graph pipeline
+  // (big_pipe.cuh) = full planes [fd][N][Np], tile = 128 columns of one row, tiles below the diagonal skipped
+  const float *gs_base;
+  long long gs_stride; // floats per graph
+  int ldp, NT;         // plane stride; valid rows of a plane (triangle path)
+  int big, Np, nseg;   // large-graph path: row pitch, 128-column segments per row
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan *__restrict__ P, TcFinArgs ta) {
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const ccsd_mlp_t &fin = d.neta.fin;
-  const int N = d.N, NP = N * N, NT = L.NT, ldp = L.ldp, fd = ta.fd, dh = fin.dhid;
+  const int N = d.N, NP = N * N, NT = ta.NT, ldp = ta.ldp, fd = ta.fd, dh = fin.dhid;
   const int K1p = TL.K1p, Hp = TL.Hp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float *W = P->W;
@@ -65,10 +73,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
   uint8_t *gen = tf_smem_raw + (base - raw);
   const uint32_t bar = base + TL.bars, tslot = bar + 8;
   uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen + TL.bars + 8);
-  float *vb1 = reinterpret_cast<float *>(gen + TL.vec), *vb2 = vb1 + 128, *vw3 = vb2 + 128, *red = vw3 + 128;
+  float *vb1 = reinterpret_cast<float *>(gen + TL.vec), *vb2 = vb1 + 128, *vw3 = vb2 + 128, *red = vw3 + 128, *part = red + 64;
 
   if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
-  if (warp == 4) tc::tmem_alloc(tslot, 256);
+  if (warp == TF_MMAW) tc::tmem_alloc(tslot, 256);
   // ---- zero the operand buffers, then convert the weights (resident for the whole kernel) ----
   for (uint32_t o = threadIdx.x * 16u; o < TL.vec; o += TF_THREADS * 16u) *reinterpret_cast<uint4 *>(gen + o) = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < 128; i += TF_THREADS) {
@@ -111,11 +119,24 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
   const int ntiles = d.B * ta.ntg;
 
   for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
-    const int b = w / ta.ntg, tt = w - b * ta.ntg, t0 = tt * 128;
-    const float *gs = a.g_stack + (size_t)b * L.g_stack;
+    const int b = w / ta.ntg, tt = w - b * ta.ntg;
+    int t0 = tt * 128, bi = 0, bj0 = 0, rows = NT - t0;   // rows: valid rows of this tile
+    if (ta.big) {
+      bi = tt / ta.nseg; bj0 = (tt - bi * ta.nseg) * 128;
+      if (bj0 + 128 <= bi) {   // wholly below the diagonal: the mirrored tile covers it (uniform branch)
+        if (a.mode == MODE_SCORE && threadIdx.x == 0) {
+          float *np = a.norm_part + ((size_t)(1 * d.B + b) * P->ntile_max + tt) * 2;
+          np[0] = 0.f; np[1] = 0.f;
+        }
+        continue;
+      }
+      t0 = bi * ta.Np + bj0;
+      rows = N - bj0;
+    }
+    const float *gs = ta.gs_base + (size_t)b * ta.gs_stride;
     // ---- X tile -> A1 (MN-major): chunk = 8 consecutive rows of one channel ----
-    if (warp < 4) {
-      for (int t = threadIdx.x; t < fd * 16; t += 128) {
+    if (warp < TF_MMAW) {
+      for (int t = threadIdx.x; t < fd * 16; t += TF_EPI) {
         const int k = t >> 4, mc = t & 15, m0 = mc << 3;
         const float *src = gs + (size_t)k * ldp + t0 + m0;
         float x[8];
@@ -128,7 +149,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          if (t0 + m0 + q >= NT) x[q] = 0.f;
+          if (m0 + q >= rows) x[q] = 0.f;
         uint4 hi, lo;
         tc::split8(x, hi, lo);
         const uint32_t off = TL.a1 + (uint32_t)(m0 >> 6) * ((uint32_t)K1p * 128u) + (uint32_t)k * 128u +
@@ -141,7 +162,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     tc::tc_fence_before_sync();
     __syncthreads();
     // ---- layer 1 MMAs ----
-    if (warp == 4) {
+    if (warp == TF_MMAW) {
       tc::tc_fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t blk = (uint32_t)K1p * 128u;
@@ -162,10 +183,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     phase ^= 1u;
     tc::tc_fence_after_sync();
     // ---- epilogue 1: elu(D1 + b1) -> A2 (K-major, one row per thread) ----
-    if (warp < 4) {
-      const int r = threadIdx.x;
-      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-      for (int c0 = 0; c0 < Hp; c0 += 16) {
+    const int lq = warp & 3, chalf = warp >> 2;               // TMEM lane quarter, column half of this warp
+    const int nck = Hp >> 4, ck0 = chalf ? (nck + 1) >> 1 : 0, ck1 = chalf ? nck : (nck + 1) >> 1;   // 16-column chunks
+    if (warp < TF_MMAW) {
+      const int r = lq * 32 + lane;
+      const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
+      for (int c0 = ck0 * 16; c0 < ck1 * 16; c0 += 16) {
         float v[16];
         tc::tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
@@ -189,7 +212,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     tc::tc_fence_before_sync();
     __syncthreads();
     // ---- layer 2 MMAs ----
-    if (warp == 4) {
+    if (warp == TF_MMAW) {
       tc::tc_fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t blk = (uint32_t)Hp * 128u;
@@ -212,18 +235,26 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     tc::tc_fence_after_sync();
     // ---- epilogue 2: out = elu(D2 + b2) . w3 + b3, masks, adjacency sampler epilogue ----
     float s2 = 0.f, z2 = 0.f;
-    if (warp < 4) {
-      const int r = threadIdx.x, t = t0 + r;
-      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + 128u;
-      float acc = b3;
-      for (int c0 = 0; c0 < Hp; c0 += 16) {
+    float acc = 0.f;
+    if (warp < TF_MMAW) {
+      const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16) + 128u;
+      for (int c0 = ck0 * 16; c0 < ck1 * 16; c0 += 16) {
         float v[16];
         tc::tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
         for (int q = 0; q < 16; ++q) acc += fast_elu(v[q] + vb2[c0 + q]) * vw3[c0 + q];   // vw3 = 0 past dh
       }
-      if (t < NT) {
-        const int ij = P->tri_ij[t], i = ij >> 8, j = ij & 255;
+      if (chalf) part[lq * 32 + lane] = acc;
+    }
+    __syncthreads();   // the second column half's partial dot products
+    if (warp < 4) {
+      const int r = threadIdx.x, t = t0 + r;
+      acc += part[r] + b3;
+      int i = 0, j = 0;
+      bool live = r < rows;
+      if (ta.big) { i = bi; j = bj0 + r; live = live && j >= i; }
+      else if (live) { const int ij = P->tri_ij[t]; i = ij >> 8; j = ij & 255; }
+      if (live) {
         const float fi = a.flags[(size_t)b * N + i], fj = a.flags[(size_t)b * N + j];
         const float o = (i == j) ? 0.f : acc * fi * fj;   // (1 - I) mask and mask_adjs
         const size_t ga = (size_t)b * NP;
@@ -280,7 +311,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, 256);
+  if (warp == TF_MMAW) tc::tmem_dealloc(tmem, 256);
 }
 
 static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const XaArgs &a, int fd, void *stream) {
@@ -289,6 +320,14 @@ static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const X
   ta.L = tc_afinal_layout(fd, hp.d.neta.fin.dhid);
   ta.fd = fd;
   ta.ntg = (hp.xp.NT + 127) / 128;
+  ta.gs_base = a.g_stack; ta.gs_stride = hp.xp.g_stack; ta.ldp = hp.xp.ldp; ta.NT = hp.xp.NT;
+  ta.big = 0; ta.Np = 0; ta.nseg = 1;
+  if (hp.xp.big) {
+    ta.big = 1; ta.Np = hp.xp.big_Np; ta.nseg = (hp.d.N + 127) / 128;
+    ta.ntg = hp.d.N * ta.nseg;
+    ta.gs_base = a.g_stack;          // the caller passes the large-graph stack base in g_stack
+    ta.gs_stride = hp.xp.big_total; ta.ldp = hp.xp.big_PS; ta.NT = hp.xp.big_PS;
+  }
   static size_t attr = 0;
   if (ta.L.total > attr) {
     if (cudaFuncSetAttribute(tc_afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ta.L.total) != cudaSuccess) return -1;
