@@ -16,7 +16,11 @@
 
 namespace ccsd {
 
-constexpr int TF_EPI = 256;       // 8 epilogue / loader warps: TMEM lane quarter = warp % 4, column half = warp / 4
+#ifndef TF_PARTS
+#define TF_PARTS 4
+#endif
+constexpr int TF_NP = TF_PARTS;     // column parts: the epilogue of a 128-row tile is split over TF_NP warps per TMEM lane quarter
+constexpr int TF_EPI = 128 * TF_NP; // epilogue / loader warps: TMEM lane quarter = warp % 4, column part = warp / 4
 constexpr int TF_THREADS = TF_EPI + 32;   // + 1 MMA warp
 constexpr int TF_MMAW = TF_EPI / 32;
 
@@ -37,7 +41,7 @@ static inline TcFinLayout tc_afinal_layout(int fd, int dhid) {
   L.w2_half = 2u * L.Hp * 128u;  L.w2 = o; o += 2 * L.w2_half;     // [2 n-blocks][Hp k-rows][128 B]
   L.a1_half = 2u * L.K1p * 128u; L.a1 = o; o += 2 * L.a1_half;     // [2 m-blocks][K1p k-rows][128 B]
   L.a2_half = 2u * 16384u;       L.a2 = o; o += 2 * L.a2_half;     // [2 k-blocks][128 rows][128 B]
-  L.vec = o; o += 3 * 128 * 4 + 256 + 512;                         // b1, b2, w3, reduction scratch, [128] partial dot products
+  L.vec = o; o += 3 * 128 * 4 + 256 + 512 * TF_NP;                 // b1, b2, w3, reduction scratch, [parts][128] partial dot products
   L.bars = o; o += 64;
   L.total = o + 1024;
   return L;
@@ -183,8 +187,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     phase ^= 1u;
     tc::tc_fence_after_sync();
     // ---- epilogue 1: elu(D1 + b1) -> A2 (K-major, one row per thread) ----
-    const int lq = warp & 3, chalf = warp >> 2;               // TMEM lane quarter, column half of this warp
-    const int nck = Hp >> 4, ck0 = chalf ? (nck + 1) >> 1 : 0, ck1 = chalf ? nck : (nck + 1) >> 1;   // 16-column chunks
+    const int lq = warp & 3, cpart = warp >> 2;               // TMEM lane quarter, column part of this warp
+    const int nck = Hp >> 4, cper = (nck + TF_NP - 1) / TF_NP;   // 16-column chunks, chunks per part
+    const int ck0 = cpart * cper < nck ? cpart * cper : nck, ck1 = ck0 + cper < nck ? ck0 + cper : nck;
     if (warp < TF_MMAW) {
       const int r = lq * 32 + lane;
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
@@ -244,12 +249,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
 #pragma unroll
         for (int q = 0; q < 16; ++q) acc += fast_elu(v[q] + vb2[c0 + q]) * vw3[c0 + q];   // vw3 = 0 past dh
       }
-      if (chalf) part[lq * 32 + lane] = acc;
+      if (cpart) part[(cpart - 1) * 128 + lq * 32 + lane] = acc;
     }
     __syncthreads();   // the second column half's partial dot products
     if (warp < 4) {
       const int r = threadIdx.x, t = t0 + r;
-      acc += part[r] + b3;
+#pragma unroll
+      for (int q = 0; q < TF_NP - 1; ++q) acc += part[q * 128 + r];
+      acc += b3;
       int i = 0, j = 0;
       bool live = r < rows;
       if (ta.big) { i = bi; j = bj0 + r; live = live && j >= i; }
