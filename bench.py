@@ -47,6 +47,7 @@ WORKLOADS = {
     "enzymes_small": ("enzymes_small", 64, 64),
     "enzymes": ("enzymes", 64, 8),
     "grid": ("grid", 64, 2),
+    "grid_small_cc": ("grid_small_cc", 16, 1),
     "qm9": ("qm9", 1024, 1024),
 }
 
@@ -313,7 +314,8 @@ def main():
     eng = Engine(holders, sdes, shapes, sampler=sampler, predictor=sh["predictor"], corrector=sh["corrector"],
                  snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1, denoise=True, eps=1e-4, device=dev, d_min=d_min,
                  d_max=d_max)
-    eng.enable_traj()  # the reference records sample 0 every step (solver.py:1149-1165); so do we
+    if eng.traj_bytes() <= Engine.TRAJ_LIMIT_BYTES:
+        eng.enable_traj()  # the reference records sample 0 every step (solver.py:1149-1165); so do we
 
     def barrier():
         if world > 1:

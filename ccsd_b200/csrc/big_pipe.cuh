@@ -312,6 +312,92 @@ __global__ void __launch_bounds__(128) big_edge_kernel(const DevPlan *__restrict
   }
 }
 
+// Same edge branch with ONE NODE PAIR PER THREAD (every width <= 16: c <= 8 channels, hidden = 2 max(c_in, c_out)):
+// the 2 c_in inputs and the hidden vector live in registers, the Linears are staged in shared memory as zero-padded
+// [16][16] blocks read as broadcast 16-byte loads.  ~520 instructions per pair instead of ~1950 through the row-tile
+// primitive (whose per-item epilogue dominates at K = 16).  CTA = 128 columns of row i; segments below the diagonal exit.
+constexpr int BIG_ESEG = 128;
+constexpr int BIG_EW = 16 * 16 + 16;   // floats per staged Linear
+static inline bool big_edge_fast_ok(const ccsd_attn_layer_t &ly) {
+  return 2 * ly.c_in <= 16 && ly.c_out <= 8 && ly.mlp.nl >= 1 && ly.mlp.nl <= 4 && (ly.mlp.nl == 1 || ly.mlp.dhid <= 16);
+}
+
+__global__ void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, N = d.N, Np = L.big_Np, PS = L.big_PS;
+  const int nseg = (N + BIG_ESEG - 1) / BIG_ESEG;
+  const int i = blockIdx.x / nseg, j0 = (blockIdx.x - i * nseg) * BIG_ESEG;
+  if (j0 + BIG_ESEG <= i) return;
+  const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
+  const ccsd_mlp_t &m = ly.mlp;
+  const float *W = P->W;
+  // stage: Linear l as w[k][16] (k < 16) + b[16], zero padded
+  for (int l = 0; l < m.nl; ++l) {
+    const int din = l == 0 ? m.din : m.dhid, dout = l == m.nl - 1 ? m.dout : m.dhid, opad = round_up(dout, 8);
+    for (int p = threadIdx.x; p < BIG_EW; p += blockDim.x) {
+      float v = 0.f;
+      if (p < 256) { const int k = p >> 4, o = p & 15; if (k < din && o < dout) v = __ldg(W + m.w[l] + k * opad + o); }
+      else if (p - 256 < dout) v = __ldg(W + m.b[l] + (p - 256));
+      sm[l * BIG_EW + p] = v;
+    }
+  }
+  __syncthreads();
+  const float fi = g.a.flags[(size_t)b * N + i];
+  float *S = big_ptr(P, g, b, L.big_S);
+  const float *att = big_ptr(P, g, b, L.big_ATT);
+  for (int r = threadIdx.x; r < BIG_ESEG; r += blockDim.x) {
+    const int j = j0 + r;
+    if (j < i || j >= N) continue;
+    const size_t t = (size_t)i * Np + j;
+    float h[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) h[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < ly.c_in) h[c] = att[(size_t)c * PS + t];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < ly.c_in) {
+        const float v = S[(size_t)(g.ch_in + c) * PS + t];
+        // input k = c_in + c: place with a static index
+#pragma unroll
+        for (int k = 1; k < 16; ++k)
+          if (k == ly.c_in + c) h[k] = v;
+      }
+    for (int l = 0; l < m.nl; ++l) {
+      const float *w = sm + l * BIG_EW;
+      float t16[16];
+#pragma unroll
+      for (int o4 = 0; o4 < 4; ++o4) {
+        const float4 bv = *reinterpret_cast<const float4 *>(w + 256 + 4 * o4);
+        t16[4 * o4] = bv.x; t16[4 * o4 + 1] = bv.y; t16[4 * o4 + 2] = bv.z; t16[4 * o4 + 3] = bv.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int o4 = 0; o4 < 4; ++o4) {
+          const float4 wv = *reinterpret_cast<const float4 *>(w + k * 16 + 4 * o4);
+          t16[4 * o4] += h[k] * wv.x; t16[4 * o4 + 1] += h[k] * wv.y; t16[4 * o4 + 2] += h[k] * wv.z; t16[4 * o4 + 3] += h[k] * wv.w;
+        }
+      }
+      const bool last = l == m.nl - 1;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) h[o] = last ? t16[o] : fast_elu(t16[o]);   // padded outputs: elu(0) = 0
+    }
+    const float f2 = 2.0f * fi * g.a.flags[(size_t)b * N + j];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < ly.c_out) {
+        float *pl = S + (size_t)(g.ch_out + o) * PS;
+        const float v = h[o] * f2;
+        pl[t] = v;
+        pl[(size_t)j * Np + i] = v;
+      }
+  }
+}
+
 // final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) + the adjacency sampler epilogue
 // (same arithmetic as afinal_kernel)
 __global__ void __launch_bounds__(128) big_final_kernel(const DevPlan *__restrict__ P, BigArgs g) {

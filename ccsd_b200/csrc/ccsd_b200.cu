@@ -82,6 +82,7 @@ struct ccsd_plan {
   size_t apply_smem = 0;
   int64_t launches = 0;
   int use_tc = 0, use_tc_apply = 0, use_tc_fin = 0;
+  int apply_big = 0;   // E too large for the resident F column block: hf_gemm_kernel + r2_epi_kernel (scratch = sr2)
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
   struct ProfRec { const char *name; void *e0, *e1; };
@@ -500,7 +501,13 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   const XpLayout &XL = p->hp.xp;
   const size_t xp_max = XL.big ? (size_t)imax(imax(XL.big_sm_node, XL.big_sm_edge), imax(XL.big_sm_fin, XL.big_sm_xfin)) * 4
                                : (size_t)imax(imax(imax(XL.x_total, XL.c_total), imax(XL.f_total, imax(XL.h_total, XL.hb_total))), XL.m_total) * 4;
-  if (xp_max > 227 * 1024 || p->apply_smem > 227 * 1024) {
+  if (p->apply_smem > 227 * 1024) {   // large E (grid_small_CC): GEMM into scratch + element-wise epilogue
+    p->apply_big = 1;
+    p->apply_smem = (size_t)(40 + netf_stage_floats(d.netf, p->hp.f_nlin, p->hp.f_mode) + 4) * 4;
+    p->hp.ntile_r2 = R2EPI_CHUNKS;
+    p->hp.ntile_max = imax(p->hp.ntile_max, p->hp.ntile_r2);
+  }
+  if (xp_max > 227 * 1024) {
     char buf[200];
     snprintf(buf, sizeof buf, "graph tile does not fit shared memory (x/adj pipeline %zu B, apply %zu B > 227 KB): N/E too large for the resident-tile kernels",
              xp_max, p->apply_smem);
@@ -565,7 +572,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
     if (e1 == cudaSuccess) xp_attr = xp_max;
   }
-  if (d.is_cc && p->apply_smem > apply_attr) {
+  if (d.is_cc && !p->apply_big && p->apply_smem > apply_attr) {
     e2 = cudaFuncSetAttribute(apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
@@ -577,7 +584,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
-  p->use_tc_apply = (d.is_cc && (d.nets & 4)) ? tc_apply_supported(d.E, d.K) : 0;
+  p->use_tc_apply = (d.is_cc && (d.nets & 4) && !p->apply_big) ? tc_apply_supported(d.E, d.K) : 0;
   p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = 0;  // A/B switch for tests and profiling
   if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
@@ -693,6 +700,7 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
   static const int T_pow = envt("CCSD_BIG_T_POW", 128), T_xw = envt("CCSD_BIG_T_XW", 0), T_agg = envt("CCSD_BIG_T_AGG", 0),
                    T_node = envt("CCSD_BIG_T_NODE", 64), T_edge = envt("CCSD_BIG_T_EDGE", 32), T_fin = envt("CCSD_BIG_T_FIN", 128),
                    T_xfin = envt("CCSD_BIG_T_XFIN", 128);
+  static const bool edge_fast = getenv("CCSD_BIG_EDGE_GENERIC") == nullptr;   // A/B switch: row-tile edge kernel
 #define BIG_LAUNCH(kern, grid, thr, smem) do { PROF_BEGIN(p, #kern, stream); CCSD_LAUNCH(kern, grid, thr, smem, stream, p->dP, g); PROF_END(p, stream); p->launches++; } while (0)
   BIG_LAUNCH(big_prep_kernel, dim3(imin(148 * 2, (d.N * L.big_Np + 255) / 256), B, 1), 256, 0);
   const int c0 = (a.which & 2) ? A.c_init : 1;
@@ -723,7 +731,10 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
     const int nb = (d.N + 3) / 4, nblk = nb * (nb + 1) / 2;
     BIG_LAUNCH(big_attn_kernel, dim3((nblk + 127) / 128, ly.c_in, B), 128, 0);
     BIG_LAUNCH(big_node_kernel, dim3(nrc, 1, B), T_node, (size_t)L.big_sm_node * 4);
-    BIG_LAUNCH(big_edge_kernel, dim3(d.N * L.big_nseg, 1, B), T_edge, (size_t)L.big_sm_edge * 4);
+    if (edge_fast && big_edge_fast_ok(ly))
+      BIG_LAUNCH(big_edge_pair_kernel, dim3(d.N * ((d.N + BIG_ESEG - 1) / BIG_ESEG), 1, B), BIG_ESEG, (size_t)4 * BIG_EW * 4);
+    else
+      BIG_LAUNCH(big_edge_kernel, dim3(d.N * L.big_nseg, 1, B), T_edge, (size_t)L.big_sm_edge * 4);
     ch_in = ch_out; ch_out += ly.c_out;
     float *t = xf0; xf0 = xf1; xf1 = t;
   }
@@ -821,6 +832,20 @@ static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
 #ifndef CCSD_EMU
   if (p->use_tc_apply) { tc_apply_launch(p->dP, p->hp, q, stream); return; }
 #endif
+  if (p->apply_big) {
+    const ccsd_plan_desc_t &d = p->hp.d;
+    HfArgs h; h.r2 = q.r2; h.H = q.H; h.hf = p->sr2;
+    CCSD_LAUNCH(hf_gemm_kernel, dim3((d.K + GRAM_BN - 1) / GRAM_BN, (d.E + GRAM_BM - 1) / GRAM_BM, d.B), 256,
+                2 * GRAM_BK * (GRAM_BM + 4) * 4, stream, p->dP, h);
+    const dim3 ge(R2EPI_CHUNKS, d.B, 1);
+    const float *hf = p->sr2;
+    if (p->hp.f_mode == 1) CCSD_LAUNCH(r2_epi_kernel<1>, ge, 256, p->apply_smem, stream, p->dP, q, hf);
+    else if (p->hp.f_mode == 4) CCSD_LAUNCH(r2_epi_kernel<4>, ge, 256, p->apply_smem, stream, p->dP, q, hf);
+    else if (p->hp.f_mode >= 2) CCSD_LAUNCH(r2_epi_kernel<2>, ge, 256, p->apply_smem, stream, p->dP, q, hf);
+    else CCSD_LAUNCH(r2_epi_kernel<0>, ge, 256, p->apply_smem, stream, p->dP, q, hf);
+    p->launches++;
+    return;
+  }
   const dim3 grid(p->hp.ntile_r2, p->hp.d.B, 1);
   if (p->hp.f_mode == 1) CCSD_LAUNCH(apply_kernel<1>, grid, 256, p->apply_smem, stream, p->dP, q);
   else if (p->hp.f_mode == 4) CCSD_LAUNCH(apply_kernel<4>, grid, 256, p->apply_smem, stream, p->dP, q);

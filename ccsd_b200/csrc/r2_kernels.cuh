@@ -644,6 +644,124 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Large-E fallback of the apply pass (E > 192 and an F column block [E][64] that no longer fits shared memory:
+// grid_small_CC, E = 1176, K = 18424): HF = H F as a plain tiled fp32 GEMM into a scratch tensor, then an
+// element-wise kernel that runs the same per-entry epilogue (r2_epilogue4) as apply_kernel.
+struct HfArgs {
+  const float *r2, *H;   // [B,E,K] [B,E,Ep]
+  float *hf;             // [B,E,K]
+};
+
+__global__ void __launch_bounds__(256) hf_gemm_kernel(const DevPlan *__restrict__ P, HfArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int E = d.E, K = d.K, Ep = P->Ep;
+  const int b = blockIdx.z, m0 = blockIdx.y * GRAM_BM, n0 = blockIdx.x * GRAM_BN;
+  const float *Fb = a.r2 + (size_t)b * E * K;
+  const float *Hb = a.H + (size_t)b * E * Ep;
+  float *Ob = a.hf + (size_t)b * E * K;
+  constexpr int LDT = GRAM_BM + 4;
+  float *As = sm;                      // [BK][LDT]   As[kk][m] = H[m0 + m][e0 + kk]
+  float *Bs = sm + GRAM_BK * LDT;      // [BK][LDT]   Bs[kk][n] = F[e0 + kk][n0 + n]
+#ifdef CCSD_EMU
+  (void)As; (void)Bs;
+  for (int i = 0; i < GRAM_BM; ++i)
+    for (int j = 0; j < GRAM_BN; ++j) {
+      const int m = m0 + i, n = n0 + j;
+      if (m >= E || n >= K) continue;
+      float s = 0.f;
+      for (int e2 = 0; e2 < E; ++e2) s += Hb[(size_t)m * Ep + e2] * Fb[(size_t)e2 * K + n];
+      Ob[(size_t)m * K + n] = s;
+    }
+#else
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ar = t >> 2, aq = (t & 3) << 2;      // A loader: row ar, 4 consecutive k
+  const int bk = t >> 4, bn = (t & 15) << 2;     // B loader: k row bk, 4 consecutive n
+  for (int e0 = 0; e0 < E; e0 += GRAM_BK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int m = m0 + ar, e2 = e0 + aq + q;
+      As[(aq + q) * LDT + ar] = (m < E && e2 < E) ? __ldg(Hb + (size_t)m * Ep + e2) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e2 = e0 + bk, n = n0 + bn + q;
+      Bs[bk * LDT + bn + q] = (e2 < E && n < K) ? __ldg(Fb + (size_t)e2 * K + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GRAM_BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4 *>(As + kk * LDT + ty * 4);
+      const float4 bv = *reinterpret_cast<const float4 *>(Bs + kk * LDT + tx * 4);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += aa[i] * bb[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < E && n < K) Ob[(size_t)m * K + n] = acc[i][j];
+    }
+#endif
+}
+
+constexpr int R2EPI_CHUNKS = 64;   // CTAs (= norm partial slots) per sample of r2_epi_kernel
+
+// a.out may alias hf (MODE_SCORE) or a.r2 (CORR / PRED): every entry is read before it is written by its own thread
+template <int FMODE>
+__global__ void __launch_bounds__(256) r2_epi_kernel(const DevPlan *__restrict__ P, ApplyArgs a, const float *hf) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int N = d.N, E = d.E, K = d.K, Kg = P->Kp >> 2;
+  const int b = blockIdx.y;
+  const float *Fb = a.r2 + (size_t)b * E * K;
+  const float *HFb = hf + (size_t)b * E * K;
+  const float *fl = a.flags + (size_t)b * N;
+  float *red = sm, *fw = sm + 40;
+  if (FMODE == 2) netf_stage_w8(d.netf, P->W, fw);
+  if (FMODE == 4) netf_stage_w8f2(d.netf, P->W, fw);
+  R2Epi c;
+  c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
+  c.gs = (unsigned long long)(a.nz.sample_offset + b);
+  if (a.mode != MODE_EVAL) c.co = P->sched[a.nz.step * 3 + 2];
+  c.b = b; c.E = E; c.K = K; c.Kg = Kg; c.f_nlin = P->f_nlin;
+  c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
+  __syncthreads();
+  float s2 = 0.f, z2 = 0.f;
+  const long long groups = (long long)E * Kg;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(g / Kg), k0 = (int)(g - (long long)e * Kg) << 2;
+    float f4[4], h4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool in = k0 + q < K;
+      f4[q] = in ? Fb[(size_t)e * K + k0 + q] : 0.f;
+      h4[q] = in ? HFb[(size_t)e * K + k0 + q] : 0.f;
+    }
+    r2_epilogue4<FMODE>(c, a, e, k0, f4, h4, s2, z2);
+  }
+  if (a.mode == MODE_SCORE || a.mode == MODE_NORM) {
+    s2 = block_sum(s2, red);
+    z2 = block_sum(z2, red);
+    if (threadIdx.x == 0) {
+      float *np = a.norm_part + ((size_t)(2 * d.B + b) * P->ntile_max + blockIdx.x) * 2;
+      np[0] = s2; np[1] = z2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // prior: state = mask(raw normal)  (solver.py:963-968, 1111-1118; sde.py:436, 448-449)
 struct InitArgs {
   const float *flags;

@@ -523,12 +523,19 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
               o4[i] = r2_entry<FMODE, MODE>(c, w, fv[i], v[4 * c4 + i], z4[i], mv[i], s2, z2, mu4[i], pre[i]);
             if (MODE != MODE_NORM) *cell = make_float4(o4[0], o4[1], o4[2], o4[3]);
             if (MODE == MODE_PRED && side) {
+              const bool tr = a.traj && b == 0;
+              if (inside && !(K & 3)) {   // whole 16-byte groups (rows are 16-byte aligned when K % 4 == 0)
+                const float4 m4 = make_float4(mu4[0], mu4[1], mu4[2], mu4[3]);
+                if (a.write_mean) *reinterpret_cast<float4 *>(a.mean + ((size_t)b * E + e) * K + k) = m4;
+                if (tr) *reinterpret_cast<float4 *>(a.traj + (size_t)e * K + k) = a.denoise ? m4 : make_float4(o4[0], o4[1], o4[2], o4[3]);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (inside || k + i < K) {
-                  if (a.write_mean) a.mean[((size_t)b * E + e) * K + k + i] = mu4[i];
-                  if (a.traj && b == 0) a.traj[(size_t)e * K + k + i] = a.denoise ? mu4[i] : o4[i];
-                }
+                for (int i = 0; i < 4; ++i)
+                  if (inside || k + i < K) {
+                    if (a.write_mean) a.mean[((size_t)b * E + e) * K + k + i] = mu4[i];
+                    if (tr) a.traj[(size_t)e * K + k + i] = a.denoise ? mu4[i] : o4[i];
+                  }
+              }
             }
           }
         }

@@ -147,6 +147,12 @@ class Engine:
             pass
 
     # -- API --
+    TRAJ_LIMIT_BYTES = 16 << 30   # diff_traj of sample 0 on the device: grid_small_CC would need 87 GB
+
+    def traj_bytes(self) -> int:
+        d = self.desc
+        return 4 * d.n_diff_steps * (d.N * d.F + d.N * d.N + (d.E * d.K if self.is_cc else 0))
+
     def enable_traj(self) -> None:
         n = self.desc.n_diff_steps
         d = self.desc
@@ -294,6 +300,12 @@ def _make_sampler(
         n = eng.desc.n_diff_steps
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if record_traj and eng.traj_bytes() > Engine.TRAJ_LIMIT_BYTES:
+            # the reference appends sample 0 of every object at every step (solver.py:1149-1165); at E x K = 2e7 that
+            # list does not fit any memory -- return an empty trajectory instead of failing
+            import warnings
+            warnings.warn(f"diff_traj would need {eng.traj_bytes() / 2 ** 30:.0f} GiB; not recorded")
+            record_traj = False
         if record_traj and eng.traj is None:
             eng.enable_traj()
         eng.init(init_flags, prior=noise.prior if noise is not None else None, seed=seed, sample_offset=sample_offset)

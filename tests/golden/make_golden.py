@@ -58,6 +58,8 @@ CONFIGS = {
     # large graphs (N > 64): no sample_*.yaml is shipped for them; GDSS's sampler settings
     "enzymes": ("ENZYMES/gdss_enzymes", ("Reverse", "Langevin", 0.1, 0.7), 2),
     "grid": ("grid/gdss_grid", ("Reverse", "Langevin", 0.1, 0.7), 1),
+    # config/sample_grid_small_CC.yaml (N = 49, E = 1176, K = 18424: 87 MB of rank-2 state per sample)
+    "grid_small_cc": ("grid_small_CC/ccsd_grid_small_CC", ("Reverse", "Langevin", 0.1, 0.7), 1),
 }
 
 

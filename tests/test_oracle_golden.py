@@ -159,7 +159,7 @@ def test_pow_tensor_cc_hodge_mask():
 # ---- outputs of the unmodified reference on the shipped checkpoints --------------------------
 CFGS = ["qm9", "community_small", "ego_small", "qm9_cc", "community_small_cc", "enzymes_small_cc", "ego_small_cc",
         "qm9_base_cc", "community_small_base_cc", "enzymes_small_base_cc", "ego_small_cc_v2", "zinc250k", "enzymes_small",
-        "enzymes", "grid"]
+        "enzymes", "grid", "grid_small_cc"]
 
 
 @pytest.mark.parametrize("name", CFGS)

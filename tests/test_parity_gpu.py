@@ -24,7 +24,7 @@ def test_product_library_is_loaded():
                                     ("community_small_cc", 4), ("ego_small", 8), ("ego_small_cc", 2),
                                     ("qm9_base_cc", 16), ("community_small_base_cc", 4), ("enzymes_small_base_cc", 8),
                                     ("ego_small_cc_v2", 2), ("zinc250k", 8), ("enzymes_small", 16),
-                                    ("enzymes", 4), ("grid", 2)])
+                                    ("enzymes", 4), ("grid", 2), ("grid_small_cc", 1)])
 def test_score_parity(name, B):
     """per-step score outputs within 1e-4 relative of the fp32 reference path (north_star)."""
     errs = score_parity(name, B, DEV)
@@ -34,7 +34,7 @@ def test_score_parity(name, B):
 
 @pytest.mark.parametrize("name", ["qm9", "community_small", "ego_small", "qm9_cc", "community_small_cc", "enzymes_small_cc",
                                   "ego_small_cc", "qm9_base_cc", "community_small_base_cc", "enzymes_small_base_cc",
-                                  "ego_small_cc_v2", "zinc250k", "enzymes_small", "enzymes", "grid"])
+                                  "ego_small_cc_v2", "zinc250k", "enzymes_small", "enzymes", "grid", "grid_small_cc"])
 def test_scores_against_committed_reference_outputs(name):
     """The same inputs the unmodified reference was run on (tests/golden/io_<cfg>.npz)."""
     cfg = Config(name)
@@ -76,6 +76,7 @@ def test_scores_against_committed_reference_outputs(name):
     ("enzymes", "PC", "Reverse", "Langevin", 4, 3),
     ("enzymes", "S4", "None", "None", 4, 2),
     ("grid", "PC", "Reverse", "Langevin", 2, 2),
+    ("grid_small_cc", "PC", "Reverse", "Langevin", 1, 1),
     ("ego_small_cc", "PC", "Euler", "None", 2, 2),
     ("ego_small_cc", "PC", "Reverse", "Langevin", 2, 2),
 ])
