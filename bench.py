@@ -417,7 +417,7 @@ def main():
         peak_hbm = peaks.get("hbm_gbs", 6650.0)
         XA = ("x_net_kernel", "attn_channel_kernel", "attn_finish_kernel", "proj1_kernel", "hodge_kernel", "hodge_base_kernel", "afinal_kernel",
               "tc_afinal_kernel", "big_prep_kernel", "big_pow_kernel", "big_deg_kernel", "big_xw_kernel", "big_agg_kernel", "big_attn_kernel",
-              "big_node_kernel", "big_edge_kernel", "big_final_kernel", "big_xfin_kernel")
+              "big_node_kernel", "big_edge_kernel", "big_edge_pair_kernel", "big_mirror_kernel", "big_final_kernel", "big_xfin_kernel")
         kern = {}
         for k_, v in prof_summary.items():
             ms_l = v[0] / v[1]

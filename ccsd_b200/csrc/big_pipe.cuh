@@ -136,13 +136,30 @@ __global__ void __launch_bounds__(128) big_xw_kernel(const DevPlan *__restrict__
 
 // T = diag(d) A^ Y + bias: the aggregation of DenseGCNConv (layers.py:147-156).  A^ = plane with a unit
 // diagonal: sum_j a_ij y_j over the stored plane plus the rank-one fix-up (1 - a_ii) y_i, applied by the item
-// that owns the tile (no second pass).
+// that owns the tile (no second pass).  Item = 8 rows x 8 columns in registers: four 16-byte loads per 64 FMAs
+// (the operands come through L1, whose bandwidth -- not the FMA pipe -- bounds the 4 x 8 tile), software pipelined.
 // xmode 0: Q | K rows -> TQK (feature-major [2 adp][Np]), V -> TV ([c nh + o][Np]);  xmode 1: tanh -> HC rows.
+constexpr int BIG_RCA = 64;    // node rows per CTA of the aggregation kernel
+
+struct AggOps { float4 a0, a1, w0, w1; };
+__device__ __forceinline__ void agg_load(AggOps &t, const float *pa, const float *__restrict__ pw) {
+  t.a0 = ld4(pa); t.a1 = ld4(pa + 4);
+  t.w0 = __ldg(reinterpret_cast<const float4 *>(pw)); t.w1 = __ldg(reinterpret_cast<const float4 *>(pw + 4));
+}
+__device__ __forceinline__ void agg_fma(float acc[8][8], const AggOps &t) {
+  const float av[8] = {t.a0.x, t.a0.y, t.a0.z, t.a0.w, t.a1.x, t.a1.y, t.a1.z, t.a1.w};
+  const float wv[8] = {t.w0.x, t.w0.y, t.w0.z, t.w0.w, t.w1.x, t.w1.y, t.w1.z, t.w1.w};
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[rr][j] += av[rr] * wv[j];
+}
+
 __global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
-  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC, ngrp = (R + 3) >> 2;
+  const int i0 = blockIdx.x * BIG_RCA, R = (N - i0 < BIG_RCA) ? N - i0 : BIG_RCA, ngrp = (R + 7) >> 3;
   const float *W = P->W;
   const float *dv = big_ptr(P, g, b, L.big_DV) + c * Np;
   const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
@@ -154,13 +171,28 @@ __global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict_
   float *tqk = big_ptr(P, g, b, L.big_TQK) + (size_t)c * w2 * Np, *tv = big_ptr(P, g, b, L.big_TV) + (size_t)c * nh * Np;
   float *hc = big_ptr(P, g, b, L.big_HC) + (size_t)g.out_row * Np;
   for (int it = threadIdx.x; it < (YW >> 3) * ngrp; it += blockDim.x) {
-    const int cc = it / ngrp, r0 = i0 + ((it - cc * ngrp) << 2), o0 = cc << 3;
-    float acc[4][8];
+    const int cc = it / ngrp, r0 = i0 + ((it - cc * ngrp) << 3), o0 = cc << 3;   // r0 + 7 < Np (Np is a multiple of 8)
+    float acc[8][8];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr)
+    for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[rr][j] = 0.f;
-    dense_tile(acc, pl, Np, N, nullptr, 0, 0, y, YW, r0, o0);
+    const float *pa = pl + r0, *pw = y + o0;
+    AggOps A, Bq;
+    agg_load(A, pa, pw);
+    int k = 1;
+#pragma unroll 1
+    for (; k + 1 < N; k += 2) {
+      agg_load(Bq, pa + (size_t)k * Np, pw + (size_t)k * YW);
+      agg_fma(acc, A);
+      agg_load(A, pa + (size_t)(k + 1) * Np, pw + (size_t)(k + 1) * YW);
+      agg_fma(acc, Bq);
+    }
+    agg_fma(acc, A);
+    if (k < N) {
+      agg_load(Bq, pa + (size_t)k * Np, pw + (size_t)k * YW);
+      agg_fma(acc, Bq);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int o = o0 + j;
@@ -179,7 +211,7 @@ __global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict_
         dst = tv + (size_t)(o - w2) * Np; bias = __ldg(W + ly.v[c].b + (o - w2));
       }
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
+      for (int rr = 0; rr < 8; ++rr) {
         const int i = r0 + rr;
         if (i < N) {
           const float fix = 1.f - pl[(size_t)i * Np + i];
@@ -247,8 +279,7 @@ __global__ void __launch_bounds__(128) big_attn_kernel(const DevPlan *__restrict
         const int i = i0 + u, j = j0 + v;
         if (i <= j && j < N) {
           const float o = inv * sum[u][v];
-          att[(size_t)i * Np + j] = o;
-          att[(size_t)j * Np + i] = o;
+          att[(size_t)i * Np + j] = o;   // upper triangle only: the edge kernels read att at j >= i
         }
       }
   }
@@ -317,6 +348,7 @@ __global__ void __launch_bounds__(128) big_edge_kernel(const DevPlan *__restrict
 // [16][16] blocks read as broadcast 16-byte loads.  ~520 instructions per pair instead of ~1950 through the row-tile
 // primitive (whose per-item epilogue dominates at K = 16).  CTA = 128 columns of row i; segments below the diagonal exit.
 constexpr int BIG_ESEG = 128;
+constexpr int BIG_EROWS = 4;    // rows per CTA (amortises the weight staging)
 constexpr int BIG_EW = 16 * 16 + 16;   // floats per staged Linear
 static inline bool big_edge_fast_ok(const ccsd_attn_layer_t &ly) {
   return 2 * ly.c_in <= 16 && ly.c_out <= 8 && ly.mlp.nl >= 1 && ly.mlp.nl <= 4 && (ly.mlp.nl == 1 || ly.mlp.dhid <= 16);
@@ -328,8 +360,8 @@ __global__ void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, N = d.N, Np = L.big_Np, PS = L.big_PS;
   const int nseg = (N + BIG_ESEG - 1) / BIG_ESEG;
-  const int i = blockIdx.x / nseg, j0 = (blockIdx.x - i * nseg) * BIG_ESEG;
-  if (j0 + BIG_ESEG <= i) return;
+  const int ib = (blockIdx.x / nseg) * BIG_EROWS, j0 = (blockIdx.x - (blockIdx.x / nseg) * nseg) * BIG_ESEG;
+  if (j0 + BIG_ESEG <= ib) return;   // every row of this CTA lies below the segment
   const ccsd_attn_layer_t &ly = d.neta.layer[g.layer];
   const ccsd_mlp_t &m = ly.mlp;
   const float *W = P->W;
@@ -344,12 +376,12 @@ __global__ void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *
     }
   }
   __syncthreads();
-  const float fi = g.a.flags[(size_t)b * N + i];
   float *S = big_ptr(P, g, b, L.big_S);
   const float *att = big_ptr(P, g, b, L.big_ATT);
-  for (int r = threadIdx.x; r < BIG_ESEG; r += blockDim.x) {
-    const int j = j0 + r;
-    if (j < i || j >= N) continue;
+  for (int r = threadIdx.x; r < BIG_ESEG * BIG_EROWS; r += blockDim.x) {
+    const int i = ib + r / BIG_ESEG, j = j0 + r % BIG_ESEG;
+    if (i >= N || j < i || j >= N) continue;
+    const float fi = g.a.flags[(size_t)b * N + i];
     const size_t t = (size_t)i * Np + j;
     float h[16];
 #pragma unroll
@@ -392,9 +424,30 @@ __global__ void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *
       if (o < ly.c_out) {
         float *pl = S + (size_t)(g.ch_out + o) * PS;
         const float v = h[o] * f2;
-        pl[t] = v;
-        pl[(size_t)j * Np + i] = v;
+        pl[t] = v;   // upper triangle; big_mirror_kernel fills the lower one with coalesced stores
       }
+  }
+}
+
+// lower triangle <- upper triangle of planes [ch_out, ch_out + nch): 32 x 32 tiles through shared memory, so that both
+// the reads and the writes are coalesced (a per-row kernel can only write its mirrored entries as scattered 4-byte stores)
+__global__ void __launch_bounds__(256) big_mirror_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+  CCSD_SMEM(sm);
+  const XpLayout &L = P->xp;
+  const int b = blockIdx.z, N = P->d.N, Np = L.big_Np;
+  float *pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_out + blockIdx.y) * L.big_PS;
+  const int nt = (N + 31) >> 5, it = blockIdx.x;
+  int I = 0, rem = it;
+  while (rem >= nt - I) { rem -= nt - I; ++I; }
+  const int J = I + rem;
+  for (int p = threadIdx.x; p < 1024; p += blockDim.x) {
+    const int r = p >> 5, q = p & 31, i = I * 32 + r, j = J * 32 + q;
+    sm[r * 33 + q] = (i < N && j < N) ? pl[(size_t)i * Np + j] : 0.f;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < 1024; p += blockDim.x) {
+    const int r = p >> 5, q = p & 31, jj = J * 32 + r, ii = I * 32 + q;
+    if (jj < N && ii < N && jj > ii) pl[(size_t)jj * Np + ii] = sm[q * 33 + r];
   }
 }
 

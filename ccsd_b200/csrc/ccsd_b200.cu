@@ -694,7 +694,7 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
   const ccsd_netx_t &X = d.netx;
   BigArgs g; memset(&g, 0, sizeof g);
   g.a = a; g.base = p->g_big;
-  const int B = d.B, nrc = L.big_nrc;
+  const int B = d.B, nrc = L.big_nrc, nrca = (d.N + BIG_RCA - 1) / BIG_RCA;
   // threads per CTA (<= 128, the kernels' launch bound); environment overrides are tuning experiments
   static const auto envt = [](const char *nm, int dflt) { const char *e = getenv(nm); const int v = e ? atoi(e) : dflt; return v >= 32 && v <= 128 ? v / 32 * 32 : dflt; };
   static const int T_pow = envt("CCSD_BIG_T_POW", 128), T_xw = envt("CCSD_BIG_T_XW", 0), T_agg = envt("CCSD_BIG_T_AGG", 0),
@@ -713,7 +713,7 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
     for (int k = 0; k < X.depth; ++k) {
       g.gk = k; g.in_row = in_row; g.out_row = out_row;
       BIG_LAUNCH(big_xw_kernel, dim3(nrc, 1, B), 32, 0);    // 4 x 8 items (nhid <= 32)
-      BIG_LAUNCH(big_agg_kernel, dim3(nrc, 1, B), 32, 0);
+      BIG_LAUNCH(big_agg_kernel, dim3(nrca, 1, B), 32, 0);   // 4 x 8 items of 8 x 8 (nhid <= 32)
       in_row = out_row; out_row += X.gcn[k].dout;
     }
     BIG_LAUNCH(big_xfin_kernel, dim3(nrc, 1, B), T_xfin, (size_t)L.big_sm_xfin * 4);
@@ -727,12 +727,15 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
     g.layer = l; g.ch_in = ch_in; g.ch_out = ch_out; g.xin = xf0; g.xout = xf1;
     if (l > 0) { g.nch = ly.c_in; BIG_LAUNCH(big_deg_kernel, dim3((d.N + 127) / 128, ly.c_in, B), 128, 0); }
     BIG_LAUNCH(big_xw_kernel, dim3(nrc, ly.c_in, B), T_xw ? T_xw : L.big_T_xw, 0);
-    BIG_LAUNCH(big_agg_kernel, dim3(nrc, ly.c_in, B), T_agg ? T_agg : L.big_T_xw, 0);
+    BIG_LAUNCH(big_agg_kernel, dim3(nrca, ly.c_in, B), T_agg ? T_agg : L.big_T_xw, 0);
     const int nb = (d.N + 3) / 4, nblk = nb * (nb + 1) / 2;
     BIG_LAUNCH(big_attn_kernel, dim3((nblk + 127) / 128, ly.c_in, B), 128, 0);
     BIG_LAUNCH(big_node_kernel, dim3(nrc, 1, B), T_node, (size_t)L.big_sm_node * 4);
-    if (edge_fast && big_edge_fast_ok(ly))
-      BIG_LAUNCH(big_edge_pair_kernel, dim3(d.N * ((d.N + BIG_ESEG - 1) / BIG_ESEG), 1, B), BIG_ESEG, (size_t)4 * BIG_EW * 4);
+    if (edge_fast && big_edge_fast_ok(ly)) {
+      BIG_LAUNCH(big_edge_pair_kernel, dim3(((d.N + BIG_EROWS - 1) / BIG_EROWS) * ((d.N + BIG_ESEG - 1) / BIG_ESEG), 1, B), BIG_ESEG, (size_t)4 * BIG_EW * 4);
+      const int nt = (d.N + 31) / 32;
+      BIG_LAUNCH(big_mirror_kernel, dim3(nt * (nt + 1) / 2, ly.c_out, B), 256, (size_t)32 * 33 * 4);
+    }
     else
       BIG_LAUNCH(big_edge_kernel, dim3(d.N * L.big_nseg, 1, B), T_edge, (size_t)L.big_sm_edge * 4);
     ch_in = ch_out; ch_out += ly.c_out;
