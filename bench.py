@@ -150,6 +150,7 @@ def kernel_alg_work(meta, B, pr0):
         agg += cin * 2 * N * N * (2 * a_ + nh)
         cin = ch if l < L_ - 1 or L_ == 1 else cf
     out["big_agg_kernel"] = (B * agg / (px["depth"] + L_), 0)
+    out["tc_agg_kernel"] = (B * (agg - px["depth"] * 2 * N * N * px["nhid"]) / L_, 0)
     if meta["is_cc"]:
         st = 4 * E * K * B
         out["gram_kernel"] = out["tc_gram_kernel"] = (B * 2 * E * (E + pr0) * K, st)
@@ -416,7 +417,7 @@ def main():
         work = kernel_alg_work(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
         peak_hbm = peaks.get("hbm_gbs", 6650.0)
         XA = ("x_net_kernel", "attn_channel_kernel", "attn_finish_kernel", "proj1_kernel", "hodge_kernel", "hodge_base_kernel", "afinal_kernel",
-              "tc_afinal_kernel", "big_prep_kernel", "big_pow_kernel", "big_deg_kernel", "big_xw_kernel", "big_agg_kernel", "big_attn_kernel",
+              "tc_afinal_kernel", "big_prep_kernel", "big_pow_kernel", "big_deg_kernel", "big_xw_kernel", "big_agg_kernel", "tc_agg_kernel", "big_attn_kernel",
               "big_node_kernel", "big_edge_kernel", "big_edge_pair_kernel", "big_mirror_kernel", "big_final_kernel", "big_xfin_kernel")
         kern = {}
         for k_, v in prof_summary.items():

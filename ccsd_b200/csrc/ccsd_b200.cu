@@ -22,6 +22,7 @@
 #include "tc_gram.cuh"
 #include "tc_apply.cuh"
 #include "tc_afinal.cuh"
+#include "tc_agg.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -81,7 +82,7 @@ struct ccsd_plan {
   long long sample_offset = 0;
   size_t apply_smem = 0;
   int64_t launches = 0;
-  int use_tc = 0, use_tc_apply = 0, use_tc_fin = 0;
+  int use_tc = 0, use_tc_apply = 0, use_tc_fin = 0, use_tc_agg = 0;
   int apply_big = 0;   // E too large for the resident F column block: hf_gemm_kernel + r2_epi_kernel (scratch = sr2)
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
@@ -586,7 +587,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
   p->use_tc_apply = (d.is_cc && (d.nets & 4) && !p->apply_big) ? tc_apply_supported(d.E, d.K) : 0;
   p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = 0;  // A/B switch for tests and profiling
+  p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;
+  if (getenv("CCSD_B200_NO_TC_AGG")) p->use_tc_agg = 0;
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = 0;  // A/B switch for tests and profiling
   if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
     p->hp.ntile_adj = XL.big ? d.N * ((d.N + 127) / 128) : (p->hp.xp.NT + 127) / 128;
     p->hp.ntile_max = imax(p->hp.ntile_max, p->hp.ntile_adj);
@@ -727,6 +730,14 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
     g.layer = l; g.ch_in = ch_in; g.ch_out = ch_out; g.xin = xf0; g.xout = xf1;
     if (l > 0) { g.nch = ly.c_in; BIG_LAUNCH(big_deg_kernel, dim3((d.N + 127) / 128, ly.c_in, B), 128, 0); }
     BIG_LAUNCH(big_xw_kernel, dim3(nrc, ly.c_in, B), T_xw ? T_xw : L.big_T_xw, 0);
+#ifndef CCSD_EMU
+    if (p->use_tc_agg && tc_agg_supported(ly)) {
+      PROF_BEGIN(p, "tc_agg_kernel", stream);
+      if (tc_agg_launch(p->dP, p->hp, g, stream)) return fail(CCSD_ERR_CUDA, "tc_agg launch failed");
+      PROF_END(p, stream);
+      p->launches++;
+    } else
+#endif
     BIG_LAUNCH(big_agg_kernel, dim3(nrca, ly.c_in, B), T_agg ? T_agg : L.big_T_xw, 0);
     const int nb = (d.N + 3) / 4, nblk = nb * (nb + 1) / 2;
     BIG_LAUNCH(big_attn_kernel, dim3((nblk + 127) / 128, ly.c_in, B), 128, 0);
