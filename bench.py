@@ -265,11 +265,34 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "complexes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ---- main -------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under torchrun), so
+    fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -473,7 +496,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload).items() if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
