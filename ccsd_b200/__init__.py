@@ -5,6 +5,6 @@ Public surface mirrors the reference: ``get_pc_sampler`` / ``S4_solver`` (ccsd/s
 242, 337).  The compute path is the CUDA extension in ``ccsd_b200/_lib``; there is no CPU fallback.
 """
 from .sde import VPSDE, VESDE, subVPSDE  # noqa: F401
-from .solver import Engine, InjectedNoise, S4_solver, get_pc_sampler, quantize  # noqa: F401
+from .solver import Engine, InjectedNoise, S4_solver, get_pc_sampler, mol_onehot, quantize  # noqa: F401
 
 __version__ = "0.1.0"

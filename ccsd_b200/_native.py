@@ -139,6 +139,8 @@ def load():
     lib.ccsd_plan_read.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     lib.ccsd_score_eval.restype = C.c_int
     lib.ccsd_score_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.ccsd_mol_onehot.restype = C.c_int
+    lib.ccsd_mol_onehot.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.ccsd_quantize.restype = C.c_int
     lib.ccsd_quantize.argtypes = [vp, vp, sz, C.c_float, C.c_int, vp]
     lib.ccsd_plan_launch_count.restype = C.c_int64

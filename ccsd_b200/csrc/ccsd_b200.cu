@@ -1031,6 +1031,14 @@ int ccsd_quantize(const float *in, uint8_t *out, size_t n, float thr, int mol, v
   return dev_check("quantize_kernel");
 }
 
+int ccsd_mol_onehot(const float *x, const float *adj, int64_t *x_out, int64_t *adj_out, int B, int N, int F, void *stream) {
+  if (!x || !adj || !x_out || !adj_out) return fail(CCSD_ERR_INVALID, "null argument");
+  if (B < 1 || N < 1 || F < 1) return fail(CCSD_ERR_INVALID, "B, N, F must be positive");
+  CCSD_LAUNCH(mol_onehot_kernel, dim3(grid_for((size_t)B * N * N), 1, 1), 256, 0, stream, x, adj, (long long *)x_out,
+              (long long *)adj_out, B, N, F);
+  return dev_check("mol_onehot_kernel");
+}
+
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }
 
 int ccsd_debug_apply_trace(ccsd_plan_t *p, long long *trace_dev) {

@@ -972,4 +972,32 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__
   }
 }
 
+// Molecule post-processing of Sampler_mol.sample (sampler.py:814-825) in one pass over the sampler outputs:
+//   adj_out[b][c][i][j] = one_hot((quantize_mol(adj) - 1) mod 4)   (classes: 0 single, 1 double, 2 triple, 3 no bond), int64
+//   x_out[b][i][f] = x > 0.5 (f < F),  x_out[b][i][F] = 1 - sum_f x_out[b][i][f]   (the "no atom" column), int64
+__global__ void __launch_bounds__(256) mol_onehot_kernel(const float *__restrict__ x, const float *__restrict__ adj,
+                                                          long long *__restrict__ x_out, long long *__restrict__ adj_out,
+                                                          int B, int N, int F) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t na = (size_t)B * N * N, nn = (size_t)N * N;
+  for (size_t g = start; g < na; g += stride) {
+    const size_t b = g / nn, p = g - b * nn;
+    const float v = adj[g];
+    const int q = v >= 2.5f ? 3 : (v >= 1.5f ? 2 : (v >= 0.5f ? 1 : 0));
+    const int cls = q == 0 ? 3 : q - 1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) adj_out[(b * 4 + c) * nn + p] = (c == cls) ? 1 : 0;
+  }
+  const size_t nx = (size_t)B * N;
+  for (size_t g = start; g < nx; g += stride) {
+    long long s = 0;
+    for (int f = 0; f < F; ++f) {
+      const long long o = x[g * F + f] > 0.5f ? 1 : 0;
+      x_out[g * (F + 1) + f] = o;
+      s += o;
+    }
+    x_out[g * (F + 1) + F] = 1 - s;
+  }
+}
+
 }  // namespace ccsd

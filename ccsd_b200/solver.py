@@ -258,6 +258,24 @@ def quantize(t: torch.Tensor, thr: float = 0.5, mol: bool = False) -> torch.Tens
     return out
 
 
+def mol_onehot(x: torch.Tensor, adj: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The tensor post-processing between the sampler and ``gen_mol`` in ``Sampler_mol.sample``
+    (ccsd/src/sampler.py:814-825) as one device pass: returns ``(x [B,N,F+1] int64, adj [B,4,N,N] int64)``."""
+    lib = nat.load()
+    x = x.contiguous().to(torch.float32)
+    adj = adj.contiguous().to(torch.float32)
+    if x.dim() != 3 or adj.dim() != 3 or adj.shape[0] != x.shape[0] or adj.shape[1] != x.shape[1] or adj.shape[2] != x.shape[1]:
+        raise ValueError("mol_onehot: x must be [B,N,F] and adj [B,N,N]")
+    if x.device.type != "cuda" and not nat.is_emulation():
+        raise RuntimeError("ccsd_b200 needs a CUDA device; there is no CPU fallback")
+    B, N, F = x.shape
+    x_out = torch.empty(B, N, F + 1, dtype=torch.int64, device=x.device)
+    adj_out = torch.empty(B, 4, N, N, dtype=torch.int64, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream if x.device.type == "cuda" else None
+    nat.check(lib.ccsd_mol_onehot(x.data_ptr(), adj.data_ptr(), x_out.data_ptr(), adj_out.data_ptr(), B, N, F, stream))
+    return x_out, adj_out
+
+
 # ---------------------------------------------------------------------------------------------
 def _check_sdes(sdes, continuous: bool) -> None:
     for s in sdes:

@@ -205,6 +205,12 @@ int ccsd_score_eval(ccsd_plan_t *plan, int which, const float *x, const float *a
  * (graph_utils.py:195-213): thresholds .5/1.5/2.5 -> {0,1,2,3}. */
 int ccsd_quantize(const float *in_dev, uint8_t *out_dev, size_t n, float thr, int mol, void *stream);
 
+/* Molecule post-processing of Sampler_mol.sample (ccsd/src/sampler.py:814-825) on the device, one pass:
+ * adj_out [B,4,N,N] int64 = one_hot(quantize_mol(adj) - 1 with -1 -> 3) permuted to channels-first,
+ * x_out [B,N,F+1] int64 = (x > 0.5) with the appended "no atom" column 1 - sum_f. */
+int ccsd_mol_onehot(const float *x_dev, const float *adj_dev, int64_t *x_out_dev, int64_t *adj_out_dev, int B, int N, int F,
+                    void *stream);
+
 /* Number of kernel launches issued by this plan so far (bench.py's gpu_launches). */
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *plan);
 

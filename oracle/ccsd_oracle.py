@@ -137,6 +137,16 @@ def quantize_mol(adjs: Tensor) -> Tensor:
     return out.to(torch.int64)
 
 
+def mol_onehot(x: Tensor, adj: Tensor) -> Tuple[Tensor, Tensor]:
+    """Tensor post-processing of Sampler_mol.sample between the sampler and gen_mol.  sampler.py:814-825."""
+    s = quantize_mol(adj) - 1
+    s[s == -1] = 3  # 0, 1, 2, 3 (no, S, D, T) -> 3, 0, 1, 2
+    a = Fnn.one_hot(s, num_classes=4).permute(0, 3, 1, 2)
+    xi = torch.where(x > 0.5, 1, 0)
+    xi = torch.concat([xi, 1 - xi.sum(dim=-1, keepdim=True)], dim=-1)
+    return xi, a
+
+
 # --------------------------------------------------------------------------------------
 # tensor utilities
 # --------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ def _declared():
 def test_header_declares_the_expected_surface():
     names = _declared()
     for must in ("ccsd_plan_create", "ccsd_plan_bind", "ccsd_plan_init", "ccsd_plan_step", "ccsd_plan_run", "ccsd_plan_read",
-                 "ccsd_score_eval", "ccsd_quantize", "ccsd_last_error"):
+                 "ccsd_score_eval", "ccsd_quantize", "ccsd_mol_onehot", "ccsd_last_error"):
         assert must in names
 
 

@@ -90,3 +90,18 @@ def test_large_graph_pipeline_on_small_graphs():
     r = subprocess.run([sys.executable, "-c", code], cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]), env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_mol_onehot_matches_reference_postprocessing():
+    """ccsd_mol_onehot vs the reference's own tensor code (sampler.py:814-825, restated in the oracle): bit exact."""
+    import torch
+    from ccsd_b200.solver import mol_onehot
+    from oracle import ccsd_oracle as O
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 9, 4, generator=g) * 1.2
+    adj = torch.rand(5, 9, 9, generator=g) * 3.4 - 0.2
+    adj[0, 0, :4] = torch.tensor([0.5, 1.5, 2.5, 0.4999])   # the thresholds themselves
+    xo, ao = mol_onehot(x, adj)
+    xr, ar = O.mol_onehot(x, adj)
+    assert xo.dtype == torch.int64 and ao.dtype == torch.int64 and ao.shape == (5, 4, 9, 9) and xo.shape == (5, 9, 5)
+    assert torch.equal(xo, xr) and torch.equal(ao, ar)

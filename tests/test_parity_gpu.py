@@ -243,3 +243,16 @@ def test_s4_factory_and_quantize():
     assert torch.equal(q.float(), O.quantize(adj.cpu()))
     qm = quantize(adj * 3, mol=True).cpu()
     assert torch.equal(qm.long(), O.quantize_mol(adj.cpu() * 3))
+
+
+def test_mol_onehot_on_device():
+    """Molecule post-processing (sampler.py:814-825) on the device: bit exact against the reference's tensor code, at the
+    QM9 bench batch and at ZINC250k's shape."""
+    from ccsd_b200.solver import mol_onehot
+    for B, N, F in ((10000, 9, 4), (2048, 38, 9)):
+        g = torch.Generator().manual_seed(B)
+        x = torch.rand(B, N, F, generator=g) * 1.2
+        adj = torch.rand(B, N, N, generator=g) * 3.4 - 0.2
+        xo, ao = mol_onehot(x.to(DEV), adj.to(DEV))
+        xr, ar = O.mol_onehot(x, adj)
+        assert torch.equal(xo.cpu(), xr) and torch.equal(ao.cpu(), ar)
