@@ -5,14 +5,15 @@
 // operand as it lies in memory (element (i, j) at plane[j * Np + i]), Y (node-major [N][YW]) is an MN-major B operand;
 // both are converted fp32 -> bf16 hi / lo into the canonical SWIZZLE_128B layout, bf16x3 (hi.hi + hi.lo + lo.hi) with
 // fp32 accumulation in tensor memory.  The contraction runs over 64-node chunks through a two-stage operand ring:
-// the 16 converter warps fill stage s while the MMAs of the previous chunk read stage s ^ 1.
+// the 8 converter warps fill stage s while the MMAs of the previous chunk read stage s ^ 1, and the global loads of
+// chunk k + 1 are issued into registers before chunk k is converted (one chunk of load latency is always hidden).
 #pragma once
 #include "big_pipe.cuh"
 #include "tc_common.cuh"
 
 namespace ccsd {
 
-constexpr int TGG_EPI = 512;               // converter / epilogue warps: TMEM lane quarter = warp % 4, column part = warp / 4
+constexpr int TGG_EPI = 256;               // converter / epilogue warps: TMEM lane quarter = warp % 4, column part = warp / 4
 constexpr int TGG_THREADS = TGG_EPI + 32;   // + the MMA-issuing warp
 constexpr int TGG_MMAW = TGG_EPI / 32;
 constexpr int TGG_KC = 64;                 // nodes per contraction chunk
@@ -55,12 +56,85 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
   uint32_t ph[2] = {0u, 0u};     // parity of the next completion of each stage's barrier
   uint32_t used[2] = {0u, 0u};   // stage has MMAs in flight
 
+  constexpr int NA = TGG_KC * 16 / TGG_EPI;     // A items (8 consecutive rows of one contraction index) per thread and chunk
+  constexpr int NB = TGG_KC * 16 / TGG_EPI;     // B items (8 consecutive columns), at most (YW <= 128)
+  const int nch = YW >> 3;
+  float4 ra[NA][2], rb[NB][2];                  // the next chunk's operands, in flight
+  auto load_chunk = [&](const float *pl, const float *y, int m0, int k0) {
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+      const int t = threadIdx.x + u * TGG_EPI, k = t >> 4, mc = (t & 15) << 3, j = k0 + k, i = m0 + mc;
+      float x[8];
+      if (j < N && i + 8 <= Np) {
+        ra[u][0] = *reinterpret_cast<const float4 *>(pl + (size_t)j * Np + i);
+        ra[u][1] = *reinterpret_cast<const float4 *>(pl + (size_t)j * Np + i + 4);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = (j < N && i + q < Np) ? pl[(size_t)j * Np + i + q] : 0.f;
+        ra[u][0] = make_float4(x[0], x[1], x[2], x[3]);
+        ra[u][1] = make_float4(x[4], x[5], x[6], x[7]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int t = threadIdx.x + u * TGG_EPI;
+      rb[u][0] = rb[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < TGG_KC * nch) {
+        const int k = t / nch, n0 = (t - k * nch) << 3, j = k0 + k;
+        if (j < N) {
+          rb[u][0] = __ldg(reinterpret_cast<const float4 *>(y + (size_t)j * YW + n0));
+          rb[u][1] = __ldg(reinterpret_cast<const float4 *>(y + (size_t)j * YW + n0 + 4));
+        }
+      }
+    }
+  };
+  auto store_chunk = [&](uint32_t st, int m0) {
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+      const int t = threadIdx.x + u * TGG_EPI, k = t >> 4, mc = (t & 15) << 3, i = m0 + mc;
+      float x[8] = {ra[u][0].x, ra[u][0].y, ra[u][0].z, ra[u][0].w, ra[u][1].x, ra[u][1].y, ra[u][1].z, ra[u][1].w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (i + q >= N) x[q] = 0.f;
+      uint4 hi, lo;
+      tc::split8(x, hi, lo);
+      const uint32_t off = st + (uint32_t)(mc >> 6) * (TGG_KC * 128u) + (uint32_t)k * 128u + (uint32_t)((((mc & 63) >> 3) ^ (k & 7)) << 4);
+      *reinterpret_cast<uint4 *>(gen + off) = hi;
+      *reinterpret_cast<uint4 *>(gen + off + TGG_HALF) = lo;
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int t = threadIdx.x + u * TGG_EPI;
+      if (t < TGG_KC * nch) {
+        const int k = t / nch, n0 = (t - k * nch) << 3;
+        const float x[8] = {rb[u][0].x, rb[u][0].y, rb[u][0].z, rb[u][0].w, rb[u][1].x, rb[u][1].y, rb[u][1].z, rb[u][1].w};
+        uint4 hi, lo;
+        tc::split8(x, hi, lo);
+        const uint32_t off = st + 2u * TGG_HALF + (uint32_t)(n0 >> 6) * (TGG_KC * 128u) + (uint32_t)k * 128u + (uint32_t)((((n0 & 63) >> 3) ^ (k & 7)) << 4);
+        *reinterpret_cast<uint4 *>(gen + off) = hi;
+        *reinterpret_cast<uint4 *>(gen + off + TGG_HALF) = lo;
+      }
+    }
+  };
+  auto tile_of = [&](int w, int &b, int &c, int &m0, const float *&pl, const float *&y) {
+    b = w / (ly.c_in * ntm);
+    const int rem = w - b * (ly.c_in * ntm);
+    c = rem / ntm;
+    m0 = (rem - c * ntm) << 7;
+    pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_in + c) * L.big_PS;
+    y = big_ptr(P, g, b, L.big_Y) + (size_t)c * N * YW;
+  };
+
+  if (warp < TGG_MMAW && (int)blockIdx.x < ntiles) {
+    int b, c, m0; const float *pl, *y;
+    tile_of(blockIdx.x, b, c, m0, pl, y);
+    load_chunk(pl, y, m0, 0);
+  }
   for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
-    const int b = w / (ly.c_in * ntm), rem = w - b * (ly.c_in * ntm), c = rem / ntm, m0 = (rem - c * ntm) << 7;
-    const float *pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_in + c) * L.big_PS;
-    const float *y = big_ptr(P, g, b, L.big_Y) + (size_t)c * N * YW;
+    int b, c, m0; const float *pl, *y;
+    tile_of(w, b, c, m0, pl, y);
     for (int kc = 0; kc < nkc; ++kc) {
-      const int s = kc & 1, k0 = kc * TGG_KC;
+      const int s = kc & 1;
       const uint32_t st = (uint32_t)s * TGG_STAGE;
       if (used[s]) {   // the MMAs that read this stage (two chunks ago) must have completed
         tc::mbar_wait(bar0 + 8 * s, ph[s]);
@@ -69,43 +143,13 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
         tc::tc_fence_after_sync();
       }
       if (warp < TGG_MMAW) {
-        // A chunk: (m, k) = plane[(k0 + k) * Np + m0 + m], 8 consecutive m per item
-        for (int t = threadIdx.x; t < TGG_KC * 16; t += TGG_EPI) {
-          const int k = t >> 4, mc = (t & 15) << 3, j = k0 + k, i = m0 + mc;
-          float x[8];
-          if (j < N && i + 8 <= Np) {
-            const float4 v0 = *reinterpret_cast<const float4 *>(pl + (size_t)j * Np + i), v1 = *reinterpret_cast<const float4 *>(pl + (size_t)j * Np + i + 4);
-            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) x[q] = (j < N && i + q < Np) ? pl[(size_t)j * Np + i + q] : 0.f;
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (i + q >= N) x[q] = 0.f;
-          uint4 hi, lo;
-          tc::split8(x, hi, lo);
-          const uint32_t off = st + (uint32_t)(mc >> 6) * (TGG_KC * 128u) + (uint32_t)k * 128u + (uint32_t)((((mc & 63) >> 3) ^ (k & 7)) << 4);
-          *reinterpret_cast<uint4 *>(gen + off) = hi;
-          *reinterpret_cast<uint4 *>(gen + off + TGG_HALF) = lo;
-        }
-        // B chunk: (n, k) = Y[(k0 + k) * YW + n], 8 consecutive n per item
-        const int nch = YW >> 3;
-        for (int t = threadIdx.x; t < TGG_KC * nch; t += TGG_EPI) {
-          const int k = t / nch, n0 = (t - k * nch) << 3, j = k0 + k;
-          float x[8];
-          if (j < N) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(y + (size_t)j * YW + n0)), v1 = __ldg(reinterpret_cast<const float4 *>(y + (size_t)j * YW + n0 + 4));
-            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) x[q] = 0.f;
-          }
-          uint4 hi, lo;
-          tc::split8(x, hi, lo);
-          const uint32_t off = st + 2u * TGG_HALF + (uint32_t)(n0 >> 6) * (TGG_KC * 128u) + (uint32_t)k * 128u + (uint32_t)((((n0 & 63) >> 3) ^ (k & 7)) << 4);
-          *reinterpret_cast<uint4 *>(gen + off) = hi;
-          *reinterpret_cast<uint4 *>(gen + off + TGG_HALF) = lo;
+        store_chunk(st, m0);
+        // issue the next chunk's loads (next chunk of this tile, or the first chunk of this CTA's next tile)
+        if (kc + 1 < nkc) load_chunk(pl, y, m0, (kc + 1) * TGG_KC);
+        else if (w + (int)gridDim.x < ntiles) {
+          int b2, c2, m2; const float *pl2, *y2;
+          tile_of(w + gridDim.x, b2, c2, m2, pl2, y2);
+          load_chunk(pl2, y2, m2, 0);
         }
         tc::fence_proxy_async_smem();
       }
@@ -143,7 +187,8 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
     // ---- epilogue: T = d_i (acc + (1 - a_ii) y_i) + bias, Q | K rows -> TQK, V rows -> TV (feature-major) ----
     if (warp < TGG_MMAW) {
       const int lq = warp & 3, cpart = warp >> 2, i = m0 + lq * 32 + lane;
-      const int nck = YW >> 4, cper = (nck + 3) >> 2;
+      constexpr int NPARTS = TGG_EPI / 128;
+      const int nck = YW >> 4, cper = (nck + NPARTS - 1) / NPARTS;
       const int ck0 = cpart * cper < nck ? cpart * cper : nck, ck1 = ck0 + cper < nck ? ck0 + cper : nck;
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
       float *tqk = big_ptr(P, g, b, L.big_TQK) + (size_t)c * w2 * Np, *tv = big_ptr(P, g, b, L.big_TV) + (size_t)c * nh * Np;
