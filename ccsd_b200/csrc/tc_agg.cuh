@@ -20,7 +20,8 @@ constexpr int TGG_KC = 64;                 // nodes per contraction chunk
 constexpr uint32_t TGG_HALF = 2u * TGG_KC * 128u;        // 16384: hi (or lo) of one operand chunk: [2 blocks of 64][64 k][128 B]
 constexpr uint32_t TGG_STAGE = 4u * TGG_HALF;            // A hi, A lo, B hi, B lo
 constexpr uint32_t TGG_BARS = 2u * TGG_STAGE;            // 131072
-constexpr size_t TGG_SMEM = (size_t)TGG_BARS + 64 + 1024;
+constexpr uint32_t TGG_TAB = TGG_BARS + 64;             // [128] destination offsets (int), [128] biases (float)
+constexpr size_t TGG_SMEM = (size_t)TGG_TAB + 1024 + 1024;
 
 static inline int tc_agg_supported(const ccsd_attn_layer_t &ly) {
   const int adp = (ly.attn_dim + 7) / 8 * 8, nhp = (ly.conv_out + 7) / 8 * 8, YW = 2 * adp + nhp;
@@ -42,6 +43,8 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
   uint8_t *gen = tg_smem_raw + (base - raw);
   const uint32_t bar0 = base + TGG_BARS, tslot = bar0 + 16;     // bar0 + 8 s: MMAs that read stage s have completed
   uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen + TGG_BARS + 16);
+  int *soff = reinterpret_cast<int *>(gen + TGG_TAB);
+  float *sbias = reinterpret_cast<float *>(gen + TGG_TAB + 512);
   if (threadIdx.x == 0) { tc::mbar_init(bar0, 1); tc::mbar_init(bar0 + 8, 1); tc::mbar_fence_init(); }
   if (warp == TGG_MMAW) tc::tmem_alloc(tslot, 128);
   // the n columns [YW, 128) of the B blocks are never read (N = YW); everything else is rewritten per chunk
@@ -79,8 +82,8 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
     for (int u = 0; u < NB; ++u) {
       const int t = threadIdx.x + u * TGG_EPI;
       rb[u][0] = rb[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < TGG_KC * nch) {
-        const int k = t / nch, n0 = (t - k * nch) << 3, j = k0 + k;
+      if ((t & 15) < nch) {
+        const int k = t >> 4, n0 = (t & 15) << 3, j = k0 + k;
         if (j < N) {
           rb[u][0] = __ldg(reinterpret_cast<const float4 *>(y + (size_t)j * YW + n0));
           rb[u][1] = __ldg(reinterpret_cast<const float4 *>(y + (size_t)j * YW + n0 + 4));
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
       const int t = threadIdx.x + u * TGG_EPI;
-      if (t < TGG_KC * nch) {
-        const int k = t / nch, n0 = (t - k * nch) << 3;
+      if ((t & 15) < nch) {
+        const int k = t >> 4, n0 = (t & 15) << 3;
         const float x[8] = {rb[u][0].x, rb[u][0].y, rb[u][0].z, rb[u][0].w, rb[u][1].x, rb[u][1].y, rb[u][1].z, rb[u][1].w};
         uint4 hi, lo;
         tc::split8(x, hi, lo);
@@ -185,13 +188,27 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
       }
     tc::tc_fence_after_sync();
     // ---- epilogue: T = d_i (acc + (1 - a_ii) y_i) + bias, Q | K rows -> TQK, V rows -> TV (feature-major) ----
+    // per-column destination (float offset from the graph's scratch base, -1 = padding column) and bias
+    if (threadIdx.x < 128) {
+      const int o = threadIdx.x;
+      int off = -1;
+      float bias = 0.f;
+      if (o < w2) {
+        const int oo = o < adp ? o : o - adp;
+        if (oo < ad) { off = L.big_TQK + (c * w2 + o) * Np; bias = __ldg(W + (o < adp ? ly.q[c].b : ly.k[c].b) + oo); }
+      } else if (o < YW && o - w2 < nh) {
+        off = L.big_TV + (c * nh + (o - w2)) * Np; bias = __ldg(W + ly.v[c].b + (o - w2));
+      }
+      soff[o] = off; sbias[o] = bias;
+    }
+    __syncthreads();
     if (warp < TGG_MMAW) {
-      const int lq = warp & 3, cpart = warp >> 2, i = m0 + lq * 32 + lane;
       constexpr int NPARTS = TGG_EPI / 128;
+      const int lq = warp & 3, cpart = warp >> 2, i = m0 + lq * 32 + lane;
       const int nck = YW >> 4, cper = (nck + NPARTS - 1) / NPARTS;
       const int ck0 = cpart * cper < nck ? cpart * cper : nck, ck1 = ck0 + cper < nck ? ck0 + cper : nck;
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
-      float *tqk = big_ptr(P, g, b, L.big_TQK) + (size_t)c * w2 * Np, *tv = big_ptr(P, g, b, L.big_TV) + (size_t)c * nh * Np;
+      float *gb = big_ptr(P, g, b, 0);
       const float *dvp = big_ptr(P, g, b, L.big_DV) + c * Np;
       const bool live = i < N;
       const float di = live ? dvp[i] : 0.f, fix = live ? 1.f - pl[(size_t)i * Np + i] : 0.f;
@@ -199,16 +216,13 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
         float v[16];
         tc::tmem_ld16(trow + (uint32_t)c0, v);
         if (live) {
+          const float4 *yp = reinterpret_cast<const float4 *>(y + (size_t)i * YW + c0);
+          const float4 y0 = __ldg(yp), y1 = __ldg(yp + 1), y2 = __ldg(yp + 2), y3 = __ldg(yp + 3);
+          const float yv[16] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w, y2.x, y2.y, y2.z, y2.w, y3.x, y3.y, y3.z, y3.w};
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const int o = c0 + q;
-            const float val = di * (v[q] + fix * y[(size_t)i * YW + o]);
-            if (o < w2) {
-              const int oo = o < adp ? o : o - adp;
-              if (oo < ad) tqk[(size_t)o * Np + i] = val + __ldg(W + (o < adp ? ly.q[c].b : ly.k[c].b) + oo);
-            } else if (o - w2 < nh) {
-              tv[(size_t)(o - w2) * Np + i] = val + __ldg(W + ly.v[c].b + (o - w2));
-            }
+            const int off = soff[c0 + q];
+            if (off >= 0) gb[(size_t)off + i] = di * (v[q] + fix * yv[q]) + sbias[c0 + q];
           }
         }
       }
