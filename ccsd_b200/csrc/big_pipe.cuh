@@ -24,6 +24,7 @@
 namespace ccsd {
 
 constexpr int BIG_RC = 32;     // node rows per CTA of the row-chunk kernels
+constexpr int BIG_RCX = 8;     // node rows per CTA of the ScoreNetworkX final MLP (few rows per graph: many small CTAs)
 constexpr int BIG_SEG = 64;    // node pairs (columns of one row) per CTA of the per-pair kernels
 
 struct BigArgs {
@@ -527,13 +528,13 @@ __global__ void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restrict
   const XpLayout &L = P->xp;
   const XaArgs &a = g.a;
   const int b = blockIdx.z, N = d.N, F = d.F, Np = L.big_Np;
-  const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
+  const int i0 = blockIdx.x * BIG_RCX, R = (N - i0 < BIG_RCX) ? N - i0 : BIG_RCX;
   const ccsd_netx_t &X = d.netx;
   const ccsd_mlp_t &m = X.fin;
   const int hid = m.nl > 1 ? m.dhid : 1;
-  float *so = sm, *red = sm + round_up(F, 4) * BIG_RC, *hA = red + 40, *hB = m.nl > 2 ? hA + hid * BIG_RC : hA;
+  float *so = sm, *red = sm + round_up(F, 4) * BIG_RCX, *hA = red + 40, *hB = m.nl > 2 ? hA + hid * BIG_RCX : hA;
   const float *hc = big_ptr(P, g, b, L.big_HC);
-  mlp_fm(m, P->W, hc + i0, Np, X.fdim, nullptr, 0, 0, R, hA, hB, BIG_RC, so, 1, BIG_RC, ACT_ELU, ACT_NONE);
+  mlp_fm(m, P->W, hc + i0, Np, X.fdim, nullptr, 0, 0, R, hA, hB, BIG_RCX, so, 1, BIG_RCX, ACT_ELU, ACT_NONE);
   const size_t gxo = (size_t)b * N * F;
   const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 0];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restrict
   for (int q = threadIdx.x; q < R * F; q += blockDim.x) {
     const int r = q / F, f = q - r * F, i = i0 + r, p = i * F + f;
     const float fl = a.flags[(size_t)b * N + i];
-    const float o = so[f * BIG_RC + r] * fl;   // mask_x
+    const float o = so[f * BIG_RCX + r] * fl;   // mask_x
     if (a.mode == MODE_EVAL) { a.out_x[gxo + p] = o; continue; }
     const float s = cx.score_scale * o;
     const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, a.nz.step, a.slot), p)) * fl;

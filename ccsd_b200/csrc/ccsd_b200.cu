@@ -373,7 +373,7 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
     for (int k = 0; k < X.depth; ++k) xdp = imax(xdp, (X.gcn[k].dout + 7) / 8 * 8);
     L.big_sm_node = sm_node + 8; L.big_sm_edge = sm_edge + 8;
     L.big_sm_fin = BIG_SEG + 40 + (A.fin.nl > 1 ? A.fin.dhid : 1) * BIG_SEG * (A.fin.nl > 2 ? 2 : 1) + 8;
-    L.big_sm_xfin = a4(F) * BIG_RC + 40 + (X.fin.nl > 1 ? X.fin.dhid : 1) * BIG_RC * (X.fin.nl > 2 ? 2 : 1) + 8;
+    L.big_sm_xfin = a4(F) * BIG_RCX + 40 + (X.fin.nl > 1 ? X.fin.dhid : 1) * BIG_RCX * (X.fin.nl > 2 ? 2 : 1) + 8;
     int ob = 0;
     auto tk = [&](long long n) { int r = ob; ob += (int)((n + 7) / 8 * 8); return r; };
     const int cm = imax(cin_max, imax(A.c_init, 1));
@@ -478,7 +478,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.ntile_r2 = d.is_cc ? (d.K + APPLY_TN - 1) / APPLY_TN : 1;
   p->hp.ntile_adj = p->hp.xp.m_nchunk;
   p->hp.ntile_x = 1;
-  if (p->hp.xp.big) { p->hp.ntile_adj = d.N * p->hp.xp.big_nseg; p->hp.ntile_x = p->hp.xp.big_nrc; }
+  if (p->hp.xp.big) { p->hp.ntile_adj = d.N * p->hp.xp.big_nseg; p->hp.ntile_x = (d.N + BIG_RCX - 1) / BIG_RCX; }
   p->hp.ntile_max = imax(imax(imax(1, p->hp.ntile_r2), p->hp.ntile_adj), p->hp.ntile_x);
   p->hp.f_mode = 0; p->hp.f_nlin = 0;
   p->hp.ap_group = d.is_cc ? imax(1, imin(8, 192 / imax(d.E, 1))) : 1;
@@ -702,7 +702,7 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
   static const auto envt = [](const char *nm, int dflt) { const char *e = getenv(nm); const int v = e ? atoi(e) : dflt; return v >= 32 && v <= 128 ? v / 32 * 32 : dflt; };
   static const int T_pow = envt("CCSD_BIG_T_POW", 128), T_xw = envt("CCSD_BIG_T_XW", 0), T_agg = envt("CCSD_BIG_T_AGG", 0),
                    T_node = envt("CCSD_BIG_T_NODE", 64), T_edge = envt("CCSD_BIG_T_EDGE", 32), T_fin = envt("CCSD_BIG_T_FIN", 128),
-                   T_xfin = envt("CCSD_BIG_T_XFIN", 128);
+                   T_xfin = envt("CCSD_BIG_T_XFIN", 64);
   static const bool edge_fast = getenv("CCSD_BIG_EDGE_GENERIC") == nullptr;   // A/B switch: row-tile edge kernel
 #define BIG_LAUNCH(kern, grid, thr, smem) do { PROF_BEGIN(p, #kern, stream); CCSD_LAUNCH(kern, grid, thr, smem, stream, p->dP, g); PROF_END(p, stream); p->launches++; } while (0)
   BIG_LAUNCH(big_prep_kernel, dim3(imin(148 * 2, (d.N * L.big_Np + 255) / 256), B, 1), 256, 0);
@@ -719,7 +719,7 @@ static int launch_xa_big(ccsd_plan *p, const XaArgs &a, void *stream) {
       BIG_LAUNCH(big_agg_kernel, dim3(nrca, 1, B), 32, 0);   // 4 x 8 items of 8 x 8 (nhid <= 32)
       in_row = out_row; out_row += X.gcn[k].dout;
     }
-    BIG_LAUNCH(big_xfin_kernel, dim3(nrc, 1, B), T_xfin, (size_t)L.big_sm_xfin * 4);
+    BIG_LAUNCH(big_xfin_kernel, dim3((d.N + BIG_RCX - 1) / BIG_RCX, 1, B), T_xfin, (size_t)L.big_sm_xfin * 4);
   }
   if (!(a.which & 2)) return dev_check("large-graph x network");
   g.xmode = 0;
