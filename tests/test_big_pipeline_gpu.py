@@ -61,3 +61,20 @@ def test_full_size_grid_batch_properties():
     eng.run(0, 3)
     x2, adj2 = [t.cpu() for t in eng.read(True)]
     assert torch.equal(x, x2) and torch.equal(adj, adj2)
+
+
+@pytest.mark.parametrize("N", [65, 127, 128, 129, 192, 200, 256, 257])
+def test_tile_boundary_sizes(N):
+    """The ENZYMES checkpoint at graph sizes around the tile sizes of the large-graph kernels (128-row tiles and 64-node
+    contraction chunks of tc_agg, 128-column segments of tc_afinal, 32 x 32 mirror tiles): the score networks have no
+    N-dependent parameters."""
+    cfg = Config("enzymes")
+    cfg.N = N
+    B = 3
+    x, adj, r2, flags = cfg.random_state(B, seed=N)
+    eng = make_engine(cfg, B, "cuda")
+    for w in (0, 1):
+        ref = cfg.oracle_models[w](x, adj, flags)
+        out = eng.score(w, x, adj, r2, flags).cpu()
+        assert torch.isfinite(out).all()
+        assert rel_err(out, ref) < 1e-4, (N, w, rel_err(out, ref))

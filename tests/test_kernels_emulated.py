@@ -105,3 +105,21 @@ def test_mol_onehot_matches_reference_postprocessing():
     xr, ar = O.mol_onehot(x, adj)
     assert xo.dtype == torch.int64 and ao.dtype == torch.int64 and ao.shape == (5, 4, 9, 9) and xo.shape == (5, 9, 5)
     assert torch.equal(xo, xr) and torch.equal(ao, ar)
+
+
+@pytest.mark.parametrize("N", [65, 96, 129])
+def test_large_graph_pipeline_at_tile_boundaries(N):
+    """The score networks have no N-dependent parameters, so the ENZYMES checkpoint (N = 125) is evaluated at other graph
+    sizes around the large-graph pipeline's tile sizes (8-row groups, 32-row chunks, 64 / 128-column segments)."""
+    import torch
+    from tests.helpers import Config, rel_err
+    from tests.parity_cases import make_engine
+    cfg = Config("enzymes")
+    cfg.N = N
+    x, adj, r2, flags = cfg.random_state(2, seed=N)
+    eng = make_engine(cfg, 2, "cpu")
+    for w in (0, 1):
+        ref = cfg.oracle_models[w](x, adj, flags)
+        out = eng.score(w, x, adj, r2, flags).cpu()
+        assert torch.isfinite(out).all()
+        assert rel_err(out, ref) < 1e-4, (N, w, rel_err(out, ref))
