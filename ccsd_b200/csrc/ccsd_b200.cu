@@ -322,6 +322,9 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
     L.h_hk = take(A.c_init * E * A.hodge[0].attn_dim);
     L.h_h1 = take(A.hodge[0].c_out * E * L.lde);
     L.h_hdeg = take(A.hodge[0].c_out * E);
+    L.h_att1 = take(A.hodge[0].c_out * E);
+    L.h_alpha = take(E);
+    L.h_part = take(128);
   }
   L.h_total = o;
   // ---- hodge_base_kernel ----

@@ -25,7 +25,8 @@ struct XpLayout {
   // attn_finish_kernel
   int f_flags, f_hs, f_hs2 /*[mc_hid x N4]*/, f_eha, f_ehb /*[hid x ldp]*/, f_total;
   // hodge_kernel (two hodge layers: hq, hk [c0 x E x ad0], h1 [c1 x E x lde], hdeg [c1 x E])
-  int h_flags, h_hq, h_hk, h_h1, lde, h_hdeg, h_p1 /*[E x n1] folded projections*/, h_u /*[n1]*/, h_total;
+  int h_flags, h_hq, h_hk, h_h1, lde, h_hdeg, h_p1 /*[E x n1] folded projections*/, h_u /*[n1]*/,
+      h_att1 /*[c1 x E] layer-1 attention diagonals*/, h_alpha /*[E]*/, h_part /*[threads] partial sums*/, h_total;
   // hodge_base_kernel (ScoreNetworkA_Base_CC; shares h_flags): u0 [c_init x E x hid_pad], edge flags [E], tri index [E]
   int hb_u0, hb_fe, hb_tri, hb_total;
   // afinal_kernel

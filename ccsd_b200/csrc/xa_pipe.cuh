@@ -340,7 +340,7 @@ __device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, 
     const int d0 = c * ds, d1 = (d0 + ds < ad) ? d0 + ds : ad;
     float a = 0.f;
     for (int dd = d0; dd < d1; ++dd) a += q[dd] * k[dd];
-    s += tanhf(a * scale);
+    s += fast_tanh(a * scale);
   }
   return s / (float)nch;
 }
@@ -420,21 +420,45 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
     const int Kw = P->Kp, K = d.K;
     const unsigned long long zm = zero_mask_of(flags, N);
     const float *Wp = W + A.proj_w + (size_t)P->PR0h * Kw;
-    for (int r = threadIdx.x; r < PR1; r += blockDim.x) {
-      float s = 0.f;
-      for (int k = 0; k < K; ++k)
-        if (!(P->cell_mask[k] & zm)) s += __ldg(Wp + (size_t)r * Kw + k);
-      u[r] = s;
+    // u[r]: every thread sums a strided share of the cells (fixed order per (r, part), then a fixed-order sum over parts)
+    float *part = sm + L.h_part, *alpha_e = sm + L.h_alpha;
+    const int nthr = (int)blockDim.x < 128 ? (int)blockDim.x : 128;
+    const int nparts = PR1 <= nthr ? nthr / PR1 : 1;
+    if (PR1 <= nthr) {
+      if ((int)threadIdx.x < nparts * PR1) {
+        const int r = threadIdx.x % PR1, pt = threadIdx.x / PR1;
+        float s = 0.f;
+        for (int k = pt; k < K; k += nparts)
+          if (!(P->cell_mask[k] & zm)) s += __ldg(Wp + (size_t)r * Kw + k);
+        part[threadIdx.x] = s;
+      }
+      __syncthreads();
+      for (int r = threadIdx.x; r < PR1; r += blockDim.x) {
+        float s = 0.f;
+        for (int pt = 0; pt < nparts; ++pt) s += part[pt * PR1 + r];
+        u[r] = s;
+      }
+    } else {
+      for (int r = threadIdx.x; r < PR1; r += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < K; ++k)
+          if (!(P->cell_mask[k] & zm)) s += __ldg(Wp + (size_t)r * Kw + k);
+        u[r] = s;
+      }
     }
-    __syncthreads();
     const ccsd_mlp_t &mv = h0.mlp_value;
     const float beta = __ldg(W + mv.b[0]);
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const int t = tri_index(P->edge_ij[2 * e], P->edge_ij[2 * e + 1], N);
+      float alpha = 0.f;
+      for (int c = 0; c < c0; ++c) alpha += __ldg(W + mv.w[0] + c * 8) * stack[c * ldp + t];
+      alpha_e[e] = alpha;
+    }
+    __syncthreads();
     for (int p = threadIdx.x; p < E * PR1; p += blockDim.x) {
       const int e = p / PR1, r = p - e * PR1;
-      const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
-      float alpha = 0.f;
-      for (int c = 0; c < c0; ++c) alpha += __ldg(W + mv.w[0] + c * 8) * stack[c * ldp + tri_index(i, j, N)];
-      p1s[p] = alpha * P0[(size_t)e * PR0 + P->PR0h + r] + beta * flags[i] * flags[j] * u[r];
+      const float fe = flags[P->edge_ij[2 * e]] * flags[P->edge_ij[2 * e + 1]];
+      p1s[p] = alpha_e[e] * P0[(size_t)e * PR0 + P->PR0h + r] + beta * fe * u[r];
     }
     __syncthreads();
     P1 = p1s;
@@ -486,30 +510,48 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
     stack[(ch_hodge0 + c0 + c) * ldp + tri_index(i, j, N)] = row[e];
   }
   __syncthreads();
-  // layer 1 (last): only diag(attention) is read back (cc_utils.py:1571)
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
-    const float fe = flags[i] * flags[j];
-    float att[CCSD_MAX_CH], q[SMALL_MAX], k[SMALL_MAX], out[SMALL_MAX];
-    for (int c = 0; c < c1; ++c) {
-      for (int dd = 0; dd < ad1; ++dd) { q[dd] = 0.f; k[dd] = 0.f; }
-      const float *row = H1 + (c * E + e) * lde;
-      const float de = hdeg[c * E + e];
+  // layer 1 (last): only diag(attention) is read back (cc_utils.py:1571).  Item = (edge, channel): aggregate the
+  // layer-1 projections with row e of the layer-0 output, then the diagonal attention value
+  float *att1 = sm + L.h_att1;
+  for (int p = threadIdx.x; p < c1 * E; p += blockDim.x) {
+    const int c = p / E, e = p - c * E;
+    float q[SMALL_MAX], k[SMALL_MAX];
+    for (int dd = 0; dd < ad1; ++dd) { q[dd] = 0.f; k[dd] = 0.f; }
+    const float *row = H1 + (c * E + e) * lde;
+    const float de = hdeg[c * E + e];
+    const float *pq0 = P1 + h1.proj_row + (c * 2 + 0) * ad1;
+    if (ad1 == 4) {   // the shipped width: registers instead of the dynamically indexed arrays
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f;
       for (int e2 = 0; e2 < E; ++e2) {
         const float w = de * row[e2] * hdeg[c * E + e2];
-        const float *pq = P1 + (size_t)e2 * PR1 + h1.proj_row + (c * 2 + 0) * ad1;
+        const float *pq = pq0 + (size_t)e2 * PR1;
+        q0 += w * pq[0]; q1 += w * pq[1]; q2 += w * pq[2]; q3 += w * pq[3];
+        k0 += w * pq[4]; k1 += w * pq[5]; k2 += w * pq[6]; k3 += w * pq[7];
+      }
+      q[0] = q0; q[1] = q1; q[2] = q2; q[3] = q3; k[0] = k0; k[1] = k1; k[2] = k2; k[3] = k3;
+    } else {
+      for (int e2 = 0; e2 < E; ++e2) {
+        const float w = de * row[e2] * hdeg[c * E + e2];
+        const float *pq = pq0 + (size_t)e2 * PR1;
         const float *pk = pq + ad1;
         for (int dd = 0; dd < ad1; ++dd) { q[dd] += w * pq[dd]; k[dd] += w * pk[dd]; }
       }
-      for (int dd = 0; dd < ad1; ++dd) {
-        q[dd] += __ldg(W + h1.bq[c] + dd);
-        k[dd] += __ldg(W + h1.bk[c] + dd);
-      }
-      att[c] = hodge_diag_att(q, k, ad1, A.num_heads_h, scale);
     }
+    for (int dd = 0; dd < ad1; ++dd) {
+      q[dd] += __ldg(W + h1.bq[c] + dd);
+      k[dd] += __ldg(W + h1.bk[c] + dd);
+    }
+    att1[c * E + e] = hodge_diag_att(q, k, ad1, A.num_heads_h, scale);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
+    const float fe = flags[i] * flags[j];
+    float att[CCSD_MAX_CH], out[SMALL_MAX];
+    for (int c = 0; c < c1; ++c) att[c] = att1[c * E + e];
     small_mlp(h1.mlp_attention, W, att, out, ACT_ELU);
     for (int c = 0; c < h1.c_out; ++c)
-      stack[(ch_hodge0 + c0 + c1 + c) * ldp + tri_index(i, j, N)] = 2.0f * tanhf(fe * fe * out[c]);
+      stack[(ch_hodge0 + c0 + c1 + c) * ldp + tri_index(i, j, N)] = 2.0f * fast_tanh(fe * fe * out[c]);
   }
 }
 
