@@ -420,31 +420,38 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
     const int Kw = P->Kp, K = d.K;
     const unsigned long long zm = zero_mask_of(flags, N);
     const float *Wp = W + A.proj_w + (size_t)P->PR0h * Kw;
-    // u[r]: every thread sums a strided share of the cells (fixed order per (r, part), then a fixed-order sum over parts)
+    // u[r] = sum of the projection weights over the live cells: lanes run along the cells (coalesced weight rows, one
+    // mask test per cell for 8 projection rows), fixed-order warp tree + sum over warps
     float *part = sm + L.h_part, *alpha_e = sm + L.h_alpha;
-    const int nthr = (int)blockDim.x < 128 ? (int)blockDim.x : 128;
-    const int nparts = PR1 <= nthr ? nthr / PR1 : 1;
-    if (PR1 <= nthr) {
-      if ((int)threadIdx.x < nparts * PR1) {
-        const int r = threadIdx.x % PR1, pt = threadIdx.x / PR1;
-        float s = 0.f;
-        for (int k = pt; k < K; k += nparts)
-          if (!(P->cell_mask[k] & zm)) s += __ldg(Wp + (size_t)r * Kw + k);
-        part[threadIdx.x] = s;
+#ifdef CCSD_EMU
+    const int lane = 0, warp = 0, nwarp = 1;
+#else
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#endif
+    for (int r0 = 0; r0 < PR1; r0 += 8) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        if (!(P->cell_mask[k] & zm)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (r0 + j < PR1) acc[j] += __ldg(Wp + (size_t)(r0 + j) * Kw + k);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#ifndef CCSD_EMU
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+#endif
+        if (lane == 0) part[warp * 8 + j] = acc[j];
       }
       __syncthreads();
-      for (int r = threadIdx.x; r < PR1; r += blockDim.x) {
-        float s = 0.f;
-        for (int pt = 0; pt < nparts; ++pt) s += part[pt * PR1 + r];
-        u[r] = s;
+      for (int j = threadIdx.x; j < 8 && r0 + j < PR1; j += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < nwarp; ++w) t += part[w * 8 + j];
+        u[r0 + j] = t;
       }
-    } else {
-      for (int r = threadIdx.x; r < PR1; r += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < K; ++k)
-          if (!(P->cell_mask[k] & zm)) s += __ldg(Wp + (size_t)r * Kw + k);
-        u[r] = s;
-      }
+      __syncthreads();
     }
     const ccsd_mlp_t &mv = h0.mlp_value;
     const float beta = __ldg(W + mv.b[0]);
