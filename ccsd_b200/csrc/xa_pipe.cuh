@@ -332,6 +332,29 @@ __global__ void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__restr
 // =============================================================================================
 // hodge_kernel: hodge branch of ScoreNetworkA_CC on the channel stack in global memory
 // =============================================================================================
+// mlp_attention of a hodge layer on a register vector of <= 8 channels -> <= 8 channels: the single-Linear case (every
+// shipped two-layer checkpoint) runs on statically indexed registers, anything else through small_mlp
+__device__ __forceinline__ void hodge_channel_mlp(const ccsd_mlp_t &m, const float *__restrict__ W, const float att[CCSD_MAX_CH],
+                                                  float out[CCSD_MAX_CH]) {
+  if (m.nl == 1 && m.din <= CCSD_MAX_CH && m.dout <= CCSD_MAX_CH) {
+    const float *w = W + m.w[0], *bb = W + m.b[0];   // (in, out_pad = 8)
+#pragma unroll
+    for (int o = 0; o < CCSD_MAX_CH; ++o) out[o] = o < m.dout ? __ldg(bb + o) : 0.f;
+#pragma unroll
+    for (int c = 0; c < CCSD_MAX_CH; ++c)
+      if (c < m.din) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w + c * 8)), w1 = __ldg(reinterpret_cast<const float4 *>(w + c * 8 + 4));
+        out[0] += att[c] * w0.x; out[1] += att[c] * w0.y; out[2] += att[c] * w0.z; out[3] += att[c] * w0.w;
+        out[4] += att[c] * w1.x; out[5] += att[c] * w1.y; out[6] += att[c] * w1.z; out[7] += att[c] * w1.w;
+      }
+    return;
+  }
+  float o32[SMALL_MAX];
+  small_mlp(m, W, att, o32, ACT_ELU);
+#pragma unroll
+  for (int o = 0; o < CCSD_MAX_CH; ++o) out[o] = o < m.dout ? o32[o] : 0.f;
+}
+
 __device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, int ad, int heads, float scale) {
   const int ds = ad / heads;
   const int nch = (ad + ds - 1) / ds;
@@ -487,23 +510,32 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
   __syncthreads();
   // layer-0 output  H1[c'][e][e'] = 2 tanh(fe fe' MLP_att(A_.[e,e'])),  A symmetric
   for (int p = threadIdx.x; p < E * (E + 1) / 2; p += blockDim.x) {
-    int e = 0, rem = p;
-    while (rem >= E - e) { rem -= E - e; ++e; }
-    const int e2 = e + rem;
+    // row-major upper triangle: rows before e hold e E - e (e - 1) / 2 pairs
+    int e = (int)(((float)(2 * E + 1) - sqrtf((float)(2 * E + 1) * (float)(2 * E + 1) - 8.f * (float)p)) * 0.5f);
+    e = e < 0 ? 0 : (e > E - 1 ? E - 1 : e);
+    while (e > 0 && e * E - e * (e - 1) / 2 > p) --e;
+    while ((e + 1) * E - (e + 1) * e / 2 <= p) ++e;
+    const int e2 = e + (p - (e * E - e * (e - 1) / 2));
     const float fe = flags[P->edge_ij[2 * e]] * flags[P->edge_ij[2 * e + 1]];
     const float fe2 = flags[P->edge_ij[2 * e2]] * flags[P->edge_ij[2 * e2 + 1]];
-    float att[CCSD_MAX_CH], out[SMALL_MAX];
-    for (int c = 0; c < c0; ++c) {
-      const float s1 = hodge_diag_att(hq + (c * E + e) * ad0, hk + (c * E + e2) * ad0, ad0, A.num_heads_h, scale);
-      const float s2 = hodge_diag_att(hq + (c * E + e2) * ad0, hk + (c * E + e) * ad0, ad0, A.num_heads_h, scale);
-      att[c] = 0.5f * (s1 + s2);
+    float att[CCSD_MAX_CH], out[CCSD_MAX_CH];
+#pragma unroll
+    for (int c = 0; c < CCSD_MAX_CH; ++c) {
+      att[c] = 0.f;
+      if (c < c0) {
+        const float s1 = hodge_diag_att(hq + (c * E + e) * ad0, hk + (c * E + e2) * ad0, ad0, A.num_heads_h, scale);
+        const float s2 = hodge_diag_att(hq + (c * E + e2) * ad0, hk + (c * E + e) * ad0, ad0, A.num_heads_h, scale);
+        att[c] = 0.5f * (s1 + s2);
+      }
     }
-    small_mlp(h0.mlp_attention, W, att, out, ACT_ELU);
-    for (int c = 0; c < c1; ++c) {
-      const float v = 2.0f * tanhf(fe * fe2 * out[c]);
-      H1[(c * E + e) * lde + e2] = v;
-      H1[(c * E + e2) * lde + e] = v;
-    }
+    hodge_channel_mlp(h0.mlp_attention, W, att, out);
+#pragma unroll
+    for (int c = 0; c < CCSD_MAX_CH; ++c)
+      if (c < c1) {
+        const float v = 2.0f * fast_tanh(fe * fe2 * out[c]);
+        H1[(c * E + e) * lde + e2] = v;
+        H1[(c * E + e2) * lde + e] = v;
+      }
   }
   __syncthreads();
   // diag of layer-0 output -> stack ; DenseHCNConv degrees of layer 1 (hodge_layers.py:186)
@@ -554,11 +586,13 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int i = P->edge_ij[2 * e], j = P->edge_ij[2 * e + 1];
     const float fe = flags[i] * flags[j];
-    float att[CCSD_MAX_CH], out[SMALL_MAX];
-    for (int c = 0; c < c1; ++c) att[c] = att1[c * E + e];
-    small_mlp(h1.mlp_attention, W, att, out, ACT_ELU);
-    for (int c = 0; c < h1.c_out; ++c)
-      stack[(ch_hodge0 + c0 + c1 + c) * ldp + tri_index(i, j, N)] = 2.0f * fast_tanh(fe * fe * out[c]);
+    float att[CCSD_MAX_CH], out[CCSD_MAX_CH];
+#pragma unroll
+    for (int c = 0; c < CCSD_MAX_CH; ++c) att[c] = c < c1 ? att1[c * E + e] : 0.f;
+    hodge_channel_mlp(h1.mlp_attention, W, att, out);
+#pragma unroll
+    for (int c = 0; c < CCSD_MAX_CH; ++c)
+      if (c < h1.c_out) stack[(ch_hodge0 + c0 + c1 + c) * ldp + tri_index(i, j, N)] = 2.0f * fast_tanh(fe * fe * out[c]);
   }
 }
 
