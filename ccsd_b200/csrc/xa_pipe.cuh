@@ -349,6 +349,34 @@ __device__ __forceinline__ void hodge_channel_mlp(const ccsd_mlp_t &m, const flo
       }
     return;
   }
+  if (m.nl == 2 && m.din <= CCSD_MAX_CH && m.dhid <= 8 && m.dout <= CCSD_MAX_CH) {   // din -> hid (<= 8) -> dout, elu
+    float h[8];
+    {
+      const float *w = W + m.w[0], *bb = W + m.b[0];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) h[o] = o < m.dhid ? __ldg(bb + o) : 0.f;
+#pragma unroll
+      for (int c = 0; c < CCSD_MAX_CH; ++c)
+        if (c < m.din) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w + c * 8)), w1 = __ldg(reinterpret_cast<const float4 *>(w + c * 8 + 4));
+          h[0] += att[c] * w0.x; h[1] += att[c] * w0.y; h[2] += att[c] * w0.z; h[3] += att[c] * w0.w;
+          h[4] += att[c] * w1.x; h[5] += att[c] * w1.y; h[6] += att[c] * w1.z; h[7] += att[c] * w1.w;
+        }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) h[o] = o < m.dhid ? fast_elu(h[o]) : 0.f;
+    }
+    const float *w = W + m.w[1], *bb = W + m.b[1];
+#pragma unroll
+    for (int o = 0; o < CCSD_MAX_CH; ++o) out[o] = o < m.dout ? __ldg(bb + o) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < m.dhid) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w + c * 8)), w1 = __ldg(reinterpret_cast<const float4 *>(w + c * 8 + 4));
+        out[0] += h[c] * w0.x; out[1] += h[c] * w0.y; out[2] += h[c] * w0.z; out[3] += h[c] * w0.w;
+        out[4] += h[c] * w1.x; out[5] += h[c] * w1.y; out[6] += h[c] * w1.z; out[7] += h[c] * w1.w;
+      }
+    return;
+  }
   float o32[SMALL_MAX];
   small_mlp(m, W, att, o32, ACT_ELU);
 #pragma unroll
