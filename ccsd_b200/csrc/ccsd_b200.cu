@@ -485,6 +485,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->hp.ntile_max = imax(imax(imax(1, p->hp.ntile_r2), p->hp.ntile_adj), p->hp.ntile_x);
   p->hp.f_mode = 0; p->hp.f_nlin = 0;
   p->hp.ap_group = d.is_cc ? imax(1, imin(8, 192 / imax(d.E, 1))) : 1;
+  p->hp.gram_group = 1;
   if (d.is_cc && (d.nets & 4)) {
     const ccsd_netf_t &Fn = d.netf;
     bool w8 = Fn.fdim <= 40, w4 = true;
@@ -588,6 +589,12 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
+  if (p->use_tc) {   // small complexes: stack G samples per Gram work unit
+    int G = imin(8, 192 / imax(d.E, 1));
+    while (G > 1 && tc_gram_ncols(G * d.E, p->hp.PR0) > 256) --G;
+    if (getenv("CCSD_B200_NO_GRAM_GROUP")) G = 1;   // A/B switch for tests and profiling
+    p->hp.gram_group = imax(G, 1);
+  }
   p->use_tc_apply = (d.is_cc && (d.nets & 4) && !p->apply_big) ? tc_apply_supported(d.E, d.K) : 0;
   p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;

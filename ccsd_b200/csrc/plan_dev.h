@@ -69,6 +69,7 @@ struct DevPlan {
   int ntile_max;                  // stride of the per-object norm partials
   int f_mode;                     // ScoreNetworkF entry path: 0 generic, 1 affine fold, 2 <=8-wide unrolled, 3 <=4-wide x4 entries, 4 <=8-wide + 2-Linear final
   int f_nlin;                     // number of Linears staged for f_mode 2
+  int gram_group;                 // tensor-core Gram kernel: samples per work unit (stacked rows <= 192, columns <= 256)
   int ap_group;                   // tensor-core apply kernel: samples per work group (min(8, 192 / E))
 };
 

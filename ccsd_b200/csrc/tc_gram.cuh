@@ -50,13 +50,18 @@ static inline int tc_gram_supported(int E, int K, int PR0) {
   return E >= 8 && E <= 192 && PR0 <= 64 && tc_gram_ncols(E, PR0) <= 256;
 }
 
+template <bool GROUPED>   // GROUPED = false: one sample per work unit (G = 1 folds away at compile time)
 __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *__restrict__ P, TcGramArgs a) {
   extern __shared__ uint8_t tg_smem_raw[];
   const ccsd_plan_desc_t &d = P->d;
   const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp, B = d.B;
-  const int wp0 = (E + 7) & ~7;
+  // small complexes: G consecutive samples form one work unit -- their rows are contiguous in the state, so the operand
+  // tile is simply taller; the Gram of the stacked rows holds the G per-sample Grams as its diagonal blocks (the
+  // cross-sample blocks are computed and never stored)
+  const int G = GROUPED ? P->gram_group : 1, EG = G * E, NV = (B + G - 1) / G;
+  const int wp0 = (EG + 7) & ~7;
   const int ncols = (wp0 + PR0 + 15) & ~15;
-  const int mtiles = E > 128 ? 2 : 1;
+  const int mtiles = EG > 128 ? 2 : 1;
   const int nkb = (K + TG_BK - 1) / TG_BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -95,19 +100,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
     const int grp = warp / (TG_PROD_WARPS / 2), tg = threadIdx.x - grp * TG_GRP;
     const int c = tg & 7, r0 = tg >> 3;
     const uint32_t off0 = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
-    const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nmine = (NV - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const long total = (long)nmine * nkb;
     for (long g = grp; g < total; g += 2) {
-      const int b = (int)blockIdx.x + (int)(g / nkb) * (int)gridDim.x;
+      const int vb = (int)blockIdx.x + (int)(g / nkb) * (int)gridDim.x;
       const int kb = (int)(g % nkb);
-      const float *Fb = a.r2 + (size_t)b * E * K;
+      const float *Fb = a.r2 + (size_t)vb * EG * K;
+      const int rows_valid = ((B - vb * G < G) ? B - vb * G : G) * E;   // the last unit may hold fewer samples
       const int k = kb * TG_BK + c * 8;
       const bool fast = vec && (kb * TG_BK + TG_BK <= K);
       const float *src = Fb + (size_t)r0 * K + k;
       float x[NT][8];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        if (r0 + TG_RSTEP * j < E) {
+        if (r0 + TG_RSTEP * j < rows_valid) {
           const float *sj = src + (size_t)(TG_RSTEP * j) * K;
           if (fast) {
             const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sj));
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       uint8_t *st = gen_base + (size_t)s * TG_STAGE;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        if (r0 + TG_RSTEP * j < E) {
+        if (r0 + TG_RSTEP * j < rows_valid) {
           uint4 hi, lo;
           tc::split8(x[j], hi, lo);
           *reinterpret_cast<uint4 *>(st + off0 + j * (TG_RSTEP * 128u)) = hi;
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
     const uint32_t idesc = tc::make_idesc_bf16(128, ncols, 0, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy (uniform-register MMA operands)
     uint32_t it = 0, tile = 0;
-    for (int b = blockIdx.x; b < B; b += gridDim.x, ++tile) {
+    for (int vb = blockIdx.x; vb < NV; vb += gridDim.x, ++tile) {
       tc::mbar_wait(tempty, (tile & 1) ^ 1);   // epilogue has drained the previous accumulators
       tc::tc_fence_after_sync();
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -195,24 +201,31 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
     const int q = warp & 3;
     const int mask_diag = d.netf.use_hodge_mask;
     uint32_t tile = 0;
-    for (int b = blockIdx.x; b < B; b += gridDim.x, ++tile) {
+    for (int vb = blockIdx.x; vb < NV; vb += gridDim.x, ++tile) {
       tc::mbar_wait(tfull, tile & 1);
       tc::tc_fence_after_sync();
       for (int mt = 0; mt < mtiles; ++mt) {
         const int row = mt * 128 + q * 32 + lane;
+        const int gs = G == 1 ? 0 : row / E, er = row - gs * E, b = vb * G + gs;   // sample of this row inside the unit, edge row
+        const bool live = row < EG && b < B;
         // H is symmetric: lane `row` holds H[row][c0 .. c0+15]; it is stored as H[c0+j][row], so that for
         // every j the 32 lanes of the warp write 32 CONSECUTIVE floats (one coalesced 128-byte store)
         // instead of 32 rows 760 bytes apart.
-        float *Hcol = a.H + (size_t)b * E * P->Ep + row;
-        float *Prow = a.P0 + ((size_t)b * E + row) * PR0;
+        float *Hcol = a.H + (size_t)b * E * P->Ep + er;
+        float *Prow = a.P0 + ((size_t)b * E + er) * PR0;
+        const int cb0 = gs * E, cb1 = cb0 + E;   // this sample's diagonal block of the stacked Gram
+        // warp-uniform range of columns that hold a diagonal block of the warp's 32 rows (G = 1: all of [0, E))
+        const int rlo = mt * 128 + q * 32, rhi = rlo + 31 < EG ? rlo + 31 : EG - 1;
+        const int blo = G == 1 ? 0 : (rlo / E) * E, bhi = G == 1 ? E : (rhi / E) * E + E;
         for (int c0 = 0; c0 < ncols; c0 += 16) {
+          if (!((c0 < bhi && c0 + 16 > blo) || c0 + 16 > wp0)) continue;   // neither a diagonal block nor projections
           float v[16];
           tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ncols + c0), v);
-          if (row < E) {
+          if (live) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = c0 + j;
-              if (col < E) Hcol[(size_t)col * P->Ep] = (mask_diag && col == row) ? 0.f : v[j];
+              if (col >= cb0 && col < cb1) Hcol[(size_t)(col - cb0) * P->Ep] = (mask_diag && col == row) ? 0.f : v[j];
               else if (col >= wp0 && col - wp0 < PR0) Prow[col - wp0] = v[j];
             }
           }
@@ -228,14 +241,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
 }
 
 static inline int tc_gram_prepare() {
-  return cudaFuncSetAttribute(tc_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) == cudaSuccess ? 0 : -1;
+  if (cudaFuncSetAttribute(tc_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) != cudaSuccess) return -1;
+  return cudaFuncSetAttribute(tc_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) == cudaSuccess ? 0 : -1;
 }
 
 static inline int tc_gram_launch(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, void *stream) {
   TcGramArgs a;
   a.r2 = r2; a.H = H; a.P0 = P0;
-  int grid = hp.d.B < 148 ? hp.d.B : 148;
-  tc_gram_kernel<<<grid, TG_THREADS, TG_SMEM, (cudaStream_t)stream>>>(dP, a);
+  const int nv = (hp.d.B + hp.gram_group - 1) / hp.gram_group;
+  int grid = nv < 148 ? nv : 148;
+  if (hp.gram_group > 1) tc_gram_kernel<true><<<grid, TG_THREADS, TG_SMEM, (cudaStream_t)stream>>>(dP, a);
+  else tc_gram_kernel<false><<<grid, TG_THREADS, TG_SMEM, (cudaStream_t)stream>>>(dP, a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
