@@ -36,7 +36,7 @@ class NetX(C.Structure):
 class AttnLayer(C.Structure):
     _fields_ = [
         ("c_in", i32), ("c_out", i32), ("conv_in", i32), ("attn_dim", i32), ("conv_out", i32),
-        ("q", Gcn * MAX_CH), ("k", Gcn * MAX_CH), ("v", Gcn * MAX_CH), ("mlp", Mlp), ("multi_channel", Mlp),
+        ("q", Gcn * MAX_CH), ("k", Gcn * MAX_CH), ("v", Gcn * MAX_CH), ("vw", Gcn * MAX_CH), ("mlp", Mlp), ("multi_channel", Mlp),
     ]
 
 

@@ -30,22 +30,56 @@ def _stale(target: Path) -> bool:
     return any(s.stat().st_mtime > t for s in _sources())
 
 
+def _nvcc_base():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+# translation units: (object name, source, extra flags, headers it depends on besides its own source)
+_APPLY_DEPS = ["tc_apply.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]
+
+
+def _units():
+    units = [("ccsd_b200", "ccsd_b200.cu", [], None)]   # None: depends on every header
+    for k in range(5):
+        units.append((f"tc_apply_f{k}", "tc_apply_tu.cu", [f"-DTA_FMODE={k}"], _APPLY_DEPS))
+    units.append(("tc_attn", "tc_attn_tu.cu", [], ["tc_attn.cuh", "xa_pipe.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
+    return units
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the translation units in parallel (objects cached under build/obj by source mtime) and link."""
     if not force and not _stale(LIB):
         return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    from concurrent.futures import ThreadPoolExecutor
+
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [
-        nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-        "-Xcompiler", "-fPIC", "-shared", "-o", str(LIB), str(CSRC / "ccsd_b200.cu"),
-    ]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = ROOT / "build" / "obj"
+    objdir.mkdir(parents=True, exist_ok=True)
+    hdr_all = [s for s in _sources() if s.suffix != ".cu"]
+    jobs = []
+    for name, src, flags, deps in _units():
+        obj = objdir / f"{name}.o"
+        dep_files = [CSRC / src] + (hdr_all if deps is None else [CSRC / d for d in deps] + [ROOT / "include" / "ccsd_b200.h"])
+        fresh = obj.exists() and all(f.stat().st_mtime <= obj.stat().st_mtime for f in dep_files)
+        if force or not fresh:
+            cmd = _nvcc_base() + flags + (["-Xptxas=-v"] if verbose else []) + ["-c", str(CSRC / src), "-o", str(obj)]
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for log in ex.map(run, jobs):
+            if verbose:
+                print(log)
+    objs = [str(objdir / f"{name}.o") for name, _, _, _ in _units()]
+    r = subprocess.run(_nvcc_base() + ["-shared", "-o", str(LIB)] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -45,7 +45,7 @@ __device__ __forceinline__ float *big_ptr(const DevPlan *P, const BigArgs &g, in
 }
 
 // plane 0 of the stack <- adj; node features (feature-major) <- x, also rows [0, F) of the X net's concat
-__global__ void __launch_bounds__(256) big_prep_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(256) big_prep_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.y, N = d.N, F = d.F, Np = L.big_Np;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) big_prep_kernel(const DevPlan *__restrict
 }
 
 // pow_tensor (graph_utils.py:274-292): plane c = plane (c-1) . plane 0
-__global__ void __launch_bounds__(128) big_pow_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_pow_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, N = P->d.N, Np = L.big_Np, PS = L.big_PS;
   const int i0 = blockIdx.x * BIG_RC, R = (N - i0 < BIG_RC) ? N - i0 : BIG_RC;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) big_pow_kernel(const DevPlan *__restrict_
 }
 
 // DenseGCNConv degrees (layers.py:139-146): d_i = clamp(sum_j A^_ij, 1)^-1/2 with the unit diagonal of A^
-__global__ void __launch_bounds__(128) big_deg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_deg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = P->d.N, Np = L.big_Np;
   const float *pl = big_ptr(P, g, b, L.big_S) + (size_t)(g.ch_in + c) * L.big_PS;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) big_deg_kernel(const DevPlan *__restrict_
 // Y = diag(d) (x W): the feature transforms of one channel's Q | K | V convolutions (xmode 0, one node-major
 // buffer [N][2 adp + nhp]) or of one GCN layer of ScoreNetworkX (xmode 1), pre-scaled by d_j for the aggregation.
 // One pass: item = (8 output columns, 4 rows); the item picks its weight matrix and scales its own tile.
-__global__ void __launch_bounds__(128) big_xw_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_xw_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void agg_fma(float acc[8][8], const AggOps &t) {
     for (int j = 0; j < 8; ++j) acc[rr][j] += av[rr] * wv[j];
 }
 
-__global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128) big_agg_kernel(const DevPlan *__restrict_
 
 // Attention scores of one channel (attention.py:111-130): heads = chunks of ds = ad / heads features
 // (torch.split), att(i, j) = mean_h 0.5 (tanh(q_i.k_j s) + tanh(q_j.k_i s)).  Item = 4x4 node block I <= J.
-__global__ void __launch_bounds__(128) big_attn_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_attn_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, c = blockIdx.y, N = d.N, Np = L.big_Np;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(128) big_attn_kernel(const DevPlan *__restrict
 }
 
 // node branch of AttentionLayer (attention.py:292-293): x_out = tanh(mask_x(MLP(cat_c V_c)))
-__global__ void __launch_bounds__(128) big_node_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_node_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -317,7 +317,7 @@ __device__ __forceinline__ bool big_segment(const DevPlan *P, int &i, int &j0, i
 
 // edge branch of AttentionLayer (attention.py:295-303): M = MLP([att_1..att_c, adj_1..adj_c]),
 // adj_out = mask_adjs(M + M^T) = 2 M mask (M is symmetric because its inputs are)
-__global__ void __launch_bounds__(128) big_edge_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_edge_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -355,7 +355,7 @@ static inline bool big_edge_fast_ok(const ccsd_attn_layer_t &ly) {
   return 2 * ly.c_in <= 16 && ly.c_out <= 8 && ly.mlp.nl >= 1 && ly.mlp.nl <= 4 && (ly.mlp.nl == 1 || ly.mlp.dhid <= 16);
 }
 
-__global__ void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(BIG_ESEG) big_edge_pair_kernel(const DevPlan *
 
 // lower triangle <- upper triangle of planes [ch_out, ch_out + nch): 32 x 32 tiles through shared memory, so that both
 // the reads and the writes are coalesced (a per-row kernel can only write its mirrored entries as scattered 4-byte stores)
-__global__ void __launch_bounds__(256) big_mirror_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(256) big_mirror_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   CCSD_SMEM(sm);
   const XpLayout &L = P->xp;
   const int b = blockIdx.z, N = P->d.N, Np = L.big_Np;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256) big_mirror_kernel(const DevPlan *__restri
 
 // final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) + the adjacency sampler epilogue
 // (same arithmetic as afinal_kernel)
-__global__ void __launch_bounds__(128) big_final_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_final_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(128) big_final_kernel(const DevPlan *__restric
 
 // final MLP of ScoreNetworkX over a row chunk (ScoreNetwork_X.py:127-133) + the x sampler epilogue
 // (same arithmetic as x_net_kernel)
-__global__ void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restrict__ P, BigArgs g) {
+CCSD_KERNEL void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restrict__ P, BigArgs g) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;

@@ -23,6 +23,7 @@
 #include "tc_apply.cuh"
 #include "tc_afinal.cuh"
 #include "tc_agg.cuh"
+#include "tc_attn.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -83,6 +84,10 @@ struct ccsd_plan {
   size_t apply_smem = 0;
   int64_t launches = 0;
   int use_tc = 0, use_tc_apply = 0, use_tc_fin = 0, use_tc_agg = 0;
+#ifndef CCSD_EMU
+  int use_tc_attn[CCSD_MAX_LAYERS] = {0};   // per attention layer: tcgen05 attention-channel kernel (tc_attn.cuh)
+  TcAttnLayout tattn[CCSD_MAX_LAYERS];
+#endif
   int apply_big = 0;   // E too large for the resident F column block: hf_gemm_kernel + r2_epi_kernel (scratch = sr2)
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
@@ -599,7 +604,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;
   if (getenv("CCSD_B200_NO_TC_AGG")) p->use_tc_agg = 0;
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = 0;  // A/B switch for tests and profiling
+  if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_ATTN"))
+    for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_attn[l] = tc_attn_layout(d, XL, d.neta.layer[l], p->tattn[l]);
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); }  // A/B switch for tests and profiling
   if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
     p->hp.ntile_adj = XL.big ? d.N * ((d.N + 127) / 128) : (p->hp.xp.NT + 127) / 128;
     p->hp.ntile_max = imax(p->hp.ntile_max, p->hp.ntile_adj);
@@ -797,9 +804,18 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
   for (int l = 0; l < A.num_layers; ++l) {
     const ccsd_attn_layer_t &ly = A.layer[l];
     a.layer = l; a.ch_in = ch_in; a.ch_out = ch_out; a.g_xin = xin; a.g_xout = xout;
-    PROF_BEGIN(p, "attn_channel_kernel", stream);
-    CCSD_LAUNCH(attn_channel_kernel, dim3(ly.c_in, d.B, 1), L.Tc, (size_t)L.c_total * 4, stream, p->dP, a);
-    PROF_END(p, stream);
+#ifndef CCSD_EMU
+    if (p->use_tc_attn[l]) {
+      PROF_BEGIN(p, "tc_attn_kernel", stream);
+      if (tc_attn_launch(p->dP, p->hp, a, p->tattn[l], stream)) return fail(CCSD_ERR_CUDA, "tc_attn launch failed");
+      PROF_END(p, stream);
+    } else
+#endif
+    {
+      PROF_BEGIN(p, "attn_channel_kernel", stream);
+      CCSD_LAUNCH(attn_channel_kernel, dim3(ly.c_in, d.B, 1), L.Tc, (size_t)L.c_total * 4, stream, p->dP, a);
+      PROF_END(p, stream);
+    }
     PROF_BEGIN(p, "attn_finish_kernel", stream);
     CCSD_LAUNCH(attn_finish_kernel, dim3(d.B, 1, 1), L.Tf, (size_t)L.f_total * 4, stream, p->dP, a);
     PROF_END(p, stream);
@@ -1069,6 +1085,9 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
     case 6: return p->hp.xp.m_rows;
     case 12: return p->hp.PR0;
     case 13: return p->use_tc_fin;
+#ifndef CCSD_EMU
+    case 14: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_attn[l]; return n; }   // layers on the tcgen05 attention kernel
+#endif
     case 7: return p->hp.xp.x_total * 4;
     case 8: return p->hp.xp.c_total * 4;
     case 9: return p->hp.xp.f_total * 4;

@@ -10,6 +10,14 @@
 // run time -- the product library has no CPU path.
 #pragma once
 
+// Non-template kernels of the shared headers: a translation unit that only needs the device helpers (the
+// per-FMODE tc_apply units) defines CCSD_AUX_TU, which gives them internal linkage so the linker sees one copy.
+#ifdef CCSD_AUX_TU
+#define CCSD_KERNEL static __global__
+#else
+#define CCSD_KERNEL __global__
+#endif
+
 #include <stddef.h>
 #include <stdint.h>
 

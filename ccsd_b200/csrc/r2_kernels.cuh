@@ -28,7 +28,7 @@ struct GramArgs {
   float *P0;         // [B,E,PR0]
 };
 
-__global__ void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P, GramArgs a) {
+CCSD_KERNEL void __launch_bounds__(256) gram_kernel(const DevPlan *__restrict__ P, GramArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp, Ep = P->Ep;
@@ -132,7 +132,7 @@ struct Proj1Args {
 // (an element-wise function of F, see the file header) goes to shared memory, then every warp takes
 // projection rows r and accumulates the epc dot products with ONE pass over the weight row, so the weights
 // (PR1 x K floats, shared by all CTAs through L2) are read once per edge block instead of once per edge.
-__global__ void __launch_bounds__(128) proj1_kernel(const DevPlan *__restrict__ P, Proj1Args a) {
+CCSD_KERNEL void __launch_bounds__(128) proj1_kernel(const DevPlan *__restrict__ P, Proj1Args a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const ccsd_neta_t &A = d.neta;
@@ -652,7 +652,7 @@ struct HfArgs {
   float *hf;             // [B,E,K]
 };
 
-__global__ void __launch_bounds__(256) hf_gemm_kernel(const DevPlan *__restrict__ P, HfArgs a) {
+CCSD_KERNEL void __launch_bounds__(256) hf_gemm_kernel(const DevPlan *__restrict__ P, HfArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const int E = d.E, K = d.K, Ep = P->Ep;
@@ -770,7 +770,7 @@ struct InitArgs {
   NoiseCtx nz;
 };
 
-__global__ void __launch_bounds__(256) init_kernel(const DevPlan *__restrict__ P, InitArgs a) {
+CCSD_KERNEL void __launch_bounds__(256) init_kernel(const DevPlan *__restrict__ P, InitArgs a) {
   const ccsd_plan_desc_t &d = P->d;
   const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
   const int obj = blockIdx.y;
@@ -820,7 +820,7 @@ struct CoefArgs {
   int step, s4;
 };
 
-__global__ void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ P, CoefArgs a) {
+CCSD_KERNEL void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ P, CoefArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const int nobj = d.is_cc ? 3 : 2;
@@ -874,7 +874,7 @@ __device__ __forceinline__ float upd_elem(const ccsd_objcoef_t &co, float cs, fl
   return mu + co.s4_s2 * z[2];
 }
 
-__global__ void __launch_bounds__(256) update_kernel(const DevPlan *__restrict__ P, UpdateArgs a) {
+CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict__ P, UpdateArgs a) {
   const ccsd_plan_desc_t &d = P->d;
   const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
   const int obj = blockIdx.y;
@@ -953,14 +953,14 @@ __global__ void __launch_bounds__(256) update_kernel(const DevPlan *__restrict__
 }
 
 // zero-flag node mask of every sample (bit n set <=> flags[b][n] == 0): a cell is masked iff it shares a bit
-__global__ void __launch_bounds__(256) zmask_kernel(const float *__restrict__ flags, unsigned long long *__restrict__ zmask,
+CCSD_KERNEL void __launch_bounds__(256) zmask_kernel(const float *__restrict__ flags, unsigned long long *__restrict__ zmask,
                                                     int B, int N) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x)
     zmask[b] = zero_mask_of(flags + (size_t)b * N, N);
 }
 
 // quantize / quantize_mol (graph_utils.py:181-213)
-__global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__ in, uint8_t *__restrict__ out,
+CCSD_KERNEL void __launch_bounds__(256) quantize_kernel(const float *__restrict__ in, uint8_t *__restrict__ out,
                                                         size_t n, float thr, int mol) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__
 // Molecule post-processing of Sampler_mol.sample (sampler.py:814-825) in one pass over the sampler outputs:
 //   adj_out[b][c][i][j] = one_hot((quantize_mol(adj) - 1) mod 4)   (classes: 0 single, 1 double, 2 triple, 3 no bond), int64
 //   x_out[b][i][f] = x > 0.5 (f < F),  x_out[b][i][F] = 1 - sum_f x_out[b][i][f]   (the "no atom" column), int64
-__global__ void __launch_bounds__(256) mol_onehot_kernel(const float *__restrict__ x, const float *__restrict__ adj,
+CCSD_KERNEL void __launch_bounds__(256) mol_onehot_kernel(const float *__restrict__ x, const float *__restrict__ adj,
                                                           long long *__restrict__ x_out, long long *__restrict__ adj_out,
                                                           int B, int N, int F) {
   const size_t stride = (size_t)gridDim.x * blockDim.x, start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

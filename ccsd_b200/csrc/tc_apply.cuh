@@ -73,6 +73,7 @@ constexpr uint32_t TA_COL_D = 384;                // first accumulator column
 
 static inline int tc_apply_supported(int E, int K) { return E >= 8 && E <= TA_NE && K >= 8; }
 
+#ifdef TC_APPLY_KERNEL_TU
 // Per-pass constants of the entry update, folded so that the affine ScoreNetworkF path is a handful of FMAs:
 //   score s = sc * o,  o = m * (a0 f + a1 hf + a2)  (FMODE 1)  ->  s = m * (k0 f + k1 hf + k2)
 struct R2Fold {
@@ -565,11 +566,14 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
   if (warp == TA_MMAW) tc::tmem_dealloc(tmem, 512);
 }
 
+#endif  // TC_APPLY_KERNEL_TU
+
 struct TcApplyMaps {   // host side: tensor maps of the state read and the state / score written, or use_tma = 0
   CUtensorMap in, out;
   int use_tma;
 };
 
+#ifdef TC_APPLY_KERNEL_TU
 template <int FMODE, int MODE>
 static inline int tc_apply_launch_fm(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream) {
   static bool attr_set = false;   // per instantiation
@@ -592,6 +596,16 @@ static inline int tc_apply_launch_f(const DevPlan *dP, int grid, const ApplyArgs
   }
   return -1;
 }
+
+#endif  // TC_APPLY_KERNEL_TU
+
+// One translation unit per ScoreNetworkF entry path (tc_apply_tu.cu compiled with -DTA_FMODE=k): the 25
+// (FMODE, MODE) instantiations are most of the library's compile time, so they build in parallel.
+int tc_apply_launch_f0(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream);
+int tc_apply_launch_f1(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream);
+int tc_apply_launch_f2(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream);
+int tc_apply_launch_f3(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream);
+int tc_apply_launch_f4(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream);
 
 // 2-D tensor map of a [B*E rows][K cols] fp32 tensor with a box of E rows x 32 columns, SWIZZLE_128B.
 // Returns 0 on success; fails (-> cp.async path) when the pitch or the base is not 16-byte aligned.
@@ -630,11 +644,11 @@ static inline int tc_apply_launch(const DevPlan *dP, const DevPlan &hp, const Ap
       (a.mode == MODE_NORM || tc_apply_make_map(&m.out, a.out, hp.d.B, hp.d.E, hp.d.K, box_rows) == 0))
     m.use_tma = 1;
   if (a.mode == MODE_NORM) m.out = m.in;
-  if (hp.f_mode == 1) return tc_apply_launch_f<1>(dP, grid, a, m, stream);
-  if (hp.f_mode == 2) return tc_apply_launch_f<2>(dP, grid, a, m, stream);
-  if (hp.f_mode == 3) return tc_apply_launch_f<3>(dP, grid, a, m, stream);
-  if (hp.f_mode == 4) return tc_apply_launch_f<4>(dP, grid, a, m, stream);
-  return tc_apply_launch_f<0>(dP, grid, a, m, stream);
+  if (hp.f_mode == 1) return tc_apply_launch_f1(dP, grid, a, m, stream);
+  if (hp.f_mode == 2) return tc_apply_launch_f2(dP, grid, a, m, stream);
+  if (hp.f_mode == 3) return tc_apply_launch_f3(dP, grid, a, m, stream);
+  if (hp.f_mode == 4) return tc_apply_launch_f4(dP, grid, a, m, stream);
+  return tc_apply_launch_f0(dP, grid, a, m, stream);
 }
 
 }  // namespace ccsd

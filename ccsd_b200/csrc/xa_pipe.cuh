@@ -31,6 +31,7 @@
 // layer's value output with it.
 #pragma once
 #include "prims.cuh"
+#include "r2_kernels.cuh"   // zero_mask_of, Philox helpers of the sampler epilogues
 
 #ifndef XP_MINB_C
 #define XP_MINB_C 1
@@ -69,7 +70,7 @@ struct XaArgs {
 // =============================================================================================
 // x_net_kernel: ScoreNetworkX, x epilogue, adjacency powers + feature-major x for the A pipeline
 // =============================================================================================
-__global__ void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__ 
 // =============================================================================================
 // attn_channel_kernel: Attention.forward of ONE channel of one graph (attention.py:84-132)
 // =============================================================================================
-__global__ void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+CCSD_KERNEL void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const DevP
 // =============================================================================================
 // attn_finish_kernel: the rest of AttentionLayer.forward (attention.py:292-302) for one graph
 // =============================================================================================
-__global__ void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+CCSD_KERNEL void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -396,7 +397,7 @@ __device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, 
   return s / (float)nch;
 }
 
-__global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+CCSD_KERNEL void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ 
 // that owns row e accumulates the first Linear of every layer-1 block over e'.  Only the DIAGONALS of the
 // layer outputs reach the final MLP (hodgedual_to_adj, cc_utils.py:1571).
 // =============================================================================================
-__global__ void __launch_bounds__(128) hodge_base_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+CCSD_KERNEL void __launch_bounds__(128) hodge_base_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(128) hodge_base_kernel(const DevPlan *__restri
 // afinal_kernel: final per-edge MLP of ScoreNetworkA (ScoreNetwork_A.py:529-539) on a chunk of node
 // pairs + the adjacency sampler epilogue
 // =============================================================================================
-__global__ void __launch_bounds__(128, XP_MINB_M) afinal_kernel(const DevPlan *__restrict__ P, XaArgs a) {
+CCSD_KERNEL void __launch_bounds__(128, XP_MINB_M) afinal_kernel(const DevPlan *__restrict__ P, XaArgs a) {
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;

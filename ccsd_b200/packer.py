@@ -154,6 +154,17 @@ def pack_neta(dst: nat.NetA, blob: Blob, model, K: int) -> None:
             _fill_gcn(ly.v[c], blob, sd, f"layers.{l}.attn.{c}.gnn_v")
         _fill_mlp(ly.mlp, blob, sd, f"layers.{l}.mlp")
         _fill_mlp(ly.multi_channel, blob, sd, f"layers.{l}.multi_channel")
+        # value convolution folded with the channel's slice of multi_channel's first Linear (float64 on the host):
+        # V_c W1_c = An x (W_v W1_c) + b_v W1_c  (attention.py:292; csrc/tc_attn.cuh)
+        mcp = f"layers.{l}.multi_channel"
+        w1 = sd[f"{mcp}.linear.weight"] if f"{mcp}.linear.weight" in sd else sd[f"{mcp}.linears.0.weight"]   # (o1, c_in * nh)
+        for c in range(c_in):
+            wv = sd[f"layers.{l}.attn.{c}.gnn_v.weight"].astype(np.float64)     # (kin, nh)
+            bv = sd[f"layers.{l}.attn.{c}.gnn_v.bias"].astype(np.float64)
+            nh = wv.shape[1]
+            w1c = w1[:, c * nh:(c + 1) * nh].astype(np.float64).T                # (nh, o1)
+            ly.vw[c].din, ly.vw[c].dout = wv.shape[0], w1c.shape[1]
+            ly.vw[c].w, ly.vw[c].b = blob.add_in_out((wv @ w1c).astype(np.float32), (bv @ w1c).astype(np.float32))
         ly.c_in, ly.c_out = c_in, ly.mlp.dout
         ly.conv_in, ly.attn_dim, ly.conv_out = ly.q[0].din, ly.q[0].dout, ly.v[0].dout
         if l == 0:

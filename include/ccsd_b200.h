@@ -71,6 +71,11 @@ typedef struct {
 typedef struct {
   int32_t c_in, c_out, conv_in, attn_dim, conv_out;
   ccsd_gcn_t q[CCSD_MAX_CH], k[CCSD_MAX_CH], v[CCSD_MAX_CH];
+  /* Optional (dout = 0 when absent): the value convolution of channel c folded with that channel's slice of
+   * multi_channel's first Linear, W_vw = W_v . W1[c*conv_out:(c+1)*conv_out, :] ((conv_in, o1_pad) row-major,
+   * o1 = width of that Linear) and b_vw = b_v . W1[...] -- the node MLP is linear in the channel concat
+   * (attention.py:292), so the tensor-core attention kernel never materialises V.  Computed by the packer. */
+  ccsd_gcn_t vw[CCSD_MAX_CH];
   ccsd_mlp_t mlp;           /* per-edge MLP, in = 2*c_in                      */
   ccsd_mlp_t multi_channel; /* node MLP, in = c_in*conv_out                   */
 } ccsd_attn_layer_t;

@@ -187,12 +187,14 @@ def test_full_size_community_small_cc_invariants():
 def test_shard_invariance_without_batch_coupling():
     """Philox is keyed by the GLOBAL sample index, so with no Langevin batch mean (corrector None)
     a batch run as one piece or as shards with sample_offset gives the same samples.  Shards whose sizes
-    are multiples of the rank-2 kernel's work-group size (tc_apply packs 192 // E consecutive samples per
-    group: 5 for QM9_CC) reproduce the whole-batch run bit for bit; other splits change only the position
-    of a sample inside its group, i.e. the fp32 summation order of H.F (1e-6 relative per step)."""
+    are multiples of every kernel's work-group size (tc_apply packs 192 // E = 5 consecutive QM9_CC samples
+    per group, tc_attn 128 // N = 14 graphs per MMA tile: lcm 70) reproduce the whole-batch run bit for bit;
+    other splits change only the position of a sample inside its group, i.e. the fp32 summation order of
+    the block-diagonal products (1e-6 relative per step)."""
     cfg = Config("qm9_cc")
     sd = cfg.sdes()
-    flags = _flags(cfg, 10)
+    unit = 70
+    flags = _flags(cfg, 2 * unit)
 
     def run(fl, off):
         B = fl.shape[0]
@@ -202,10 +204,10 @@ def test_shard_invariance_without_batch_coupling():
         return fn(*cfg.holders, fl.to(DEV), seed=5, sample_offset=off, max_steps=20, record_traj=False)[:3]
 
     whole = run(flags, 0)
-    a, b = run(flags[:5], 0), run(flags[5:], 5)          # group-aligned shards
+    a, b = run(flags[:unit], 0), run(flags[unit:], unit)          # group-aligned shards
     for w, p, q in zip(whole, a, b):
         assert torch.equal(w, torch.cat([p, q]))
-    a, b = run(flags[:4], 0), run(flags[4:], 4)          # unaligned shards
+    a, b = run(flags[:4], 0), run(flags[4:], 4)                    # unaligned shards
     for w, p, q in zip(whole, a, b):
         assert rel_err(torch.cat([p, q]), w) < 1e-4
 
