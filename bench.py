@@ -173,6 +173,32 @@ def xa_flops_split(meta):
     return fl, tot - fl
 
 
+# ---- whole-step algorithmic work (FLOPs per score EVALUATION of one sample, necessary computation) --
+SURVEY_8D_EVAL_FLOPS = {
+    "community_small": 3.916e7 / 2, "community_small_cc": 3.924e8 / 2, "qm9_cc": 1.304e7 / 2, "qm9": 2.832e6 / 2,
+    "enzymes_small_cc": 4.051e7, "grid_small_cc": 2.061e11 / 2, "grid": 1.455e10 / 2,
+}
+
+
+# X + A_alg of the same table (the x / adj networks alone; graph-only configs: the whole evaluation)
+SURVEY_8D_XA_FLOPS = {
+    "community_small": 3.916e7 / 2, "community_small_cc": 3.015e6 + 2.511e7, "qm9_cc": 7.14e4 + 3.227e6, "qm9": 2.832e6 / 2,
+    "enzymes_small_cc": 4.395e6 + 1.837e7, "grid_small_cc": 6.74e6 + 7.667e8, "grid": 1.455e10 / 2,
+}
+
+
+def step_alg_work(meta, wname, n_eval):
+    """(F_alg, Bytes_alg) per sample and sampler step: SURVEY 8d's per-evaluation FLOPs x evaluations per step, and
+    2 * 4 * (N F + N^2 + E K) bytes (read + write the fp32 state once per step)."""
+    N, F, E, K, _, _ = dims(meta)
+    if wname in SURVEY_8D_EVAL_FLOPS:
+        fl, src = SURVEY_8D_EVAL_FLOPS[wname], "SURVEY 8d table"
+    else:
+        x_fl, a_fl = xa_flops_split(meta)
+        fl, src = x_fl + a_fl + 4.0 * E * E * K, "2mnk formula (config not in the SURVEY 8d table)"
+    return fl * n_eval, 2.0 * 4.0 * (N * F + N * N + E * K), src
+
+
 # ---- clocks -----------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -212,7 +238,18 @@ class ClockSampler:
 
 
 # ---- CPU baseline (oracle port) ---------------------------------------------------------------
-def cpu_baseline(workload, budget_s=20.0, threads=None):
+def shipped_sampler(meta, override=None):
+    """(predictor, corrector) of the checkpoint's own sample_*.yaml, or the --sampler override: S4, or PC with the
+    shipped predictor / corrector (Reverse + Langevin where the checkpoint ships S4)."""
+    sh = meta["shipped_sampler"]
+    if override == "S4":
+        return "S4", "None"
+    if override == "PC" and sh["predictor"] == "S4":
+        return "Reverse", "Langevin"
+    return sh["predictor"], sh["corrector"]
+
+
+def cpu_baseline(workload, budget_s=20.0, threads=None, sampler=None, max_steps=50):
     from oracle import ccsd_oracle as O
     wname, _, B = WORKLOADS[workload]
     meta, keys, holders = load_workload(wname)
@@ -230,21 +267,22 @@ def cpu_baseline(workload, budget_s=20.0, threads=None):
         kw = dict(snr=sh["snr"], scale_eps=sh["scale_eps"], denoise=True, eps=1e-4, d_min=d_min, d_max=d_max,
                   noise=O.NoiseSource(0), max_steps=steps)
         t0 = time.perf_counter()
-        if sh["predictor"] == "S4":
+        if pred == "S4":
             O.s4_solver(models, sdes, shapes, flags, **kw)
         else:
-            O.pc_sampler(models, sdes, shapes, flags, predictor=sh["predictor"], corrector=sh["corrector"], n_steps=1, **kw)
+            O.pc_sampler(models, sdes, shapes, flags, predictor=pred, corrector=corr, n_steps=1, **kw)
         return time.perf_counter() - t0
 
+    pred, corr = shipped_sampler(meta, sampler)
     t1 = run(1)  # also warms the allocator; includes prior sampling
-    steps = int(max(2, min(50, budget_s / max(t1, 1e-3))))
+    steps = int(max(2, min(max_steps, budget_s / max(t1, 1e-3))))
     t = run(steps)
     ms_step = 1000.0 * t / steps
     value = B / (ms_step * 1e-3 * 1000)
     return {"value": value, "unit": "complexes/s", "cores": threads, "kind": "port",
             "sample": f"{steps} sampler steps of the real 1000-step schedule at B={B} (the reference's own per-call batch), "
                       f"oracle port of ccsd/src/solver.py on torch CPU fp32, {ms_step:.1f} ms/step, extrapolated to 1000 steps",
-            "ms_per_step": ms_step, "batch": B}
+            "ms_per_step": ms_step, "batch": B, "steps": steps, "warmup": 1}
 
 
 def run_reference(args):
@@ -253,11 +291,14 @@ def run_reference(args):
         return
     t0 = time.perf_counter()
     # steps/warmup are honoured as bounded samples: each "step" is one sampler iteration at the CPU batch
-    cb = cpu_baseline(args.workload, budget_s=float(os.environ.get("CCSD_CPU_BUDGET_S", "45")))
+    # --steps K is honoured up to the time budget: the record carries the number of steps that were actually timed
+    cb = cpu_baseline(args.workload, budget_s=float(os.environ.get("CCSD_CPU_BUDGET_S", "45")), sampler=args.sampler,
+                      max_steps=max(2, args.steps))
     wname, B_gpu, _ = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": "sampled complexes/sec (full PC sampler)", "value": cb["value"],
-        "unit": "complexes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "unit": "complexes/s", "n_gpus": args.gpus, "steps": cb["steps"], "warmup": cb["warmup"],
+        "steps_requested": args.steps,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic flags + torch CPU noise; shipped-checkpoint weights",
         "config": {"workload": f"{wname} PC sampler, CPU port of the reference at B={cb['batch']}", "timed": cb["sample"]},
@@ -300,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="community_small_cc", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: BASELINE size)")
+    ap.add_argument("--sampler", default=None, choices=["PC", "S4"], help="override the checkpoint's shipped sampler "
+                    "(BASELINE configs[2] words QM9_CC with S4; its sample_qm9_CC.yaml ships Reverse + Langevin)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=8)
     args = ap.parse_args()
@@ -309,6 +352,7 @@ def main():
     from ccsd_b200 import build as _build
     _build.build_cuda()  # no-op when the in-tree .so is current
     from ccsd_b200.solver import Engine, get_pc_sampler, S4_solver, quantize
+    from ccsd_b200.shard import gather_rows, sharded_sample
     from ccsd_b200 import sde as bsde
 
     if not torch.cuda.is_available():
@@ -329,17 +373,20 @@ def main():
     mk = {"VP": bsde.VPSDE, "VE": bsde.VESDE, "subVP": bsde.subVPSDE}
     sdes = [mk[s[k]["type"]](s[k]["beta_min"], s[k]["beta_max"], s[k]["num_scales"]) for k in keys]
     sh = meta["shipped_sampler"]
+    pred, corr = shipped_sampler(meta, args.sampler)
     shapes = shapes_of(meta, B)
-    sampler = "S4" if sh["predictor"] == "S4" else "PC"
+    sampler = "S4" if pred == "S4" else "PC"
+    n_eval = 2 if (sampler == "PC" and corr == "Langevin") else 1
     n_total = sdes[1].N
     K_steps = max(1, min(args.steps, n_total))
     flags_host = make_flags(N, B, seed=rank).pin_memory()
     flags = flags_host.to(dev, non_blocking=True)
-    eng = Engine(holders, sdes, shapes, sampler=sampler, predictor=sh["predictor"], corrector=sh["corrector"],
-                 snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1, denoise=True, eps=1e-4, device=dev, d_min=d_min,
-                 d_max=d_max)
+    ekw = dict(sampler=sampler, predictor=pred, corrector=corr, snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1,
+               denoise=True, eps=1e-4, device=dev, d_min=d_min, d_max=d_max)
+    eng = Engine(holders, sdes, shapes, **ekw)
     if eng.traj_bytes() <= Engine.TRAJ_LIMIT_BYTES:
         eng.enable_traj()  # the reference records sample 0 every step (solver.py:1149-1165); so do we
+    sizes = [B] * world
 
     def barrier():
         if world > 1:
@@ -347,13 +394,10 @@ def main():
         torch.cuda.synchronize()
 
     def gather(outs):
-        """single NCCL gather of the (quantised) results, BASELINE.json north_star"""
+        """single NCCL gather of the (quantised) results, BASELINE.json north_star (ccsd_b200/shard.py)"""
         if world == 1:
-            return
-        q = [outs[0]] + [quantize(t) for t in outs[1:]]
-        for t in q:
-            bufs = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(bufs, t)
+            return outs
+        return [gather_rows(outs[0], sizes)] + [gather_rows(quantize(t), sizes) for t in outs[1:]]
 
     # warm-up: W untimed steps
     eng.init(flags, seed=1234, sample_offset=rank * B)
@@ -383,22 +427,51 @@ def main():
     ms_per_step = ms / K_steps
     value = (B * world) / (ms_per_step * 1e-3 * n_total)
 
-    # ---- e2e: public API, host buffers, H2D of the inputs and D2H of the results in the timed region
+    # ---- e2e: the public API a user calls -- sampler factory (+ shard.sharded_sample on several GPUs) -- with HOST
+    # buffers: pinned flags in (H2D), results quantised on the device as the reference does right after sampling
+    # (sampler.py:531-543; x stays fp32) and copied to pinned host memory (D2H), everything inside the timed region.
+    # On N GPUs every rank copies ITS shard of the gathered result (the downstream graph conversion is per-sample CPU
+    # work of that rank's process).
     fac = S4_solver if sampler == "S4" else get_pc_sampler
-    kw = dict(predictor=sh["predictor"], corrector=sh["corrector"], snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1,
+    kw = dict(predictor=pred, corrector=corr, snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1,
               probability_flow=False, continuous=True, denoise=True, eps=1e-4, device=dev)
-    if meta["is_cc"]:
-        kw.update(is_cc=True, sde_rank2=sdes[2], shape_rank2=shapes[2], d_min=d_min, d_max=d_max)
     del eng
     torch.cuda.empty_cache()
-    fn = fac(sdes[0], sdes[1], shapes[0], shapes[1], **kw)
-    host_out = [torch.empty(sh_, dtype=torch.float32).pin_memory() for sh_ in shapes]
-    fn(*holders, flags_host.to(dev, non_blocking=True), seed=1, sample_offset=rank * B, max_steps=3)  # builds the plan
+
+    def make_sampler(b):
+        k2 = dict(kw)
+        sh3 = shapes_of(meta, b)
+        if meta["is_cc"]:
+            k2.update(is_cc=True, sde_rank2=sdes[2], shape_rank2=sh3[2], d_min=d_min, d_max=d_max)
+        return fac(sdes[0], sdes[1], sh3[0], sh3[1], **k2)
+
+    cache = {}
+
+    def sampler_of(b):   # one plan per shard size (the factory's own cache lives in the returned callable)
+        if b not in cache:
+            cache[b] = make_sampler(b)
+        return cache[b]
+
+    host_out = [torch.empty(shapes[0], dtype=torch.float32).pin_memory()] + \
+               [torch.empty(sh_, dtype=torch.uint8).pin_memory() for sh_ in shapes[1:]]
+    all_flags_host = torch.cat([make_flags(N, B, seed=r) for r in range(world)]).pin_memory() if world > 1 else flags_host
+
+    def e2e_call(seed, steps):
+        fl = all_flags_host.to(dev, non_blocking=True)                                    # H2D
+        if world > 1:
+            res = sharded_sample(sampler_of, holders, fl, seed=seed, quantize_fn=quantize, max_steps=steps, record_traj=True)
+            res = [t[rank * B:(rank + 1) * B] for t in res]
+        else:
+            out = sampler_of(B)(*holders, fl, seed=seed, sample_offset=0, max_steps=steps)
+            res = [out[0]] + [quantize(t) for t in out[1:len(shapes)]]
+        for h, t in zip(host_out, res):
+            h.copy_(t, non_blocking=True)                                                 # D2H
+        return res
+
+    e2e_call(1, 3)   # builds the plan
     barrier()
     t0 = time.perf_counter()
-    res = fn(*holders, flags_host.to(dev, non_blocking=True), seed=1234, sample_offset=rank * B, max_steps=K_steps)
-    for h, t in zip(host_out, res[: len(shapes)]):
-        h.copy_(t, non_blocking=True)
+    e2e_call(1234, K_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -406,16 +479,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = (B * world) / (e2e_s / K_steps * n_total)
-    h2d = flags_host.numel() * 4
-    d2h = sum(int(np.prod(s_)) for s_ in shapes) * 4
+    h2d = all_flags_host.numel() * 4
+    d2h = sum(h.numel() * h.element_size() for h in host_out)
+    cache.clear()
+    torch.cuda.empty_cache()
 
-    # ---- per-kernel device times (CUDA events on the launching stream) + roofline of the dominant kernel
+    # ---- per-kernel device times (CUDA events on the launching stream) + roofline of the dominant unit and of the step
     roofline = None
     prof_summary = {}
     if rank == 0:
-        eng2 = Engine(holders, sdes, shapes, sampler=sampler, predictor=sh["predictor"], corrector=sh["corrector"],
-                      snr=sh["snr"], scale_eps=sh["scale_eps"], n_steps=1, denoise=True, eps=1e-4, device=dev,
-                      d_min=d_min, d_max=d_max)
+        eng2 = Engine(holders, sdes, shapes, **ekw)
         eng2.init(flags, seed=1234, sample_offset=0)
         eng2.run(0, 3)
         torch.cuda.synchronize()
@@ -428,7 +501,6 @@ def main():
             a[0] += t
             a[1] += 1
         tot = sum(v[0] for v in prof_summary.values()) or 1.0
-        dom = max(prof_summary, key=lambda k_: prof_summary[k_][0])
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         src = "measured (MEASURED_PEAKS.json, sustained)"
@@ -439,41 +511,62 @@ def main():
             src = "fallback (B200_PROFILING.md)"
         work = kernel_alg_work(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
         peak_hbm = peaks.get("hbm_gbs", 6650.0)
-        XA = ("x_net_kernel", "tc_xfin_kernel", "attn_channel_kernel", "tc_attn_kernel", "attn_finish_kernel", "proj1_kernel", "hodge_kernel", "hodge_base_kernel", "afinal_kernel",
-              "tc_afinal_kernel", "big_prep_kernel", "big_pow_kernel", "big_deg_kernel", "big_xw_kernel", "big_agg_kernel", "tc_agg_kernel", "big_attn_kernel",
-              "big_node_kernel", "big_edge_kernel", "big_edge_pair_kernel", "big_mirror_kernel", "big_final_kernel", "big_xfin_kernel")
+        XA = ("x_net_kernel", "tc_xfin_kernel", "attn_channel_kernel", "tc_attn_kernel", "attn_finish_kernel", "proj1_kernel", "hodge_kernel",
+              "hodge_base_kernel", "afinal_kernel", "tc_afinal_kernel", "big_prep_kernel", "big_pow_kernel", "big_deg_kernel", "big_xw_kernel",
+              "big_agg_kernel", "tc_agg_kernel", "big_attn_kernel", "big_node_kernel", "big_edge_kernel", "big_edge_pair_kernel",
+              "big_mirror_kernel", "big_final_kernel", "big_xfin_kernel")
+        R2 = ("tc_gram_kernel", "gram_kernel", "tc_apply_kernel", "apply_kernel", "tc_r2big_kernel")
         kern = {}
         for k_, v in prof_summary.items():
             ms_l = v[0] / v[1]
             fl, by = work.get(k_, (0, 0))
             kern[k_] = {"ms_per_launch": ms_l, "launches": v[1], "share": v[0] / tot,
                         "alg_tflops": fl / (ms_l * 1e-3) / 1e12, "alg_gbs": by / (ms_l * 1e-3) / 1e9}
-        # the x / adj network pipeline as ONE unit of work (its five kernels implement one score evaluation)
+        # the x / adj network pipeline as ONE unit of work (its kernels implement one score evaluation); likewise the
+        # rank-2 passes (Gram + apply passes of one step)
         xa_ms = sum(prof_summary[k_][0] for k_ in XA if k_ in prof_summary)
-        n_eval = prof_summary.get("x_net_kernel", prof_summary.get("big_prep_kernel", [0, 0]))[1]
-        if n_eval:
-            kern["xa_pipeline"] = {"ms_per_launch": xa_ms / n_eval, "launches": n_eval, "share": xa_ms / tot,
-                                   "alg_tflops": work["xa_pipeline"][0] / (xa_ms / n_eval * 1e-3) / 1e12, "alg_gbs": 0.0,
+        r2_ms = sum(prof_summary[k_][0] for k_ in R2 if k_ in prof_summary)
+        n_evals = n_eval * args.profile_steps
+        x_fl, a_fl = xa_flops_split(meta)
+        xa_alg = SURVEY_8D_XA_FLOPS.get(wname, x_fl + a_fl)
+        if xa_ms:
+            kern["xa_pipeline"] = {"ms_per_launch": xa_ms / n_evals, "launches": n_evals, "share": xa_ms / tot,
+                                   "alg_tflops": B * xa_alg / (xa_ms / n_evals * 1e-3) / 1e12, "alg_gbs": 0.0,
                                    "kernels": [k_ for k_ in XA if k_ in prof_summary]}
-        dom = max((k_ for k_ in prof_summary), key=lambda k_: prof_summary[k_][0])
-        avg_ms = prof_summary[dom][0] / prof_summary[dom][1]
-        fl, by = work.get(dom, (0, 0))
+        Fs, Bs, wsrc = step_alg_work(meta, wname, n_eval)
+        if r2_ms:
+            kern["rank2_passes"] = {"ms_per_launch": r2_ms / args.profile_steps, "launches": args.profile_steps, "share": r2_ms / tot,
+                                    "alg_tflops": B * n_eval * 4.0 * E * E * K / (r2_ms / args.profile_steps * 1e-3) / 1e12,
+                                    "alg_gbs": B * 8.0 * E * K / (r2_ms / args.profile_steps * 1e-3) / 1e9,
+                                    "kernels": [k_ for k_ in R2 if k_ in prof_summary]}
+        # dominant UNIT by aggregated time: the x/adj pipeline (tensor roofline) or the rank-2 passes (HBM roofline)
         traffic = None
         tf = ROOT / "profiles" / "ncu_traffic.json"
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get(wname, {}).get(dom)
-        if by:   # a kernel that streams the rank-2 state: HBM roofline
-            if dom == "tc_apply_kernel" and sampler == "PC" and sh["corrector"] == "Langevin":
+            traffic = json.loads(tf.read_text()).get(wname, {})
+        if r2_ms >= xa_ms:
+            dom = max((k_ for k_ in R2 if k_ in prof_summary), key=lambda k_: prof_summary[k_][0])
+            avg_ms = prof_summary[dom][0] / prof_summary[dom][1]
+            fl, by = work.get(dom, (0, 0))
+            if dom == "tc_apply_kernel" and sampler == "PC" and corr == "Langevin":
                 by = (work["tc_apply_kernel:norm"][1] + 2 * work["tc_apply_kernel"][1]) / 3.0   # NORM, CORR, PRED passes
             ach = by / (avg_ms * 1e-3) / 1e9
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
-                        "traffic": traffic, "peak_source": src.replace("sustained", "hbm_gbs"), "avg_launch_ms": avg_ms,
-                        "algorithmic_bytes_per_launch": by}
+            roofline = {"unit_of_work": "rank2_passes", "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
+                        "frac": ach / peak_hbm, "traffic": (traffic or {}).get(dom), "peak_source": src.replace("sustained", "hbm_gbs"),
+                        "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": by, "share_of_step": prof_summary[dom][0] / tot,
+                        "unit_share_of_step": r2_ms / tot}
         else:
-            ach = fl / (avg_ms * 1e-3) / 1e12
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                        "traffic": traffic, "peak_source": src, "avg_launch_ms": avg_ms}
-        roofline["share_of_step"] = prof_summary[dom][0] / tot
+            avg_ms = xa_ms / n_evals
+            ach = B * xa_alg / (avg_ms * 1e-3) / 1e12
+            roofline = {"unit_of_work": "xa_pipeline", "kernel": "xa_pipeline (all kernels of one score evaluation of the x / adj networks)",
+                        "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                        "peak_source": src, "avg_launch_ms": avg_ms, "algorithmic_flops_per_launch": B * xa_alg,
+                        "share_of_step": xa_ms / tot, "unit_share_of_step": xa_ms / tot}
+        # the WHOLE step against both rooflines (F_alg and Bytes_alg per sample and step)
+        step_s = ms_per_step * 1e-3
+        roofline["step_frac_tensor"] = B * Fs / step_s / (peak_tf * 1e12)
+        roofline["step_frac_hbm"] = B * Bs / step_s / (peak_hbm * 1e9)
+        roofline["step_alg"] = {"flops_per_sample_step": Fs, "bytes_per_sample_step": Bs, "source": wsrc}
         roofline["kernels"] = kern
         del eng2
 
@@ -483,7 +576,7 @@ def main():
             "n_gpus": world, "steps": K_steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "us_per_score_step": ms_per_step * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic node-count flags + Philox noise; shipped-checkpoint weights (tests/golden)",
-            "config": {"workload": f"{wname}: N={N} F={F} E={E} K={K}, {sampler} sampler {sh['predictor']}+{sh['corrector']} "
+            "config": {"workload": f"{wname}: N={N} F={F} E={E} K={K}, {sampler} sampler {pred}+{corr} "
                                    f"snr={sh['snr']} scale_eps={sh['scale_eps']}, {n_total}-step schedule, batch {B} per GPU",
                        "global_batch": B * world, "parallelism": f"dp{world} (batch shards, no per-step collective, one NCCL gather)",
                        "l2": ("state per step (rank-2 tensors) is larger than L2; no flush needed" if meta["is_cc"] else
@@ -491,11 +584,14 @@ def main():
                        "timed": f"{K_steps} sampler steps incl. prior sampling" + (" = the whole sampler run" if K_steps == n_total else " (scaled to 1000)")},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "complexes/s", "h2d_bytes_per_step": h2d / K_steps, "d2h_bytes_per_step": d2h / K_steps,
-                    "seconds": e2e_s, "call": "ccsd_b200.get_pc_sampler(...)(models, init_flags) with pinned host flags in, pinned host results out"},
+                    "seconds": e2e_s,
+                    "call": ("ccsd_b200.get_pc_sampler / S4_solver(...)(models, init_flags)" + (" through ccsd_b200.shard.sharded_sample" if world > 1 else "") +
+                             ": pinned host flags in, ccsd_b200.quantize of adj / rank2 on the device (sampler.py:531-543), x fp32 + "
+                             "adj / rank2 uint8 to pinned host memory")},
             "roofline": roofline,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload).items() if k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload, sampler=args.sampler).items() if k in ("value", "unit", "cores", "kind", "sample")}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

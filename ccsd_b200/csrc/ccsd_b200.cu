@@ -145,7 +145,7 @@ static int validate(const ccsd_plan_desc_t &d, size_t nw) {
     return fail(CCSD_ERR_UNSUPPORTED, "max_node_num > 64 is only supported for graph-only plans (the large-graph pipeline has no hodge branch)");
   if (d.N > 1024) return fail(CCSD_ERR_UNSUPPORTED, "max_node_num > 1024 is not supported");
   if (d.sampler != CCSD_SAMPLER_PC && d.sampler != CCSD_SAMPLER_S4) return fail(CCSD_ERR_INVALID, "unknown sampler");
-  if (d.n_lang_steps != 1) return fail(CCSD_ERR_UNSUPPORTED, "Langevin n_steps != 1 is not implemented");
+  if (d.n_lang_steps < 1 || d.n_lang_steps > 16) return fail(CCSD_ERR_UNSUPPORTED, "Langevin n_steps must be in 1..16");
   if (d.n_diff_steps < 1) return fail(CCSD_ERR_INVALID, "n_diff_steps must be >= 1");
   const ccsd_netx_t &X = d.netx;
   if (d.nets & 1) {
@@ -562,36 +562,25 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     }
   }
 #ifndef CCSD_EMU
-  // the attribute is per function, not per plan: only ever raise it (several plans may coexist)
-  static size_t xp_attr = 0, apply_attr = 0, big_attr = 0;
-  cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-  if (XL.big) {
-    if (xp_max > big_attr) {
-      e1 = cudaFuncSetAttribute(big_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(big_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(big_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(big_xfin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-      if (e1 == cudaSuccess) big_attr = xp_max;
+  // the attribute is per (function, device), not per plan: only ever raise it (several plans may coexist)
+  {
+    static CcsdSmemAttr at_big[4], at_xp[6], at_apply[4];
+    int bad = 0;
+    if (XL.big) {
+      bad |= ccsd_ensure_smem(big_node_kernel, xp_max, at_big[0]) | ccsd_ensure_smem(big_edge_kernel, xp_max, at_big[1]) |
+             ccsd_ensure_smem(big_final_kernel, xp_max, at_big[2]) | ccsd_ensure_smem(big_xfin_kernel, xp_max, at_big[3]);
+    } else {
+      bad |= ccsd_ensure_smem(x_net_kernel, xp_max, at_xp[0]) | ccsd_ensure_smem(attn_channel_kernel, xp_max, at_xp[1]) |
+             ccsd_ensure_smem(attn_finish_kernel, xp_max, at_xp[2]) | ccsd_ensure_smem(hodge_kernel, xp_max, at_xp[3]) |
+             ccsd_ensure_smem(hodge_base_kernel, xp_max, at_xp[4]) | ccsd_ensure_smem(afinal_kernel, xp_max, at_xp[5]);
     }
-  } else if (xp_max > xp_attr) {
-    e1 = cudaFuncSetAttribute(x_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hodge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hodge_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xp_max);
-    if (e1 == cudaSuccess) xp_attr = xp_max;
-  }
-  if (d.is_cc && !p->apply_big && p->apply_smem > apply_attr) {
-    e2 = cudaFuncSetAttribute(apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->apply_smem);
-    if (e2 == cudaSuccess) apply_attr = p->apply_smem;
-  }
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    delete p;
-    return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    if (d.is_cc && !p->apply_big)
+      bad |= ccsd_ensure_smem(apply_kernel<0>, p->apply_smem, at_apply[0]) | ccsd_ensure_smem(apply_kernel<1>, p->apply_smem, at_apply[1]) |
+             ccsd_ensure_smem(apply_kernel<2>, p->apply_smem, at_apply[2]) | ccsd_ensure_smem(apply_kernel<4>, p->apply_smem, at_apply[3]);
+    if (bad) {
+      delete p;
+      return fail(CCSD_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(cudaGetLastError()));
+    }
   }
   p->use_tc = d.is_cc ? tc_gram_supported(d.E, d.K, p->hp.PR0) : 0;
   if (p->use_tc) {   // small complexes: stack G samples per Gram work unit
@@ -622,7 +611,13 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   return 0;
 }
 
-void ccsd_plan_destroy(ccsd_plan_t *plan) { delete plan; }
+void ccsd_plan_destroy(ccsd_plan_t *plan) {
+  if (!plan) return;
+#ifndef CCSD_EMU
+  for (auto &r : plan->prof) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
+#endif
+  delete plan;
+}
 
 size_t ccsd_plan_workspace_bytes(const ccsd_plan_t *plan) { return plan ? ws_layout(plan).total : 0; }
 
@@ -945,53 +940,89 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     return dev_check("apply pass");
   };
   // x / adj networks (+ the Gram pre-pass their hodge branch and the rank-2 network need)
-  auto score_phase = [&](int mode, int slot, int r2_mode) -> int {
-    if (d.is_cc)
-      if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
+  auto xa_phase = [&](int mode, int slot, int which, const float *xin, const float *adjin) -> int {
     XaArgs a; memset(&a, 0, sizeof a);
-    a.x = p->x; a.adj = p->adj; a.flags = p->flags; a.P0 = p->P0; a.P1 = p->P1; a.r2 = p->r2;
-    a.mode = mode; a.which = 3; a.slot = slot; a.denoise = d.denoise; a.nz = nz;
+    a.x = xin; a.adj = adjin; a.flags = p->flags; a.P0 = p->P0; a.P1 = p->P1; a.r2 = p->r2;
+    a.mode = mode; a.which = which; a.slot = slot; a.denoise = d.denoise; a.nz = nz;
     a.norm_part = p->norm_part;
     a.noise_x = nx ? nx + (size_t)slot * sx : nullptr;
     a.noise_adj = nadj ? nadj + (size_t)slot * sa : nullptr;
     if (mode == MODE_SCORE) { a.out_x = p->sx; a.out_adj = p->sadj; }
     else { a.out_x = p->x; a.out_adj = p->adj; a.mean_x = p->mx; a.mean_adj = p->madj; a.traj_x = tx; a.traj_adj = ta; }
-    if (int r = launch_xa(p, a, stream)) return r;
+    return launch_xa(p, a, stream);
+  };
+  auto score_phase = [&](int mode, int slot, int r2_mode) -> int {
+    if (d.is_cc)
+      if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
+    if (int r = xa_phase(mode, slot, 3, p->x, p->adj)) return r;
     if (d.is_cc) return apply_pass(r2_mode, slot);
     return 0;
   };
-  // Langevin step sizes, then the corrector update (PC: x and adj here, the rank-2 state in its own CORR
-  // apply pass) or the whole S4 chain for every object
-  auto update_phase = [&](int nobj) -> int {
-    CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4;
+  // Langevin / S4 step sizes of the objects in obj_mask from the batch means of their norm partials
+  auto coef_phase = [&](int obj_mask) -> int {
+    CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4; c.obj_mask = obj_mask;
     PROF_BEGIN(p, "coef_kernel", stream);
     CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
     PROF_END(p, stream);
+    p->launches++;
+    return dev_check("coef_kernel");
+  };
+  // the corrector update of objects [obj0, obj0 + nobj) with noise draw `slot` (PC: x and / or adj here, the rank-2
+  // state in its own CORR apply pass) or the whole S4 chain for every object
+  auto update_phase = [&](int obj0, int nobj, int slot) -> int {
     UpdateArgs u; memset(&u, 0, sizeof u);
     u.flags = p->flags; u.x = p->x; u.adj = p->adj; u.r2 = p->r2; u.sx = p->sx; u.sadj = p->sadj; u.sr2 = p->sr2;
     u.coef = p->coef; u.mx = p->mx; u.madj = p->madj; u.mr2 = p->mr2; u.nx = nx; u.nadj = nadj; u.nr2 = nr2;
     u.tx = tx; u.tadj = ta; u.tr2 = tr; u.s4 = s4; u.denoise = d.denoise; u.write_mean_r2 = write_mean; u.nz = nz;
-    const size_t units = nobj == 3 ? (size_t)d.B * d.E * (p->hp.Kp / 4) : sa;
+    u.obj0 = obj0; u.slot0 = slot;
+    const size_t units = obj0 + nobj == 3 ? (size_t)d.B * d.E * (p->hp.Kp / 4) : (obj0 + nobj == 2 ? sa : sx);
     PROF_BEGIN(p, "update_kernel", stream);
     CCSD_LAUNCH(update_kernel, dim3(grid_for(units), nobj, 1), 256, 0, stream, p->dP, u);
     PROF_END(p, stream);
-    p->launches += 2;
+    p->launches++;
     return dev_check("update phase");
   };
 
   if (s4) {
     if (int r = score_phase(MODE_SCORE, 0, MODE_SCORE)) return r;
-    return update_phase(d.is_cc ? 3 : 2);
+    if (int r = coef_phase(7)) return r;
+    return update_phase(0, d.is_cc ? 3 : 2, 0);
   }
   int slot = 0;
   if (d.use_corrector) {
+    const int n = d.n_lang_steps;
     // corrector: the rank-2 score is never written to HBM -- a NORM pass produces the norms, and after
     // the step sizes are known a CORR pass recomputes the score and updates the state in place
     if (int r = score_phase(MODE_SCORE, 0, MODE_NORM)) return r;
-    if (int r = update_phase(2)) return r;
-    if (d.is_cc)
+    if (int r = coef_phase(7)) return r;
+    if (n > 1) {
+      // LangevinCorrector.update_fn loops n_steps times PER OBJECT, every object's loop seeing the other objects
+      // at their PRE-corrector values (solver.py:692-701, 760-785; the three correctors are called with the same
+      // x, adj, rank2, :1123-1140).  The mean buffers are free during the corrector: they keep x0 / adj0.
+      if (int r = dev_copy(p->mx, p->x, sx * 4, stream)) return r;
+      if (int r = dev_copy(p->madj, p->adj, sa * 4, stream)) return r;
+    }
+    if (int r = update_phase(0, 2, 0)) return r;
+    for (int s = 1; s < n; ++s) {   // x: score_x(x_s, adj0)
+      if (int r = xa_phase(MODE_SCORE, s, 1, p->x, p->madj)) return r;
+      if (int r = coef_phase(1)) return r;
+      if (int r = update_phase(0, 1, s)) return r;
+    }
+    for (int s = 1; s < n; ++s) {   // adj: score_adj(x0, adj_s, rank2_0); the Gram products of rank2_0 are still in H / P0
+      if (int r = xa_phase(MODE_SCORE, s, 2, p->mx, p->adj)) return r;
+      if (int r = coef_phase(2)) return r;
+      if (int r = update_phase(1, 1, s)) return r;
+    }
+    if (d.is_cc) {
       if (int r = apply_pass(MODE_CORR, 0)) return r;
-    slot = d.n_lang_steps;
+      for (int s = 1; s < n; ++s) {   // rank2: score_rank2(rank2_s) (ScoreNetworkF ignores x and adj)
+        if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
+        if (int r = apply_pass(MODE_NORM, s)) return r;
+        if (int r = coef_phase(4)) return r;
+        if (int r = apply_pass(MODE_CORR, s)) return r;
+      }
+    }
+    slot = n;
   }
   return score_phase(MODE_PRED, slot, MODE_PRED);
 }

@@ -21,6 +21,21 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#ifndef CCSD_EMU
+#include <cuda_runtime.h>
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, DEVICE): remember what was raised on each device so
+// that plans on several devices of one process all get the limit they need (only ever raised, several plans coexist).
+struct CcsdSmemAttr { size_t v[64] = {0}; };
+template <class F> static inline int ccsd_ensure_smem(F func, size_t bytes, CcsdSmemAttr &rec) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (bytes <= rec.v[dev]) return 0;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+  rec.v[dev] = bytes;
+  return 0;
+}
+#endif
+
 #ifdef CCSD_EMU
 #include <cmath>
 #include <cstdlib>
@@ -197,9 +212,9 @@ __device__ __forceinline__ float normal1(uint64_t seed, uint64_t sample, uint32_
   return z[idx & 3];
 }
 
-// draw ids: object in the top bits, (step+1)*4 + slot below; the prior uses step = -1.
+// draw ids: object in the top bits, (step+1)*32 + slot below; the prior uses step = -1.
 __device__ __forceinline__ uint32_t draw_id(int obj, int step, int slot) {
-  return ((uint32_t)obj << 28) | (uint32_t)((step + 1) * 4 + slot);
+  return ((uint32_t)obj << 28) | (uint32_t)((step + 1) * 32 + slot);   // slot < 32: Langevin inner steps + predictor
 }
 
 }  // namespace ccsd

@@ -818,6 +818,7 @@ struct CoefArgs {
   const float *norm_part;  // [3][B][ntile_max][2]
   float *coef;             // [3][2]
   int step, s4;
+  int obj_mask;            // bit k: compute object k's step sizes (the others keep their previous values)
 };
 
 CCSD_KERNEL void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ P, CoefArgs a) {
@@ -825,6 +826,7 @@ CCSD_KERNEL void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ 
   const ccsd_plan_desc_t &d = P->d;
   const int nobj = d.is_cc ? 3 : 2;
   for (int obj = 0; obj < nobj; ++obj) {
+    if (!((a.obj_mask >> obj) & 1)) continue;   // uniform branch
     const int nt = (obj == 2) ? P->ntile_r2 : (obj == 1 ? P->ntile_adj : P->ntile_x);
     float gs = 0.f, zs = 0.f;
     for (int b = threadIdx.x; b < d.B; b += blockDim.x) {
@@ -860,6 +862,8 @@ struct UpdateArgs {
   const float *nx, *nadj, *nr2;        // injected raw normals [n_draws][B][...] or nullptr
   float *tx, *tadj, *tr2;              // traj destinations (S4) or nullptr
   int s4, denoise, write_mean_r2;
+  int obj0;                            // first object of this launch (object = obj0 + blockIdx.y)
+  int slot0;                           // draw slot of the (first) noise draw: Langevin inner step (PC), 0 (S4)
   NoiseCtx nz;
 };
 
@@ -877,7 +881,7 @@ __device__ __forceinline__ float upd_elem(const ccsd_objcoef_t &co, float cs, fl
 CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict__ P, UpdateArgs a) {
   const ccsd_plan_desc_t &d = P->d;
   const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
-  const int obj = blockIdx.y;
+  const int obj = a.obj0 + blockIdx.y;
   const int ndraw = a.s4 ? 3 : 1;
   const ccsd_objcoef_t co = P->sched[a.nz.step * 3 + obj];
   const float cs = a.coef[obj * 2], cn = a.coef[obj * 2 + 1];
@@ -889,8 +893,8 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
       const float f = a.flags[(size_t)b * N + i];
       float z[3] = {0.f, 0.f, 0.f};
       for (int s = 0; s < ndraw; ++s)
-        z[s] = f * (a.nx ? a.nx[(size_t)s * tot + g]
-                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, a.nz.step, s), p));
+        z[s] = f * (a.nx ? a.nx[(size_t)(a.slot0 + s) * tot + g]
+                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, a.nz.step, a.slot0 + s), p));
       float mean;
       const float v = upd_elem(co, cs, cn, a.s4, a.x[g], a.sx[g], z, &mean);
       a.x[g] = v;
@@ -908,8 +912,8 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
       if (i != j) {
         const int q = (i < j) ? i * N + j : j * N + i;
         for (int s = 0; s < ndraw; ++s)
-          z[s] = f * (a.nadj ? a.nadj[(size_t)s * tot + (size_t)b * N * N + q]
-                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, a.nz.step, s), q));
+          z[s] = f * (a.nadj ? a.nadj[(size_t)(a.slot0 + s) * tot + (size_t)b * N * N + q]
+                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, a.nz.step, a.slot0 + s), q));
       }
       float mean;
       const float v = upd_elem(co, cs, cn, a.s4, a.adj[g], a.sadj[g], z, &mean);
@@ -932,14 +936,14 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
         for (int q = 0; q < 4; ++q) zz[s][q] = 0.f;
       if (!a.nr2)
         for (int s = 0; s < ndraw; ++s)
-          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, a.nz.step, s), (uint32_t)(e * Kg + kg), zz[s]);
+          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, a.nz.step, a.slot0 + s), (uint32_t)(e * Kg + kg), zz[s]);
       for (int q = 0; q < 4; ++q) {
         const int k = kg * 4 + q;
         if (k >= K) break;
         const size_t g = ((size_t)b * E + e) * K + k;
         const float m = fe * ((P->cell_mask[k] & zm) ? 0.f : 1.f);
         float z[3] = {0.f, 0.f, 0.f};
-        for (int s = 0; s < ndraw; ++s) z[s] = m * (a.nr2 ? a.nr2[(size_t)s * tot + g] : zz[s][q]);
+        for (int s = 0; s < ndraw; ++s) z[s] = m * (a.nr2 ? a.nr2[(size_t)(a.slot0 + s) * tot + g] : zz[s][q]);
         float mean;
         const float v = upd_elem(co, cs, cn, a.s4, a.r2[g], a.sr2[g], z, &mean);
         a.r2[g] = v;

@@ -335,11 +335,8 @@ static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const X
     ta.gs_base = a.g_stack;          // the caller passes the large-graph stack base in g_stack
     ta.gs_stride = hp.xp.big_total; ta.ldp = hp.xp.big_PS; ta.NT = hp.xp.big_PS;
   }
-  static size_t attr = 0;
-  if (ta.L.total > attr) {
-    if (cudaFuncSetAttribute(tc_afinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ta.L.total) != cudaSuccess) return -1;
-    attr = ta.L.total;
-  }
+  static CcsdSmemAttr attr;
+  if (ccsd_ensure_smem(tc_afinal_kernel, ta.L.total, attr)) return -1;
   const int ntiles = hp.d.B * ta.ntg;
   tc_afinal_kernel<<<ntiles < 148 ? ntiles : 148, TF_THREADS, ta.L.total, (cudaStream_t)stream>>>(dP, ta);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

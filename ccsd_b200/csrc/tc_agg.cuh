@@ -236,11 +236,8 @@ __global__ void __launch_bounds__(TGG_THREADS, 1) tc_agg_kernel(const DevPlan *_
 }
 
 static inline int tc_agg_launch(const DevPlan *dP, const DevPlan &hp, const BigArgs &g, void *stream) {
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(tc_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TGG_SMEM) != cudaSuccess) return -1;
-    attr = true;
-  }
+  static CcsdSmemAttr attr;
+  if (ccsd_ensure_smem(tc_agg_kernel, TGG_SMEM, attr)) return -1;
   const ccsd_attn_layer_t &ly = hp.d.neta.layer[g.layer];
   const int ntiles = hp.d.B * ly.c_in * ((hp.d.N + 127) / 128);
   tc_agg_kernel<<<ntiles < 148 ? ntiles : 148, TGG_THREADS, TGG_SMEM, (cudaStream_t)stream>>>(dP, g);

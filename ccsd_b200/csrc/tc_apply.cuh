@@ -576,12 +576,8 @@ struct TcApplyMaps {   // host side: tensor maps of the state read and the state
 #ifdef TC_APPLY_KERNEL_TU
 template <int FMODE, int MODE>
 static inline int tc_apply_launch_fm(const DevPlan *dP, int grid, const ApplyArgs &a, const TcApplyMaps &m, void *stream) {
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_apply_kernel<FMODE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TA_SMEM) != cudaSuccess)
-      return -1;
-    attr_set = true;
-  }
+  static CcsdSmemAttr attr;   // per instantiation
+  if (ccsd_ensure_smem(tc_apply_kernel<FMODE, MODE>, TA_SMEM, attr)) return -1;
   tc_apply_kernel<FMODE, MODE><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(dP, a, m.in, m.out, m.use_tma);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

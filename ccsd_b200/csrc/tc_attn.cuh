@@ -433,11 +433,8 @@ int tc_attn_launch(const DevPlan *dP, const DevPlan &hp, const XaArgs &a, const 
   if (nper < 1) nper = 1;
   if (nper > ngroups) nper = ngroups;
   ta.nper = nper;
-  static size_t attr = 0;
-  if (T.total > attr) {
-    if (cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total) != cudaSuccess) return -1;
-    attr = T.total;
-  }
+  static CcsdSmemAttr attr;
+  if (ccsd_ensure_smem(tc_attn_kernel, T.total, attr)) return -1;
   tc_attn_kernel<<<nper * ly.c_in, TT_THREADS, T.total, (cudaStream_t)stream>>>(dP, ta);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

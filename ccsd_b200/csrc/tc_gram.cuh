@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
 }
 
 static inline int tc_gram_prepare() {
-  if (cudaFuncSetAttribute(tc_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) != cudaSuccess) return -1;
-  return cudaFuncSetAttribute(tc_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM) == cudaSuccess ? 0 : -1;
+  static CcsdSmemAttr a0, a1;
+  if (ccsd_ensure_smem(tc_gram_kernel<false>, TG_SMEM, a0)) return -1;
+  return ccsd_ensure_smem(tc_gram_kernel<true>, TG_SMEM, a1);
 }
 
 static inline int tc_gram_launch(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, void *stream) {

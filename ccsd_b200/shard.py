@@ -26,7 +26,9 @@ def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def gather_rows(t: torch.Tensor, sizes: Sequence[int], group=None) -> torch.Tensor:
-    """All-gather row shards of different lengths (padded to the largest) and concatenate."""
+    """All-gather row shards (padded to the largest when their lengths differ) and concatenate.  One collective writing
+    straight into the result tensor (``all_gather_into_tensor``); the list API is only the fallback for backends
+    without it."""
     world = len(sizes)
     if world == 1:
         return t
@@ -34,9 +36,15 @@ def gather_rows(t: torch.Tensor, sizes: Sequence[int], group=None) -> torch.Tens
     pad = t
     if t.shape[0] < mx:
         pad = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))])
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad.contiguous(), group=group)
-    return torch.cat([b[:n] for b, n in zip(bufs, sizes)])
+    pad = pad.contiguous()
+    out = pad.new_empty((world * mx,) + tuple(pad.shape[1:]))
+    try:
+        dist.all_gather_into_tensor(out, pad, group=group)
+    except (RuntimeError, NotImplementedError):
+        dist.all_gather(list(out.view((world, mx) + tuple(pad.shape[1:])).unbind(0)), pad, group=group)
+    if all(n == mx for n in sizes):
+        return out
+    return torch.cat([out[r * mx:r * mx + n] for r, n in enumerate(sizes)])
 
 
 def sharded_sample(
@@ -58,14 +66,34 @@ def sharded_sample(
     if seed is None:
         s = torch.randint(0, 2 ** 62, (1,))
         if world > 1:
-            s = s.to(init_flags.device)
-            dist.broadcast(s, src=0, group=group)
+            # the collective's device: CUDA for NCCL (whatever device the flags live on), CPU for gloo
+            backend = dist.get_backend(group)
+            s = s.to(torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else "cpu")
+            src = dist.get_global_rank(group, 0) if group is not None else 0   # `src` is a GLOBAL rank
+            dist.broadcast(s, src=src, group=group)
         seed = int(s.item())
-    fn = make_sampler(hi - lo)
-    out = fn(*models, init_flags[lo:hi], seed=seed, sample_offset=lo, **kw)
-    n_obj = len(out) - 2
-    res = list(out[:n_obj])
+    sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
+    if hi > lo:
+        fn = make_sampler(hi - lo)
+        out = fn(*models, init_flags[lo:hi], seed=seed, sample_offset=lo, **kw)
+        n_obj = len(out) - 2
+        res = list(out[:n_obj])
+        if quantize_fn is not None:
+            res = [res[0]] + [quantize_fn(t) for t in res[1:]]
+    else:
+        # more ranks than samples: this rank has nothing to sample but still takes part in the gather.  It needs the
+        # per-object shapes / dtypes, which it gets from a one-sample dry construction of the sampler's outputs.
+        res = _empty_results(make_sampler, models, init_flags, quantize_fn, **kw)
+    return [gather_rows(t, sizes, group) for t in res]
+
+
+def _empty_results(make_sampler, models, init_flags, quantize_fn, **kw) -> List[torch.Tensor]:
+    """Zero-row tensors with the shapes / dtypes / device a non-empty shard would return (one sample, zero steps)."""
+    kw = dict(kw)
+    kw["max_steps"] = 0
+    kw["record_traj"] = False
+    out = make_sampler(1)(*models, init_flags[:1], seed=0, sample_offset=0, **kw)
+    res = list(out[: len(out) - 2])
     if quantize_fn is not None:
         res = [res[0]] + [quantize_fn(t) for t in res[1:]]
-    sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
-    return [gather_rows(t, sizes, group) for t in res]
+    return [t[:0] for t in res]

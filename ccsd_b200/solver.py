@@ -42,16 +42,24 @@ class InjectedNoise:
         self.prior, self.steps = list(prior), [list(s) for s in steps]
 
     @staticmethod
-    def from_flat_log(log: Sequence[torch.Tensor], n_obj: int, n_draws: int, n_steps: int) -> "InjectedNoise":
-        """Regroup a flat draw log in reference order: prior (one draw per object), then per step
-        ``n_draws`` rounds of one draw per object (corrector round, predictor round / the three S4
-        rounds) -- exactly the order solver.py consumes torch's generator."""
+    def from_flat_log(log: Sequence[torch.Tensor], n_obj: int, n_draws: int, n_steps: int,
+                      n_lang: Optional[int] = None) -> "InjectedNoise":
+        """Regroup a flat draw log in reference order: prior (one draw per object), then per step the draws in
+        the order solver.py consumes torch's generator.  S4 / PC with ``n_lang`` in (None, 1): ``n_draws`` rounds
+        of one draw per object.  PC + Langevin with ``n_lang`` inner steps: every corrector runs its whole loop
+        before the next object's (solver.py:692, 760, 1123-1140) -- x's n_lang draws, adj's, rank2's -- then one
+        predictor round."""
         prior = list(log[:n_obj])
         steps, pos = [], n_obj
         for _ in range(n_steps):
             chunk = log[pos:pos + n_draws * n_obj]
             pos += n_draws * n_obj
-            steps.append([torch.stack([chunk[dr * n_obj + k] for dr in range(n_draws)]) for k in range(n_obj)])
+            if n_lang is None or n_lang <= 1:
+                steps.append([torch.stack([chunk[dr * n_obj + k] for dr in range(n_draws)]) for k in range(n_obj)])
+            else:
+                assert n_draws == n_lang + 1
+                steps.append([torch.stack([chunk[k * n_lang + s] for s in range(n_lang)] + [chunk[n_obj * n_lang + k]])
+                              for k in range(n_obj)])
         return InjectedNoise(prior, steps)
 
 
@@ -94,6 +102,33 @@ class Engine:
         d.denoise = int(bool(denoise))
         d.n_diff_steps = int(sdes[1].N)
         d.snr, d.scale_eps = float(snr), float(scale_eps)
+        present, blob_host = self._pack(d, models)
+        d.nets = present if nets is None else nets
+        self.desc = d
+        self.n_obj = 3 if self.is_cc else 2
+        self.n_draws = 3 if sampler == "S4" else (d.n_lang_steps + 1 if d.use_corrector else 1)
+        self.sizes = [B * N * F, B * N * N] + ([B * d.E * d.K] if self.is_cc else [])
+        self.shapes = [tuple(int(v) for v in s) for s in shapes]
+        sched = build_schedule(list(sdes), sampler=sampler, predictor=predictor, probability_flow=probability_flow, eps=eps)
+        self.schedule = np.ascontiguousarray(sched, np.float32)
+        self._blob_host = blob_host
+        self._nets_arg = nets
+        with self._guard():
+            self.weights = torch.from_numpy(blob_host).to(self.device)
+            handle = C.c_void_p()
+            nat.check(self.lib.ccsd_plan_create(
+                C.byref(d), self.schedule.ctypes.data_as(C.c_void_p), self.weights.data_ptr(), self.weights.numel(), C.byref(handle)))
+            self.handle = handle
+            nbytes = int(self.lib.ccsd_plan_workspace_bytes(handle))
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = self.workspace.data_ptr()
+            self._ws_ptr = (base + 255) // 256 * 256
+            nat.check(self.lib.ccsd_plan_bind(handle, self._ws_ptr, nbytes, self._stream()))
+        self.traj: Optional[List[torch.Tensor]] = None
+
+    # -- helpers --
+    def _pack(self, d, models):
+        """Fill the topology part of descriptor `d` and return (present-network bits, packed fp32 blob)."""
         blob = packer.Blob()
         present = 0
         mx, ma = models[0], models[1]
@@ -107,27 +142,34 @@ class Engine:
         if mf is not None:
             packer.pack_netf(d.netf, blob, mf)
             present |= 4
-        d.nets = present if nets is None else nets
-        self.desc = d
-        self.n_obj = 3 if self.is_cc else 2
-        self.n_draws = 3 if sampler == "S4" else (d.n_lang_steps + 1 if d.use_corrector else 1)
-        self.sizes = [B * N * F, B * N * N] + ([B * d.E * d.K] if self.is_cc else [])
-        self.shapes = [tuple(int(v) for v in s) for s in shapes]
-        sched = build_schedule(list(sdes), sampler=sampler, predictor=predictor, probability_flow=probability_flow, eps=eps)
-        self.schedule = np.ascontiguousarray(sched, np.float32)
-        self.weights = torch.from_numpy(blob.finish()).to(self.device)
-        handle = C.c_void_p()
-        nat.check(self.lib.ccsd_plan_create(
-            C.byref(d), self.schedule.ctypes.data_as(C.c_void_p), self.weights.data_ptr(), self.weights.numel(), C.byref(handle)))
-        self.handle = handle
-        nbytes = int(self.lib.ccsd_plan_workspace_bytes(handle))
-        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
-        base = self.workspace.data_ptr()
-        self._ws_ptr = (base + 255) // 256 * 256
-        nat.check(self.lib.ccsd_plan_bind(handle, self._ws_ptr, nbytes, self._stream()))
-        self.traj: Optional[List[torch.Tensor]] = None
+        return present, blob.finish()
 
-    # -- helpers --
+    def refresh_weights(self, models: Sequence[Any]) -> bool:
+        """Re-read the models' CURRENT parameters (the reference reads the live modules on every call: an EMA
+        ``copy_to``, ``load_state_dict`` or optimizer step between two calls must be seen).  Returns False when the
+        topology changed, i.e. the plan has to be rebuilt; otherwise uploads the blob if any weight differs."""
+        d2 = nat.PlanDesc()
+        C.memmove(C.byref(d2), C.byref(self.desc), C.sizeof(nat.PlanDesc))
+        C.memset(C.byref(d2.netx), 0, C.sizeof(d2.netx)); C.memset(C.byref(d2.neta), 0, C.sizeof(d2.neta))
+        C.memset(C.byref(d2.netf), 0, C.sizeof(d2.netf))
+        present, blob = self._pack(d2, models)
+        d2.nets = present if self._nets_arg is None else self._nets_arg
+        if bytes(d2) != bytes(self.desc) or blob.shape != self._blob_host.shape:
+            return False
+        if not np.array_equal(blob, self._blob_host):
+            # folded constants of the affine ScoreNetworkF live in the descriptor: covered by the bytes() comparison above
+            self._blob_host = blob
+            with self._guard():
+                self.weights.copy_(torch.from_numpy(blob), non_blocking=False)
+        return True
+
+    def _guard(self):
+        """Every ABI call launches on the CURRENT device: make it the engine's (a plan on cuda:1 must not launch on cuda:0)."""
+        if self.device.type == "cuda":
+            return torch.cuda.device(self.device)
+        import contextlib
+        return contextlib.nullcontext()
+
     def _stream(self):
         if self.device.type == "cuda":
             return torch.cuda.current_stream(self.device).cuda_stream
@@ -162,6 +204,10 @@ class Engine:
         nat.check(self.lib.ccsd_plan_set_traj(
             self.handle, _ptr(self.traj[0]), _ptr(self.traj[1]), _ptr(self.traj[2]) if self.is_cc else None))
 
+    def disable_traj(self) -> None:
+        self.traj = None
+        nat.check(self.lib.ccsd_plan_set_traj(self.handle, None, None, None))
+
     def init(self, flags: torch.Tensor, prior: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
              sample_offset: int = 0) -> None:
         d = self.desc
@@ -175,8 +221,9 @@ class Engine:
             if p is not None and tuple(p.shape) != s:
                 raise ValueError(f"prior shape {tuple(p.shape)} != {s}")
         self._keep = (fl, pr)
-        nat.check(self.lib.ccsd_plan_init(self.handle, _ptr(fl), _ptr(pr[0]), _ptr(pr[1]), _ptr(pr[2]),
-                                          C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(sample_offset), self._stream()))
+        with self._guard():
+            nat.check(self.lib.ccsd_plan_init(self.handle, _ptr(fl), _ptr(pr[0]), _ptr(pr[1]), _ptr(pr[2]),
+                                              C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(sample_offset), self._stream()))
 
     def step(self, i: int, noise: Optional[Sequence[torch.Tensor]] = None) -> None:
         nz = [None] * 3
@@ -187,15 +234,18 @@ class Engine:
                     raise ValueError(f"noise[{k}] has {t.numel()} elements, expected {self.n_draws} x {self.sizes[k]}")
                 nz[k] = t
         self._keep_noise = nz
-        nat.check(self.lib.ccsd_plan_step(self.handle, int(i), _ptr(nz[0]), _ptr(nz[1]), _ptr(nz[2]), self._stream()))
+        with self._guard():
+            nat.check(self.lib.ccsd_plan_step(self.handle, int(i), _ptr(nz[0]), _ptr(nz[1]), _ptr(nz[2]), self._stream()))
 
     def run(self, begin: int, end: int) -> None:
-        nat.check(self.lib.ccsd_plan_run(self.handle, int(begin), int(end), self._stream()))
+        with self._guard():
+            nat.check(self.lib.ccsd_plan_run(self.handle, int(begin), int(end), self._stream()))
 
     def read(self, want_mean: bool) -> List[torch.Tensor]:
         outs = [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.shapes]
-        nat.check(self.lib.ccsd_plan_read(self.handle, int(want_mean), _ptr(outs[0]), _ptr(outs[1]),
-                                          _ptr(outs[2]) if self.is_cc else None, self._stream()))
+        with self._guard():
+            nat.check(self.lib.ccsd_plan_read(self.handle, int(want_mean), _ptr(outs[0]), _ptr(outs[1]),
+                                              _ptr(outs[2]) if self.is_cc else None, self._stream()))
         return outs
 
     def score(self, which: int, x: torch.Tensor, adj: torch.Tensor, rank2: Optional[torch.Tensor],
@@ -208,8 +258,9 @@ class Engine:
         if tuple(x.shape) != self.shapes[0] or tuple(adj.shape) != self.shapes[1]:
             raise ValueError("score(): input shapes do not match the plan")
         out = torch.empty(self.shapes[which], dtype=torch.float32, device=self.device)
-        nat.check(self.lib.ccsd_score_eval(self.handle, int(which), _ptr(x), _ptr(adj), _ptr(rank2), _ptr(flags),
-                                           _ptr(out), self._stream()))
+        with self._guard():
+            nat.check(self.lib.ccsd_score_eval(self.handle, int(which), _ptr(x), _ptr(adj), _ptr(rank2), _ptr(flags),
+                                               _ptr(out), self._stream()))
         return out
 
     def debug_gram(self, rank2: torch.Tensor, use_tc: bool):
@@ -219,8 +270,9 @@ class Engine:
         pr0 = int(self.lib.ccsd_plan_info(self.handle, 12))   # Gram projection columns (hodge layer 0 [+ folded layer 1])
         H = torch.empty(d.B, d.E, d.E, dtype=torch.float32, device=self.device)
         P0 = torch.empty(d.B, d.E, max(pr0, 1), dtype=torch.float32, device=self.device)
-        nat.check(self.lib.ccsd_debug_gram(self.handle, _ptr(r2), _ptr(H), _ptr(P0) if pr0 else None, int(use_tc),
-                                           self._stream()))
+        with self._guard():
+            nat.check(self.lib.ccsd_debug_gram(self.handle, _ptr(r2), _ptr(H), _ptr(P0) if pr0 else None, int(use_tc),
+                                               self._stream()))
         return H, P0[:, :, :pr0]
 
     def set_profiling(self, on: bool) -> None:
@@ -301,20 +353,24 @@ def _make_sampler(
             raise NotImplementedError(f"Corrector {corrector} not yet supported. Select from [Langevin, None].")
     sdes = [sde_x, sde_adj] + ([sde_rank2] if is_cc else [])
     shapes = [tuple(shape_x), tuple(shape_adj)] + ([tuple(shape_rank2)] if is_cc else [])
-    cache: Dict[Tuple[int, ...], Engine] = {}
+    cache: Dict[str, Any] = {}
 
     def run(models: Sequence[Any], init_flags: torch.Tensor, *, seed: Optional[int] = None, sample_offset: int = 0,
             noise: Optional[InjectedNoise] = None, max_steps: Optional[int] = None, record_traj: bool = True):
         _check_sdes(sdes, continuous)
         _set_eval(models)
-        key = tuple(id(m) for m in models)
-        eng = cache.get(key)
+        # One cached plan per factory call.  The key holds the model objects themselves (so an id cannot be reused by
+        # another object) and the weights are re-read from the live modules on EVERY call, as the reference does.
+        eng = None
+        ent = cache.get("engine")
+        if ent is not None and len(ent[0]) == len(models) and all(a is b for a, b in zip(ent[0], models)):
+            if ent[1].refresh_weights(models):
+                eng = ent[1]
         if eng is None:
             eng = Engine(models, sdes, shapes, sampler=sampler, predictor=predictor, corrector=corrector, snr=snr,
                          scale_eps=scale_eps, n_steps=n_steps, probability_flow=probability_flow, denoise=denoise,
                          eps=eps, device=device, d_min=d_min, d_max=d_max)
-            cache.clear()
-            cache[key] = eng
+            cache["engine"] = (list(models), eng)
         n = eng.desc.n_diff_steps
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -326,6 +382,8 @@ def _make_sampler(
             record_traj = False
         if record_traj and eng.traj is None:
             eng.enable_traj()
+        elif not record_traj and eng.traj is not None:
+            eng.disable_traj()
         eng.init(init_flags, prior=noise.prior if noise is not None else None, seed=seed, sample_offset=sample_offset)
         steps = n if max_steps is None else min(n, max_steps)
         if noise is not None:
@@ -335,7 +393,10 @@ def _make_sampler(
             eng.run(0, steps)
         outs = eng.read(want_mean=bool(denoise))
         if record_traj:
-            diff_traj = [[t[i] for t in eng.traj] for i in range(n)]
+            # detached copies (the reference appends clones, solver.py:987-995): a later call of this sampler reuses the
+            # engine's buffers; the reference's list has one entry per executed step
+            snap = [t[:steps].clone() for t in eng.traj]
+            diff_traj = [[t[i] for t in snap] for i in range(steps)]
         else:
             diff_traj = []
         n_evals = n * (n_steps + 1) if sampler == "PC" else 0  # solver.py:1001, 1172, 1369, 1559

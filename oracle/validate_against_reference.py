@@ -91,12 +91,13 @@ def check(name, B=3):
     # samplers
     rs, os_ = make_sdes(ck, is_cc)
     shapes = [(B, N, Fd), (B, N, N)] + ([(B, E, K)] if is_cc else [])
-    combos = [("Euler", "Langevin"), ("Reverse", "Langevin"), ("Reverse", "None"), ("S4", "None")]
-    for pred, corr in combos:
+    combos = [("Euler", "Langevin", 1), ("Reverse", "Langevin", 1), ("Reverse", "None", 1), ("S4", "None", 1),
+              ("Reverse", "Langevin", 2)]   # last: Langevin n_steps = 2 (per-object inner loops, solver.py:692, 760)
+    for pred, corr, n_lang in combos:
         if pred == "S4" and any(isinstance(s, rsde.subVPSDE) for s in rs):
             continue
         kw = dict(
-            predictor=pred, corrector=corr, snr=0.15, scale_eps=0.7, n_steps=1, probability_flow=False,
+            predictor=pred, corrector=corr, snr=0.15, scale_eps=0.7, n_steps=n_lang, probability_flow=False,
             continuous=True, denoise=True, eps=1e-4, device="cpu",
         )
         if is_cc:
@@ -120,11 +121,11 @@ def check(name, B=3):
         if pred == "S4":
             res, _ = O.s4_solver(om, os_, shapes, flags, **okw)
         else:
-            res, _ = O.pc_sampler(om, os_, shapes, flags, predictor=pred, corrector=corr, n_steps=1, **okw)
+            res, _ = O.pc_sampler(om, os_, shapes, flags, predictor=pred, corrector=corr, n_steps=n_lang, **okw)
         for nm, a, b in zip(["x", "adj", "rank2"], out[: len(res)], res):
             diff = (a - b).abs().max().item()
             rel = diff / (a.abs().max().item() + 1e-30)
-            print(f"  [{name}] {pred}+{corr} {nm}: max|d|={diff:.3e} rel={rel:.3e}")
+            print(f"  [{name}] {pred}+{corr} n_steps={n_lang} {nm}: max|d|={diff:.3e} rel={rel:.3e}")
             worst = max(worst, rel)
     return worst
 

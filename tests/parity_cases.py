@@ -12,11 +12,11 @@ SCORE_TOL = 1e-4  # BASELINE.json north_star: per-step score outputs within 1e-4
 
 
 def make_engine(cfg: Config, B: int, device: str, sampler="PC", predictor="Euler", corrector="Langevin", snr=None,
-                scale_eps=None, denoise=True, probability_flow=False, sdes=None):
+                scale_eps=None, denoise=True, probability_flow=False, sdes=None, n_steps=1):
     sh = cfg.shipped
     return Engine(cfg.holders, sdes or cfg.sdes(), cfg.shapes(B), sampler=sampler, predictor=predictor, corrector=corrector,
                   snr=sh["snr"] if snr is None else snr, scale_eps=sh["scale_eps"] if scale_eps is None else scale_eps,
-                  n_steps=1, denoise=denoise, eps=1e-4, device=device, d_min=cfg.d_min, d_max=cfg.d_max,
+                  n_steps=n_steps, denoise=denoise, eps=1e-4, device=device, d_min=cfg.d_min, d_max=cfg.d_max,
                   probability_flow=probability_flow)
 
 
@@ -42,7 +42,8 @@ def score_parity(name: str, B: int, device: str, seed: int = 1):
 
 
 def sampler_parity(name: str, sampler: str, predictor: str, corrector: str, B: int, steps: int, device: str,
-                   seed: int = 5, denoise: bool = True, probability_flow: bool = False, sde_kind: str = None):
+                   seed: int = 5, denoise: bool = True, probability_flow: bool = False, sde_kind: str = None,
+                   n_steps: int = 1):
     """`steps` sampler iterations on the real schedule with an injected noise stream.  Returns per
     object (rel err of the returned tensor, rel err of the raw state, quantised agreement)."""
     cfg = Config(name)
@@ -57,10 +58,11 @@ def sampler_parity(name: str, sampler: str, predictor: str, corrector: str, B: i
         res, _ = O.s4_solver(cfg.oracle_models, sdes, cfg.shapes(B), flags, **kw)
     else:
         res, _ = O.pc_sampler(cfg.oracle_models, sdes, cfg.shapes(B), flags, predictor=predictor,
-                              corrector=corrector, n_steps=1, probability_flow=probability_flow, **kw)
+                              corrector=corrector, n_steps=n_steps, probability_flow=probability_flow, **kw)
     eng = make_engine(cfg, B, device, sampler, predictor, corrector, denoise=denoise, probability_flow=probability_flow,
-                      sdes=sdes)
-    inj = InjectedNoise.from_flat_log(src.log, len(cfg.keys), eng.n_draws, steps)
+                      sdes=sdes, n_steps=n_steps)
+    inj = InjectedNoise.from_flat_log(src.log, len(cfg.keys), eng.n_draws, steps,
+                                      n_lang=n_steps if (sampler == "PC" and corrector == "Langevin") else None)
     eng.init(flags, prior=inj.prior)
     for i in range(steps):
         eng.step(i, inj.steps[i])

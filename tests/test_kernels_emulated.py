@@ -49,6 +49,17 @@ def test_sampler_steps(name, sampler, pred, corr):
         assert agree >= 0.999
 
 
+@pytest.mark.parametrize("name,pred,n_lang", [("qm9", "Reverse", 2), ("qm9_cc", "Reverse", 2), ("qm9_cc", "Euler", 3),
+                                              ("enzymes_small_cc", "Reverse", 2)])
+def test_langevin_inner_steps(name, pred, n_lang):
+    """Langevin n_steps > 1: every object's corrector loops on its own with the other objects at their pre-corrector
+    values (solver.py:692-701, 760-785, 1123-1140); noise draws in the reference's order."""
+    res = sampler_parity(name, "PC", pred, "Langevin", B=2, steps=2, device="cpu", n_steps=n_lang)
+    for k, (e_ret, e_state, agree) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4, (name, k, e_ret, e_state)
+        assert agree >= 0.999
+
+
 def test_sampler_not_denoised():
     res = sampler_parity("qm9_cc", "PC", "Reverse", "Langevin", B=2, steps=2, device="cpu", denoise=False)
     for k, (e_ret, e_state, _) in res.items():

@@ -106,6 +106,18 @@ def test_sampler_sde_variants(pred, corr, pf, kind):
         assert e_ret < 1e-4 and e_state < 1e-4, (pred, corr, pf, kind, k, e_ret, e_state)
 
 
+@pytest.mark.parametrize("name,pred,n_lang,B", [("qm9", "Reverse", 2, 32), ("qm9_cc", "Reverse", 2, 8), ("qm9_cc", "Euler", 3, 8),
+                                                ("enzymes_small_cc", "Reverse", 2, 4), ("community_small_cc", "Euler", 2, 2),
+                                                ("enzymes", "Reverse", 2, 2)])
+def test_langevin_inner_steps(name, pred, n_lang, B):
+    """Langevin n_steps > 1 (solver.py:692-701, 760-785): per-object inner loops, the other objects at their
+    pre-corrector values, the reference's draw order."""
+    res = sampler_parity(name, "PC", pred, "Langevin", B, 2, DEV, n_steps=n_lang)
+    for k, (e_ret, e_state, agree) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4, (name, k, e_ret, e_state)
+        assert agree >= 0.999, (name, k, agree)
+
+
 def test_longer_horizon_with_injected_noise():
     """60 sampler iterations (360 network evaluations) on the real schedule with the reference's own noise
     stream: the per-step error (~1e-6) must not compound into a different sample -- quantised adjacency and

@@ -37,6 +37,19 @@ def _maker(cfg, corrector):
     return make
 
 
+def _worker_tiny(rank, world, port, out):
+    """More ranks than samples: rank 1 gets an empty shard and must still take part in the gather."""
+    from ccsd_b200 import _native as nat
+
+    nat.enable_test_emulation(os.environ["CCSD_B200_TEST_EMU"])
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = Config("qm9_cc")
+    res = sharded_sample(_maker(cfg, "None"), cfg.holders, _flags(cfg)[:1], max_steps=2, record_traj=False)   # seed broadcast
+    torch.save([t.clone() for t in res], out + f".{rank}")
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, corrector, out):
     from ccsd_b200 import _native as nat
 
@@ -81,3 +94,15 @@ def test_two_rank_gloo_matches_single_process(tmp_path, corrector):
         ref = [torch.cat([p[k] for p in parts]) for k in range(3)]
     for g, r in zip(got, ref):
         assert g.shape == r.shape and torch.equal(g, r)
+
+
+def test_more_ranks_than_samples(tmp_path):
+    """One sample, two ranks: the rank with the empty shard joins the gather with zero rows (no hang), the seed is
+    broadcast from rank 0, and both ranks end up with the same full result."""
+    out = str(tmp_path / "tiny.pt")
+    mp.spawn(_worker_tiny, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = torch.load(out + ".0"), torch.load(out + ".1")
+    cfg = Config("qm9_cc")
+    assert [tuple(t.shape) for t in a] == [tuple(s) for s in cfg.shapes(1)]
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
