@@ -153,16 +153,22 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 + Box-Muller: 4 standard normals per call.
+// Philox4x32-7 + Box-Muller: 4 standard normals per call.  Seven rounds is the smallest Philox4x32 variant that passes
+// BigCrush (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11, table 2; ten rounds is their safety
+// margin): the draw sits on the per-entry hot path of every rank-2 pass (ncu: ~40 % of tc_apply's instructions with
+// ten rounds), and bit-identity with torch's generator is not a goal -- distributional parity is tested.
 // counter = (group, draw_id, sample_lo, sample_hi), key = seed.  `group` is the element index / 4
 // inside one sample (rank-2 rows are padded to a multiple of 4 cells so that a group never
 // straddles rows); the sample index is GLOBAL (shard offset + local), so a sample's noise does
 // not depend on how the batch is split across GPUs.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#ifndef CCSD_PHILOX_ROUNDS
+#define CCSD_PHILOX_ROUNDS 7
+#endif
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t out[4]) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < CCSD_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -190,8 +196,8 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t sample, uint32_t
 #ifdef CCSD_EXPERIMENT_NO_PHILOX
   r[0] = group; r[1] = draw_id; r[2] = (uint32_t)sample; r[3] = (uint32_t)seed;   // timing experiment only
 #else
-  philox4x32_10(group, draw_id, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed,
-                (uint32_t)(seed >> 32), r);
+  philox4x32(group, draw_id, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed,
+             (uint32_t)(seed >> 32), r);
 #endif
   // Box-Muller on the SFU: radius = sqrt(t) = t * rsqrt(t) with t = -2 ln u > 0, angle through the fast
   // sin/cos (|err| ~1e-6 on a unit normal: irrelevant for noise).  The draw is on the per-entry hot path of

@@ -503,8 +503,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
           for (int c4 = 0; c4 < 4; ++c4) {
             const int k = kbase + 4 * c4;
             float4 *cell = reinterpret_cast<float4 *>(row + (((chalf * 4 + c4) ^ (er & 7)) << 4));
-            const float4 f4 = *cell;
             const float4 fc4 = *reinterpret_cast<const float4 *>(fcp + 4 * c4);   // 0 for cells >= K
+            // Four cells that are all masked for this sample (or a masked edge row): the state there is zero and stays
+            // zero, the score and the masked noise are zero -- no network, no Philox, no store.  The test is uniform
+            // over the lanes that share a sample (every lane of the warp when one sample fills the group).
+            if (!(MODE == MODE_PRED && side) && (fe == 0.f || (fc4.x == 0.f && fc4.y == 0.f && fc4.z == 0.f && fc4.w == 0.f))) {
+              if (MODE == MODE_EVAL || MODE == MODE_SCORE) *cell = make_float4(0.f, 0.f, 0.f, 0.f);   // out != in: the caller's input may be unmasked
+              continue;
+            }
+            const float4 f4 = *cell;
             const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
             const float mv[4] = {fe * fc4.x, fe * fc4.y, fe * fc4.z, fe * fc4.w};
             float z4[4] = {0.f, 0.f, 0.f, 0.f};
