@@ -143,6 +143,8 @@ def load():
     lib.ccsd_mol_onehot.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.ccsd_quantize.restype = C.c_int
     lib.ccsd_quantize.argtypes = [vp, vp, sz, C.c_float, C.c_int, vp]
+    lib.ccsd_cc_cells.restype = C.c_int
+    lib.ccsd_cc_cells.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.ccsd_plan_launch_count.restype = C.c_int64
     lib.ccsd_plan_launch_count.argtypes = [vp]
     lib.ccsd_plan_info.restype = C.c_int

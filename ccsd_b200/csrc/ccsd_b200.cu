@@ -590,6 +590,10 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     p->hp.gram_group = imax(G, 1);
   }
   p->use_tc_apply = (d.is_cc && (d.nets & 4) && !p->apply_big) ? tc_apply_supported(d.E, d.K) : 0;
+  // Wider non-affine ScoreNetworkF (entry paths 0 / 2 / 4: the Base_CC checkpoints) is ill conditioned -- two fp32
+  // evaluations that differ in summation order already disagree by 4.5e-6 and the 2^-16 product error of the bf16x3
+  // contractions grows to 6e-5 per evaluation -- so its rank-2 contractions stay on the fp32 FMA kernels (flat 1e-4 bar).
+  if (d.is_cc && (d.nets & 4) && p->hp.f_mode != 1 && p->hp.f_mode != 3) p->use_tc = p->use_tc_apply = 0;
   p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;
   if (getenv("CCSD_B200_NO_TC_AGG")) p->use_tc_agg = 0;
@@ -1094,6 +1098,13 @@ int ccsd_mol_onehot(const float *x, const float *adj, int64_t *x_out, int64_t *a
   CCSD_LAUNCH(mol_onehot_kernel, dim3(grid_for((size_t)B * N * N), 1, 1), 256, 0, stream, x, adj, (long long *)x_out,
               (long long *)adj_out, B, N, F);
   return dev_check("mol_onehot_kernel");
+}
+
+int ccsd_cc_cells(const float *r2, uint8_t *present, int32_t *row, float *label, int B, int E, int K, void *stream) {
+  if (!r2 || !present || !row || !label) return fail(CCSD_ERR_INVALID, "null argument");
+  if (B < 1 || E < 1 || K < 1) return fail(CCSD_ERR_INVALID, "B, E, K must be positive");
+  CCSD_LAUNCH(cc_cells_kernel, dim3(grid_for((size_t)B * K), 1, 1), 256, 0, stream, r2, present, (int *)row, label, B, E, K);
+  return dev_check("cc_cells_kernel");
 }
 
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *p) { return p ? p->launches : 0; }

@@ -1004,4 +1004,32 @@ CCSD_KERNEL void __launch_bounds__(256) mol_onehot_kernel(const float *__restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched core of cc_from_incidence (cc_utils.py:156-265): for every sample and every candidate rank-2 cell k
+//   present[b, k] = any_e (rank2[b, e, k] != 0)                            (:244 incidence_matrix[:, i].any())
+//   row[b, k]     = argmax_e |rank2[b, e, k]|  (first maximum, as torch)   (:245)
+//   label[b, k]   = rank2[b, row, k]                                       (:247)
+// The reference walks the K columns of every sample in Python with three .item() synchronisations per column;
+// here one thread owns a column (lanes run along k: coalesced) and walks the E rows once.
+CCSD_KERNEL void __launch_bounds__(256) cc_cells_kernel(const float *__restrict__ r2, uint8_t *__restrict__ present,
+                                                       int *__restrict__ row, float *__restrict__ label, int B, int E, int K) {
+  const size_t tot = (size_t)B * K;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < tot; g += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(g / K), k = (int)(g - (size_t)b * K);
+    const float *col = r2 + (size_t)b * E * K + k;
+    float best = -1.f, val = 0.f;
+    int arg = 0;
+    bool any = false;
+    for (int e = 0; e < E; ++e) {
+      const float v = col[(size_t)e * K];
+      any = any || (v != 0.f);
+      const float a = fabsf(v);
+      if (a > best) { best = a; arg = e; val = v; }   // strict: keeps the FIRST maximum
+    }
+    present[g] = any ? 1 : 0;
+    row[g] = arg;
+    label[g] = val;
+  }
+}
+
 }  // namespace ccsd

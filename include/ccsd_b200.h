@@ -216,6 +216,12 @@ int ccsd_quantize(const float *in_dev, uint8_t *out_dev, size_t n, float thr, in
 int ccsd_mol_onehot(const float *x_dev, const float *adj_dev, int64_t *x_out_dev, int64_t *adj_out_dev, int B, int N, int F,
                     void *stream);
 
+/* Batched core of cc_from_incidence (ccsd/src/utils/cc_utils.py:156-265, the rank-2 part :236-258): for every sample b
+ * and candidate cell k of rank2 [B,E,K]: present[b,k] = any_e rank2[b,e,k] != 0, row[b,k] = argmax_e |rank2[b,e,k]|
+ * (first maximum), label[b,k] = rank2[b,row,k].  The caller builds the complex from the present cells only. */
+int ccsd_cc_cells(const float *rank2_dev, uint8_t *present_dev, int32_t *row_dev, float *label_dev, int B, int E, int K,
+                  void *stream);
+
 /* Number of kernel launches issued by this plan so far (bench.py's gpu_launches). */
 int64_t ccsd_plan_launch_count(const ccsd_plan_t *plan);
 

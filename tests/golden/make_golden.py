@@ -164,11 +164,12 @@ def make_config(name):
 KAT_TESTS = {
     "test_ScoreNetwork_A_CC.py": ["test_ScoreNetworkA_CC"],
     "test_ScoreNetwork_F.py": ["test_ScoreNetworkF"],
-    "test_hodge_layers.py": ["test_DenseHCNConv", "test_HodgeNetworkLayer"],
+    "test_hodge_layers.py": ["test_DenseHCNConv", "test_HodgeNetworkLayer", "test_BaselineBlock", "test_HodgeBaselineLayer"],
     "test_hodge_attention.py": ["test_HodgeAttention", "test_HodgeAdjAttentionLayer"],
+    "test_ScoreNetwork_A_Base_CC.py": ["test_ScoreNetworkA_Base_CC"],
 }
 KAT_CLASSES = {"ScoreNetworkA_CC", "ScoreNetworkF", "DenseHCNConv", "HodgeNetworkLayer", "HodgeAttention",
-               "HodgeAdjAttentionLayer"}
+               "HodgeAdjAttentionLayer", "BaselineBlock", "HodgeBaselineLayer", "ScoreNetworkA_Base_CC"}
 
 
 def _raw(fixture):

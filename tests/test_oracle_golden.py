@@ -93,6 +93,35 @@ def test_kat_hodge_adj_attention_layer():
     _assert_kat(z, t, [ho, ro], [lambda o: o[0][0, 0, 0], lambda o: o[1][0, 0]])
 
 
+def test_kat_baseline_block():
+    """reference tests/models/test_hodge_layers.py:244-306 (out_rank2[0, 0, :], out_hodge_adj[0, 0, :])."""
+    z, _ = _kat()
+    t = "test_BaselineBlock"
+    h, r2 = torch.from_numpy(z[f"{t}/arg0"]), torch.from_numpy(z[f"{t}/arg1"])
+    ro, ho = O.baseline_block(_sd(z, t), h, r2)
+    _assert_kat(z, t, [ro, ho], [lambda o: o[0][0, 0, :], lambda o: o[1][0, 0, :]])
+
+
+def test_kat_hodge_baseline_layer():
+    """reference tests/models/test_hodge_layers.py:309-375 (out_hodge_adj[0, 0, 0], out_rank2[0, 0])."""
+    z, idx = _kat()
+    t = "test_HodgeBaselineLayer"
+    hp = idx[t]["hp"]
+    h, r2 = torch.from_numpy(z[f"{t}/arg0"]), torch.from_numpy(z[f"{t}/arg1"])
+    ho, ro = O.hodge_baseline_layer(_sd(z, t), h, r2, None, hp["N"], hp["d_min"], hp["d_max"])
+    _assert_kat(z, t, [ho, ro], [lambda o: o[0][0, 0, 0], lambda o: o[1][0, 0]])
+
+
+def test_kat_score_network_a_base_cc():
+    """reference tests/models/test_ScoreNetwork_A_Base_CC.py:115-158 (5x5 expected score)."""
+    z, idx = _kat()
+    t = "test_ScoreNetworkA_Base_CC"
+    hp = idx[t]["hp"]
+    x, adj, r2 = (torch.from_numpy(z[f"{t}/arg{i}"]) for i in range(3))
+    out = O.score_network_a_base_cc(_sd(z, t), hp, x, adj, r2, None)
+    _assert_kat(z, t, [out], [lambda o: o[0]])
+
+
 # ---- utility known answers (values from the reference's tests/utils) -------------------------
 def test_mask_x_and_adjs():
     """reference tests/utils/test_graph_utils.py:35-59."""

@@ -82,11 +82,7 @@ def test_scores_against_committed_reference_outputs(name):
 ])
 def test_sampler_steps_with_injected_noise(name, sampler, pred, corr, B, steps):
     res = sampler_parity(name, sampler, pred, corr, B, steps, DEV)
-    # The bar is 1e-4 PER STEP.  The non-affine ScoreNetworkF of ccsd_qm9_Base_CC is ill conditioned: two fp32
-    # evaluations that differ only in summation order already disagree by 4.5e-6 (20x the other checkpoints), the
-    # bf16x3 H.F product gives 6e-5 per evaluation, and the Langevin dynamics compound it: 5.8e-5 after one step,
-    # 1.2e-4 after three (tools/diag_parity.py).  So the multi-step run of that checkpoint gets steps x 1e-4.
-    tol = 1e-4 * (steps if name == "qm9_base_cc" else 1)
+    tol = 1e-4   # flat bar (the ill-conditioned non-affine ScoreNetworkF of the Base_CC checkpoints keeps its rank-2 contractions in fp32)
     for k, (e_ret, e_state, agree) in res.items():
         assert e_ret < tol and e_state < tol, (name, k, e_ret, e_state)
         assert agree >= 0.999, (name, k, agree)
