@@ -24,6 +24,7 @@
 #include "tc_afinal.cuh"
 #include "tc_agg.cuh"
 #include "tc_attn.cuh"
+#include "tc_xfin.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -87,6 +88,10 @@ struct ccsd_plan {
 #ifndef CCSD_EMU
   int use_tc_attn[CCSD_MAX_LAYERS] = {0};   // per attention layer: tcgen05 attention-channel kernel (tc_attn.cuh)
   TcAttnLayout tattn[CCSD_MAX_LAYERS];
+  int use_tc_xfin = 0;                      // ScoreNetworkX final MLP on tcgen05 (tc_xfin.cuh)
+  TcXfinLayout txf;
+  float *g_hcat = nullptr;                  // [B][fdimX x N4]
+  uint8_t *ximg = nullptr;                  // weight operand image of tc_xfin
 #endif
   int apply_big = 0;   // E too large for the resident F column block: hf_gemm_kernel + r2_epi_kernel (scratch = sr2)
   // optional per-kernel timing (CUDA events on the launching stream)
@@ -418,7 +423,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -438,6 +443,12 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.ghmc = take(B * (size_t)p->hp.xp.g_hmc * 4);
   w.gx0 = take(B * (size_t)p->hp.xp.g_x * 4);
   w.gx1 = take(B * (size_t)p->hp.xp.g_x * 4);
+#ifndef CCSD_EMU
+  w.ghcat = take(p->use_tc_xfin ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
+  w.ximg = take(p->use_tc_xfin ? (size_t)p->txf.img_bytes : 16);
+#else
+  w.ghcat = take(16); w.ximg = take(16);
+#endif
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
@@ -597,9 +608,10 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->use_tc_fin = (d.nets & 2) ? tc_afinal_supported(d.neta, d.neta.fdim) : 0;
   p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;
   if (getenv("CCSD_B200_NO_TC_AGG")) p->use_tc_agg = 0;
+  if ((d.nets & 1) && !getenv("CCSD_B200_NO_TC_XFIN")) p->use_tc_xfin = tc_xfin_layout(d, XL, p->txf);
   if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_ATTN"))
     for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_attn[l] = tc_attn_layout(d, XL, d.neta.layer[l], p->tattn[l]);
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); }  // A/B switch for tests and profiling
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = p->use_tc_xfin = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); }  // A/B switch for tests and profiling
   if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
     p->hp.ntile_adj = XL.big ? d.N * ((d.N + 127) / 128) : (p->hp.xp.NT + 127) / 128;
     p->hp.ntile_max = imax(p->hp.ntile_max, p->hp.ntile_adj);
@@ -642,6 +654,9 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->g_stack = (float *)(ws + w.gstack); p->g_att = (float *)(ws + w.gatt); p->g_hmc = (float *)(ws + w.ghmc);
   p->g_x0 = (float *)(ws + w.gx0); p->g_x1 = (float *)(ws + w.gx1);
   p->g_big = (float *)(ws + w.gbig);
+#ifndef CCSD_EMU
+  p->g_hcat = (float *)(ws + w.ghcat); p->ximg = (uint8_t *)(ws + w.ximg);
+#endif
   if (p->hp.xp.big) {
     // pad columns / rows of the planes are read as don't-care operands: make them finite once
     const size_t nb = (size_t)p->hp.d.B * p->hp.xp.big_total * 4;
@@ -689,6 +704,11 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
   const ccsd_plan_desc_t &d = p->hp.d;
   if (int r = dev_copy(p->flags, flags_dev, (size_t)d.B * d.N * 4, stream)) return r;
   p->seed = seed; p->sample_offset = sample_offset;
+#ifndef CCSD_EMU
+  // the caller may have refreshed the weight blob since the last run: rebuild the bf16 operand image of the X network's MLP
+  if (p->use_tc_xfin)
+    if (tc_xfin_prep(p->dP, p->txf, p->ximg, stream)) return fail(CCSD_ERR_CUDA, "tc_xfin_prep launch failed");
+#endif
   CCSD_LAUNCH(zmask_kernel, dim3(grid_for(d.B), 1, 1), 256, 0, stream, p->flags, p->zmask, d.B, d.N);
   InitArgs a;
   a.flags = p->flags; a.px = px; a.padj = padj; a.pr2 = pr2; a.x = p->x; a.adj = p->adj; a.r2 = p->r2;
@@ -792,10 +812,21 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
   const XpLayout &L = p->hp.xp;
   const ccsd_neta_t &A = d.neta;
   a.g_stack = p->g_stack; a.g_att = p->g_att; a.g_hmc = p->g_hmc; a.g_x0 = p->g_x0; a.g_x1 = p->g_x1;
+#ifndef CCSD_EMU
+  if (p->use_tc_xfin && (a.which & 1)) a.g_hcat = p->g_hcat;
+#endif
   PROF_BEGIN(p, "x_net_kernel", stream);
   CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, stream, p->dP, a);
   PROF_END(p, stream);
   p->launches++;
+#ifndef CCSD_EMU
+  if (a.g_hcat) {
+    PROF_BEGIN(p, "tc_xfin_kernel", stream);
+    if (tc_xfin_launch(p->dP, p->hp, a, p->txf, p->g_hcat, d.netx.fdim * L.N4, p->ximg, stream)) return fail(CCSD_ERR_CUDA, "tc_xfin launch failed");
+    PROF_END(p, stream);
+    p->launches++;
+  }
+#endif
   if (!(a.which & 2)) return dev_check("x_net_kernel");
   int ch_in = 0, ch_out = A.c_init;
   const float *xin = p->g_x0;
@@ -1067,6 +1098,10 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
   if (which == CCSD_NET_X || which == CCSD_NET_ADJ) {
     if (which == CCSD_NET_ADJ && d.is_cc)
       if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;
+#ifndef CCSD_EMU
+    if (p->use_tc_xfin && which == CCSD_NET_X)
+      if (tc_xfin_prep(p->dP, p->txf, p->ximg, stream)) return fail(CCSD_ERR_CUDA, "tc_xfin_prep launch failed");
+#endif
     XaArgs a; memset(&a, 0, sizeof a);
     a.x = x; a.adj = adj; a.flags = flags; a.P0 = p->P0; a.P1 = p->P1; a.r2 = r2; a.mode = MODE_EVAL;
     a.which = which == CCSD_NET_X ? 1 : 2;
@@ -1128,6 +1163,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
     case 12: return p->hp.PR0;
     case 13: return p->use_tc_fin;
 #ifndef CCSD_EMU
+    case 15: return p->use_tc_xfin;
     case 14: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_attn[l]; return n; }   // layers on the tcgen05 attention kernel
 #endif
     case 7: return p->hp.xp.x_total * 4;

@@ -65,6 +65,8 @@ struct XaArgs {
   int layer, ch_in, ch_out;
   const float *g_xin;            // node features read by this layer  [kin x N4] per graph
   float *g_xout;                 // node features written by this layer
+  float *g_hcat;                 // not null: x_net_kernel stops after the GCN stack and writes [x, h_1 .. h_D] ([fdim x N4] per
+                                 // graph) here for the tensor-core final MLP (tc_xfin.cuh)
 };
 
 // =============================================================================================
@@ -125,6 +127,12 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
     in = hcat + row * N4;
     din = g.dout;
     row += g.dout;
+  }
+  if (a.g_hcat) {
+    float *gh = a.g_hcat + (size_t)b * (size_t)X.fdim * N4;
+    for (int p = threadIdx.x; p < F * N4; p += blockDim.x) gh[p] = x0[p];
+    for (int p = threadIdx.x; p < row * N4; p += blockDim.x) gh[F * N4 + p] = hcat[p];
+    return;
   }
   mlp_fm(X.fin, W, x0, N4, F, hcat, N4, row, N, hA, hB, N4, sx, 1, N4, ACT_ELU, ACT_NONE);
   for (int p = threadIdx.x; p < F * N4; p += blockDim.x) {
