@@ -25,6 +25,7 @@
 #include "tc_agg.cuh"
 #include "tc_attn.cuh"
 #include "tc_xfin.cuh"
+#include "tc_hnorm.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -88,6 +89,11 @@ struct ccsd_plan {
 #ifndef CCSD_EMU
   int use_tc_attn[CCSD_MAX_LAYERS] = {0};   // per attention layer: tcgen05 attention-channel kernel (tc_attn.cuh)
   TcAttnLayout tattn[CCSD_MAX_LAYERS];
+  int use_hnorm = 0;                        // rank-2 Langevin norms from Gram quantities instead of a NORM pass (tc_hnorm.cuh)
+  cudaStream_t side = nullptr;              // internal stream: the norm kernels run beside the x / adj pipeline
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
+  float *Dg = nullptr, *Rs = nullptr;       // [B][E] diag(F F^T), F 1
   int use_tc_xfin = 0;                      // ScoreNetworkX final MLP on tcgen05 (tc_xfin.cuh)
   TcXfinLayout txf;
   float *g_hcat = nullptr;                  // [B][fdimX x N4]
@@ -423,7 +429,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -444,10 +450,12 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.gx0 = take(B * (size_t)p->hp.xp.g_x * 4);
   w.gx1 = take(B * (size_t)p->hp.xp.g_x * 4);
 #ifndef CCSD_EMU
+  w.dg = take(p->use_hnorm ? B * E * 4 : 16);
+  w.rs = take(p->use_hnorm ? B * E * 4 : 16);
   w.ghcat = take(p->use_tc_xfin ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
   w.ximg = take(p->use_tc_xfin ? (size_t)p->txf.img_bytes : 16);
 #else
-  w.ghcat = take(16); w.ximg = take(16);
+  w.ghcat = take(16); w.ximg = take(16); w.dg = take(16); w.rs = take(16);
 #endif
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
@@ -612,6 +620,19 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_ATTN"))
     for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_attn[l] = tc_attn_layout(d, XL, d.neta.layer[l], p->tattn[l]);
   if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = p->use_tc_xfin = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); }  // A/B switch for tests and profiling
+  // rank-2 Langevin norms from Gram quantities (affine ScoreNetworkF on the tensor-core Gram / apply kernels, PC + Langevin)
+  p->use_hnorm = p->use_tc && p->use_tc_apply && d.sampler == CCSD_SAMPLER_PC && d.use_corrector && tc_hnorm_supported(d, p->hp.f_mode) &&
+                 tc_gram_supported(d.E, d.K, p->hp.PR0 + 1) && !getenv("CCSD_B200_NO_HNORM");
+  if (p->use_hnorm && !getenv("CCSD_B200_NO_SIDE_STREAM")) {
+    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      delete p;
+      return fail(CCSD_ERR_CUDA, "cannot create the internal stream / events");
+    }
+  }
+  if (p->use_hnorm && p->hp.gram_group > 1)
+    while (p->hp.gram_group > 1 && tc_gram_ncols(p->hp.gram_group * d.E, p->hp.PR0 + 1) > 256) --p->hp.gram_group;
   if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
     p->hp.ntile_adj = XL.big ? d.N * ((d.N + 127) / 128) : (p->hp.xp.NT + 127) / 128;
     p->hp.ntile_max = imax(p->hp.ntile_max, p->hp.ntile_adj);
@@ -631,6 +652,9 @@ void ccsd_plan_destroy(ccsd_plan_t *plan) {
   if (!plan) return;
 #ifndef CCSD_EMU
   for (auto &r : plan->prof) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
+  if (plan->side) { cudaStreamSynchronize(plan->side); cudaStreamDestroy(plan->side); }
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+  if (plan->ev_join) cudaEventDestroy(plan->ev_join);
 #endif
   delete plan;
 }
@@ -656,6 +680,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->g_big = (float *)(ws + w.gbig);
 #ifndef CCSD_EMU
   p->g_hcat = (float *)(ws + w.ghcat); p->ximg = (uint8_t *)(ws + w.ximg);
+  p->Dg = (float *)(ws + w.dg); p->Rs = (float *)(ws + w.rs);
 #endif
   if (p->hp.xp.big) {
     // pad columns / rows of the planes are read as don't-care operands: make them finite once
@@ -929,7 +954,7 @@ static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, con
 #ifndef CCSD_EMU
   if (p->use_tc) {
     PROF_BEGIN(p, "tc_gram_kernel", stream);
-    if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, stream)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
+    if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, p->use_hnorm ? p->Dg : nullptr, p->use_hnorm ? p->Rs : nullptr, stream)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
     PROF_END(p, stream);
     p->launches++;
   } else
@@ -974,6 +999,49 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     p->launches++;
     return dev_check("apply pass");
   };
+  // ||score||^2 and ||z||^2 of the rank-2 object for the Langevin step size: from Gram quantities + a Philox-only
+  // reduction when ScoreNetworkF is affine (tc_hnorm.cuh), else a NORM pass over the state
+  auto norm_pass = [&](int slot) -> int {
+#ifndef CCSD_EMU
+    if (p->use_hnorm) {
+      // fork: everything enqueued on `stream` so far (the Gram kernel) precedes the norm kernels; they run on the internal
+      // stream beside whatever the caller's stream gets next (the x / adj pipeline) and are joined before coef_kernel
+      void *ns = stream;
+      if (p->side) {
+        if (cudaEventRecord(p->ev_fork, (cudaStream_t)stream) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev_fork, 0) != cudaSuccess)
+          return fail(CCSD_ERR_CUDA, "stream fork failed");
+        ns = (void *)p->side;
+      }
+      TcHnormArgs h; memset(&h, 0, sizeof h);
+      h.H = p->H; h.Dg = p->Dg; h.Rs = p->Rs; h.flags = p->flags; h.norm_part = p->norm_part; h.step = step; h.G = p->hp.ap_group;
+      PROF_BEGIN(p, "tc_hnorm_kernel", ns);
+      if (tc_hnorm_launch(p->dP, p->hp, h, ns)) return fail(CCSD_ERR_CUDA, "tc_hnorm launch failed");
+      PROF_END(p, ns);
+      ZnormArgs z; memset(&z, 0, sizeof z);
+      z.flags = p->flags; z.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr; z.zmask = p->zmask; z.norm_part = p->norm_part;
+      z.slot = slot; z.nz = nz;
+      PROF_BEGIN(p, "znorm_kernel", ns);
+      CCSD_LAUNCH(znorm_kernel, dim3(p->hp.ntile_r2, d.B, 1), 256, (size_t)(40 + ((d.E + 3) & ~3) + APPLY_TN / 4 + 8) * 4, ns, p->dP, z);
+      PROF_END(p, ns);
+      p->launches += 2;
+      if (p->side) {
+        if (cudaEventRecord(p->ev_join, p->side) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
+        p->side_pending = true;
+      }
+      return dev_check("rank-2 norms");
+    }
+#endif
+    return apply_pass(MODE_NORM, slot);
+  };
+  auto join_side = [&]() -> int {
+#ifndef CCSD_EMU
+    if (p->side_pending) {
+      p->side_pending = false;
+      if (cudaStreamWaitEvent((cudaStream_t)stream, p->ev_join, 0) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
+    }
+#endif
+    return 0;
+  };
   // x / adj networks (+ the Gram pre-pass their hodge branch and the rank-2 network need)
   auto xa_phase = [&](int mode, int slot, int which, const float *xin, const float *adjin) -> int {
     XaArgs a; memset(&a, 0, sizeof a);
@@ -989,12 +1057,20 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
   auto score_phase = [&](int mode, int slot, int r2_mode) -> int {
     if (d.is_cc)
       if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
+    bool normed = false;
+#ifndef CCSD_EMU
+    if (d.is_cc && r2_mode == MODE_NORM && p->use_hnorm) {   // the norm kernels only need the Gram products: start them beside the x / adj pipeline
+      if (int r = norm_pass(slot)) return r;
+      normed = true;
+    }
+#endif
     if (int r = xa_phase(mode, slot, 3, p->x, p->adj)) return r;
-    if (d.is_cc) return apply_pass(r2_mode, slot);
+    if (d.is_cc && !normed) return r2_mode == MODE_NORM ? norm_pass(slot) : apply_pass(r2_mode, slot);
     return 0;
   };
   // Langevin / S4 step sizes of the objects in obj_mask from the batch means of their norm partials
   auto coef_phase = [&](int obj_mask) -> int {
+    if (int r = join_side()) return r;
     CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4; c.obj_mask = obj_mask;
     PROF_BEGIN(p, "coef_kernel", stream);
     CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
@@ -1052,7 +1128,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
       if (int r = apply_pass(MODE_CORR, 0)) return r;
       for (int s = 1; s < n; ++s) {   // rank2: score_rank2(rank2_s) (ScoreNetworkF ignores x and adj)
         if (int r = launch_rank2_pre(p, p->r2, p->adj, p->flags, stream)) return r;
-        if (int r = apply_pass(MODE_NORM, s)) return r;
+        if (int r = norm_pass(s)) return r;
         if (int r = coef_phase(4)) return r;
         if (int r = apply_pass(MODE_CORR, s)) return r;
       }
@@ -1164,6 +1240,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
     case 13: return p->use_tc_fin;
 #ifndef CCSD_EMU
     case 15: return p->use_tc_xfin;
+    case 16: return p->use_hnorm;
     case 14: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_attn[l]; return n; }   // layers on the tcgen05 attention kernel
 #endif
     case 7: return p->hp.xp.x_total * 4;

@@ -1032,4 +1032,62 @@ CCSD_KERNEL void __launch_bounds__(256) cc_cells_kernel(const float *__restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// ||z||^2 of the rank-2 corrector noise of every sample WITHOUT touching the state (solver.py:765-767): the draw is
+// a pure function of (seed, sample, draw id, entry) -- or the injected stream -- and the mask of the flags.  One CTA =
+// (APPLY_TN-cell tile t, sample b): partial sum -> norm_part slot t of the rank-2 object (fixed-order block reduction, so the
+// Langevin step size is bit-reproducible).  Fully masked 4-cell groups / edge rows cost nothing.
+struct ZnormArgs {
+  const float *flags;
+  const float *noise;                  // raw normals [B,E,K] of this draw or nullptr (Philox)
+  const unsigned long long *zmask;     // [B]
+  float *norm_part;
+  int slot;
+  NoiseCtx nz;
+};
+
+CCSD_KERNEL void __launch_bounds__(256) znorm_kernel(const DevPlan *__restrict__ P, ZnormArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int N = d.N, E = d.E, K = d.K, Kg = P->Kp >> 2;
+  constexpr int GPT = APPLY_TN / 4;   // 4-cell groups per tile
+  const int t = blockIdx.x, b = blockIdx.y;
+  const float *fl = a.flags + (size_t)b * N;
+  const unsigned long long zm = a.zmask[b];
+  const unsigned long long gs = (unsigned long long)(a.nz.sample_offset + b);
+  const uint32_t did = draw_id(2, a.nz.step, a.slot);
+  // staged once per CTA: edge flags [E] and the live-cell bits of this tile's 4-cell groups [GPT]
+  float *fes = sm + 40;
+  unsigned *gm = reinterpret_cast<unsigned *>(fes + ((E + 3) & ~3));
+  for (int e = threadIdx.x; e < E; e += blockDim.x) fes[e] = fl[P->edge_ij[2 * e]] * fl[P->edge_ij[2 * e + 1]];
+  for (int g = threadIdx.x; g < GPT; g += blockDim.x) {
+    unsigned m = 0;
+    for (int q = 0; q < 4; ++q) {
+      const int k = (t * GPT + g) * 4 + q;
+      if (k < K && !(P->cell_mask[k] & zm)) m |= 1u << q;
+    }
+    gm[g] = m;
+  }
+  __syncthreads();
+  float z2 = 0.f;
+  for (int it = threadIdx.x; it < E * GPT; it += blockDim.x) {
+    const int e = it / GPT, g = it - e * GPT;
+    const unsigned m = gm[g];
+    if (m == 0u || fes[e] == 0.f) continue;
+    const int kg = t * GPT + g, k = kg * 4;
+    float z4[4];
+    if (a.noise) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) z4[q] = k + q < K ? a.noise[((size_t)b * E + e) * K + k + q] : 0.f;
+    } else {
+      normal4(a.nz.seed, gs, did, (uint32_t)(e * Kg + kg), z4);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((m >> q) & 1u) z2 += z4[q] * z4[q];
+  }
+  z2 = block_sum(z2, sm);
+  if (threadIdx.x == 0) a.norm_part[((size_t)(2 * d.B + b) * P->ntile_max + t) * 2 + 1] = z2;
+}
+
 }  // namespace ccsd

@@ -41,10 +41,12 @@ struct TcGramArgs {
   const float *r2;  // [B,E,K]
   float *H;         // [B,E,E]
   float *P0;        // [B,E,PR0]
+  float *Dg, *Rs;   // optional [B,E]: diag(F F^T) (before the (1 - I) mask) and the row sums F 1 (one more all-ones
+                    // projection row) -- the Gram quantities the Langevin norm of an affine ScoreNetworkF needs (tc_hnorm.cuh)
 };
 
 static inline int tc_gram_wp0(int E) { return (E + 7) & ~7; }
-static inline int tc_gram_ncols(int E, int PR0) { return (tc_gram_wp0(E) + PR0 + 15) & ~15; }
+static inline int tc_gram_ncols(int E, int PR0) { return (tc_gram_wp0(E) + PR0 + 15) & ~15; }   // PR0 incl. the ones row
 static inline int tc_gram_supported(int E, int K, int PR0) {
   (void)K;
   return E >= 8 && E <= 192 && PR0 <= 64 && tc_gram_ncols(E, PR0) <= 256;
@@ -60,7 +62,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   // cross-sample blocks are computed and never stored)
   const int G = GROUPED ? P->gram_group : 1, EG = G * E, NV = (B + G - 1) / G;
   const int wp0 = (EG + 7) & ~7;
-  const int ncols = (wp0 + PR0 + 15) & ~15;
+  const int rsum = a.Rs != nullptr;                 // one more operand row: all ones (Gram column = row sums of F)
+  const int rcol = wp0 > EG ? EG : wp0 + PR0;       // it takes a pad row of the F block when there is one, else a new column
+  const int ncols = (wp0 + PR0 + (rsum && rcol >= wp0 ? 1 : 0) + 15) & ~15;
   const int mtiles = EG > 128 ? 2 : 1;
   const int nkb = (K + TG_BK - 1) / TG_BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,6 +162,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
         *reinterpret_cast<uint4 *>(st + off) = hi;
         *reinterpret_cast<uint4 *>(st + TG_HALF + off) = lo;
       }
+      if (rsum && r0 == 0) {   // the all-ones row (row sums of F as one more Gram column): exact in bf16, lo = 0
+        const int row = rcol;
+        const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (k + 2 * q < K ? 0x3F80u : 0u) | (k + 2 * q + 1 < K ? 0x3F800000u : 0u);
+        *reinterpret_cast<uint4 *>(st + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(st + TG_HALF + off) = make_uint4(0u, 0u, 0u, 0u);
+      }
       tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(full0 + 8 * s);
     }
@@ -218,14 +231,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
         const int rlo = mt * 128 + q * 32, rhi = rlo + 31 < EG ? rlo + 31 : EG - 1;
         const int blo = G == 1 ? 0 : (rlo / E) * E, bhi = G == 1 ? E : (rhi / E) * E + E;
         for (int c0 = 0; c0 < ncols; c0 += 16) {
-          if (!((c0 < bhi && c0 + 16 > blo) || c0 + 16 > wp0)) continue;   // neither a diagonal block nor projections
+          if (!((c0 < bhi && c0 + 16 > blo) || c0 + 16 > wp0 || (rsum && c0 <= rcol && rcol < c0 + 16))) continue;   // neither a diagonal block nor projections / row sums
           float v[16];
           tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ncols + c0), v);
           if (live) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = c0 + j;
-              if (col >= cb0 && col < cb1) Hcol[(size_t)(col - cb0) * P->Ep] = (mask_diag && col == row) ? 0.f : v[j];
+              if (col >= cb0 && col < cb1) {
+                Hcol[(size_t)(col - cb0) * P->Ep] = (mask_diag && col == row) ? 0.f : v[j];
+                if (col == row && a.Dg) a.Dg[(size_t)b * E + er] = v[j];
+              } else if (rsum && col == rcol) a.Rs[(size_t)b * E + er] = v[j];
               else if (col >= wp0 && col - wp0 < PR0) Prow[col - wp0] = v[j];
             }
           }
@@ -246,9 +262,10 @@ static inline int tc_gram_prepare() {
   return ccsd_ensure_smem(tc_gram_kernel<true>, TG_SMEM, a1);
 }
 
-static inline int tc_gram_launch(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, void *stream) {
+static inline int tc_gram_launch(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, float *Dg, float *Rs,
+                                 void *stream) {
   TcGramArgs a;
-  a.r2 = r2; a.H = H; a.P0 = P0;
+  a.r2 = r2; a.H = H; a.P0 = P0; a.Dg = Dg; a.Rs = Rs;
   const int nv = (hp.d.B + hp.gram_group - 1) / hp.gram_group;
   int grid = nv < 148 ? nv : 148;
   if (hp.gram_group > 1) tc_gram_kernel<true><<<grid, TG_THREADS, TG_SMEM, (cudaStream_t)stream>>>(dP, a);
