@@ -511,7 +511,7 @@ def main():
             src = "fallback (B200_PROFILING.md)"
         work = kernel_alg_work(meta, B, eng2.desc.neta.n_proj_rows[0] if meta["is_cc"] else 0)
         peak_hbm = peaks.get("hbm_gbs", 6650.0)
-        XA = ("x_net_kernel", "tc_xfin_kernel", "attn_channel_kernel", "tc_attn_kernel", "attn_finish_kernel", "proj1_kernel", "hodge_kernel",
+        XA = ("x_net_kernel", "tc_xfin_kernel", "attn_channel_kernel", "tc_attn_kernel", "attn_finish_kernel", "tc_edge_kernel", "proj1_kernel", "hodge_kernel",
               "hodge_base_kernel", "afinal_kernel", "tc_afinal_kernel", "big_prep_kernel", "big_pow_kernel", "big_deg_kernel", "big_xw_kernel",
               "big_agg_kernel", "tc_agg_kernel", "big_attn_kernel", "big_node_kernel", "big_edge_kernel", "big_edge_pair_kernel",
               "big_mirror_kernel", "big_final_kernel", "big_xfin_kernel")

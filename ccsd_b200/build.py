@@ -44,6 +44,7 @@ def _units():
     for k in range(5):
         units.append((f"tc_apply_f{k}", "tc_apply_tu.cu", [f"-DTA_FMODE={k}"], _APPLY_DEPS))
     units.append(("tc_hnorm", "tc_hnorm_tu.cu", [], ["tc_hnorm.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
+    units.append(("tc_edge", "tc_edge_tu.cu", [], ["tc_edge.cuh", "xa_pipe.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
     units.append(("tc_xfin", "tc_xfin_tu.cu", [], ["tc_xfin.cuh", "xa_pipe.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
     units.append(("tc_attn", "tc_attn_tu.cu", [], ["tc_attn.cuh", "xa_pipe.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
     return units

@@ -26,6 +26,7 @@
 #include "tc_attn.cuh"
 #include "tc_xfin.cuh"
 #include "tc_hnorm.cuh"
+#include "tc_edge.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -89,6 +90,7 @@ struct ccsd_plan {
 #ifndef CCSD_EMU
   int use_tc_attn[CCSD_MAX_LAYERS] = {0};   // per attention layer: tcgen05 attention-channel kernel (tc_attn.cuh)
   TcAttnLayout tattn[CCSD_MAX_LAYERS];
+  int use_tc_edge[CCSD_MAX_LAYERS] = {0};   // per attention layer: per-edge MLP on tcgen05 (tc_edge.cuh)
   int use_hnorm = 0;                        // rank-2 Langevin norms from Gram quantities instead of a NORM pass (tc_hnorm.cuh)
   cudaStream_t side = nullptr;              // internal stream: the norm kernels run beside the x / adj pipeline
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -617,9 +619,11 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;
   if (getenv("CCSD_B200_NO_TC_AGG")) p->use_tc_agg = 0;
   if ((d.nets & 1) && !getenv("CCSD_B200_NO_TC_XFIN")) p->use_tc_xfin = tc_xfin_layout(d, XL, p->txf);
+  if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_EDGE"))
+    for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_edge[l] = tc_edge_supported(d, XL, d.neta.layer[l]);
   if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_ATTN"))
     for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_attn[l] = tc_attn_layout(d, XL, d.neta.layer[l], p->tattn[l]);
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = p->use_tc_xfin = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); }  // A/B switch for tests and profiling
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = p->use_tc_xfin = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); memset(p->use_tc_edge, 0, sizeof p->use_tc_edge); }  // A/B switch for tests and profiling
   // rank-2 Langevin norms from Gram quantities (affine ScoreNetworkF on the tensor-core Gram / apply kernels, PC + Langevin)
   p->use_hnorm = p->use_tc && p->use_tc_apply && d.sampler == CCSD_SAMPLER_PC && d.use_corrector && tc_hnorm_supported(d, p->hp.f_mode) &&
                  tc_gram_supported(d.E, d.K, p->hp.PR0 + 1) && !getenv("CCSD_B200_NO_HNORM");
@@ -871,10 +875,21 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
       CCSD_LAUNCH(attn_channel_kernel, dim3(ly.c_in, d.B, 1), L.Tc, (size_t)L.c_total * 4, stream, p->dP, a);
       PROF_END(p, stream);
     }
+#ifndef CCSD_EMU
+    a.skip_edge = p->use_tc_edge[l];
+#endif
     PROF_BEGIN(p, "attn_finish_kernel", stream);
     CCSD_LAUNCH(attn_finish_kernel, dim3(d.B, 1, 1), L.Tf, (size_t)L.f_total * 4, stream, p->dP, a);
     PROF_END(p, stream);
     p->launches += 2;
+#ifndef CCSD_EMU
+    if (p->use_tc_edge[l]) {
+      PROF_BEGIN(p, "tc_edge_kernel", stream);
+      if (tc_edge_launch(p->dP, p->hp, a, stream)) return fail(CCSD_ERR_CUDA, "tc_edge launch failed");
+      PROF_END(p, stream);
+      p->launches++;
+    }
+#endif
     ch_in = ch_out;
     ch_out += ly.c_out;
     const float *t = xout; xout = (float *)xin; xin = t;
@@ -1241,6 +1256,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
 #ifndef CCSD_EMU
     case 15: return p->use_tc_xfin;
     case 16: return p->use_hnorm;
+    case 17: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_edge[l]; return n; }
     case 14: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_attn[l]; return n; }   // layers on the tcgen05 attention kernel
 #endif
     case 7: return p->hp.xp.x_total * 4;

@@ -65,6 +65,7 @@ struct XaArgs {
   int layer, ch_in, ch_out;
   const float *g_xin;            // node features read by this layer  [kin x N4] per graph
   float *g_xout;                 // node features written by this layer
+  int skip_edge;                 // attn_finish_kernel: the per-edge MLP runs on the tensor cores (tc_edge.cuh) instead
   float *g_hcat;                 // not null: x_net_kernel stops after the GCN stack and writes [x, h_1 .. h_D] ([fdim x N4] per
                                  // graph) here for the tensor-core final MLP (tc_xfin.cuh)
 };
@@ -321,6 +322,7 @@ CCSD_KERNEL void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__rest
       gx[p] = i < N ? fast_tanh(cur[p] * flags[i]) : 0.f;
     }
   }
+  if (a.skip_edge) return;
   // edge branch: M = MLP(cat[A_1..A_c, adj_1..adj_c]) ; adj_out = mask_adjs(M + M^T) = 2 M mask (M symmetric)
   float *gs = a.g_stack + (size_t)b * L.g_stack;
   const float *ga = a.g_att + (size_t)b * L.g_att;

@@ -17,9 +17,9 @@ for name, B in cases:
     try:
         cfg = Config(name)
         eng = make_engine(cfg, B, "cuda")
-        ntc = (eng.lib.ccsd_plan_info(eng.handle, 14), eng.lib.ccsd_plan_info(eng.handle, 15))
+        ntc = tuple(eng.lib.ccsd_plan_info(eng.handle, i) for i in (14, 15, 16, 17))
         errs = score_parity(name, B, "cuda")
-        print(f"{name:24s} B={B:4d} tc_attn_layers,tc_xfin={ntc} errs={ {k: float('%.3g' % v) for k, v in errs.items()} } {time.time()-t:.1f}s", flush=True)
+        print(f"{name:24s} B={B:4d} tc(attn,xfin,hnorm,edge)={ntc} errs={ {k: float('%.3g' % v) for k, v in errs.items()} } {time.time()-t:.1f}s", flush=True)
     except Exception as e:
         print(f"{name:24s} B={B:4d} FAILED: {type(e).__name__}: {e}", flush=True)
         if "CUDA" in str(e) or "cuda" in str(e):
