@@ -43,6 +43,7 @@ def _units():
     units = [("ccsd_b200", "ccsd_b200.cu", [], None)]   # None: depends on every header
     for k in range(5):
         units.append((f"tc_apply_f{k}", "tc_apply_tu.cu", [f"-DTA_FMODE={k}"], _APPLY_DEPS))
+    units.append(("tc_r2big", "tc_r2big_tu.cu", [], ["tc_r2big.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
     units.append(("tc_hnorm", "tc_hnorm_tu.cu", [], ["tc_hnorm.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
     units.append(("tc_edge", "tc_edge_tu.cu", [], ["tc_edge.cuh", "xa_pipe.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))
     units.append(("tc_xfin", "tc_xfin_tu.cu", [], ["tc_xfin.cuh", "xa_pipe.cuh", "r2_kernels.cuh", "prims.cuh", "plan_dev.h", "common.cuh", "tc_common.cuh"]))

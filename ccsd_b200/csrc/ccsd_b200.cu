@@ -27,6 +27,7 @@
 #include "tc_xfin.cuh"
 #include "tc_hnorm.cuh"
 #include "tc_edge.cuh"
+#include "tc_r2big.cuh"
 #endif
 
 #ifdef CCSD_EMU
@@ -90,6 +91,7 @@ struct ccsd_plan {
 #ifndef CCSD_EMU
   int use_tc_attn[CCSD_MAX_LAYERS] = {0};   // per attention layer: tcgen05 attention-channel kernel (tc_attn.cuh)
   TcAttnLayout tattn[CCSD_MAX_LAYERS];
+  int use_tc_big = 0;                       // E > 192: K-chunked tcgen05 GEMMs for the Gram product and H . F (tc_r2big.cuh)
   int use_tc_edge[CCSD_MAX_LAYERS] = {0};   // per attention layer: per-edge MLP on tcgen05 (tc_edge.cuh)
   int use_hnorm = 0;                        // rank-2 Langevin norms from Gram quantities instead of a NORM pass (tc_hnorm.cuh)
   cudaStream_t side = nullptr;              // internal stream: the norm kernels run beside the x / adj pipeline
@@ -619,11 +621,13 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   p->use_tc_agg = (XL.big && (d.nets & 2)) ? 1 : 0;
   if (getenv("CCSD_B200_NO_TC_AGG")) p->use_tc_agg = 0;
   if ((d.nets & 1) && !getenv("CCSD_B200_NO_TC_XFIN")) p->use_tc_xfin = tc_xfin_layout(d, XL, p->txf);
+  p->use_tc_big = (d.is_cc && !getenv("CCSD_B200_NO_TC_BIG")) ? tc_r2big_supported(d, p->hp.PR0) : 0;
+  if (d.is_cc && (d.nets & 4) && p->hp.f_mode != 1 && p->hp.f_mode != 3) p->use_tc_big = 0;   // ill-conditioned non-affine networks stay in fp32
   if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_EDGE"))
     for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_edge[l] = tc_edge_supported(d, XL, d.neta.layer[l]);
   if ((d.nets & 2) && !getenv("CCSD_B200_NO_TC_ATTN"))
     for (int l = 0; l < d.neta.num_layers; ++l) p->use_tc_attn[l] = tc_attn_layout(d, XL, d.neta.layer[l], p->tattn[l]);
-  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = p->use_tc_xfin = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); memset(p->use_tc_edge, 0, sizeof p->use_tc_edge); }  // A/B switch for tests and profiling
+  if (const char *e = getenv("CCSD_B200_NO_TC")) if (e[0] == '1') { p->use_tc = p->use_tc_apply = p->use_tc_fin = p->use_tc_agg = p->use_tc_xfin = p->use_tc_big = 0; memset(p->use_tc_attn, 0, sizeof p->use_tc_attn); memset(p->use_tc_edge, 0, sizeof p->use_tc_edge); }  // A/B switch for tests and profiling
   // rank-2 Langevin norms from Gram quantities (affine ScoreNetworkF on the tensor-core Gram / apply kernels, PC + Langevin)
   p->use_hnorm = p->use_tc && p->use_tc_apply && d.sampler == CCSD_SAMPLER_PC && d.use_corrector && tc_hnorm_supported(d, p->hp.f_mode) &&
                  tc_gram_supported(d.E, d.K, p->hp.PR0 + 1) && !getenv("CCSD_B200_NO_HNORM");
@@ -944,9 +948,20 @@ static void launch_apply(ccsd_plan *p, const ApplyArgs &q, void *stream) {
 #endif
   if (p->apply_big) {
     const ccsd_plan_desc_t &d = p->hp.d;
-    HfArgs h; h.r2 = q.r2; h.H = q.H; h.hf = p->sr2;
-    CCSD_LAUNCH(hf_gemm_kernel, dim3((d.K + GRAM_BN - 1) / GRAM_BN, (d.E + GRAM_BM - 1) / GRAM_BM, d.B), 256,
-                2 * GRAM_BK * (GRAM_BM + 4) * 4, stream, p->dP, h);
+#ifndef CCSD_EMU
+    if (p->use_tc_big) {
+      PROF_END(p, stream);                                   // (close the caller's "apply_kernel" record: it times nothing)
+      PROF_BEGIN(p, "tc_r2big_kernel<hf>", stream);
+      if (tc_r2big_hf(p->dP, p->hp, q.r2, q.H, p->sr2, stream)) { fail(CCSD_ERR_CUDA, "tc_r2big (H F) launch failed"); return; }
+      PROF_END(p, stream);
+      PROF_BEGIN(p, "r2_epi_kernel", stream);
+    } else
+#endif
+    {
+      HfArgs h; h.r2 = q.r2; h.H = q.H; h.hf = p->sr2;
+      CCSD_LAUNCH(hf_gemm_kernel, dim3((d.K + GRAM_BN - 1) / GRAM_BN, (d.E + GRAM_BM - 1) / GRAM_BM, d.B), 256,
+                  2 * GRAM_BK * (GRAM_BM + 4) * 4, stream, p->dP, h);
+    }
     const dim3 ge(R2EPI_CHUNKS, d.B, 1);
     const float *hf = p->sr2;
     if (p->hp.f_mode == 1) CCSD_LAUNCH(r2_epi_kernel<1>, ge, 256, p->apply_smem, stream, p->dP, q, hf);
@@ -970,6 +985,14 @@ static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, con
   if (p->use_tc) {
     PROF_BEGIN(p, "tc_gram_kernel", stream);
     if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, p->use_hnorm ? p->Dg : nullptr, p->use_hnorm ? p->Rs : nullptr, stream)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
+    PROF_END(p, stream);
+    p->launches++;
+  } else
+#endif
+#ifndef CCSD_EMU
+  if (p->use_tc_big) {
+    PROF_BEGIN(p, "tc_r2big_kernel<gram>", stream);
+    if (tc_r2big_gram(p->dP, p->hp, r2, p->H, p->P0, stream)) return fail(CCSD_ERR_CUDA, "tc_r2big (Gram) launch failed");
     PROF_END(p, stream);
     p->launches++;
   } else
@@ -1256,6 +1279,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
 #ifndef CCSD_EMU
     case 15: return p->use_tc_xfin;
     case 16: return p->use_hnorm;
+    case 18: return p->use_tc_big;
     case 17: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_edge[l]; return n; }
     case 14: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_attn[l]; return n; }   // layers on the tcgen05 attention kernel
 #endif
@@ -1273,12 +1297,21 @@ int ccsd_debug_gram(ccsd_plan_t *p, const float *r2, float *H_out, float *P0_out
   const ccsd_plan_desc_t &d = p->hp.d;
   const int saved = p->use_tc;
 #ifndef CCSD_EMU
-  if (use_tc && !tc_gram_supported(d.E, d.K, p->hp.PR0)) return fail(CCSD_ERR_UNSUPPORTED, "tensor-core Gram kernel does not cover this shape");
-  if (use_tc) tc_gram_prepare();
-#endif
+  const int saved_big = p->use_tc_big;
+  const bool big = d.E > 192;
+  if (use_tc && !(big ? tc_r2big_supported(d, p->hp.PR0) : tc_gram_supported(d.E, d.K, p->hp.PR0)))
+    return fail(CCSD_ERR_UNSUPPORTED, "tensor-core Gram kernel does not cover this shape");
+  if (use_tc && !big) tc_gram_prepare();
+  p->use_tc_big = big ? use_tc : 0;
+  p->use_tc = big ? 0 : use_tc;
+#else
   p->use_tc = use_tc;
+#endif
   int r = launch_rank2_pre(p, r2, p->adj, p->flags, stream);
   p->use_tc = saved;
+#ifndef CCSD_EMU
+  p->use_tc_big = saved_big;
+#endif
   if (r) return r;
   if (H_out) {
     const size_t rows = (size_t)d.B * d.E, rb = (size_t)d.E * 4, pitch = (size_t)p->hp.Ep * 4;

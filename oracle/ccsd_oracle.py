@@ -243,9 +243,14 @@ def _tanh_attention(Q: Tensor, K: Tensor, heads: int, out_dim: int) -> Tensor:
 
 
 def attention(sd: SD, x: Tensor, adj: Tensor, heads: int) -> Tuple[Tensor, Tensor]:
-    """Attention.forward with conv == "GCN".  attention.py:84-132."""
-    Q = dense_gcn(_sub(sd, "gnn_q"), x, adj)
-    K = dense_gcn(_sub(sd, "gnn_k"), x, adj)
+    """Attention.forward.  attention.py:84-132; conv == "GCN": Q, K = DenseGCNConv; conv == "MLP": Q, K = 2-layer
+    tanh MLPs of x alone (attention.py:170-180).  V is a DenseGCNConv in both."""
+    if "gnn_q.weight" in sd:
+        Q = dense_gcn(_sub(sd, "gnn_q"), x, adj)
+        K = dense_gcn(_sub(sd, "gnn_k"), x, adj)
+    else:
+        Q = mlp(_sub(sd, "gnn_q"), x, act=torch.tanh)
+        K = mlp(_sub(sd, "gnn_k"), x, act=torch.tanh)
     V = dense_gcn(_sub(sd, "gnn_v"), x, adj)
     out_dim = sd["gnn_v.weight"].shape[1]
     return V, _tanh_attention(Q, K, heads, out_dim)
@@ -311,6 +316,19 @@ def score_network_x(sd: SD, hp: dict, x: Tensor, adj: Tensor, flags: Optional[Te
     xs = [x]
     for k in range(hp["depth"]):
         x = torch.tanh(dense_gcn(_sub(sd, f"layers.{k}"), x, adj))
+        xs.append(x)
+    out = mlp(_sub(sd, "final"), torch.cat(xs, dim=-1))
+    return mask_x(out, flags)
+
+
+def score_network_x_gmh(sd: SD, hp: dict, x: Tensor, adj: Tensor, flags: Optional[Tensor]) -> Tensor:
+    """ScoreNetworkX_GMH.forward_graph.  ScoreNetwork_X.py:280-314: AttentionLayers on (x, A^1..A^c), tanh of every
+    layer's node output (on top of the layer's own tanh), concat, 3-layer MLP, mask."""
+    adjc = pow_tensor(adj, hp["c_init"])
+    xs = [x]
+    for k in range(hp["depth"]):
+        x, adjc = attention_layer(_sub(sd, f"layers.{k}"), x, adjc, flags, hp["num_heads"])
+        x = torch.tanh(x)
         xs.append(x)
     out = mlp(_sub(sd, "final"), torch.cat(xs, dim=-1))
     return mask_x(out, flags)
@@ -418,6 +436,9 @@ class Model:
         if self.kind == "ScoreNetworkX":
             x, adj, flags = (args[0], args[1], args[-1])
             return score_network_x(self.sd, self.hp, x, adj, flags)
+        if self.kind == "ScoreNetworkX_GMH":
+            x, adj, flags = (args[0], args[1], args[-1])
+            return score_network_x_gmh(self.sd, self.hp, x, adj, flags)
         if self.kind == "ScoreNetworkA":
             x, adj, flags = (args[0], args[1], args[-1])
             return score_network_a(self.sd, self.hp, x, adj, flags)

@@ -86,9 +86,49 @@ def put(store, key, t):
         store[f"{key}/{k}"] = v
 
 
+# Model / layer options that no shipped checkpoint uses: ScoreNetworkX_GMH and the conv == "MLP"
+# attention variant.  The reference's own classes with their default initialisation under torch.manual_seed(42).
+SYNTH = {
+    "synth_gmh_mlpconv": {
+        "data": {"data": "synth", "max_node_num": 7, "max_feat_num": 3, "batch_size": 4},
+        "sde": {k: {"type": "VP", "beta_min": 0.1, "beta_max": 1.0, "num_scales": 1000} for k in ("x", "adj")},
+        "x": {"model_type": "ScoreNetworkX_GMH", "max_feat_num": 3, "depth": 2, "nhid": 8, "num_linears": 2, "c_init": 2,
+              "c_hid": 4, "c_final": 3, "adim": 8, "num_heads": 4, "conv": "GCN"},
+        "adj": {"model_type": "ScoreNetworkA", "max_feat_num": 3, "max_node_num": 7, "nhid": 8, "num_layers": 3,
+                "num_linears": 2, "c_init": 2, "c_hid": 4, "c_final": 3, "adim": 8, "num_heads": 4, "conv": "MLP"},
+        "sampler": ("Reverse", "Langevin", 0.1, 0.7), "B": 4,
+    },
+    "synth_gmh_mlpconv2": {   # GMH with the MLP convolution, three linears in the edge MLP
+        "data": {"data": "synth", "max_node_num": 9, "max_feat_num": 4, "batch_size": 4},
+        "sde": {k: {"type": "VE", "beta_min": 0.1, "beta_max": 1.0, "num_scales": 1000} for k in ("x", "adj")},
+        "x": {"model_type": "ScoreNetworkX_GMH", "max_feat_num": 4, "depth": 3, "nhid": 12, "num_linears": 3, "c_init": 2,
+              "c_hid": 5, "c_final": 4, "adim": 12, "num_heads": 4, "conv": "MLP"},
+        "adj": {"model_type": "ScoreNetworkA", "max_feat_num": 4, "max_node_num": 9, "nhid": 12, "num_layers": 2,
+                "num_linears": 3, "c_init": 2, "c_hid": 5, "c_final": 4, "adim": 12, "num_heads": 4, "conv": "GCN"},
+        "sampler": ("Euler", "Langevin", 0.1, 0.7), "B": 4,
+    },
+}
+
+
+def _synth_ckpt(name):
+    from easydict import EasyDict
+    sp = SYNTH[name]
+    ck = {"model_config": EasyDict({"data": sp["data"], "sde": sp["sde"]})}
+    torch.manual_seed(42)
+    for k in ("x", "adj"):
+        ck[f"params_{k}"] = dict(sp[k])
+        m = rloader.load_model(dict(sp[k]))
+        ck[f"{k}_state_dict"] = {kk: v.detach().clone() for kk, v in m.state_dict().items()}
+    return ck
+
+
 def make_config(name):
-    ckpt, (pred, corr, snr, seps), B = CONFIGS[name]
-    ck = torch.load(f"/root/reference/checkpoints/{ckpt}.pth", map_location="cpu", weights_only=False)
+    if name in SYNTH:
+        ckpt, (pred, corr, snr, seps), B = f"synthetic:{name} (torch.manual_seed(42) default init)", SYNTH[name]["sampler"], SYNTH[name]["B"]
+        ck = _synth_ckpt(name)
+    else:
+        ckpt, (pred, corr, snr, seps), B = CONFIGS[name]
+        ck = torch.load(f"/root/reference/checkpoints/{ckpt}.pth", map_location="cpu", weights_only=False)
     is_cc = "params_rank2" in ck
     keys = ["x", "adj"] + (["rank2"] if is_cc else [])
     cfg = ck["model_config"]
