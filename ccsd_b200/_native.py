@@ -29,15 +29,17 @@ class Gcn(C.Structure):
     _fields_ = [("din", i32), ("dout", i32), ("w", i32), ("b", i32)]
 
 
-class NetX(C.Structure):
-    _fields_ = [("nfeat", i32), ("depth", i32), ("nhid", i32), ("fdim", i32), ("gcn", Gcn * MAX_LAYERS), ("fin", Mlp)]
-
-
 class AttnLayer(C.Structure):
     _fields_ = [
         ("c_in", i32), ("c_out", i32), ("conv_in", i32), ("attn_dim", i32), ("conv_out", i32),
-        ("q", Gcn * MAX_CH), ("k", Gcn * MAX_CH), ("v", Gcn * MAX_CH), ("vw", Gcn * MAX_CH), ("mlp", Mlp), ("multi_channel", Mlp),
+        ("q", Gcn * MAX_CH), ("k", Gcn * MAX_CH), ("v", Gcn * MAX_CH), ("vw", Gcn * MAX_CH), ("conv_mlp", i32), ("qm", Mlp * MAX_CH), ("km", Mlp * MAX_CH),
+        ("mlp", Mlp), ("multi_channel", Mlp),
     ]
+
+
+class NetX(C.Structure):
+    _fields_ = [("nfeat", i32), ("depth", i32), ("nhid", i32), ("fdim", i32), ("gcn", Gcn * MAX_LAYERS), ("fin", Mlp),
+                ("gmh", i32), ("gmh_c_init", i32), ("gmh_heads", i32), ("glayer", AttnLayer * MAX_LAYERS)]
 
 
 class HodgeLayer(C.Structure):

@@ -100,9 +100,9 @@ struct ccsd_plan {
   float *Dg = nullptr, *Rs = nullptr;       // [B][E] diag(F F^T), F 1
   int use_tc_xfin = 0;                      // ScoreNetworkX final MLP on tcgen05 (tc_xfin.cuh)
   TcXfinLayout txf;
-  float *g_hcat = nullptr;                  // [B][fdimX x N4]
   uint8_t *ximg = nullptr;                  // weight operand image of tc_xfin
 #endif
+  float *g_hcat = nullptr;                  // [B][fdimX x N4] node features x, h_1 .. h_D (tc_xfin / ScoreNetworkX_GMH)
   int apply_big = 0;   // E too large for the resident F column block: hf_gemm_kernel + r2_epi_kernel (scratch = sr2)
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
@@ -154,6 +154,38 @@ static int check_gcn(const ccsd_gcn_t &g, size_t nw, const char *name) {
   return 0;
 }
 
+// a chain of AttentionLayers (ScoreNetworkA's trunk, ScoreNetworkX_GMH's layers): dims, weights, supported variants
+static int check_attn_chain(const ccsd_attn_layer_t *layers, int n, int c_init, int F, int heads, size_t nw, int N, int *ch_total) {
+  int ch = c_init, cin = c_init, kin = F;
+  for (int l = 0; l < n; ++l) {
+    const ccsd_attn_layer_t &ly = layers[l];
+    if (ly.c_in != cin || ly.conv_in != kin) return fail(CCSD_ERR_INVALID, "AttentionLayer: layer chaining mismatch");
+    if (ly.c_in > CCSD_MAX_CH || ly.c_out > CCSD_MAX_CH || ly.c_out < 1) return fail(CCSD_ERR_UNSUPPORTED, "AttentionLayer: more than 8 channels per layer");
+    if (ly.attn_dim < heads || heads < 1) return fail(CCSD_ERR_INVALID, "AttentionLayer: attn_dim < num_heads");
+    if (ly.conv_mlp && N > 64) return fail(CCSD_ERR_UNSUPPORTED, "conv == 'MLP' attention is not implemented on the large-graph pipeline (max_node_num > 64)");
+    for (int c = 0; c < ly.c_in; ++c) {
+      if (ly.conv_mlp) {
+        if (int r = check_mlp(ly.qm[c], nw, "attn.gnn_q (MLP)", 0)) return r;
+        if (int r = check_mlp(ly.km[c], nw, "attn.gnn_k (MLP)", 0)) return r;
+        if (ly.qm[c].nl != 2 || ly.km[c].nl != 2 || ly.qm[c].din != kin || ly.qm[c].dout != ly.attn_dim || ly.km[c].dout != ly.attn_dim)
+          return fail(CCSD_ERR_INVALID, "conv == 'MLP': Q / K must be 2-layer MLPs conv_in -> 2 attn_dim -> attn_dim");
+      } else {
+        if (int r = check_gcn(ly.q[c], nw, "attn.gnn_q")) return r;
+        if (int r = check_gcn(ly.k[c], nw, "attn.gnn_k")) return r;
+      }
+      if (int r = check_gcn(ly.v[c], nw, "attn.gnn_v")) return r;
+    }
+    if (int r = check_mlp(ly.mlp, nw, "AttentionLayer.mlp", 0)) return r;
+    if (int r = check_mlp(ly.multi_channel, nw, "AttentionLayer.multi_channel", 0)) return r;
+    if (ly.mlp.din != 2 * ly.c_in || ly.mlp.dout != ly.c_out || ly.multi_channel.din != ly.c_in * ly.conv_out ||
+        ly.multi_channel.dout != ly.conv_out)
+      return fail(CCSD_ERR_INVALID, "AttentionLayer: MLP dims mismatch");
+    ch += ly.c_out; cin = ly.c_out; kin = ly.conv_out;
+  }
+  *ch_total = ch;
+  return 0;
+}
+
 static int validate(const ccsd_plan_desc_t &d, size_t nw) {
   if (d.B < 1 || d.N < 2 || d.F < 1) return fail(CCSD_ERR_INVALID, "B, N, F must be positive (N >= 2)");
   if (d.N > 64 && d.is_cc)
@@ -166,6 +198,14 @@ static int validate(const ccsd_plan_desc_t &d, size_t nw) {
   if (d.nets & 1) {
   if (X.nfeat != d.F || X.depth < 1 || X.depth > CCSD_MAX_LAYERS) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkX: depth 1..8, nfeat == F");
   if (X.fdim != X.nfeat + X.depth * X.nhid) return fail(CCSD_ERR_INVALID, "ScoreNetworkX: fdim mismatch");
+  if (X.gmh) {
+    if (d.N > 64) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkX_GMH is not implemented on the large-graph pipeline (max_node_num > 64)");
+    if (X.gmh_c_init < 1 || X.gmh_c_init > CCSD_MAX_CH) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkX_GMH: c_init 1..8");
+    int chx = 0;
+    if (int r = check_attn_chain(X.glayer, X.depth, X.gmh_c_init, d.F, X.gmh_heads, nw, d.N, &chx)) return r;
+    for (int k = 0; k < X.depth; ++k)
+      if (X.glayer[k].conv_out != X.nhid) return fail(CCSD_ERR_INVALID, "ScoreNetworkX_GMH: every layer must output nhid node features");
+  } else
   for (int k = 0; k < X.depth; ++k)
     if (int r = check_gcn(X.gcn[k], nw, "ScoreNetworkX.layers")) return r;
   if (int r = check_mlp(X.fin, nw, "ScoreNetworkX.final", 0)) return r;
@@ -176,24 +216,8 @@ static int validate(const ccsd_plan_desc_t &d, size_t nw) {
   if (d.nets & 2) {
   if (A.num_layers < 1 || A.num_layers > CCSD_MAX_LAYERS || A.c_init < 1 || A.c_init > CCSD_MAX_CH)
     return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA: num_layers 1..8, c_init 1..8");
-  int ch = A.c_init, cin = A.c_init, kin = d.F;
-  for (int l = 0; l < A.num_layers; ++l) {
-    const ccsd_attn_layer_t &ly = A.layer[l];
-    if (ly.c_in != cin || ly.conv_in != kin) return fail(CCSD_ERR_INVALID, "ScoreNetworkA: layer chaining mismatch");
-    if (ly.c_in > CCSD_MAX_CH || ly.c_out > CCSD_MAX_CH || ly.c_out < 1) return fail(CCSD_ERR_UNSUPPORTED, "ScoreNetworkA: more than 8 channels per layer");
-    if (ly.attn_dim < A.num_heads || A.num_heads < 1) return fail(CCSD_ERR_INVALID, "ScoreNetworkA: attn_dim < num_heads");
-    for (int c = 0; c < ly.c_in; ++c) {
-      if (int r = check_gcn(ly.q[c], nw, "attn.gnn_q")) return r;
-      if (int r = check_gcn(ly.k[c], nw, "attn.gnn_k")) return r;
-      if (int r = check_gcn(ly.v[c], nw, "attn.gnn_v")) return r;
-    }
-    if (int r = check_mlp(ly.mlp, nw, "AttentionLayer.mlp", 0)) return r;
-    if (int r = check_mlp(ly.multi_channel, nw, "AttentionLayer.multi_channel", 0)) return r;
-    if (ly.mlp.din != 2 * ly.c_in || ly.mlp.dout != ly.c_out || ly.multi_channel.din != ly.c_in * ly.conv_out ||
-        ly.multi_channel.dout != ly.conv_out)
-      return fail(CCSD_ERR_INVALID, "AttentionLayer: MLP dims mismatch");
-    ch += ly.c_out; cin = ly.c_out; kin = ly.conv_out;
-  }
+  int ch = A.c_init;
+  if (int r = check_attn_chain(A.layer, A.num_layers, A.c_init, d.F, A.num_heads, nw, d.N, &ch)) return r;
   if (A.is_cc && !d.is_cc) return fail(CCSD_ERR_INVALID, "ScoreNetworkA_CC needs a combinatorial-complex plan (is_cc)");
   if (A.is_cc && A.base_cc) {
     if (A.num_layers_h < 1 || A.num_layers_h > CCSD_MAX_HODGE_LAYERS)
@@ -267,9 +291,13 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   L.Tx = envi("CCSD_XP_TX", L.Tx); L.Tc = envi("CCSD_XP_TC", L.Tc); L.Tf = envi("CCSD_XP_TF", L.Tf);
   L.Tm = envi("CCSD_XP_TM", L.Tm);
   int nh_max = 1, ad_max = 1, cin_max = 1, kin_max = F, mc_hid = 1, mc_o1 = 1, eh = 1, eh_bufs = 1, nch_max = 1;
-  const int heads = imax(A.num_heads, 1);
-  for (int l = 0; l < A.num_layers; ++l) {
-    const ccsd_attn_layer_t &ly = A.layer[l];
+  // every AttentionLayer of the plan: ScoreNetworkA's trunk, then ScoreNetworkX_GMH's layers (they share the kernels)
+  const int nA = (d.nets & 2) ? A.num_layers : 0, nG = ((d.nets & 1) && X.gmh) ? X.depth : 0;
+  int gmh_ch = 0;
+  for (int l = 0; l < nG; ++l) gmh_ch += X.glayer[l].c_out;
+  for (int l = 0; l < nA + nG; ++l) {
+    const ccsd_attn_layer_t &ly = l < nA ? A.layer[l] : X.glayer[l - nA];
+    const int heads = imax(l < nA ? A.num_heads : X.gmh_heads, 1);
     nh_max = imax(nh_max, ly.conv_out);
     ad_max = imax(ad_max, ly.attn_dim);
     cin_max = imax(cin_max, ly.c_in);
@@ -288,7 +316,7 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   for (int k = 0; k < X.depth; ++k) din_max = imax(din_max, X.gcn[k].din);
   o = 0;
   L.x_flags = take(N4); L.x_dvec = take(N4);
-  L.x_adj = take(imax(A.c_init, 1) * ldp);
+  L.x_adj = take(imax(imax(A.c_init, nG ? X.gmh_c_init : 1), 1) * ldp);
   L.x_an = take(N * N4);
   L.x_x0 = take(F * N4);
   L.x_sx = take(F * N4);
@@ -311,8 +339,8 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   L.c_atp = take(nch_max * ldp);
   {
     int wmax = 0;
-    for (int l = 0; l < A.num_layers; ++l) {
-      const ccsd_attn_layer_t &ly = A.layer[l];
+    for (int l = 0; l < nA + nG; ++l) {
+      const ccsd_attn_layer_t &ly = l < nA ? A.layer[l] : X.glayer[l - nA];
       const int o1 = ly.multi_channel.nl == 1 ? ly.multi_channel.dout : ly.multi_channel.dhid;
       const int r8a = (ly.attn_dim + 7) / 8 * 8, r8n = (ly.conv_out + 7) / 8 * 8, r8o = (o1 + 7) / 8 * 8;
       wmax = imax(wmax, ly.conv_in * (2 * r8a + r8n) + ly.conv_out * r8o);
@@ -323,6 +351,7 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
     L.c_w = o; (void)wmax;
 #endif
   }
+  L.c_mh = take(2 * ad_max * N4);   // hidden layer of the conv == "MLP" Q / K networks
   L.c_total = o;
   // ---- attn_finish_kernel ----
   o = 0;
@@ -367,8 +396,8 @@ static void make_layout(const ccsd_plan_desc_t &d, XpLayout &L) {
   L.m_fb = A.fin.nl > 2 ? take(fin_h * L.m_rows) : L.m_fa;
   L.m_total = o;
   // ---- global scratch ----
-  L.g_stack = imax(A.fdim, 1) * ldp;
-  L.g_att = cin_max * ldp;
+  L.g_stack = imax(imax(A.fdim, nG ? X.gmh_c_init + gmh_ch : 1), 1) * ldp;
+  L.g_att = imax(cin_max, nG ? X.gmh_c_init : 1) * ldp;
   L.mc_o1_max = mc_o1;
   L.g_hmc = cin_max * mc_o1 * N4;
   L.g_x = imax(F, nh_max) * N4;
@@ -453,13 +482,14 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.ghmc = take(B * (size_t)p->hp.xp.g_hmc * 4);
   w.gx0 = take(B * (size_t)p->hp.xp.g_x * 4);
   w.gx1 = take(B * (size_t)p->hp.xp.g_x * 4);
+  const bool gmh = (d.nets & 1) && d.netx.gmh;
 #ifndef CCSD_EMU
   w.dg = take(p->use_hnorm ? B * E * 4 : 16);
   w.rs = take(p->use_hnorm ? B * E * 4 : 16);
-  w.ghcat = take(p->use_tc_xfin ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
+  w.ghcat = take((p->use_tc_xfin || gmh) ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
   w.ximg = take(p->use_tc_xfin ? (size_t)p->txf.img_bytes : 16);
 #else
-  w.ghcat = take(16); w.ximg = take(16); w.dg = take(16); w.rs = take(16);
+  w.ghcat = take(gmh ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16); w.ximg = take(16); w.dg = take(16); w.rs = take(16);
 #endif
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
@@ -686,8 +716,9 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->g_stack = (float *)(ws + w.gstack); p->g_att = (float *)(ws + w.gatt); p->g_hmc = (float *)(ws + w.ghmc);
   p->g_x0 = (float *)(ws + w.gx0); p->g_x1 = (float *)(ws + w.gx1);
   p->g_big = (float *)(ws + w.gbig);
+  p->g_hcat = (float *)(ws + w.ghcat);
 #ifndef CCSD_EMU
-  p->g_hcat = (float *)(ws + w.ghcat); p->ximg = (uint8_t *)(ws + w.ximg);
+  p->ximg = (uint8_t *)(ws + w.ximg);
   p->Dg = (float *)(ws + w.dg); p->Rs = (float *)(ws + w.rs);
 #endif
   if (p->hp.xp.big) {
@@ -845,6 +876,52 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
   const XpLayout &L = p->hp.xp;
   const ccsd_neta_t &A = d.neta;
   a.g_stack = p->g_stack; a.g_att = p->g_att; a.g_hmc = p->g_hmc; a.g_x0 = p->g_x0; a.g_x1 = p->g_x1;
+  if ((a.which & 1) && d.netx.gmh) {
+    // ScoreNetworkX_GMH (ScoreNetwork_X.py:280-314): adjacency powers + x hand-over, the AttentionLayers (the same
+    // kernels as ScoreNetworkA's trunk, reading netx.glayer), then the final MLP + x epilogue
+    const ccsd_netx_t &X = d.netx;
+    XaArgs g = a;
+    g.which = 1; g.gmh = 1; g.gmh_phase = 1; g.g_hcat = p->g_hcat;
+    PROF_BEGIN(p, "x_net_kernel", stream);
+    CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, stream, p->dP, g);
+    PROF_END(p, stream);
+    p->launches++;
+    int gin = 0, gout = X.gmh_c_init;
+    const float *gxin = p->g_x0;
+    float *gxout = p->g_x1;
+    for (int l = 0; l < X.depth; ++l) {
+      g.layer = l; g.ch_in = gin; g.ch_out = gout; g.g_xin = gxin; g.g_xout = gxout; g.skip_edge = 0;
+      PROF_BEGIN(p, "attn_channel_kernel", stream);
+      CCSD_LAUNCH(attn_channel_kernel, dim3(X.glayer[l].c_in, d.B, 1), L.Tc, (size_t)L.c_total * 4, stream, p->dP, g);
+      PROF_END(p, stream);
+      PROF_BEGIN(p, "attn_finish_kernel", stream);
+      CCSD_LAUNCH(attn_finish_kernel, dim3(d.B, 1, 1), L.Tf, (size_t)L.f_total * 4, stream, p->dP, g);
+      PROF_END(p, stream);
+      p->launches += 2;
+      gin = gout; gout += X.glayer[l].c_out;
+      const float *t = gxout; gxout = (float *)gxin; gxin = t;
+    }
+    bool done = false;
+#ifndef CCSD_EMU
+    if (p->use_tc_xfin) {
+      g.gmh = 0;
+      PROF_BEGIN(p, "tc_xfin_kernel", stream);
+      if (tc_xfin_launch(p->dP, p->hp, g, p->txf, p->g_hcat, X.fdim * L.N4, p->ximg, stream)) return fail(CCSD_ERR_CUDA, "tc_xfin launch failed");
+      PROF_END(p, stream);
+      p->launches++;
+      done = true;
+    }
+#endif
+    if (!done) {
+      g.gmh_phase = 2;
+      PROF_BEGIN(p, "x_net_kernel", stream);
+      CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, stream, p->dP, g);
+      PROF_END(p, stream);
+      p->launches++;
+    }
+    a.which &= ~1;
+    if (!a.which) return dev_check("ScoreNetworkX_GMH");
+  }
 #ifndef CCSD_EMU
   if (p->use_tc_xfin && (a.which & 1)) a.g_hcat = p->g_hcat;
 #endif

@@ -21,7 +21,7 @@ struct XpLayout {
       x_ax, x_ha, x_hb /*[dhid x N4]*/, x_sx /*[F x N4]*/, x_red, x_total;
   // attn_channel_kernel
   int c_dvec, c_adj /*[ldp]*/, c_an, c_xin /*[kin x N4]*/, c_ax, c_q, c_k /*[adim x N4]*/, c_v /*[nhid x N4]*/,
-      c_atp /*[heads x ldp]*/, c_w /*staged Q|K|V|W1 weights of the channel*/, c_total;
+      c_atp /*[heads x ldp]*/, c_w /*staged Q|K|V|W1 weights of the channel*/, c_mh /*[2 adim x N4] hidden layer of the conv == "MLP" Q / K networks*/, c_total;
   // attn_finish_kernel
   int f_flags, f_hs, f_hs2 /*[mc_hid x N4]*/, f_eha, f_ehb /*[hid x ldp]*/, f_total;
   // hodge_kernel (two hodge layers: hq, hk [c0 x E x ad0], h1 [c1 x E x lde], hdeg [c1 x E])

@@ -52,7 +52,7 @@ static inline int tc_attn_layout(const ccsd_plan_desc_t &d, const XpLayout &XL, 
   const int o1 = mc.nl == 1 ? mc.dout : mc.dhid;
   for (int c = 0; c < ly.c_in; ++c)
     if (ly.vw[c].dout != o1 || ly.vw[c].din != ly.conv_in || ly.vw[c].w <= 0) return 0;   // folded value weights not packed
-  if (ly.conv_in > 64 || ly.attn_dim < 1) return 0;
+  if (ly.conv_in > 64 || ly.attn_dim < 1 || ly.conv_mlp) return 0;   // conv == "MLP": Q / K are not graph convolutions
   T.G = 128 / N; T.R = T.G * N;
   T.K1p = (ly.conv_in + 15) & ~15;
   T.ad = ly.attn_dim; T.adq = (ly.attn_dim + 7) & ~7;

@@ -65,10 +65,17 @@ struct XaArgs {
   int layer, ch_in, ch_out;
   const float *g_xin;            // node features read by this layer  [kin x N4] per graph
   float *g_xout;                 // node features written by this layer
+  int gmh;                       // the attention layers of ScoreNetworkX_GMH (netx.glayer) instead of ScoreNetworkA's
+  int gmh_phase;                 // x_net_kernel of ScoreNetworkX_GMH: 1 = adjacency powers + hand-over of x, 2 = final MLP + epilogue
   int skip_edge;                 // attn_finish_kernel: the per-edge MLP runs on the tensor cores (tc_edge.cuh) instead
   float *g_hcat;                 // not null: x_net_kernel stops after the GCN stack and writes [x, h_1 .. h_D] ([fdim x N4] per
                                  // graph) here for the tensor-core final MLP (tc_xfin.cuh)
 };
+
+__device__ __forceinline__ const ccsd_attn_layer_t &xa_layer(const DevPlan *P, const XaArgs &a) {
+  return a.gmh ? P->d.netx.glayer[a.layer] : P->d.neta.layer[a.layer];
+}
+__device__ __forceinline__ int xa_heads(const DevPlan *P, const XaArgs &a) { return a.gmh ? P->d.netx.gmh_heads : P->d.neta.num_heads; }
 
 // =============================================================================================
 // x_net_kernel: ScoreNetworkX, x epilogue, adjacency powers + feature-major x for the A pipeline
@@ -94,9 +101,9 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
   }
   __syncthreads();
 
-  if (a.which & 2) {
+  if ((a.which & 2) || a.gmh_phase == 1) {
     // pow_tensor (graph_utils.py:274-292): A^c = A^(c-1) . A, symmetric; channels 0..c_init-1 of the stack
-    const int c0 = d.neta.c_init;
+    const int c0 = a.gmh_phase == 1 ? d.netx.gmh_c_init : d.neta.c_init;
     for (int c = 1; c < c0; ++c) {
       for (int t = threadIdx.x; t < NT; t += blockDim.x) {
         const int ij = P->tri_ij[t], i = ij >> 8, j = ij & 255;
@@ -116,10 +123,21 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
   // ---- ScoreNetworkX ----
   const ccsd_netx_t &X = d.netx;
   float *hcat = sm + L.x_hcat, *ax = sm + L.x_ax, *hA = sm + L.x_ha, *hB = sm + L.x_hb;
-  gcn_norm_tri(adj, N, N4, dvec, an);
+  if (a.gmh_phase == 1) {   // ScoreNetworkX_GMH: the attention layers fill rows [F, fdim) of g_hcat; x itself is rows [0, F)
+    float *gh = a.g_hcat + (size_t)b * (size_t)X.fdim * N4;
+    for (int p = threadIdx.x; p < F * N4; p += blockDim.x) gh[p] = x0[p];
+    return;
+  }
   const float *in = x0;
   int din = F, row = 0;
-  for (int k = 0; k < X.depth; ++k) {
+  if (a.gmh_phase == 2) {   // the layers' (tanh'ed) node outputs come back from g_hcat
+    const float *gh = a.g_hcat + (size_t)b * (size_t)X.fdim * N4 + F * N4;
+    row = X.depth * X.nhid;
+    for (int p = threadIdx.x; p < row * N4; p += blockDim.x) hcat[p] = gh[p];
+    __syncthreads();
+  } else
+    gcn_norm_tri(adj, N, N4, dvec, an);
+  for (int k = 0; k < (a.gmh_phase == 2 ? 0 : X.depth); ++k) {
     const ccsd_gcn_t &g = X.gcn[k];
     gcn_aggregate_fm(an, N, N4, in, din, ax);
     __syncthreads();
@@ -129,7 +147,7 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
     din = g.dout;
     row += g.dout;
   }
-  if (a.g_hcat) {
+  if (a.g_hcat && a.gmh_phase == 0) {
     float *gh = a.g_hcat + (size_t)b * (size_t)X.fdim * N4;
     for (int p = threadIdx.x; p < F * N4; p += blockDim.x) gh[p] = x0[p];
     for (int p = threadIdx.x; p < row * N4; p += blockDim.x) gh[F * N4 + p] = hcat[p];
@@ -192,8 +210,8 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const Dev
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
-  const ccsd_neta_t &A = d.neta;
-  const ccsd_attn_layer_t &ly = A.layer[a.layer];
+  const ccsd_attn_layer_t &ly = xa_layer(P, a);
+  const int heads = xa_heads(P, a);
   const int c = blockIdx.x, b = blockIdx.y;
   const int N = d.N, N4 = L.N4, NT = L.NT, ldp = L.ldp;
   const float *W = P->W;
@@ -209,8 +227,10 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const Dev
   const int adp8 = round_up(ad, 8), nhp8 = round_up(nh, 8);
   float *wq = sm + L.c_w, *wk = wq + kin * adp8, *wv = wk + kin * adp8, *w1 = wv + kin * nhp8;
 #if XP_STAGE_W
-  stage_async(wq, W + ly.q[c].w, kin * adp8);
-  stage_async(wk, W + ly.k[c].w, kin * adp8);
+  if (!ly.conv_mlp) {
+    stage_async(wq, W + ly.q[c].w, kin * adp8);
+    stage_async(wk, W + ly.k[c].w, kin * adp8);
+  }
   stage_async(wv, W + ly.v[c].w, kin * nhp8);
   stage_async(w1, W + mc.w[0] + (size_t)c * nh * o1p, nh * o1p);
 #else
@@ -229,7 +249,7 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const Dev
   {
     // Q | K | V = (A x) W_{q,k,v} + b as one item space (same input tile, three weight matrices)
     const int ngrp = N4 >> 2;
-    const int nq = (round_up(ad, 8) >> 3) * ngrp, nv = (round_up(nh, 8) >> 3) * ngrp;
+    const int nq = ly.conv_mlp ? 0 : (round_up(ad, 8) >> 3) * ngrp, nv = (round_up(nh, 8) >> 3) * ngrp;
     for (int it = threadIdx.x; it < 2 * nq + nv; it += blockDim.x) {
       const int w = it < nq ? 0 : (it < 2 * nq ? 1 : 2);
       const int li = it - (w == 0 ? 0 : (w == 1 ? nq : 2 * nq));
@@ -256,7 +276,19 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const Dev
     }
   }
   __syncthreads();
-  attn_scores_blk(q, kf, N, N4, ad, A.num_heads, scale, atp, ldp);
+  if (ly.conv_mlp) {
+    // conv == "MLP" (attention.py:170-180): Q, K = 2-layer tanh MLPs of x alone (no adjacency); mlp_fm ends with a barrier
+    float *mh = sm + L.c_mh;
+    mlp_fm(ly.qm[c], W, xin, N4, kin, nullptr, 0, 0, N, mh, mh, N4, q, 1, N4, ACT_TANH, ACT_NONE);
+    mlp_fm(ly.km[c], W, xin, N4, kin, nullptr, 0, 0, N, mh, mh, N4, kf, 1, N4, ACT_TANH, ACT_NONE);
+    // rows [N, N4) of q / k feed only discarded outputs of the 4 x 4 score blocks: keep them finite
+    for (int p = threadIdx.x; p < ad * (N4 - N); p += blockDim.x) {
+      const int dd = p / (N4 - N), i = N + p - dd * (N4 - N);
+      q[dd * N4 + i] = 0.f; kf[dd * N4 + i] = 0.f;
+    }
+    __syncthreads();
+  }
+  attn_scores_blk(q, kf, N, N4, ad, heads, scale, atp, ldp);
   {
     // V's share of the first Linear of multi_channel, which is linear in the channel concat
     // (attention.py:292): hmc_c(o, i) = sum_f V_c(i, f) W1[c*nh + f, o]; the finish kernel sums over c
@@ -265,7 +297,7 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_C) attn_channel_kernel(const Dev
   }
   __syncthreads();
   {
-    const int ds = ad / A.num_heads, nch = (ad + ds - 1) / ds;
+    const int ds = ad / heads, nch = (ad + ds - 1) / ds;
     float *ga = a.g_att + (size_t)b * L.g_att + (size_t)c * ldp;
     for (int t = threadIdx.x; t < ldp; t += blockDim.x) {
       float s = 0.f;
@@ -283,7 +315,7 @@ CCSD_KERNEL void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__rest
   CCSD_SMEM(sm);
   const ccsd_plan_desc_t &d = P->d;
   const XpLayout &L = P->xp;
-  const ccsd_attn_layer_t &ly = d.neta.layer[a.layer];
+  const ccsd_attn_layer_t &ly = xa_layer(P, a);
   const int b = blockIdx.x;
   const int N = d.N, N4 = L.N4, NT = L.NT, ldp = L.ldp;
   const float *W = P->W;
@@ -317,9 +349,13 @@ CCSD_KERNEL void __launch_bounds__(128) attn_finish_kernel(const DevPlan *__rest
       float *t = cur; cur = oth; oth = t;
     }
     float *gx = a.g_xout + (size_t)b * L.g_x;
+    // ScoreNetworkX_GMH: one more tanh on the layer's node output (ScoreNetwork_X.py:300), kept for the final concat
+    float *ghc = a.gmh ? a.g_hcat + (size_t)b * (size_t)d.netx.fdim * N4 + (size_t)(d.F + a.layer * nh) * N4 : nullptr;
     for (int p = threadIdx.x; p < nh * N4; p += blockDim.x) {
       const int i = p % N4;
-      gx[p] = i < N ? fast_tanh(cur[p] * flags[i]) : 0.f;
+      float v = i < N ? fast_tanh(cur[p] * flags[i]) : 0.f;
+      if (ghc) { v = i < N ? fast_tanh(v) : 0.f; ghc[p] = v; }
+      gx[p] = v;
     }
   }
   if (a.skip_edge) return;

@@ -63,11 +63,14 @@ class MLP(nn.Module):
 class Attention(nn.Module):
     def __init__(self, in_dim: int, attn_dim: int, out_dim: int, num_heads: int = 4, conv: str = "GCN") -> None:
         super().__init__()
-        if conv != "GCN":
-            raise NotImplementedError(f"Convolution layer {conv} not implemented.")
         self.num_heads, self.attn_dim, self.out_dim, self.conv = num_heads, attn_dim, out_dim, conv
-        self.gnn_q, self.gnn_k, self.gnn_v = (DenseGCNConv(in_dim, attn_dim), DenseGCNConv(in_dim, attn_dim),
-                                              DenseGCNConv(in_dim, out_dim))
+        if conv == "GCN":       # attention.py:164-168
+            self.gnn_q, self.gnn_k = DenseGCNConv(in_dim, attn_dim), DenseGCNConv(in_dim, attn_dim)
+        elif conv == "MLP":     # attention.py:170-180
+            self.gnn_q, self.gnn_k = MLP(2, in_dim, 2 * attn_dim, attn_dim), MLP(2, in_dim, 2 * attn_dim, attn_dim)
+        else:
+            raise NotImplementedError(f"Convolution layer {conv} not implemented.")
+        self.gnn_v = DenseGCNConv(in_dim, out_dim)
 
 
 class AttentionLayer(nn.Module):
@@ -185,6 +188,34 @@ class ScoreNetworkX(_ScoreNet):
 
     def forward(self, x, adj, *rest):
         flags = rest[-1] if rest else None  # forward_cc(x, adj, rank2, flags) ignores rank2 (ScoreNetwork_X.py:135-153)
+        return self._score(x, adj, None, flags)
+
+
+class ScoreNetworkX_GMH(_ScoreNet):
+    """ScoreNetwork_X.py:156-341."""
+
+    _which = 0
+
+    def __init__(self, max_feat_num, depth, nhid, num_linears, c_init, c_hid, c_final, adim, num_heads=4, conv="GCN",
+                 use_bn=False, is_cc=False) -> None:
+        super().__init__()
+        self.nfeat, self.depth, self.nhid, self.num_linears = max_feat_num, depth, nhid, num_linears
+        self.c_init, self.c_hid, self.c_final, self.adim = c_init, c_hid, c_final, adim
+        self.num_heads, self.conv, self.use_bn, self.is_cc = num_heads, conv, use_bn, is_cc
+        ls = []
+        for k in range(depth):
+            if k == 0:
+                ls.append(AttentionLayer(num_linears, max_feat_num, nhid, nhid, c_init, c_hid, num_heads, conv, use_bn))
+            elif k == depth - 1:
+                ls.append(AttentionLayer(num_linears, nhid, adim, nhid, c_hid, c_final, num_heads, conv, use_bn))
+            else:
+                ls.append(AttentionLayer(num_linears, nhid, adim, nhid, c_hid, c_hid, num_heads, conv, use_bn))
+        self.layers = nn.ModuleList(ls)
+        self.fdim = max_feat_num + depth * nhid
+        self.final = MLP(3, self.fdim, 2 * self.fdim, max_feat_num, use_bn)
+
+    def forward(self, x, adj, *rest):
+        flags = rest[-1] if rest else None
         return self._score(x, adj, None, flags)
 
 
@@ -319,10 +350,8 @@ def load_model(params: dict) -> nn.Module:
     """ccsd/src/utils/loader.py:70-100."""
     p = dict(params)
     model_type = p.pop("model_type", None)
-    table = {"ScoreNetworkX": ScoreNetworkX, "ScoreNetworkA": ScoreNetworkA, "ScoreNetworkA_CC": ScoreNetworkA_CC,
+    table = {"ScoreNetworkX": ScoreNetworkX, "ScoreNetworkX_GMH": ScoreNetworkX_GMH, "ScoreNetworkA": ScoreNetworkA, "ScoreNetworkA_CC": ScoreNetworkA_CC,
              "ScoreNetworkA_Base_CC": ScoreNetworkA_Base_CC, "ScoreNetworkF": ScoreNetworkF}
-    if model_type in ("ScoreNetworkX_GMH",):
-        raise NotImplementedError(f"{model_type} is not on the accelerated path yet (SURVEY.md 8f)")
     if model_type not in table:
         raise ValueError(
             f"Model Name <{model_type}> is unknown. Please select from [ScoreNetworkX, ScoreNetworkX_GMH, ScoreNetworkA, "

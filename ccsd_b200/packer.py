@@ -113,17 +113,68 @@ def _count(sd, prefix: str) -> int:
     return max(idx) + 1 if idx else 0
 
 
+def _fill_attn_layer(ly: nat.AttnLayer, blob: Blob, sd, prefix: str, conv: str) -> int:
+    """One AttentionLayer (attention.py:186-304) under `prefix`; returns c_in."""
+    c_in = _count(sd, f"{prefix}.attn")
+    if c_in > nat.MAX_CH:
+        raise NotImplementedError(f"{c_in} channels per attention layer; at most {nat.MAX_CH} are supported")
+    if conv not in ("GCN", "MLP"):
+        raise NotImplementedError(f"Convolution layer {conv} not implemented.")   # attention.py:183
+    ly.conv_mlp = 1 if conv == "MLP" else 0
+    for c in range(c_in):
+        if ly.conv_mlp:      # Q, K: MLP(2, in, 2 attn_dim, attn_dim, tanh) of x (attention.py:170-180)
+            _fill_mlp(ly.qm[c], blob, sd, f"{prefix}.attn.{c}.gnn_q")
+            _fill_mlp(ly.km[c], blob, sd, f"{prefix}.attn.{c}.gnn_k")
+            if ly.qm[c].nl != 2 or ly.km[c].nl != 2:
+                raise NotImplementedError("conv == 'MLP': the Q / K networks must be 2-layer MLPs")
+        else:
+            _fill_gcn(ly.q[c], blob, sd, f"{prefix}.attn.{c}.gnn_q")
+            _fill_gcn(ly.k[c], blob, sd, f"{prefix}.attn.{c}.gnn_k")
+        _fill_gcn(ly.v[c], blob, sd, f"{prefix}.attn.{c}.gnn_v")
+    _fill_mlp(ly.mlp, blob, sd, f"{prefix}.mlp")
+    _fill_mlp(ly.multi_channel, blob, sd, f"{prefix}.multi_channel")
+    # value convolution folded with the channel's slice of multi_channel's first Linear (float64 on the host):
+    # V_c W1_c = An x (W_v W1_c) + b_v W1_c  (attention.py:292; csrc/tc_attn.cuh)
+    mcp = f"{prefix}.multi_channel"
+    w1 = sd[f"{mcp}.linear.weight"] if f"{mcp}.linear.weight" in sd else sd[f"{mcp}.linears.0.weight"]   # (o1, c_in * nh)
+    for c in range(c_in):
+        wv = sd[f"{prefix}.attn.{c}.gnn_v.weight"].astype(np.float64)     # (kin, nh)
+        bv = sd[f"{prefix}.attn.{c}.gnn_v.bias"].astype(np.float64)
+        nh = wv.shape[1]
+        w1c = w1[:, c * nh:(c + 1) * nh].astype(np.float64).T              # (nh, o1)
+        ly.vw[c].din, ly.vw[c].dout = wv.shape[0], w1c.shape[1]
+        ly.vw[c].w, ly.vw[c].b = blob.add_in_out((wv @ w1c).astype(np.float32), (bv @ w1c).astype(np.float32))
+    ly.c_in, ly.c_out = c_in, ly.mlp.dout
+    if ly.conv_mlp:
+        ly.conv_in, ly.attn_dim = ly.qm[0].din, ly.qm[0].dout
+    else:
+        ly.conv_in, ly.attn_dim = ly.q[0].din, ly.q[0].dout
+    ly.conv_out = ly.v[0].dout
+    return c_in
+
+
 def pack_netx(dst: nat.NetX, blob: Blob, model) -> None:
-    """ScoreNetworkX (ScoreNetwork_X.py:22-133)."""
+    """ScoreNetworkX (ScoreNetwork_X.py:22-133) or ScoreNetworkX_GMH (ScoreNetwork_X.py:156-341)."""
+    m = _unwrap(model)
     sd = _sd(model)
     depth = _count(sd, "layers")
     if depth < 1 or depth > nat.MAX_LAYERS:
         raise NotImplementedError(f"ScoreNetworkX depth {depth} not in 1..{nat.MAX_LAYERS}")
-    for k in range(depth):
-        _fill_gcn(dst.gcn[k], blob, sd, f"layers.{k}")
     dst.depth = depth
-    dst.nfeat = dst.gcn[0].din
-    dst.nhid = dst.gcn[0].dout
+    if model_kind(model) == "ScoreNetworkX_GMH":
+        dst.gmh = 1
+        dst.gmh_heads = int(getattr(m, "num_heads", 4))
+        for k in range(depth):
+            c_in = _fill_attn_layer(dst.glayer[k], blob, sd, f"layers.{k}", getattr(m, "conv", "GCN"))
+            if k == 0:
+                dst.gmh_c_init = c_in
+        dst.nfeat = dst.glayer[0].conv_in
+        dst.nhid = dst.glayer[0].conv_out
+    else:
+        for k in range(depth):
+            _fill_gcn(dst.gcn[k], blob, sd, f"layers.{k}")
+        dst.nfeat = dst.gcn[0].din
+        dst.nhid = dst.gcn[0].dout
     dst.fdim = dst.nfeat + depth * dst.nhid
     _fill_mlp(dst.fin, blob, sd, "final")
 
@@ -133,8 +184,6 @@ def pack_neta(dst: nat.NetA, blob: Blob, model, K: int) -> None:
     m = _unwrap(model)
     sd = _sd(model)
     kind = model_kind(model)
-    if getattr(m, "conv", "GCN") != "GCN":
-        raise NotImplementedError("attention conv == 'MLP' is not implemented (no shipped config uses it)")
     L = _count(sd, "layers")
     if L < 1 or L > nat.MAX_LAYERS:
         raise NotImplementedError(f"ScoreNetworkA num_layers {L} not in 1..{nat.MAX_LAYERS}")
@@ -145,28 +194,7 @@ def pack_neta(dst: nat.NetA, blob: Blob, model, K: int) -> None:
     fdim = 0
     for l in range(L):
         ly = dst.layer[l]
-        c_in = _count(sd, f"layers.{l}.attn")
-        if c_in > nat.MAX_CH:
-            raise NotImplementedError(f"{c_in} channels per attention layer; at most {nat.MAX_CH} are supported")
-        for c in range(c_in):
-            _fill_gcn(ly.q[c], blob, sd, f"layers.{l}.attn.{c}.gnn_q")
-            _fill_gcn(ly.k[c], blob, sd, f"layers.{l}.attn.{c}.gnn_k")
-            _fill_gcn(ly.v[c], blob, sd, f"layers.{l}.attn.{c}.gnn_v")
-        _fill_mlp(ly.mlp, blob, sd, f"layers.{l}.mlp")
-        _fill_mlp(ly.multi_channel, blob, sd, f"layers.{l}.multi_channel")
-        # value convolution folded with the channel's slice of multi_channel's first Linear (float64 on the host):
-        # V_c W1_c = An x (W_v W1_c) + b_v W1_c  (attention.py:292; csrc/tc_attn.cuh)
-        mcp = f"layers.{l}.multi_channel"
-        w1 = sd[f"{mcp}.linear.weight"] if f"{mcp}.linear.weight" in sd else sd[f"{mcp}.linears.0.weight"]   # (o1, c_in * nh)
-        for c in range(c_in):
-            wv = sd[f"layers.{l}.attn.{c}.gnn_v.weight"].astype(np.float64)     # (kin, nh)
-            bv = sd[f"layers.{l}.attn.{c}.gnn_v.bias"].astype(np.float64)
-            nh = wv.shape[1]
-            w1c = w1[:, c * nh:(c + 1) * nh].astype(np.float64).T                # (nh, o1)
-            ly.vw[c].din, ly.vw[c].dout = wv.shape[0], w1c.shape[1]
-            ly.vw[c].w, ly.vw[c].b = blob.add_in_out((wv @ w1c).astype(np.float32), (bv @ w1c).astype(np.float32))
-        ly.c_in, ly.c_out = c_in, ly.mlp.dout
-        ly.conv_in, ly.attn_dim, ly.conv_out = ly.q[0].din, ly.q[0].dout, ly.v[0].dout
+        c_in = _fill_attn_layer(ly, blob, sd, f"layers.{l}", getattr(m, "conv", "GCN"))
         if l == 0:
             dst.c_init = c_in
             fdim += c_in

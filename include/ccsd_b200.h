@@ -60,13 +60,6 @@ typedef struct {
   int32_t w, b;
 } ccsd_gcn_t;
 
-/* ScoreNetworkX (ScoreNetwork_X.py:22-133) */
-typedef struct {
-  int32_t nfeat, depth, nhid, fdim;
-  ccsd_gcn_t gcn[CCSD_MAX_LAYERS];
-  ccsd_mlp_t fin;
-} ccsd_netx_t;
-
 /* AttentionLayer (attention.py:186-304) with conv == "GCN" */
 typedef struct {
   int32_t c_in, c_out, conv_in, attn_dim, conv_out;
@@ -76,9 +69,24 @@ typedef struct {
    * o1 = width of that Linear) and b_vw = b_v . W1[...] -- the node MLP is linear in the channel concat
    * (attention.py:292), so the tensor-core attention kernel never materialises V.  Computed by the packer. */
   ccsd_gcn_t vw[CCSD_MAX_CH];
+  /* conv == "MLP" (attention.py:170-180): Q and K are 2-layer tanh MLPs of x alone (in -> 2 attn_dim -> attn_dim), V stays
+   * a DenseGCNConv; q[] / k[] are unused then */
+  int32_t conv_mlp;
+  ccsd_mlp_t qm[CCSD_MAX_CH], km[CCSD_MAX_CH];
   ccsd_mlp_t mlp;           /* per-edge MLP, in = 2*c_in                      */
   ccsd_mlp_t multi_channel; /* node MLP, in = c_in*conv_out                   */
 } ccsd_attn_layer_t;
+
+/* ScoreNetworkX (ScoreNetwork_X.py:22-133), or ScoreNetworkX_GMH (ScoreNetwork_X.py:156-341) when gmh = 1: `depth`
+ * AttentionLayers on (x, A^1 .. A^gmh_c_init) instead of GCN layers (nhid = their conv_out), tanh of every layer's node
+ * output, then the same concat + 3-layer MLP */
+typedef struct {
+  int32_t nfeat, depth, nhid, fdim;
+  ccsd_gcn_t gcn[CCSD_MAX_LAYERS];
+  ccsd_mlp_t fin;
+  int32_t gmh, gmh_c_init, gmh_heads;
+  ccsd_attn_layer_t glayer[CCSD_MAX_LAYERS];
+} ccsd_netx_t;
 
 /* HodgeAdjAttentionLayer (hodge_attention.py:185-325), conv == "HCN".  The q/k weights
  * (K x attn_dim) are stored TRANSPOSED as rows of length K ("projection rows"): row index

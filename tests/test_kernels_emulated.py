@@ -134,3 +134,28 @@ def test_large_graph_pipeline_at_tile_boundaries(N):
         out = eng.score(w, x, adj, r2, flags).cpu()
         assert torch.isfinite(out).all()
         assert rel_err(out, ref) < 1e-4, (N, w, rel_err(out, ref))
+
+
+@pytest.mark.parametrize("name,B", [("synth_gmh_mlpconv", 3), ("synth_gmh_mlpconv2", 2)])
+def test_gmh_and_mlp_conv_variants(name, B):
+    """ScoreNetworkX_GMH (ScoreNetwork_X.py:156-341) and the conv == "MLP" attention variant (attention.py:170-180): the
+    reference's own classes with default init (tests/golden/make_golden.py SYNTH), scores and sampler steps."""
+    for k, e in score_parity(name, B, "cpu").items():
+        assert e < SCORE_TOL, (name, k, e)
+    res = sampler_parity(name, "PC", "Reverse", "Langevin", B=B, steps=2, device="cpu")
+    for k, (e_ret, e_state, agree) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4, (name, k, e_ret, e_state)
+
+
+def test_gmh_against_committed_reference_outputs():
+    import torch
+    from tests.helpers import Config, check_compressed
+    from tests.parity_cases import make_engine
+    for name in ("synth_gmh_mlpconv", "synth_gmh_mlpconv2"):
+        cfg = Config(name)
+        io = cfg.io()
+        flags, x, adj = (torch.from_numpy(io[k]) for k in ("flags", "x", "adj"))
+        eng = make_engine(cfg, x.shape[0], "cpu")
+        for w, k in enumerate(cfg.keys):
+            out = eng.score(w, x, adj, None, flags).cpu()
+            assert check_compressed(io, f"net_{k}", out, SCORE_TOL) < SCORE_TOL, (name, k)

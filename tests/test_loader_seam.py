@@ -114,7 +114,7 @@ def test_load_model_rejects_unknown_types():
         loader.load_model({"model_type": "Nope"})
 
 
-CASES_FWD = [("qm9", 5), ("qm9_cc", 3), ("qm9_base_cc", 2)]
+CASES_FWD = [("qm9", 5), ("qm9_cc", 3), ("qm9_base_cc", 2), ("synth_gmh_mlpconv", 4)]   # last: load_model("ScoreNetworkX_GMH"), conv="MLP"
 CASES_SMP = [("qm9", 6, "Reverse", "Langevin"), ("qm9_cc", 3, "Reverse", "Langevin"), ("qm9_cc", 3, "S4", "None")]
 
 

@@ -114,6 +114,24 @@ def test_langevin_inner_steps(name, pred, n_lang, B):
         assert agree >= 0.999, (name, k, agree)
 
 
+@pytest.mark.parametrize("name,B", [("synth_gmh_mlpconv", 13), ("synth_gmh_mlpconv2", 9)])
+def test_gmh_and_mlp_conv_variants(name, B):
+    """ScoreNetworkX_GMH (ScoreNetwork_X.py:156-341) and conv == "MLP" attention (attention.py:170-180): the reference's own
+    classes with default init (fixtures from tests/golden/make_golden.py SYNTH): committed reference outputs, oracle parity
+    of the scores, sampler steps with injected noise."""
+    cfg = Config(name)
+    io = cfg.io()
+    flags, x, adj = (torch.from_numpy(io[k]) for k in ("flags", "x", "adj"))
+    eng = make_engine(cfg, x.shape[0], DEV)
+    for w, k in enumerate(cfg.keys):
+        assert check_compressed(io, f"net_{k}", eng.score(w, x, adj, None, flags).cpu(), SCORE_TOL) < SCORE_TOL, (name, k)
+    for k, e in score_parity(name, B, DEV).items():
+        assert e < SCORE_TOL, (name, k, e)
+    res = sampler_parity(name, "PC", "Reverse", "Langevin", B, 3, DEV)
+    for k, (e_ret, e_state, agree) in res.items():
+        assert e_ret < 1e-4 and e_state < 1e-4, (name, k, e_ret, e_state)
+
+
 def test_longer_horizon_with_injected_noise():
     """60 sampler iterations (360 network evaluations) on the real schedule with the reference's own noise
     stream: the per-step error (~1e-6) must not compound into a different sample -- quantised adjacency and
