@@ -98,6 +98,7 @@ struct ccsd_plan {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool side_pending = false;
   float *Dg = nullptr, *Rs = nullptr;       // [B][E] diag(F F^T), F 1
+  float *H2 = nullptr;                      // [B][E][Ep] H . H of large complexes (tc_r2big)
   int use_tc_xfin = 0;                      // ScoreNetworkX final MLP on tcgen05 (tc_xfin.cuh)
   TcXfinLayout txf;
   uint8_t *ximg = nullptr;                  // weight operand image of tc_xfin
@@ -462,7 +463,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -486,10 +487,11 @@ static WsLayout ws_layout(const ccsd_plan *p) {
 #ifndef CCSD_EMU
   w.dg = take(p->use_hnorm ? B * E * 4 : 16);
   w.rs = take(p->use_hnorm ? B * E * 4 : 16);
+  w.h2 = take((p->use_hnorm && p->use_tc_big) ? B * E * (size_t)a4((int)E) * 4 + 64 : 16);
   w.ghcat = take((p->use_tc_xfin || gmh) ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
   w.ximg = take(p->use_tc_xfin ? (size_t)p->txf.img_bytes : 16);
 #else
-  w.ghcat = take(gmh ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16); w.ximg = take(16); w.dg = take(16); w.rs = take(16);
+  w.ghcat = take(gmh ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16); w.ximg = take(16); w.dg = take(16); w.rs = take(16); w.h2 = take(16);
 #endif
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
@@ -661,6 +663,9 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   // rank-2 Langevin norms from Gram quantities (affine ScoreNetworkF on the tensor-core Gram / apply kernels, PC + Langevin)
   p->use_hnorm = p->use_tc && p->use_tc_apply && d.sampler == CCSD_SAMPLER_PC && d.use_corrector && tc_hnorm_supported(d, p->hp.f_mode) &&
                  tc_gram_supported(d.E, d.K, p->hp.PR0 + 1) && !getenv("CCSD_B200_NO_HNORM");
+  if (p->use_tc_big && d.sampler == CCSD_SAMPLER_PC && d.use_corrector && (d.nets & 4) && p->hp.f_mode == 1 && d.netf.use_hodge_mask &&
+      !getenv("CCSD_B200_NO_HNORM"))
+    p->use_hnorm = 1;   // large complexes: H . H by the K-chunked GEMM, reductions by hnorm_big_kernel
   if (p->use_hnorm && !getenv("CCSD_B200_NO_SIDE_STREAM")) {
     if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -719,7 +724,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->g_hcat = (float *)(ws + w.ghcat);
 #ifndef CCSD_EMU
   p->ximg = (uint8_t *)(ws + w.ximg);
-  p->Dg = (float *)(ws + w.dg); p->Rs = (float *)(ws + w.rs);
+  p->Dg = (float *)(ws + w.dg); p->Rs = (float *)(ws + w.rs); p->H2 = (float *)(ws + w.h2);
 #endif
   if (p->hp.xp.big) {
     // pad columns / rows of the planes are read as don't-care operands: make them finite once
@@ -1069,7 +1074,7 @@ static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, con
 #ifndef CCSD_EMU
   if (p->use_tc_big) {
     PROF_BEGIN(p, "tc_r2big_kernel<gram>", stream);
-    if (tc_r2big_gram(p->dP, p->hp, r2, p->H, p->P0, stream)) return fail(CCSD_ERR_CUDA, "tc_r2big (Gram) launch failed");
+    if (tc_r2big_gram(p->dP, p->hp, r2, p->H, p->P0, p->use_hnorm ? p->Dg : nullptr, p->use_hnorm ? p->Rs : nullptr, stream)) return fail(CCSD_ERR_CUDA, "tc_r2big (Gram) launch failed");
     PROF_END(p, stream);
     p->launches++;
   } else
@@ -1127,11 +1132,23 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
           return fail(CCSD_ERR_CUDA, "stream fork failed");
         ns = (void *)p->side;
       }
-      TcHnormArgs h; memset(&h, 0, sizeof h);
-      h.H = p->H; h.Dg = p->Dg; h.Rs = p->Rs; h.flags = p->flags; h.norm_part = p->norm_part; h.step = step; h.G = p->hp.ap_group;
-      PROF_BEGIN(p, "tc_hnorm_kernel", ns);
-      if (tc_hnorm_launch(p->dP, p->hp, h, ns)) return fail(CCSD_ERR_CUDA, "tc_hnorm launch failed");
-      PROF_END(p, ns);
+      if (p->use_tc_big) {
+        PROF_BEGIN(p, "tc_r2big_kernel<hh>", ns);
+        if (tc_r2big_gram_x(p->dP, p->hp, p->H, d.E, p->hp.Ep, 0, 0, p->H2, nullptr, nullptr, nullptr, ns)) return fail(CCSD_ERR_CUDA, "tc_r2big (H H) launch failed");
+        PROF_END(p, ns);
+        HnormBigArgs hb; memset(&hb, 0, sizeof hb);
+        hb.H = p->H; hb.H2 = p->H2; hb.Dg = p->Dg; hb.Rs = p->Rs; hb.flags = p->flags; hb.norm_part = p->norm_part; hb.step = step;
+        PROF_BEGIN(p, "hnorm_big_kernel", ns);
+        CCSD_LAUNCH(hnorm_big_kernel, dim3(d.B, 1, 1), 256, 64 * 4, ns, p->dP, hb);
+        PROF_END(p, ns);
+        p->launches++;
+      } else {
+        TcHnormArgs h; memset(&h, 0, sizeof h);
+        h.H = p->H; h.Dg = p->Dg; h.Rs = p->Rs; h.flags = p->flags; h.norm_part = p->norm_part; h.step = step; h.G = p->hp.ap_group;
+        PROF_BEGIN(p, "tc_hnorm_kernel", ns);
+        if (tc_hnorm_launch(p->dP, p->hp, h, ns)) return fail(CCSD_ERR_CUDA, "tc_hnorm launch failed");
+        PROF_END(p, ns);
+      }
       ZnormArgs z; memset(&z, 0, sizeof z);
       z.flags = p->flags; z.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr; z.zmask = p->zmask; z.norm_part = p->norm_part;
       z.slot = slot; z.nz = nz;

@@ -1051,43 +1051,98 @@ CCSD_KERNEL void __launch_bounds__(256) znorm_kernel(const DevPlan *__restrict__
   const ccsd_plan_desc_t &d = P->d;
   const int N = d.N, E = d.E, K = d.K, Kg = P->Kp >> 2;
   constexpr int GPT = APPLY_TN / 4;   // 4-cell groups per tile
-  const int t = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.y;
+  const int ntiles = (K + APPLY_TN - 1) / APPLY_TN;      // CTA t takes the tiles t, t + gridDim.x, ... (gridDim.x = norm slots)
   const float *fl = a.flags + (size_t)b * N;
   const unsigned long long zm = a.zmask[b];
   const unsigned long long gs = (unsigned long long)(a.nz.sample_offset + b);
   const uint32_t did = draw_id(2, a.nz.step, a.slot);
-  // staged once per CTA: edge flags [E] and the live-cell bits of this tile's 4-cell groups [GPT]
+  // staged once per CTA: edge flags [E]; per tile: the live-cell bits of its 4-cell groups [GPT]
   float *fes = sm + 40;
   unsigned *gm = reinterpret_cast<unsigned *>(fes + ((E + 3) & ~3));
   for (int e = threadIdx.x; e < E; e += blockDim.x) fes[e] = fl[P->edge_ij[2 * e]] * fl[P->edge_ij[2 * e + 1]];
-  for (int g = threadIdx.x; g < GPT; g += blockDim.x) {
-    unsigned m = 0;
-    for (int q = 0; q < 4; ++q) {
-      const int k = (t * GPT + g) * 4 + q;
-      if (k < K && !(P->cell_mask[k] & zm)) m |= 1u << q;
-    }
-    gm[g] = m;
-  }
-  __syncthreads();
   float z2 = 0.f;
-  for (int it = threadIdx.x; it < E * GPT; it += blockDim.x) {
-    const int e = it / GPT, g = it - e * GPT;
-    const unsigned m = gm[g];
-    if (m == 0u || fes[e] == 0.f) continue;
-    const int kg = t * GPT + g, k = kg * 4;
-    float z4[4];
-    if (a.noise) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) z4[q] = k + q < K ? a.noise[((size_t)b * E + e) * K + k + q] : 0.f;
-    } else {
-      normal4(a.nz.seed, gs, did, (uint32_t)(e * Kg + kg), z4);
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    __syncthreads();   // fes ready / the previous tile's gm no longer read
+    for (int g = threadIdx.x; g < GPT; g += blockDim.x) {
+      unsigned m = 0;
+      for (int q = 0; q < 4; ++q) {
+        const int k = (t * GPT + g) * 4 + q;
+        if (k < K && !(P->cell_mask[k] & zm)) m |= 1u << q;
+      }
+      gm[g] = m;
     }
+    __syncthreads();
+    for (int it = threadIdx.x; it < E * GPT; it += blockDim.x) {
+      const int e = it / GPT, g = it - e * GPT;
+      const unsigned m = gm[g];
+      if (m == 0u || fes[e] == 0.f) continue;
+      const int kg = t * GPT + g, k = kg * 4;
+      float z4[4];
+      if (a.noise) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if ((m >> q) & 1u) z2 += z4[q] * z4[q];
+        for (int q = 0; q < 4; ++q) z4[q] = k + q < K ? a.noise[((size_t)b * E + e) * K + k + q] : 0.f;
+      } else {
+        normal4(a.nz.seed, gs, did, (uint32_t)(e * Kg + kg), z4);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((m >> q) & 1u) z2 += z4[q] * z4[q];
+    }
   }
   z2 = block_sum(z2, sm);
-  if (threadIdx.x == 0) a.norm_part[((size_t)(2 * d.B + b) * P->ntile_max + t) * 2 + 1] = z2;
+  if (threadIdx.x == 0) a.norm_part[((size_t)(2 * d.B + b) * P->ntile_max + blockIdx.x) * 2 + 1] = z2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large complexes (E > 192): the Gram-quantity norm of tc_hnorm.cuh with H . H taken by the K-chunked GEMM
+// (tc_r2big.cuh, H2 in a scratch matrix): the E^2 reductions and the norm.  One CTA per sample, fixed summation order.
+struct HnormBigArgs {
+  const float *H, *H2, *Dg, *Rs, *flags;
+  float *norm_part;
+  int step;
+};
+
+CCSD_KERNEL void __launch_bounds__(256) hnorm_big_kernel(const DevPlan *__restrict__ P, HnormBigArgs a) {
+  CCSD_SMEM(sm);
+  const ccsd_plan_desc_t &d = P->d;
+  const int E = d.E, Ep = P->Ep, N = d.N, b = blockIdx.x;
+  const float *H = a.H + (size_t)b * E * Ep, *H2 = a.H2 + (size_t)b * E * Ep, *D = a.Dg + (size_t)b * E, *R = a.Rs + (size_t)b * E;
+  float t3 = 0.f, sfh = 0.f, sdd = 0.f, sh = 0.f, sff = 0.f, sf = 0.f;
+  for (int e = threadIdx.x >> 5; e < E; e += blockDim.x >> 5) {      // one warp per row, lanes along the columns
+#ifdef CCSD_EMU
+    const int lane = 0, nl = 1;
+#else
+    const int lane = threadIdx.x & 31, nl = 32;
+#endif
+    for (int c = lane; c < E; c += nl) {
+      const float h = H[(size_t)e * Ep + c], h2 = H2[(size_t)e * Ep + c];
+      t3 += h2 * h;
+      sh += h * R[c];
+      if (c == e) { sfh += h2; sdd += D[e] * h2; sff += D[e]; sf += R[e]; }
+    }
+  }
+  t3 = block_sum(t3, sm); sfh = block_sum(sfh, sm); sdd = block_sum(sdd, sm); sh = block_sum(sh, sm);
+  sff = block_sum(sff, sm); sf = block_sum(sf, sm);
+  if (threadIdx.x == 0) {
+    const ccsd_netf_t &Fn = d.netf;
+    const float fa = Fn.aff[0], fb = Fn.aff[1], fc = Fn.aff[2];
+    const float sc = P->sched[a.step * 3 + 2].score_scale;
+    int n = 0;
+    for (int i = 0; i < N; ++i) n += a.flags[(size_t)b * N + i] != 0.f;
+    float nkc = 0.f;
+    for (int dd = d.d_min; dd <= d.d_max; ++dd) {
+      float cmb = dd <= n ? 1.f : 0.f;
+      for (int q = 0; q < dd && dd <= n; ++q) cmb = cmb * (float)(n - q) / (float)(q + 1);
+      nkc += cmb;
+    }
+    const float ne = 0.5f * (float)n * (float)(n - 1);
+    const float shh = t3 + sdd;
+    const float s2 = sc * sc * (fa * fa * sff + fb * fb * shh + 2.f * fa * fb * sfh + 2.f * fa * fc * sf + 2.f * fb * fc * sh + fc * fc * ne * nkc);
+    float *np = a.norm_part + ((size_t)(2 * d.B + b) * P->ntile_max) * 2;
+    np[0] = s2 > 0.f ? s2 : 0.f;
+    for (int t = 1; t < P->ntile_r2; ++t) np[2 * t] = 0.f;
+  }
 }
 
 }  // namespace ccsd

@@ -32,9 +32,14 @@ constexpr size_t TB_SMEM = (size_t)TB_STAGES * TB_STAGE + 1024 + 256;
 constexpr int TB_MAX_TILES = 192;
 
 struct TcBigArgs {
-  const float *r2;        // [B,E,K]
+  const float *r2;        // MODE 0: the matrix X whose Gram product is taken, [B][E][ldx] (the rank-2 state F, or H for H . H);
+                          // MODE 1: F [B,E,K]
+  int Kx, ldx;            // MODE 0: contraction length and row pitch of X
+  int PRx;                // MODE 0: projection rows of the weight blob appended as Gram columns (0 for H . H)
+  int mask_diag;          // MODE 0: zero the diagonal of the output
   float *H;               // [B,E,Ep]      (MODE 0: written; MODE 1: read)
-  float *P0;              // [B,E,PR0]     (MODE 0)
+  float *P0;              // [B,E,PRx]     (MODE 0)
+  float *Dg, *Rs;         // MODE 0, optional [B,E]: diag(X X^T) before the mask; row sums X 1 (one more all-ones Gram column)
   float *hf;              // [B,E,K]       (MODE 1: written)
   int ntile;              // (M tile, N tile) pairs per sample
   int mt;                 // MODE 1: M tiles per sample; unit tl -> (mi = tl % mt, nj = tl / mt), so that consecutive units
@@ -47,8 +52,10 @@ template <int MODE>
 __global__ void __launch_bounds__(TB_THREADS, 1) tc_r2big_kernel(const DevPlan *__restrict__ P, TcBigArgs a) {
   extern __shared__ uint8_t tb_smem_raw[];
   const ccsd_plan_desc_t &d = P->d;
-  const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp, Ep = P->Ep, B = d.B;
+  const int E = d.E, K = MODE == 0 ? a.Kx : d.K, PR0 = MODE == 0 ? a.PRx : 0, Kw = P->Kp, Ep = P->Ep, B = d.B;
+  const int ldx = MODE == 0 ? a.ldx : d.K;                    // row pitch of the MODE 0 input
   const int Ec0 = (E + 7) & ~7;                               // first projection column of the Gram product
+  const int rsum = MODE == 0 && a.Rs != nullptr;              // all-ones operand row at Gram column Ec0 + PR0
   const int nkb = MODE == 0 ? (K + TB_BK - 1) / TB_BK : (E + TB_BK - 1) / TB_BK;
   const int nunits = B * a.ntile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,34 +82,36 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_r2big_kernel(const DevPlan *
   if (warp < TB_PROD_WARPS) {
     // ===================== producers =====================
     const float *Wp = P->W + d.neta.proj_w;
-    const bool vecK = (K & 3) == 0;
+    const bool vecK = MODE == 0 ? ((ldx & 3) == 0) : ((K & 3) == 0);
     const int t = threadIdx.x;
     long it = 0;
     for (int ul = 0; ul < nmine; ++ul) {
       const int u = (int)blockIdx.x + ul * (int)gridDim.x;
       const int b = u / a.ntile, tl = u - b * a.ntile;
       const int mi = MODE == 0 ? a.tile[tl] >> 8 : tl % a.mt, nj = MODE == 0 ? a.tile[tl] & 255 : tl / a.mt;
-      const float *Fb = a.r2 + (size_t)b * E * K;
+      const float *Fb = a.r2 + (size_t)b * E * ldx;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         float x[6][8];
         if (MODE == 0) {
           // rows r0 + 64 j: j < 2 -> A rows (edges mi*128 + r), j >= 2 -> B rows (Gram columns nj*256 + r - 128)
           const int c = t & 7, r0 = t >> 3;
           const int k = kb * TB_BK + c * 8;
-          const bool fast = vecK && (k + 8 <= K);
+          const bool fast = vecK && (k + 8 <= K) && ((reinterpret_cast<uintptr_t>(Fb) & 15) == 0);
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
             const int rr = r0 + 64 * j;
             const float *src = nullptr;
             int klim = K;
-            if (j < 2) { const int e = mi * 128 + rr; if (e < E) src = Fb + (size_t)e * K; }
+            bool ones = false;
+            if (j < 2) { const int e = mi * 128 + rr; if (e < E) src = Fb + (size_t)e * ldx; }
             else {
               const int cc = nj * 256 + rr - 128;
-              if (cc < E) src = Fb + (size_t)cc * K;
-              else if (cc >= Ec0 && cc - Ec0 < PR0) { src = Wp + (size_t)(cc - Ec0) * Kw; klim = Kw; }
+              if (cc < E) src = Fb + (size_t)cc * ldx;
+              else if (cc >= Ec0 && cc - Ec0 < PR0) { src = Wp + (size_t)(cc - Ec0) * Kw; klim = Kw < K ? Kw : K; }
+              else if (rsum && cc == Ec0 + PR0) ones = true;
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) x[j][q] = 0.f;
+            for (int q = 0; q < 8; ++q) x[j][q] = (ones && k + q < K) ? 1.f : 0.f;
             if (src) {
               if (fast) {
                 const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src + k)), v1 = __ldg(reinterpret_cast<const float4 *>(src + k + 4));
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_r2big_kernel(const DevPlan *
   } else {
     // ===================== epilogue (warps 16-19 -> TMEM lane quarters 0-3) =====================
     const int q = warp & 3;
-    const int mask_diag = d.netf.use_hodge_mask;
+    const int mask_diag = MODE == 0 ? a.mask_diag : 0;
     const bool vecK = (K & 3) == 0;
     for (int ul = 0; ul < nmine; ++ul) {
       const int u = (int)blockIdx.x + ul * (int)gridDim.x;
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_r2big_kernel(const DevPlan *
         if (MODE == 0) {
           // warp-uniform skips: columns entirely below the warp's rows (their mirrors are written by another tile),
           // or past everything
-          if ((cb + 15 < e_lo && cb + 16 <= Ec0) || cb >= Ec0 + PR0) continue;
+          if ((cb + 15 < e_lo && cb + 16 <= Ec0) || cb >= Ec0 + PR0 + rsum) continue;
         } else {
           if (cb >= K) continue;
         }
@@ -284,9 +293,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_r2big_kernel(const DevPlan *
                 const float val = (mask_diag && c == e) ? 0.f : v[j];
                 Hb[(size_t)e * Ep + c] = val;
                 if (c > e) Hb[(size_t)c * Ep + e] = val;
+                if (c == e && a.Dg) a.Dg[(size_t)b * E + e] = v[j];
               }
             } else if (c >= Ec0 && c - Ec0 < PR0) {
               a.P0[((size_t)b * E + e) * PR0 + (c - Ec0)] = v[j];
+            } else if (rsum && c == Ec0 + PR0) {
+              a.Rs[(size_t)b * E + e] = v[j];
             }
           }
         } else {
@@ -319,11 +331,14 @@ static int tc_r2big_launch_m(const DevPlan *dP, const DevPlan &hp, TcBigArgs &a,
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int tc_r2big_gram(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, void *stream) {
+// Gram product of X [B][E][ldx] (contraction length Kx): out = X X^T (diagonal zeroed when mask_diag), optionally PRx
+// projection columns (P0), the diagonal (Dg) and the row sums (Rs)
+int tc_r2big_gram_x(const DevPlan *dP, const DevPlan &hp, const float *X, int Kx, int ldx, int PRx, int mask_diag, float *out,
+                    float *P0, float *Dg, float *Rs, void *stream) {
   TcBigArgs a;
   memset(&a, 0, sizeof a);
-  a.r2 = r2; a.H = H; a.P0 = P0;
-  const int E = hp.d.E, Ec0 = (E + 7) & ~7, ctot = Ec0 + hp.PR0;
+  a.r2 = X; a.Kx = Kx; a.ldx = ldx; a.PRx = PRx; a.mask_diag = mask_diag; a.H = out; a.P0 = P0; a.Dg = Dg; a.Rs = Rs;
+  const int E = hp.d.E, Ec0 = (E + 7) & ~7, ctot = Ec0 + PRx + (Rs ? 1 : 0);
   const int mt = (E + 127) / 128, nt = (ctot + 255) / 256;
   int n = 0;
   for (int mi = 0; mi < mt; ++mi)
@@ -336,6 +351,10 @@ int tc_r2big_gram(const DevPlan *dP, const DevPlan &hp, const float *r2, float *
   return tc_r2big_launch_m<0>(dP, hp, a, stream);
 }
 
+int tc_r2big_gram(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, float *Dg, float *Rs, void *stream) {
+  return tc_r2big_gram_x(dP, hp, r2, hp.d.K, hp.d.K, hp.PR0, hp.d.netf.use_hodge_mask, H, P0, Dg, Rs, stream);
+}
+
 int tc_r2big_hf(const DevPlan *dP, const DevPlan &hp, const float *r2, const float *H, float *hf, void *stream) {
   TcBigArgs a;
   memset(&a, 0, sizeof a);
@@ -345,12 +364,14 @@ int tc_r2big_hf(const DevPlan *dP, const DevPlan &hp, const float *r2, const flo
   return tc_r2big_launch_m<1>(dP, hp, a, stream);
 }
 #else
-int tc_r2big_gram(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, void *stream);
+int tc_r2big_gram_x(const DevPlan *dP, const DevPlan &hp, const float *X, int Kx, int ldx, int PRx, int mask_diag, float *out,
+                    float *P0, float *Dg, float *Rs, void *stream);
+int tc_r2big_gram(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, float *Dg, float *Rs, void *stream);
 int tc_r2big_hf(const DevPlan *dP, const DevPlan &hp, const float *r2, const float *H, float *hf, void *stream);
 #endif
 
 static inline int tc_r2big_supported(const ccsd_plan_desc_t &d, int PR0) {
-  const int mt = (d.E + 127) / 128, nt = (((d.E + 7) & ~7) + PR0 + 255) / 256;
+  const int mt = (d.E + 127) / 128, nt = (((d.E + 7) & ~7) + PR0 + 1 + 255) / 256;
   return d.is_cc && d.E > 192 && mt * nt <= TB_MAX_TILES && mt <= 255 && (d.K + 255) / 256 <= 65535 && PR0 <= 64;
 }
 
