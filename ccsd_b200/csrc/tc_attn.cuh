@@ -4,8 +4,11 @@
 //
 // Work item = (group of G consecutive graphs, channel c); rows r = (graph gl, node i), R = G N <= 128.
 //
-//   MMA-A  AX[128 x kin] = blockdiag(An_g) . X      A2 K-major: the GCN-normalised adjacency channel (layers.py:139-147)
-//                                                   of every graph of the group on the diagonal blocks, zeros elsewhere;
+//   MMA-A  AX[128 x kin] = blockdiag(An_g) . X      A in TENSOR MEMORY (tcgen05.mma A-from-TMEM): the GCN-normalised adjacency
+//                                                   channel (layers.py:139-147) of every graph of the group on the diagonal
+//                                                   blocks, zeros elsewhere -- each row's thread packs its bf16 hi / lo pairs
+//                                                   straight into its TMEM lane, which frees 64 KB of shared memory and lets
+//                                                   TWO CTAs share an SM (the kernel is a chain of short dependent phases);
 //                                                   Bx MN-major: the node features (one node row per thread)
 //   E1     AX -> bf16 hi/lo K-major A operand (TMEM -> registers -> shared memory, one node row per thread)
 //   MMA-B  T[128 x N1]   = AX . [Wq | Wk | Wvw]     B1 MN-major: the channel's weights, converted once per CTA
@@ -25,13 +28,13 @@
 namespace ccsd {
 
 #ifndef TT_PARTS
-#define TT_PARTS 4
+#define TT_PARTS 2
 #endif
 constexpr int TT_NP = TT_PARTS;            // column parts per TMEM lane quarter
 constexpr int TT_WORK = 128 * TT_NP;       // worker threads: row = threadIdx.x % 128 (TMEM lane quarter = warp % 4)
 constexpr int TT_THREADS = TT_WORK + 32;   // + the MMA-issuing warp
 constexpr int TT_MMAW = TT_WORK / 32;
-constexpr uint32_t TT_COL_D2 = 128;        // TMEM column of the second accumulator
+constexpr uint32_t TT_COL_A = 128;         // TMEM columns of the An operand: bf16 pairs hi [128, 192), lo [192, 256); accumulators at [0, 128)
 
 struct TcAttnLayout {
   int G, R;          // graphs per group, rows of a full group
@@ -64,23 +67,22 @@ static inline int tc_attn_layout(const ccsd_plan_desc_t &d, const XpLayout &XL, 
   T.qld = ((T.ad + 3) & ~3) + 4;   // multiple of 4, >= adq (E2 stores whole 8-column groups), 4 floats of skew
   T.NP = N | 1;                    // odd pitch: column reads of the symmetrisation are conflict free
   uint32_t o = 0;
-  T.a1_half = 128u * 128u; T.a1 = o; o += 2 * T.a1_half;                         // AX    [128 rows][128 B]            K-major
-  T.b1_half = (uint32_t)T.nblk * T.K1p * 128u; T.b1 = o; o += 2 * T.b1_half;     // W     [nblk][K1p k-rows][128 B]    MN-major
-  o = (o + 1023u) & ~1023u;
-  T.a2_half = 2u * 16384u; T.a2 = o; o += 2 * T.a2_half;                         // An    [2 k-blocks][128 rows][128 B] K-major
   T.bx_half = 16384u; T.bx = o; o += 2 * T.bx_half;                              // X     [128 k-rows][128 B]          MN-major
+  T.a1 = T.bx; T.a1_half = T.bx_half;                                            // AX    [128 rows][128 B] K-major: overwrites X (dead after MMA-A)
+  T.b1_half = (uint32_t)T.nblk * T.K1p * 128u; T.b1 = o; o += 2 * T.b1_half;     // W     [nblk][K1p k-rows][128 B]    MN-major
+  T.a2 = 0; T.a2_half = 0;                                                       // (An lives in tensor memory)
   T.tij = o;                                                                     // everything above is zeroed at start
   o += (uint32_t)XL.ldp * 4u;                                                    // (i << 8) | j of the node pairs
   o = (o + 15u) & ~15u;
   T.qs = o; o += 128u * (uint32_t)T.qld * 4u;
   T.ks = o; o += 128u * (uint32_t)T.qld * 4u;
-  T.adj = o; o += (uint32_t)T.G * N * T.NP * 4u;                                 // staged adjacency channel, full matrices
-  T.tsc = o; o += (uint32_t)T.G * N * T.NP * 4u;                                 // head-summed tanh scores, full matrices
+  T.adj = o; o += (uint32_t)T.G * N * T.NP * 4u;                                 // staged adjacency channel, full matrices ...
+  T.tsc = T.adj;                                                                 // ... then the head-summed tanh scores (adj is dead after the An rows are built)
   T.dvec = o; o += 128 * 4;
   T.vec = o; o += 128 * 4;                                                       // biases of the N1p columns
   T.bars = o; o += 64;
   T.total = o + 1024;
-  return T.total <= 227u * 1024u;
+  return T.total <= 113u * 1024u;   // two CTAs per SM
 }
 
 #ifdef TC_ATTN_KERNEL_TU
@@ -114,7 +116,12 @@ __device__ __forceinline__ float tt_score_row(const float (&q)[32], const float 
   return s;
 }
 
-__global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *__restrict__ P, TcAttnArgs ta) {
+__device__ __forceinline__ void tt_tmem_st8(uint32_t taddr, const uint32_t r[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+__global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *__restrict__ P, TcAttnArgs ta) {
   extern __shared__ uint8_t tt_smem_raw[];
   const XaArgs &a = ta.x;
   const TcAttnLayout &T = ta.L;
@@ -182,6 +189,12 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *_
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tslot_gen;
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  if (warp < 4) {   // the An operand region starts as zeros: a warp only ever rewrites the chunks that hold its rows' diagonal blocks
+    const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    for (int cc = 0; cc < 16; ++cc) tt_tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + TT_COL_A + (uint32_t)(cc * 8), z);
+    tc::tmem_st_wait();
+    tc::tc_fence_before_sync();
+  }
   const uint32_t idescA = tc::make_idesc_bf16(128, K1p, /*A K-major*/ 0, /*B MN-major*/ 1);
   const uint32_t idescB = tc::make_idesc_bf16(128, N1p, /*A K-major*/ 0, /*B MN-major*/ 1);
   uint32_t phase = 0;
@@ -245,27 +258,36 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *_
     }
     __syncthreads();
     if (warp < TT_MMAW) {
-      // ---- L(d): row r of blockdiag(An): columns [k0, k0 + N), in 8-column chunks (zeros outside the block) ----
-      if (row_in) {
-        const int c8a = k0 >> 3, c8b = (k0 + N - 1) >> 3;
+      // ---- L(d): row r of blockdiag(An) -> this row's TMEM lane: element k in 32-bit column k / 2 (bf16 pairs), hi then lo.
+      //      Chunks of 16 k values (one tcgen05.st of 8 columns each for hi and lo); the chunk range is warp uniform: it covers
+      //      the diagonal blocks of the warp's 32 rows (zeros where a lane's own block does not reach) ----
+      {
+        const int rlo = lq * 32, rhi = rlo + 31 < R - 1 ? rlo + 31 : R - 1;
+        const int ck_lo = rlo < R ? ((rlo / N) * N) >> 4 : 0, ck_hi = rlo < R ? ((rhi / N) * N + N + 15) >> 4 : 0;
         const float *row = adj_s + (gl * N + ni) * NP;
-        const float di = dvec[r];
-        for (int c8 = c8a + part; c8 <= c8b; c8 += TT_NP) {
-          float x[8];
+        const float di = live ? dvec[r] : 0.f;
+        const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16) + TT_COL_A;
+        for (int ck = ck_lo + part; ck < ck_hi && ck < 8; ck += TT_NP) {
+          uint32_t hw[8], lw[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = c8 * 8 + q - k0;
-            float v = 0.f;
-            if (live && j >= 0 && j < N) v = di * (j == ni ? 1.f : row[j]) * dvec[k0 + j];
-            x[q] = v;
+          for (int h8 = 0; h8 < 2; ++h8) {
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = ck * 16 + h8 * 8 + q - k0;
+              float v = 0.f;
+              if (live && j >= 0 && j < N) v = di * (j == ni ? 1.f : row[j]) * dvec[k0 + j];
+              x[q] = v;
+            }
+            uint4 hi, lo;
+            tc::split8(x, hi, lo);
+            hw[h8 * 4 + 0] = hi.x; hw[h8 * 4 + 1] = hi.y; hw[h8 * 4 + 2] = hi.z; hw[h8 * 4 + 3] = hi.w;
+            lw[h8 * 4 + 0] = lo.x; lw[h8 * 4 + 1] = lo.y; lw[h8 * 4 + 2] = lo.z; lw[h8 * 4 + 3] = lo.w;
           }
-          uint4 hi, lo;
-          tc::split8(x, hi, lo);
-          const int kk = c8 * 8;
-          const uint32_t off = T.a2 + (uint32_t)(kk >> 6) * 16384u + (uint32_t)r * 128u + (uint32_t)((((kk & 63) >> 3) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4 *>(gen + off) = hi;
-          *reinterpret_cast<uint4 *>(gen + off + T.a2_half) = lo;
+          tt_tmem_st8(trow + (uint32_t)(ck * 8), hw);
+          tt_tmem_st8(trow + 64u + (uint32_t)(ck * 8), lw);
         }
+        tc::tmem_st_wait();
       }
       tc::fence_proxy_async_smem();
     }
@@ -276,14 +298,12 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *_
       tc::tc_fence_after_sync();
       if (tc::elect_one()) {
         for (int k4 = 0; k4 < T.nk2; ++k4) {
-          const uint32_t ao = (uint32_t)(k4 >> 2) * 16384u + (uint32_t)(k4 & 3) * 32u;
-          const uint64_t a_hi = tc::make_smem_desc(base + T.a2 + ao, 0, 1024);
-          const uint64_t a_lo = tc::make_smem_desc(base + T.a2 + T.a2_half + ao, 0, 1024);
+          const uint32_t a_hi = tmem_u + TT_COL_A + (uint32_t)(k4 * 8), a_lo = a_hi + 64u;
           const uint64_t b_hi = tc::make_smem_desc(base + T.bx + (uint32_t)k4 * 2048u, 16384, 1024);
           const uint64_t b_lo = tc::make_smem_desc(base + T.bx + T.bx_half + (uint32_t)k4 * 2048u, 16384, 1024);
-          tc::umma_bf16(tmem_u, a_hi, b_hi, idescA, k4 != 0);
-          tc::umma_bf16(tmem_u, a_hi, b_lo, idescA, 1);
-          tc::umma_bf16(tmem_u, a_lo, b_hi, idescA, 1);
+          tc::umma_bf16_ts(tmem_u, a_hi, b_hi, idescA, k4 != 0);
+          tc::umma_bf16_ts(tmem_u, a_hi, b_lo, idescA, 1);
+          tc::umma_bf16_ts(tmem_u, a_lo, b_hi, idescA, 1);
         }
         tc::umma_commit(bar);
       }
@@ -322,9 +342,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *_
           const uint64_t a_lo = tc::make_smem_desc(base + T.a1 + T.a1_half + (uint32_t)k4 * 32u, 0, 1024);
           const uint64_t b_hi = tc::make_smem_desc(base + T.b1 + (uint32_t)k4 * 2048u, blk, 1024);
           const uint64_t b_lo = tc::make_smem_desc(base + T.b1 + T.b1_half + (uint32_t)k4 * 2048u, blk, 1024);
-          tc::umma_bf16(tmem_u + TT_COL_D2, a_hi, b_hi, idescB, k4 != 0);
-          tc::umma_bf16(tmem_u + TT_COL_D2, a_hi, b_lo, idescB, 1);
-          tc::umma_bf16(tmem_u + TT_COL_D2, a_lo, b_hi, idescB, 1);
+          tc::umma_bf16(tmem_u, a_hi, b_hi, idescB, k4 != 0);
+          tc::umma_bf16(tmem_u, a_hi, b_lo, idescB, 1);
+          tc::umma_bf16(tmem_u, a_lo, b_hi, idescB, 1);
         }
         tc::umma_commit(bar);
       }
@@ -335,7 +355,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *_
     tc::tc_fence_after_sync();
     // ---- E2: Q, K (+ bias) -> fp32 shared memory; folded value columns (+ bias) -> g_hmc ----
     if (warp < TT_MMAW) {
-      const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16) + TT_COL_D2;
+      const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);   // T overwrote AX in the accumulator columns
       float *gh = a.g_hmc + (size_t)(b0 + (live ? gl : 0)) * L.g_hmc + (size_t)c * L.mc_o1_max * N4 + ni;
       for (int ck = part; ck < (N1p >> 4); ck += TT_NP) {
         float v[16];
@@ -410,7 +430,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tc_attn_kernel(const DevPlan *_
         }
       }
     }
-    // the next item's writes to qs / ks / tsc / adj_s are behind the __syncthreads of its load phase
+    __syncthreads();   // the score matrices share their buffer with the next item's staged adjacency
   }
   tc::tc_fence_before_sync();
   __syncthreads();
@@ -429,7 +449,7 @@ int tc_attn_launch(const DevPlan *dP, const DevPlan &hp, const XaArgs &a, const 
   ta.x = a;
   ta.L = T;
   const int ngroups = (hp.d.B + T.G - 1) / T.G;
-  int nper = 148 / ly.c_in;
+  int nper = (148 * 2) / ly.c_in;   // two CTAs per SM
   if (nper < 1) nper = 1;
   if (nper > ngroups) nper = ngroups;
   ta.nper = nper;
