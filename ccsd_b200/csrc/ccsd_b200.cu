@@ -952,6 +952,7 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
 #ifndef CCSD_EMU
     if (p->use_tc_attn[l]) {
       PROF_BEGIN(p, "tc_attn_kernel", stream);
+      a.trace = (l == 1 && a.mode == MODE_PRED) ? p->trace : nullptr;   // debug timeline: layer 1 of the predictor's evaluation
       if (tc_attn_launch(p->dP, p->hp, a, p->tattn[l], stream)) return fail(CCSD_ERR_CUDA, "tc_attn launch failed");
       PROF_END(p, stream);
     } else

@@ -116,10 +116,95 @@ __device__ __forceinline__ float tt_score_row(const float (&q)[32], const float 
   return s;
 }
 
+// tanh(u s) = 1 - 2 / (2^(u c) + 1) with c = 2 s log2(e): two SFU ops, no range fix-ups (2^x saturates to 0 / inf, both exact limits)
+__device__ __forceinline__ float tt_tanh_c(float u, float c) {
+  float e, rc;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * c));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(e + 1.0f));
+  return fmaf(-2.0f, rc, 1.0f);
+}
+
+// the common shape -- exactly four heads of DS features (attn_dim = 4 DS): branch free, so the four dot-product / tanh
+// chains of a column (and those of the next column) interleave instead of running back to back behind `h * DS < ad` tests
+// volatile shared-memory loads: the compiler keeps them together at the top of the column instead of sinking each one next
+// to its four FMAs (which serialised load latency x 8 per column)
+__device__ __forceinline__ void tt_lds128(uint32_t addr, float &x, float &y, float &z, float &w) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(addr));
+}
+__device__ __forceinline__ void tt_lds64(uint32_t addr, float &x, float &y) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(addr));
+}
+
+// Two heads x two columns per call: 2 x 2 DS K values are loaded first (all shared-memory loads in flight), then four
+// independent dot-product chains and four tanh run interleaved.  Only half of the Q row lives in registers per pass --
+// with the whole row (32) + a K row (32) the register allocator serialised every load behind its four FMAs.
+template <int DS>
+__device__ __forceinline__ void tt_score22(const float (&q)[2 * DS], uint32_t kj0, uint32_t kj1, float c, float &s0, float &s1) {
+  float k0[2 * DS], k1[2 * DS];
+  if (DS >= 4) {
+#pragma unroll
+    for (int dd = 0; dd < 2 * DS; dd += 4) tt_lds128(kj0 + dd * 4, k0[dd], k0[dd + 1], k0[dd + 2], k0[dd + 3]);
+#pragma unroll
+    for (int dd = 0; dd < 2 * DS; dd += 4) tt_lds128(kj1 + dd * 4, k1[dd], k1[dd + 1], k1[dd + 2], k1[dd + 3]);
+  } else {
+#pragma unroll
+    for (int dd = 0; dd < 2 * DS; dd += 2) tt_lds64(kj0 + dd * 4, k0[dd], k0[dd + 1]);
+#pragma unroll
+    for (int dd = 0; dd < 2 * DS; dd += 2) tt_lds64(kj1 + dd * 4, k1[dd], k1[dd + 1]);
+  }
+  float u[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dd = 0; dd < DS; ++dd) {
+    u[0] = fmaf(q[dd], k0[dd], u[0]);
+    u[1] = fmaf(q[DS + dd], k0[DS + dd], u[1]);
+    u[2] = fmaf(q[dd], k1[dd], u[2]);
+    u[3] = fmaf(q[DS + dd], k1[DS + dd], u[3]);
+  }
+  s0 = tt_tanh_c(u[0], c) + tt_tanh_c(u[1], c);
+  s1 = tt_tanh_c(u[2], c) + tt_tanh_c(u[3], c);
+}
+
+// one thread's share of the S phase for four whole heads of DS features: columns j = part, part + TT_NP, ...
+template <int DS>
+__device__ __forceinline__ void tt_scores4(const float *__restrict__ qr, uint32_t kb, int qld, float *__restrict__ trow_s,
+                                            int part, int N, float c) {
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    float q[2 * DS];
+    if (DS >= 4) {
+#pragma unroll
+      for (int dd = 0; dd < 2 * DS; dd += 4) {
+        const float4 t4 = ld4(qr + pass * 2 * DS + dd);
+        q[dd] = t4.x; q[dd + 1] = t4.y; q[dd + 2] = t4.z; q[dd + 3] = t4.w;
+      }
+    } else {
+#pragma unroll
+      for (int dd = 0; dd < 2 * DS; ++dd) q[dd] = qr[pass * 2 * DS + dd];
+    }
+    const uint32_t kp = kb + (uint32_t)(pass * 2 * DS) * 4u;
+    for (int j = part; j < N; j += 2 * TT_NP) {
+      const bool two = j + TT_NP < N;
+      const uint32_t kj0 = kp + (uint32_t)(j * qld) * 4u, kj1 = two ? kj0 + (uint32_t)(TT_NP * qld) * 4u : kj0;
+      float s0, s1;
+      tt_score22<DS>(q, kj0, kj1, c, s0, s1);
+      if (pass == 0) {
+        trow_s[j] = s0;
+        if (two) trow_s[j + TT_NP] = s1;
+      } else {
+        trow_s[j] += s0;
+        if (two) trow_s[j + TT_NP] += s1;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void tt_tmem_st8(uint32_t taddr, const uint32_t r[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+
+// debug timeline (ccsd_debug_apply_trace): stamp `slot` of this CTA's item `it`, CTA 0 only
+#define TT_STAMP(slot_) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) a.trace[it * 16 + (slot_)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *__restrict__ P, TcAttnArgs ta) {
   extern __shared__ uint8_t tt_smem_raw[];
@@ -143,8 +228,10 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
   uint8_t *gen = tt_smem_raw + (base - raw);
   const uint32_t bar = base + T.bars, tslot = bar + 8;
   uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen + T.bars + 8);
+  int it = 0;
+  TT_STAMP(15);
   float *adj_s = reinterpret_cast<float *>(gen + T.adj), *tsc = reinterpret_cast<float *>(gen + T.tsc);
-  float *dvec = reinterpret_cast<float *>(gen + T.dvec), *vbias = reinterpret_cast<float *>(gen + T.vec);
+  float *vbias = reinterpret_cast<float *>(gen + T.vec);
   float *qs = reinterpret_cast<float *>(gen + T.qs), *ks = reinterpret_cast<float *>(gen + T.ks);
   int *tij = reinterpret_cast<int *>(gen + T.tij);
 
@@ -209,32 +296,77 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
   const float inv = 0.5f / (float)nch;
   const int k0 = gl * N;                                    // first column of this row's diagonal block
 
-  for (int gi = g_first; gi < ngroups; gi += ta.nper) {
+  for (int gi = g_first; gi < ngroups; gi += ta.nper, ++it) {
+    TT_STAMP(0);
     const int b0 = gi * G;
     const int gsz = B - b0 < G ? B - b0 : G;
     const bool live = row_in && gl < gsz;
+    // this row's node features (its part's 8-feature chunks): issued first, consumed in L(b) after the adjacency is staged
+    constexpr int TT_XR = 64 / 8 / TT_NP * 8;   // conv_in <= 64
+    float xr[TT_XR];
+    if (warp < TT_MMAW) {
+      const float *gx = a.g_xin + (size_t)(b0 + (live ? gl : 0)) * L.g_x + ni;
+#pragma unroll
+      for (int u = 0; u < TT_XR / 8; ++u) {
+        const int q8 = part + u * TT_NP;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int f = q8 * 8 + q;
+          xr[u * 8 + q] = (live && f < kin) ? __ldg(gx + (size_t)f * N4) : 0.f;
+        }
+      }
+    }
     if (warp < TT_MMAW) {
       // ---- L(a): the group's adjacency channel (triangle storage in global memory) -> full symmetric matrices ----
-      for (int g2 = part; g2 < gsz; g2 += TT_NP) {
-        const float *src = a.g_stack + (size_t)(b0 + g2) * L.g_stack + (size_t)(a.ch_in + c) * ldp;
-        float *dst = adj_s + g2 * N * NP;
-        for (int t = r; t < NT; t += 128) {
-          const float v = src[t];
-          const int ij = tij[t], i = ij >> 8, j = ij & 255;
-          dst[i * NP + j] = v;
-          dst[j * NP + i] = v;
+      //      (all of a batch's global loads are issued before the first scatter store: one L2 round trip per batch of 8)
+      const float *src = a.g_stack + (size_t)b0 * L.g_stack + (size_t)(a.ch_in + c) * ldp;
+      const int tot = gsz * NT;
+      for (int i0 = (int)threadIdx.x; i0 < tot; i0 += 8 * TT_WORK) {
+        float v[8];
+        int gt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = i0 + u * TT_WORK;
+          const int g2 = idx / NT, t = idx - g2 * NT;
+          gt[u] = idx < tot ? ((g2 << 16) | t) : -1;
+          v[u] = idx < tot ? __ldg(src + (size_t)g2 * L.g_stack + t) : 0.f;
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (gt[u] >= 0) {
+            const int g2 = gt[u] >> 16, t = gt[u] & 0xffff;
+            const int ij = tij[t], i = ij >> 8, j = ij & 255;
+            const float vv = i == j ? 1.f : v[u];   // A^ = A with a unit diagonal (layers.py:139-141)
+            float *dst = adj_s + g2 * N * NP;
+            dst[i * NP + j] = vv;
+            dst[j * NP + i] = vv;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    TT_STAMP(1);
+    // ---- L(c): GCN degree of the thread's own node, d_i = clamp(rowsum(A^), 1)^-1/2 (layers.py:142-145).  An = D A^ D is
+    //      applied as D (A^ (D X)): X's row r is scaled by d_r here, AX's row r by d_r in E1 -- both by the row's own thread ----
+    float di = 0.f;
+    if (warp < TT_MMAW) {
+      const float *__restrict__ row = adj_s + (gl * N + ni) * NP;
+      if (live) {
+        float s0 = 0.f, s1 = 0.f;
+        int j = 0;
+        for (; j + 1 < N; j += 2) { s0 += row[j]; s1 += row[j + 1]; }
+        if (j < N) s0 += row[j];
+        di = rsqrtf(fmaxf(s0 + s1, 1.f));
       }
       // ---- L(b): node features -> Bx (MN-major: k = node row, n = feature), 8 features per 16-byte chunk ----
       {
-        const float *gx = a.g_xin + (size_t)(b0 + (live ? gl : 0)) * L.g_x + ni;
-        for (int q8 = part; q8 < (K1p >> 3); q8 += TT_NP) {
+#pragma unroll
+        for (int u = 0; u < TT_XR / 8; ++u) {
+          const int q8 = part + u * TT_NP;
+          if (q8 >= (K1p >> 3)) break;
           float x[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int f = q8 * 8 + q;
-            x[q] = (live && f < kin) ? gx[(size_t)f * N4] : 0.f;
-          }
+          for (int q = 0; q < 8; ++q) x[q] = di * xr[u * 8 + q];
           uint4 hi, lo;
           tc::split8(x, hi, lo);
           const uint32_t off = T.bx + (uint32_t)r * 128u + (uint32_t)((q8 ^ (r & 7)) << 4);
@@ -242,30 +374,13 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
           *reinterpret_cast<uint4 *>(gen + off + T.bx_half) = lo;
         }
       }
-    }
-    __syncthreads();
-    // ---- L(c): GCN degrees d_i = clamp(rowsum(A^), 1)^-1/2 with the unit diagonal (layers.py:139-145) ----
-    if (threadIdx.x < 128) {
-      float dv = 0.f;
-      if (live) {
-        const float *row = adj_s + (gl * N + ni) * NP;
-        float s = 1.f;
-        for (int j = 0; j < N; ++j)
-          if (j != ni) s += row[j];
-        dv = 1.0f / sqrtf(fmaxf(s, 1.f));
-      }
-      dvec[r] = dv;
-    }
-    __syncthreads();
-    if (warp < TT_MMAW) {
-      // ---- L(d): row r of blockdiag(An) -> this row's TMEM lane: element k in 32-bit column k / 2 (bf16 pairs), hi then lo.
+      TT_STAMP(2);
+      // ---- L(d): row r of blockdiag(A^) -> this row's TMEM lane: element k in 32-bit column k / 2 (bf16 pairs), hi then lo.
       //      Chunks of 16 k values (one tcgen05.st of 8 columns each for hi and lo); the chunk range is warp uniform: it covers
       //      the diagonal blocks of the warp's 32 rows (zeros where a lane's own block does not reach) ----
       {
         const int rlo = lq * 32, rhi = rlo + 31 < R - 1 ? rlo + 31 : R - 1;
         const int ck_lo = rlo < R ? ((rlo / N) * N) >> 4 : 0, ck_hi = rlo < R ? ((rhi / N) * N + N + 15) >> 4 : 0;
-        const float *row = adj_s + (gl * N + ni) * NP;
-        const float di = live ? dvec[r] : 0.f;
         const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16) + TT_COL_A;
         for (int ck = ck_lo + part; ck < ck_hi && ck < 8; ck += TT_NP) {
           uint32_t hw[8], lw[8];
@@ -276,7 +391,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
             for (int q = 0; q < 8; ++q) {
               const int j = ck * 16 + h8 * 8 + q - k0;
               float v = 0.f;
-              if (live && j >= 0 && j < N) v = di * (j == ni ? 1.f : row[j]) * dvec[k0 + j];
+              if (live && j >= 0 && j < N) v = row[j];
               x[q] = v;
             }
             uint4 hi, lo;
@@ -293,6 +408,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
     }
     tc::tc_fence_before_sync();
     __syncthreads();
+    TT_STAMP(3);
     // ---- MMA-A: AX = blockdiag(An) . X ----
     if (warp == TT_MMAW) {
       tc::tc_fence_after_sync();
@@ -312,12 +428,15 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
     tc::mbar_wait(bar, phase);
     phase ^= 1u;
     tc::tc_fence_after_sync();
+    TT_STAMP(4);
     // ---- E1: AX (one node row per thread) -> A1 (K-major) ----
     if (warp < TT_MMAW) {
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
       for (int ck = part; ck < (K1p >> 4); ck += TT_NP) {
         float v[16];
         tc::tmem_ld16(trow + (uint32_t)(ck * 16), v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] *= di;
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
           uint4 hi, lo;
@@ -332,6 +451,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
     }
     tc::tc_fence_before_sync();
     __syncthreads();
+    TT_STAMP(5);
     // ---- MMA-B: T = AX . [Wq | Wk | Wvw] ----
     if (warp == TT_MMAW) {
       tc::tc_fence_after_sync();
@@ -353,13 +473,25 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
     tc::mbar_wait(bar, phase);
     phase ^= 1u;
     tc::tc_fence_after_sync();
+    TT_STAMP(6);
     // ---- E2: Q, K (+ bias) -> fp32 shared memory; folded value columns (+ bias) -> g_hmc ----
     if (warp < TT_MMAW) {
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);   // T overwrote AX in the accumulator columns
       float *gh = a.g_hmc + (size_t)(b0 + (live ? gl : 0)) * L.g_hmc + (size_t)c * L.mc_o1_max * N4 + ni;
-      for (int ck = part; ck < (N1p >> 4); ck += TT_NP) {
+      for (int ck0 = part; ck0 < (N1p >> 4); ck0 += 2 * TT_NP) {
+        // two 16-column chunks per round trip to tensor memory
+        uint32_t raw2[2][16];
+        const bool two = ck0 + TT_NP < (N1p >> 4);
+        tc::tmem_ld16_nowait(trow + (uint32_t)(ck0 * 16), raw2[0]);
+        if (two) tc::tmem_ld16_nowait(trow + (uint32_t)((ck0 + TT_NP) * 16), raw2[1]);
+        tc::tmem_ld_wait();
+#pragma unroll
+       for (int cc = 0; cc < 2; ++cc) {
+        if (cc == 1 && !two) break;
+        const int ck = ck0 + cc * TT_NP;
         float v[16];
-        tc::tmem_ld16(trow + (uint32_t)(ck * 16), v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(raw2[cc][q]);
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
           const int n0 = ck * 16 + h8 * 8;
@@ -377,27 +509,39 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
             }
           }
         }
+       }
       }
     }
     tc::tc_fence_before_sync();
     __syncthreads();
+    TT_STAMP(7);
     // ---- S: head-summed tanh scores of every ordered node pair of the row's graph: thread (row, part) takes the
     //         columns j = part, part + 4, ... with the Q row in registers ----
     if (warp < TT_MMAW && live) {
-      float *trow_s = tsc + (gl * N + ni) * NP;
-      const float *kbase = ks + k0 * qld;
-      if (ad <= 32 && (ds == 8 || ds == 4 || ds == 2)) {
+      float *__restrict__ trow_s = tsc + (gl * N + ni) * NP;
+      const float *__restrict__ kbase = ks + k0 * qld;
+      if (ad == 4 * ds && (ds == 8 || ds == 4 || ds == 2)) {
+        // four whole heads (every shipped checkpoint): branch-free scores
+        const float c2 = scale * 2.885390081777927f;   // 2 log2(e)
+        const uint32_t kb = tc::smem_u32(kbase);
+        const float *__restrict__ qr = qs + r * qld;
+        if (ds == 8) tt_scores4<8>(qr, kb, qld, trow_s, part, N, c2);
+        else if (ds == 4) tt_scores4<4>(qr, kb, qld, trow_s, part, N, c2);
+        else tt_scores4<2>(qr, kb, qld, trow_s, part, N, c2);
+      } else if (ad <= 32 && (ds == 8 || ds == 4 || ds == 2)) {
         float q[32];
-        const float *qr = qs + r * qld;
+        const float *__restrict__ qr = qs + r * qld;
 #pragma unroll
         for (int dd = 0; dd < 32; dd += 4) {
           float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (dd < adq) t4 = ld4(qr + dd);
           q[dd] = t4.x; q[dd + 1] = t4.y; q[dd + 2] = t4.z; q[dd + 3] = t4.w;
         }
-        for (int j = part; j < N; j += TT_NP) {
-          const float *kj = kbase + j * qld;
-          trow_s[j] = ds == 8 ? tt_score_row<8>(q, kj, ad, scale) : (ds == 4 ? tt_score_row<4>(q, kj, ad, scale) : tt_score_row<2>(q, kj, ad, scale));
+        {
+          for (int j = part; j < N; j += TT_NP) {
+            const float *kj = kbase + j * qld;
+            trow_s[j] = ds == 8 ? tt_score_row<8>(q, kj, ad, scale) : (ds == 4 ? tt_score_row<4>(q, kj, ad, scale) : tt_score_row<2>(q, kj, ad, scale));
+          }
         }
       } else {
         const float *qr = qs + r * qld;
@@ -415,22 +559,34 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
       }
     }
     __syncthreads();
+    TT_STAMP(8);
     // ---- symmetrise (attention.py:130) and write the attention map in triangle storage ----
     if (warp < TT_MMAW) {
-      for (int g2 = part; g2 < gsz; g2 += TT_NP) {
-        const float *ts = tsc + g2 * N * NP;
-        float *dst = a.g_att + (size_t)(b0 + g2) * L.g_att + (size_t)c * ldp;
-        for (int t = r; t < ldp; t += 128) {
-          float s = 0.f;
-          if (t < NT) {
+      float *dst = a.g_att + (size_t)b0 * L.g_att + (size_t)c * ldp;
+      const int tot = gsz * ldp;
+      for (int i0 = (int)threadIdx.x; i0 < tot; i0 += 4 * TT_WORK) {
+        float sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = i0 + u * TT_WORK;
+          const int g2 = idx / ldp, t = idx - g2 * ldp;
+          sv[u] = 0.f;
+          if (idx < tot && t < NT) {
+            const float *ts = tsc + g2 * N * NP;
             const int ij = tij[t], i = ij >> 8, j = ij & 255;
-            s = inv * (ts[i * NP + j] + ts[j * NP + i]);
+            sv[u] = inv * (ts[i * NP + j] + ts[j * NP + i]);
           }
-          dst[t] = s;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = i0 + u * TT_WORK;
+          const int g2 = idx / ldp, t = idx - g2 * ldp;
+          if (idx < tot) dst[(size_t)g2 * L.g_att + t] = sv[u];
         }
       }
     }
     __syncthreads();   // the score matrices share their buffer with the next item's staged adjacency
+    TT_STAMP(9);
   }
   tc::tc_fence_before_sync();
   __syncthreads();

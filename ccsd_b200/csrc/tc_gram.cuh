@@ -30,7 +30,8 @@ constexpr int TG_PROD_WARPS = TG_PRODUCER_WARPS;   // two groups of TG_PROD_WARP
 constexpr int TG_GRP = TG_PROD_WARPS * 16;          // threads per producer group
 constexpr int TG_RSTEP = TG_GRP / 8;               // rows covered by one sweep of a group
 constexpr int TG_PROD = TG_PROD_WARPS * 32;
-constexpr int TG_THREADS = TG_PROD + 128 + 32;   // producers, 4 epilogue warps, 1 MMA warp
+constexpr int TG_EPI_WARPS = 8;                     // epilogue warps: TMEM lane quarter = warp % 4, alternate 16-column chunks by warp / 4
+constexpr int TG_THREADS = TG_PROD + TG_EPI_WARPS * 32 + 32;   // producers, epilogue warps, 1 MMA warp
 constexpr int TG_STAGES = 3;
 constexpr int TG_BK = 64;
 constexpr uint32_t TG_HALF = 256 * 128;   // bytes of the hi (or lo) half of a stage
@@ -83,10 +84,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       tc::mbar_init(empty0 + 8 * s, 1);   // tcgen05.commit
     }
     tc::mbar_init(tfull, 1);
-    tc::mbar_init(tempty, 128);           // every epilogue thread arrives
+    tc::mbar_init(tempty, TG_EPI_WARPS * 32);   // every epilogue thread arrives
     tc::mbar_fence_init();
   }
-  if (warp == TG_PROD_WARPS + 4) tc::tmem_alloc(tslot, 512);
+  if (warp == TG_PROD_WARPS + TG_EPI_WARPS) tc::tmem_alloc(tslot, 512);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -104,11 +105,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
     const int grp = warp / (TG_PROD_WARPS / 2), tg = threadIdx.x - grp * TG_GRP;
     const int c = tg & 7, r0 = tg >> 3;
     const uint32_t off0 = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
-    const int nmine = (NV - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long total = (long)nmine * nkb;
-    for (long g = grp; g < total; g += 2) {
-      const int vb = (int)blockIdx.x + (int)(g / nkb) * (int)gridDim.x;
-      const int kb = (int)(g % nkb);
+    // k-block g of this CTA = (unit vb, block kb); this group takes every other one.  32-bit incremental bookkeeping (the
+    // 64-bit divisions of the first version were a quarter of the producers' instructions)
+    int vb = (int)blockIdx.x, kb = grp;
+    while (kb >= nkb && vb < NV) { kb -= nkb; vb += (int)gridDim.x; }
+    int s = grp % TG_STAGES;
+    uint32_t ph = (uint32_t)(grp / TG_STAGES) & 1;
+    for (; vb < NV;) {
       const float *Fb = a.r2 + (size_t)vb * EG * K;
       const int rows_valid = ((B - vb * G < G) ? B - vb * G : G) * E;   // the last unit may hold fewer samples
       const int k = kb * TG_BK + c * 8;
@@ -130,8 +133,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
           }
         }
       }
-      const int s = (int)(g % TG_STAGES);
-      const uint32_t ph = (uint32_t)(g / TG_STAGES) & 1;
       tc::mbar_wait(empty0 + 8 * s, ph ^ 1);
       uint8_t *st = gen_base + (size_t)s * TG_STAGE;
 #pragma unroll
@@ -173,8 +174,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       }
       tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(full0 + 8 * s);
+      kb += 2;
+      while (kb >= nkb && vb < NV) { kb -= nkb; vb += (int)gridDim.x; }
+      s += 2;
+      if (s >= TG_STAGES) { s -= TG_STAGES; ph ^= 1u; }
     }
-  } else if (warp == TG_PROD_WARPS + 4) {
+  } else if (warp == TG_PROD_WARPS + TG_EPI_WARPS) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = tc::make_idesc_bf16(128, ncols, 0, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy (uniform-register MMA operands)
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
       }
     }
   } else {
-    // ===================== epilogue (warps 8-11 -> TMEM lane quarters 0-3) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter alternate chunks) =====================
+    const int q = warp & 3, half = (warp - TG_PROD_WARPS) >> 2;
     const int mask_diag = d.netf.use_hodge_mask;
     uint32_t tile = 0;
     for (int vb = blockIdx.x; vb < NV; vb += gridDim.x, ++tile) {
@@ -230,7 +235,29 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
         // warp-uniform range of columns that hold a diagonal block of the warp's 32 rows (G = 1: all of [0, E))
         const int rlo = mt * 128 + q * 32, rhi = rlo + 31 < EG ? rlo + 31 : EG - 1;
         const int blo = G == 1 ? 0 : (rlo / E) * E, bhi = G == 1 ? E : (rhi / E) * E + E;
-        for (int c0 = 0; c0 < ncols; c0 += 16) {
+        for (int c0 = half * 16; c0 < ncols; c0 += 16 * (TG_EPI_WARPS / 4)) {
+          if (!GROUPED && c0 + 16 <= E) {
+            // a chunk of H columns only: 16 unconditional coalesced stores (the diagonal is patched first, by the one warp
+            // whose rows the chunk crosses)
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ncols + c0), v);
+            if (live) {
+              if (c0 < rlo + 32 && c0 + 16 > rlo) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (c0 + j == row) {
+                    if (a.Dg) a.Dg[(size_t)b * E + er] = v[j];
+                    if (mask_diag) v[j] = 0.f;
+                  }
+                }
+              }
+              float *hc = Hcol + (size_t)c0 * P->Ep;
+              const size_t ep = (size_t)P->Ep;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) hc[(size_t)j * ep] = v[j];
+            }
+            continue;
+          }
           if (!((c0 < bhi && c0 + 16 > blo) || c0 + 16 > wp0 || (rsum && c0 <= rcol && rcol < c0 + 16))) continue;   // neither a diagonal block nor projections / row sums
           float v[16];
           tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ncols + c0), v);
@@ -253,7 +280,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == TG_PROD_WARPS + 4) tc::tmem_dealloc(tmem, 512);
+  if (warp == TG_PROD_WARPS + TG_EPI_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
 static inline int tc_gram_prepare() {

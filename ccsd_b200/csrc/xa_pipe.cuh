@@ -70,6 +70,7 @@ struct XaArgs {
   int skip_edge;                 // attn_finish_kernel: the per-edge MLP runs on the tensor cores (tc_edge.cuh) instead
   float *g_hcat;                 // not null: x_net_kernel stops after the GCN stack and writes [x, h_1 .. h_D] ([fdim x N4] per
                                  // graph) here for the tensor-core final MLP (tc_xfin.cuh)
+  long long *trace;              // debug phase timeline of tc_attn_kernel (ccsd_debug_apply_trace), normally nullptr
 };
 
 __device__ __forceinline__ const ccsd_attn_layer_t &xa_layer(const DevPlan *P, const XaArgs &a) {
