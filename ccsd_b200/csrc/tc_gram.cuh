@@ -30,8 +30,11 @@ constexpr int TG_PROD_WARPS = TG_PRODUCER_WARPS;   // two groups of TG_PROD_WARP
 constexpr int TG_GRP = TG_PROD_WARPS * 16;          // threads per producer group
 constexpr int TG_RSTEP = TG_GRP / 8;               // rows covered by one sweep of a group
 constexpr int TG_PROD = TG_PROD_WARPS * 32;
-constexpr int TG_EPI_WARPS = 8;                     // epilogue warps: TMEM lane quarter = warp % 4, alternate 16-column chunks by warp / 4
-constexpr int TG_THREADS = TG_PROD + TG_EPI_WARPS * 32 + 32;   // producers, epilogue warps, 1 MMA warp
+// epilogue warps: TMEM lane quarter = warp % 4, alternate 16-column chunks by warp / 4.  One sample per unit: 4 (its epilogue
+// hides behind the next unit's MMAs -- double-buffered accumulators -- and 672 threads leave the producers 96 registers);
+// stacked samples: 8 (the accumulators do not always fit twice, so the epilogue is on the critical path)
+__host__ __device__ constexpr int tg_epi_warps(bool grouped) { return grouped ? 8 : 4; }
+__host__ __device__ constexpr int tg_threads(bool grouped) { return TG_PROD + tg_epi_warps(grouped) * 32 + 32; }   // producers, epilogue warps, 1 MMA warp
 constexpr int TG_STAGES = 3;
 constexpr int TG_BK = 64;
 constexpr uint32_t TG_HALF = 256 * 128;   // bytes of the hi (or lo) half of a stage
@@ -54,9 +57,10 @@ static inline int tc_gram_supported(int E, int K, int PR0) {
 }
 
 template <bool GROUPED>   // GROUPED = false: one sample per work unit (G = 1 folds away at compile time)
-__global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *__restrict__ P, TcGramArgs a) {
+__global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const DevPlan *__restrict__ P, TcGramArgs a) {
   extern __shared__ uint8_t tg_smem_raw[];
   const ccsd_plan_desc_t &d = P->d;
+  constexpr int TG_EPI_WARPS = tg_epi_warps(GROUPED);
   const int E = d.E, K = d.K, PR0 = P->PR0, Kw = P->Kp, B = d.B;
   // small complexes: G consecutive samples form one work unit -- their rows are contiguous in the state, so the operand
   // tile is simply taller; the Gram of the stacked rows holds the G per-sample Grams as its diagonal blocks (the
@@ -67,6 +71,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   const int rcol = wp0 > EG ? EG : wp0 + PR0;       // it takes a pad row of the F block when there is one, else a new column
   const int ncols = (wp0 + PR0 + (rsum && rcol >= wp0 ? 1 : 0) + 15) & ~15;
   const int mtiles = EG > 128 ? 2 : 1;
+  // The second M tile (rows 128 ..) only needs the columns from c1 on: for one sample per unit H is symmetric, so the block
+  // [128:, :128] is the transpose of what the first tile holds (c1 = 128, the first tile's epilogue writes both orientations);
+  // for stacked samples its rows' diagonal blocks start at the block that straddles row 128.
+  const int c1 = mtiles == 1 ? 0 : (GROUPED ? ((128 / E) * E) & ~15 : 128), N1 = ncols - c1;
+  // accumulators in tensor memory: the first tile's are double buffered when 2 ncols + N1 <= 512 columns, so the epilogue of
+  // one unit overlaps the MMAs of the next (the second tile's are drained first and waited for at the start of a unit)
+  const int dbuf = 2 * ncols + (mtiles == 2 ? N1 : 0) <= 512;
+  const uint32_t acc1 = (uint32_t)((dbuf ? 2 : 1) * ncols);
   const int nkb = (K + TG_BK - 1) / TG_BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -74,17 +86,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   const uint32_t base = (raw + 1023u) & ~1023u;                       // operand stages (1024-aligned)
   uint8_t *gen_base = tg_smem_raw + (base - raw);
   const uint32_t bars = base + TG_STAGES * TG_STAGE;                  // mbarriers
-  const uint32_t full0 = bars, empty0 = bars + 8 * TG_STAGES, tfull = bars + 16 * TG_STAGES,
-                 tempty = tfull + 8, tslot = tempty + 8;
-  uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen_base + TG_STAGES * TG_STAGE + 16 * TG_STAGES + 16);
+  const uint32_t full0 = bars, empty0 = bars + 8 * TG_STAGES, tfull = bars + 16 * TG_STAGES /* [2] */,
+                 tempty0 = tfull + 16 /* [2] */, tempty1 = tempty0 + 16, tslot = tempty1 + 8;
+  uint32_t *tslot_gen = reinterpret_cast<uint32_t *>(gen_base + TG_STAGES * TG_STAGE + 16 * TG_STAGES + 40);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
       tc::mbar_init(full0 + 8 * s, TG_GRP);   // every thread of the producer group that fills it
       tc::mbar_init(empty0 + 8 * s, 1);   // tcgen05.commit
     }
-    tc::mbar_init(tfull, 1);
-    tc::mbar_init(tempty, TG_EPI_WARPS * 32);   // every epilogue thread arrives
+    for (int q2 = 0; q2 < 2; ++q2) {
+      tc::mbar_init(tfull + 8 * q2, 1);
+      tc::mbar_init(tempty0 + 8 * q2, TG_EPI_WARPS * 32);   // every epilogue thread arrives
+    }
+    tc::mbar_init(tempty1, TG_EPI_WARPS * 32);
     tc::mbar_fence_init();
   }
   if (warp == TG_PROD_WARPS + TG_EPI_WARPS) tc::tmem_alloc(tslot, 512);
@@ -182,11 +197,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
   } else if (warp == TG_PROD_WARPS + TG_EPI_WARPS) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = tc::make_idesc_bf16(128, ncols, 0, 0);
+    const uint32_t idesc1 = tc::make_idesc_bf16(128, N1 > 0 ? N1 : 16, 0, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy (uniform-register MMA operands)
     uint32_t it = 0, tile = 0;
     for (int vb = blockIdx.x; vb < NV; vb += gridDim.x, ++tile) {
-      tc::mbar_wait(tempty, (tile & 1) ^ 1);   // epilogue has drained the previous accumulators
+      const uint32_t buf = dbuf ? (tile & 1u) : 0u, use = dbuf ? (tile >> 1) : tile;
+      tc::mbar_wait(tempty0 + 8 * buf, (use & 1u) ^ 1u);   // the epilogue has drained this buffer's previous unit
+      if (mtiles == 2) tc::mbar_wait(tempty1, (tile & 1u) ^ 1u);
       tc::tc_fence_after_sync();
+      const uint32_t acc0 = tmem_u + buf * (uint32_t)ncols;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % TG_STAGES;
         const uint32_t ph = (it / TG_STAGES) & 1;
@@ -199,17 +218,26 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
             const uint32_t ko = (uint32_t)k4 * 32u;   // 16 bf16 = 32 bytes inside the 128-byte swizzle span
             const uint64_t b_hi = tc::make_smem_desc(sb + ko, 0, 1024);
             const uint64_t b_lo = tc::make_smem_desc(sb + TG_HALF + ko, 0, 1024);
-            for (int mt = 0; mt < mtiles; ++mt) {
-              const uint64_t a_hi = tc::make_smem_desc(sb + (uint32_t)mt * 16384u + ko, 0, 1024);
-              const uint64_t a_lo = tc::make_smem_desc(sb + TG_HALF + (uint32_t)mt * 16384u + ko, 0, 1024);
-              const uint32_t dcol = tmem_u + (uint32_t)(mt * ncols);
-              tc::umma_bf16(dcol, a_hi, b_hi, idesc, (kb | k4) != 0);
-              tc::umma_bf16(dcol, a_hi, b_lo, idesc, 1);
-              tc::umma_bf16(dcol, a_lo, b_hi, idesc, 1);
+            {
+              const uint64_t a_hi = tc::make_smem_desc(sb + ko, 0, 1024);
+              const uint64_t a_lo = tc::make_smem_desc(sb + TG_HALF + ko, 0, 1024);
+              tc::umma_bf16(acc0, a_hi, b_hi, idesc, (kb | k4) != 0);
+              tc::umma_bf16(acc0, a_hi, b_lo, idesc, 1);
+              tc::umma_bf16(acc0, a_lo, b_hi, idesc, 1);
+            }
+            if (mtiles == 2) {   // rows 128 .. against the operand rows c1 .. (8-row atoms of 1024 bytes)
+              const uint64_t a_hi = tc::make_smem_desc(sb + 16384u + ko, 0, 1024);
+              const uint64_t a_lo = tc::make_smem_desc(sb + TG_HALF + 16384u + ko, 0, 1024);
+              const uint64_t b1_hi = tc::make_smem_desc(sb + (uint32_t)(c1 >> 3) * 1024u + ko, 0, 1024);
+              const uint64_t b1_lo = tc::make_smem_desc(sb + TG_HALF + (uint32_t)(c1 >> 3) * 1024u + ko, 0, 1024);
+              const uint32_t dcol = tmem_u + acc1;
+              tc::umma_bf16(dcol, a_hi, b1_hi, idesc1, (kb | k4) != 0);
+              tc::umma_bf16(dcol, a_hi, b1_lo, idesc1, 1);
+              tc::umma_bf16(dcol, a_lo, b1_hi, idesc1, 1);
             }
           }
           tc::umma_commit(empty0 + 8 * s);             // stage may be refilled once these MMAs retire
-          if (kb == nkb - 1) tc::umma_commit(tfull);   // accumulators complete
+          if (kb == nkb - 1) tc::umma_commit(tfull + 8 * buf);   // accumulators complete
         }
         __syncwarp();
       }
@@ -219,29 +247,40 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
     const int q = warp & 3, half = (warp - TG_PROD_WARPS) >> 2;
     const int mask_diag = d.netf.use_hodge_mask;
     uint32_t tile = 0;
+    const size_t ep = (size_t)P->Ep;
     for (int vb = blockIdx.x; vb < NV; vb += gridDim.x, ++tile) {
-      tc::mbar_wait(tfull, tile & 1);
+      const uint32_t buf = dbuf ? (tile & 1u) : 0u, use = dbuf ? (tile >> 1) : tile;
+      tc::mbar_wait(tfull + 8 * buf, use & 1u);
       tc::tc_fence_after_sync();
-      for (int mt = 0; mt < mtiles; ++mt) {
+      for (int mi = 0; mi < mtiles; ++mi) {
+        const int mt = mtiles - 1 - mi;   // the second tile first: its single accumulator is what the next unit's MMAs wait for
         const int row = mt * 128 + q * 32 + lane;
         const int gs = G == 1 ? 0 : row / E, er = row - gs * E, b = vb * G + gs;   // sample of this row inside the unit, edge row
         const bool live = row < EG && b < B;
         // H is symmetric: lane `row` holds H[row][c0 .. c0+15]; it is stored as H[c0+j][row], so that for
         // every j the 32 lanes of the warp write 32 CONSECUTIVE floats (one coalesced 128-byte store)
         // instead of 32 rows 760 bytes apart.
-        float *Hcol = a.H + (size_t)b * E * P->Ep + er;
+        float *Hcol = a.H + (size_t)b * E * ep + er;
+        float *Hrow = a.H + ((size_t)b * E + er) * ep;   // G == 1, first tile: the columns >= 128 are ALSO stored untransposed
+        const bool both = !GROUPED && mtiles == 2 && mt == 0;
         float *Prow = a.P0 + ((size_t)b * E + er) * PR0;
         const int cb0 = gs * E, cb1 = cb0 + E;   // this sample's diagonal block of the stacked Gram
         // warp-uniform range of columns that hold a diagonal block of the warp's 32 rows (G = 1: all of [0, E))
         const int rlo = mt * 128 + q * 32, rhi = rlo + 31 < EG ? rlo + 31 : EG - 1;
         const int blo = G == 1 ? 0 : (rlo / E) * E, bhi = G == 1 ? E : (rhi / E) * E + E;
-        for (int c0 = half * 16; c0 < ncols; c0 += 16 * (TG_EPI_WARPS / 4)) {
+        const int cfirst = mt == 0 ? 0 : c1;
+        const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + (mt == 0 ? buf * (uint32_t)ncols : acc1 - (uint32_t)c1);
+        for (int c0 = cfirst + half * 16; c0 < ncols; c0 += 16 * (TG_EPI_WARPS / 4)) {
           if (!GROUPED && c0 + 16 <= E) {
             // a chunk of H columns only: 16 unconditional coalesced stores (the diagonal is patched first, by the one warp
             // whose rows the chunk crosses)
             float v[16];
-            tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ncols + c0), v);
+            tc::tmem_ld16(tcol + (uint32_t)c0, v);
             if (live) {
+              if (both && c0 >= 128) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(Hrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
               if (c0 < rlo + 32 && c0 + 16 > rlo) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -251,8 +290,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
                   }
                 }
               }
-              float *hc = Hcol + (size_t)c0 * P->Ep;
-              const size_t ep = (size_t)P->Ep;
+              float *hc = Hcol + (size_t)c0 * ep;
 #pragma unroll
               for (int j = 0; j < 16; ++j) hc[(size_t)j * ep] = v[j];
             }
@@ -260,22 +298,24 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gram_kernel(const DevPlan *_
           }
           if (!((c0 < bhi && c0 + 16 > blo) || c0 + 16 > wp0 || (rsum && c0 <= rcol && rcol < c0 + 16))) continue;   // neither a diagonal block nor projections / row sums
           float v[16];
-          tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ncols + c0), v);
+          tc::tmem_ld16(tcol + (uint32_t)c0, v);
           if (live) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = c0 + j;
               if (col >= cb0 && col < cb1) {
-                Hcol[(size_t)(col - cb0) * P->Ep] = (mask_diag && col == row) ? 0.f : v[j];
+                Hcol[(size_t)(col - cb0) * ep] = (mask_diag && col == row) ? 0.f : v[j];
+                if (both && col >= 128) Hrow[col] = v[j];
                 if (col == row && a.Dg) a.Dg[(size_t)b * E + er] = v[j];
               } else if (rsum && col == rcol) a.Rs[(size_t)b * E + er] = v[j];
               else if (col >= wp0 && col - wp0 < PR0) Prow[col - wp0] = v[j];
             }
           }
         }
+        tc::tc_fence_before_sync();
+        if (mt == 1) tc::mbar_arrive(tempty1);
+        else tc::mbar_arrive(tempty0 + 8 * buf);
       }
-      tc::tc_fence_before_sync();
-      tc::mbar_arrive(tempty);
     }
   }
   tc::tc_fence_before_sync();
@@ -295,8 +335,8 @@ static inline int tc_gram_launch(const DevPlan *dP, const DevPlan &hp, const flo
   a.r2 = r2; a.H = H; a.P0 = P0; a.Dg = Dg; a.Rs = Rs;
   const int nv = (hp.d.B + hp.gram_group - 1) / hp.gram_group;
   int grid = nv < 148 ? nv : 148;
-  if (hp.gram_group > 1) tc_gram_kernel<true><<<grid, TG_THREADS, TG_SMEM, (cudaStream_t)stream>>>(dP, a);
-  else tc_gram_kernel<false><<<grid, TG_THREADS, TG_SMEM, (cudaStream_t)stream>>>(dP, a);
+  if (hp.gram_group > 1) tc_gram_kernel<true><<<grid, tg_threads(true), TG_SMEM, (cudaStream_t)stream>>>(dP, a);
+  else tc_gram_kernel<false><<<grid, tg_threads(false), TG_SMEM, (cudaStream_t)stream>>>(dP, a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
