@@ -97,6 +97,10 @@ struct ccsd_plan {
   cudaStream_t side = nullptr;              // internal stream: the norm kernels run beside the x / adj pipeline
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool side_pending = false;
+  // x / adj pipeline forks (launch_xa): [0] ScoreNetworkX's final MLP, [1] the hodge branch, [2] the node MLP of each attention
+  // layer (beside its per-edge MLP) -- all independent of the attention chain on the caller's stream until the joins
+  cudaStream_t xs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_x0 = nullptr, ev_xj[3] = {nullptr, nullptr, nullptr}, ev_xl = nullptr;
   float *Dg = nullptr, *Rs = nullptr;       // [B][E] diag(F F^T), F 1
   float *H2 = nullptr;                      // [B][E][Ep] H . H of large complexes (tc_r2big)
   int use_tc_xfin = 0;                      // ScoreNetworkX final MLP on tcgen05 (tc_xfin.cuh)
@@ -674,6 +678,19 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
       return fail(CCSD_ERR_CUDA, "cannot create the internal stream / events");
     }
   }
+#ifndef CCSD_EMU
+  if (!XL.big && !getenv("CCSD_B200_NO_SIDE_STREAM")) {
+    bool ok = cudaEventCreateWithFlags(&p->ev_x0, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_xl, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&p->xs[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p->ev_xj[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      delete p;
+      return fail(CCSD_ERR_CUDA, "cannot create the internal streams / events of the x / adj pipeline");
+    }
+  }
+#endif
   if (p->use_hnorm && p->hp.gram_group > 1)
     while (p->hp.gram_group > 1 && tc_gram_ncols(p->hp.gram_group * d.E, p->hp.PR0 + 1) > 256) --p->hp.gram_group;
   if (p->use_tc_fin) {   // norm partial slots = 128-row tiles per graph
@@ -696,6 +713,12 @@ void ccsd_plan_destroy(ccsd_plan_t *plan) {
 #ifndef CCSD_EMU
   for (auto &r : plan->prof) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
   if (plan->side) { cudaStreamSynchronize(plan->side); cudaStreamDestroy(plan->side); }
+  for (int i = 0; i < 3; ++i) {
+    if (plan->xs[i]) { cudaStreamSynchronize(plan->xs[i]); cudaStreamDestroy(plan->xs[i]); }
+    if (plan->ev_xj[i]) cudaEventDestroy(plan->ev_xj[i]);
+  }
+  if (plan->ev_x0) cudaEventDestroy(plan->ev_x0);
+  if (plan->ev_xl) cudaEventDestroy(plan->ev_xl);
   if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
 #endif
@@ -934,15 +957,65 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
   CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, stream, p->dP, a);
   PROF_END(p, stream);
   p->launches++;
+  // Forks: everything below only needs x_net_kernel's outputs until the joins, so ScoreNetworkX's final MLP, the hodge branch and
+  // the attention chain run on three streams (they are latency-bound kernels that fill each other's idle issue slots).  Serial
+  // when profiling (the per-kernel events live on the caller's stream) or when only one network is evaluated.
+  bool forked = false, join_x = false, join_h = false;
 #ifndef CCSD_EMU
+  forked = p->xs[0] && !p->profiling && (a.which & 2);
+  if (forked && cudaEventRecord(p->ev_x0, (cudaStream_t)stream) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream fork failed");
   if (a.g_hcat) {
+    void *sx = stream;
+    if (forked) {
+      if (cudaStreamWaitEvent(p->xs[0], p->ev_x0, 0) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream fork failed");
+      sx = (void *)p->xs[0];
+    }
     PROF_BEGIN(p, "tc_xfin_kernel", stream);
-    if (tc_xfin_launch(p->dP, p->hp, a, p->txf, p->g_hcat, d.netx.fdim * L.N4, p->ximg, stream)) return fail(CCSD_ERR_CUDA, "tc_xfin launch failed");
+    if (tc_xfin_launch(p->dP, p->hp, a, p->txf, p->g_hcat, d.netx.fdim * L.N4, p->ximg, sx)) return fail(CCSD_ERR_CUDA, "tc_xfin launch failed");
     PROF_END(p, stream);
     p->launches++;
+    if (forked) {
+      if (cudaEventRecord(p->ev_xj[0], p->xs[0]) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
+      join_x = true;
+    }
   }
 #endif
   if (!(a.which & 2)) return dev_check("x_net_kernel");
+  if (A.is_cc && !A.base_cc) {
+    // The hodge branch (cc_utils.py:1503-1588, hodge_layers.py) reads the initial channels (adjacency powers) and the Gram
+    // projections only and writes its own planes of the channel stack: independent of the attention layers
+    int ch_h = A.c_init;
+    for (int l = 0; l < A.num_layers; ++l) ch_h += A.layer[l].c_out;   // first hodge channel
+    void *sh = stream;
+#ifndef CCSD_EMU
+    if (forked) {
+      if (cudaStreamWaitEvent(p->xs[1], p->ev_x0, 0) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream fork failed");
+      sh = (void *)p->xs[1];
+    }
+#endif
+    if (p->hp.PR1 > 0) {
+      // projections of hodge layer 1 (value MLP with a non-linearity: not foldable into the Gram product)
+      Proj1Args q; q.r2 = a.r2; q.flags = a.flags; q.g_stack = p->g_stack; q.g_stack_stride = L.g_stack; q.ldp = L.ldp;
+      q.P1 = p->P1;
+      q.epc = imax(1, imin(8, (48 * 1024) / (p->hp.Kp * 4)));
+      PROF_BEGIN(p, "proj1_kernel", stream);
+      CCSD_LAUNCH(proj1_kernel, dim3((d.E + q.epc - 1) / q.epc, d.B, 1), 128, ((size_t)q.epc * p->hp.Kp + 2 * 72 + 8) * 4, sh, p->dP, q);
+      PROF_END(p, stream);
+      p->launches++;
+    }
+    XaArgs h = a;
+    h.ch_in = ch_h;
+    PROF_BEGIN(p, "hodge_kernel", stream);
+    CCSD_LAUNCH(hodge_kernel, dim3(d.B, 1, 1), L.Th, (size_t)L.h_total * 4, sh, p->dP, h);
+    PROF_END(p, stream);
+    p->launches++;
+#ifndef CCSD_EMU
+    if (forked) {
+      if (cudaEventRecord(p->ev_xj[1], p->xs[1]) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
+      join_h = true;
+    }
+#endif
+  }
   int ch_in = 0, ch_out = A.c_init;
   const float *xin = p->g_x0;
   float *xout = p->g_x1;
@@ -965,8 +1038,17 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
 #ifndef CCSD_EMU
     a.skip_edge = p->use_tc_edge[l];
 #endif
+    void *sf = stream;
+#ifndef CCSD_EMU
+    const bool fork_l = forked && p->use_tc_edge[l];   // the node MLP (attn_finish) beside the per-edge MLP (tc_edge)
+    if (fork_l) {
+      if (cudaEventRecord(p->ev_xl, (cudaStream_t)stream) != cudaSuccess || cudaStreamWaitEvent(p->xs[2], p->ev_xl, 0) != cudaSuccess)
+        return fail(CCSD_ERR_CUDA, "stream fork failed");
+      sf = (void *)p->xs[2];
+    }
+#endif
     PROF_BEGIN(p, "attn_finish_kernel", stream);
-    CCSD_LAUNCH(attn_finish_kernel, dim3(d.B, 1, 1), L.Tf, (size_t)L.f_total * 4, stream, p->dP, a);
+    CCSD_LAUNCH(attn_finish_kernel, dim3(d.B, 1, 1), L.Tf, (size_t)L.f_total * 4, sf, p->dP, a);
     PROF_END(p, stream);
     p->launches += 2;
 #ifndef CCSD_EMU
@@ -975,6 +1057,10 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
       if (tc_edge_launch(p->dP, p->hp, a, stream)) return fail(CCSD_ERR_CUDA, "tc_edge launch failed");
       PROF_END(p, stream);
       p->launches++;
+    }
+    if (fork_l) {
+      if (cudaEventRecord(p->ev_xj[2], p->xs[2]) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)stream, p->ev_xj[2], 0) != cudaSuccess)
+        return fail(CCSD_ERR_CUDA, "stream join failed");
     }
 #endif
     ch_in = ch_out;
@@ -990,25 +1076,19 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     p->launches++;
     fd_have += A.c_init + A.hbase[0].c_out + (A.num_layers_h == 2 ? A.hbase[1].c_out : 0);
   }
-  if (A.is_cc && !A.base_cc && p->hp.PR1 > 0) {
-    // projections of hodge layer 1 (value MLP with a non-linearity: not foldable into the Gram product)
-    Proj1Args q; q.r2 = a.r2; q.flags = a.flags; q.g_stack = p->g_stack; q.g_stack_stride = L.g_stack; q.ldp = L.ldp;
-    q.P1 = p->P1;
-    q.epc = imax(1, imin(8, (48 * 1024) / (p->hp.Kp * 4)));
-    PROF_BEGIN(p, "proj1_kernel", stream);
-    CCSD_LAUNCH(proj1_kernel, dim3((d.E + q.epc - 1) / q.epc, d.B, 1), 128, ((size_t)q.epc * p->hp.Kp + 2 * 72 + 8) * 4, stream, p->dP, q);
-    PROF_END(p, stream);
-    p->launches++;
-  }
-  if (A.is_cc && !A.base_cc) {
-    a.ch_in = ch_out;   // first hodge channel
-    PROF_BEGIN(p, "hodge_kernel", stream);
-    CCSD_LAUNCH(hodge_kernel, dim3(d.B, 1, 1), L.Th, (size_t)L.h_total * 4, stream, p->dP, a);
-    PROF_END(p, stream);
-    p->launches++;
-    fd_have += A.c_init + A.hodge[0].c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
-  }
+  int fd_hodge = 0;
+  if (A.is_cc && !A.base_cc) fd_hodge = A.c_init + A.hodge[0].c_out + (A.num_layers_h == 2 ? A.hodge[1].c_out : 0);
+  fd_have += fd_hodge;
   a.ch_out = fd_have;   // channels the final MLP reads
+  auto join = [&]() -> int {   // the forked streams rejoin the caller's stream
+#ifndef CCSD_EMU
+    if (join_h && cudaStreamWaitEvent((cudaStream_t)stream, p->ev_xj[1], 0) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
+    if (join_x && cudaStreamWaitEvent((cudaStream_t)stream, p->ev_xj[0], 0) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
+#endif
+    join_h = join_x = false;
+    return 0;
+  };
+  if (int r = join()) return r;
 #ifndef CCSD_EMU
   if (p->use_tc_fin) {
     PROF_BEGIN(p, "tc_afinal_kernel", stream);
