@@ -80,6 +80,8 @@ struct ccsd_plan {
   unsigned long long *zmask = nullptr, *zmask_eval = nullptr;
   float *g_stack = nullptr, *g_att = nullptr, *g_hmc = nullptr, *g_x0 = nullptr, *g_x1 = nullptr;
   float *g_big = nullptr;       // scratch of the large-graph pipeline [B][xp.big_total]
+  float *g_hu = nullptr;        // [B][n1] hodge_u_kernel's sums for the plan's own flags (valid after ccsd_plan_init)
+  bool hu_ready = false;
   float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
   bool bound = false, inited = false;
   long long *trace = nullptr;   // debug timeline buffer for the tensor-core apply kernel
@@ -467,7 +469,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, hu, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -497,6 +499,7 @@ static WsLayout ws_layout(const ccsd_plan *p) {
 #else
   w.ghcat = take(gmh ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16); w.ximg = take(16); w.dg = take(16); w.rs = take(16); w.h2 = take(16);
 #endif
+  w.hu = take(p->hp.p1_fold ? B * (size_t)imax(1, d.neta.n_proj_rows[1]) * 4 : 16);
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
@@ -749,6 +752,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->ximg = (uint8_t *)(ws + w.ximg);
   p->Dg = (float *)(ws + w.dg); p->Rs = (float *)(ws + w.rs); p->H2 = (float *)(ws + w.h2);
 #endif
+  p->g_hu = (float *)(ws + w.hu); p->hu_ready = false;
   if (p->hp.xp.big) {
     // pad columns / rows of the planes are read as don't-care operands: make them finite once
     const size_t nb = (size_t)p->hp.d.B * p->hp.xp.big_total * 4;
@@ -802,6 +806,10 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
     if (tc_xfin_prep(p->dP, p->txf, p->ximg, stream)) return fail(CCSD_ERR_CUDA, "tc_xfin_prep launch failed");
 #endif
   CCSD_LAUNCH(zmask_kernel, dim3(grid_for(d.B), 1, 1), 256, 0, stream, p->flags, p->zmask, d.B, d.N);
+  if (p->hp.p1_fold && !p->hp.xp.big) {   // flag-only sums of the hodge branch: once per run
+    CCSD_LAUNCH(hodge_u_kernel, dim3(d.B, 1, 1), 128, 96 * 4, stream, p->dP, p->flags, p->g_hu, p->hp.xp.Th);
+    p->hu_ready = true;
+  }
   InitArgs a;
   a.flags = p->flags; a.px = px; a.padj = padj; a.pr2 = pr2; a.x = p->x; a.adj = p->adj; a.r2 = p->r2;
   a.nz.seed = seed; a.nz.sample_offset = sample_offset; a.nz.step = -1;
@@ -1005,6 +1013,7 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     }
     XaArgs h = a;
     h.ch_in = ch_h;
+    h.g_hu = (p->hu_ready && a.flags == p->flags) ? p->g_hu : nullptr;   // (score_eval with the caller's own flags: computed in the kernel)
     PROF_BEGIN(p, "hodge_kernel", stream);
     CCSD_LAUNCH(hodge_kernel, dim3(d.B, 1, 1), L.Th, (size_t)L.h_total * 4, sh, p->dP, h);
     PROF_END(p, stream);

@@ -198,6 +198,43 @@ __device__ __forceinline__ void tt_scores4(const float *__restrict__ qr, uint32_
   }
 }
 
+// Narrow attention (attn_dim <= 12, e.g. QM9: attn_dim 10 in 5 heads of 2): the whole Q row (AP = attn_dim rounded up to 4,
+// zero padded) stays in registers, two K rows are loaded per iteration, NH independent head chains per column.
+template <int AP, int DS, int NH>
+__device__ __forceinline__ void tt_scores_w(const float *__restrict__ qr, uint32_t kb, int qld, float *__restrict__ trow_s,
+                                            int part, int N, float c) {
+  static_assert(NH * DS <= AP && AP % 4 == 0, "head layout");
+  float q[AP];
+#pragma unroll
+  for (int dd = 0; dd < AP; dd += 4) {
+    const float4 t4 = ld4(qr + dd);
+    q[dd] = t4.x; q[dd + 1] = t4.y; q[dd + 2] = t4.z; q[dd + 3] = t4.w;
+  }
+  for (int j = part; j < N; j += 2 * TT_NP) {
+    const bool two = j + TT_NP < N;
+    const uint32_t kj0 = kb + (uint32_t)(j * qld) * 4u, kj1 = two ? kj0 + (uint32_t)(TT_NP * qld) * 4u : kj0;
+    float k0[AP], k1[AP];
+#pragma unroll
+    for (int dd = 0; dd < AP; dd += 4) tt_lds128(kj0 + dd * 4, k0[dd], k0[dd + 1], k0[dd + 2], k0[dd + 3]);
+#pragma unroll
+    for (int dd = 0; dd < AP; dd += 4) tt_lds128(kj1 + dd * 4, k1[dd], k1[dd + 1], k1[dd + 2], k1[dd + 3]);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < DS; ++dd) {
+        u0 = fmaf(q[h * DS + dd], k0[h * DS + dd], u0);
+        u1 = fmaf(q[h * DS + dd], k1[h * DS + dd], u1);
+      }
+      s0 += tt_tanh_c(u0, c);
+      s1 += tt_tanh_c(u1, c);
+    }
+    trow_s[j] = s0;
+    if (two) trow_s[j + TT_NP] = s1;
+  }
+}
+
 __device__ __forceinline__ void tt_tmem_st8(uint32_t taddr, const uint32_t r[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
@@ -528,6 +565,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
         if (ds == 8) tt_scores4<8>(qr, kb, qld, trow_s, part, N, c2);
         else if (ds == 4) tt_scores4<4>(qr, kb, qld, trow_s, part, N, c2);
         else tt_scores4<2>(qr, kb, qld, trow_s, part, N, c2);
+      } else if (ad == 10 && ds == 2) {   // QM9 / QM9_CC: adim 10, 4 "heads" -> torch.split gives 5 chunks of 2
+        tt_scores_w<12, 2, 5>(qs + r * qld, tc::smem_u32(kbase), qld, trow_s, part, N, scale * 2.885390081777927f);
       } else if (ad <= 32 && (ds == 8 || ds == 4 || ds == 2)) {
         float q[32];
         const float *__restrict__ qr = qs + r * qld;

@@ -70,6 +70,8 @@ struct XaArgs {
   int skip_edge;                 // attn_finish_kernel: the per-edge MLP runs on the tensor cores (tc_edge.cuh) instead
   float *g_hcat;                 // not null: x_net_kernel stops after the GCN stack and writes [x, h_1 .. h_D] ([fdim x N4] per
                                  // graph) here for the tensor-core final MLP (tc_xfin.cuh)
+  const float *g_hu;             // hodge_kernel: per-graph sums of the folded layer-1 projection weights over the live cells
+                                 // ([B x n1]; they depend on the node flags only, hodge_u_kernel fills them once per run) or nullptr
   long long *trace;              // debug phase timeline of tc_attn_kernel (ccsd_debug_apply_trace), normally nullptr
 };
 
@@ -432,6 +434,8 @@ __device__ __forceinline__ void hodge_channel_mlp(const ccsd_mlp_t &m, const flo
 }
 
 __device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, int ad, int heads, float scale) {
+  if (ad == 4 && heads == 2)   // every shipped checkpoint (adim_h = 4, num_heads_h = 2): no loops, no divisions
+    return 0.5f * (fast_tanh((q[0] * k[0] + q[1] * k[1]) * scale) + fast_tanh((q[2] * k[2] + q[3] * k[3]) * scale));
   const int ds = ad / heads;
   const int nch = (ad + ds - 1) / ds;
   float s = 0.f;
@@ -442,6 +446,58 @@ __device__ __forceinline__ float hodge_diag_att(const float *q, const float *k, 
     s += fast_tanh(a * scale);
   }
   return s / (float)nch;
+}
+
+// u[b][r] = sum over the live cells of sample b of the folded layer-1 projection weights (see hodge_kernel): a function of the
+// node flags only, so it is computed once per sampler run (ccsd_plan_init) instead of in every evaluation.  Same summation
+// order as the in-kernel fallback (lanes along the cells, warp tree, sum over warps): bit-identical.
+CCSD_KERNEL void __launch_bounds__(128) hodge_u_kernel(const DevPlan *__restrict__ P, const float *__restrict__ flags_g, float *__restrict__ g_hu, int nthr) {
+  CCSD_SMEM(sm);   // [32] partial sums + [64] flags
+  float *part = sm, *fl = sm + 32;
+  const ccsd_plan_desc_t &d = P->d;
+  const ccsd_neta_t &A = d.neta;
+  const int b = blockIdx.x, N = d.N, K = d.K, Kw = P->Kp, PR1 = A.n_proj_rows[1];
+  // the reduction tree must match hodge_kernel's block size (nthr): threads beyond it idle
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) fl[i] = i < N ? flags_g[(size_t)b * N + i] : 0.f;
+  __syncthreads();
+  const unsigned long long zm = zero_mask_of(fl, N);
+  const float *Wp = P->W + A.proj_w + (size_t)P->PR0h * Kw;
+#ifdef CCSD_EMU
+  const int lane = 0, warp = 0, nwarp = 1;
+#else
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (nthr + 31) >> 5;
+#endif
+  for (int r0 = 0; r0 < PR1; r0 += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#ifdef CCSD_EMU
+    const int stride = blockDim.x;   // (host emulation: one thread per block walks every cell, like hodge_kernel's own loop)
+#else
+    const int stride = nthr;
+#endif
+    if ((int)threadIdx.x < stride)
+      for (int k = threadIdx.x; k < K; k += stride) {
+        if (!(P->cell_mask[k] & zm)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (r0 + j < PR1) acc[j] += __ldg(Wp + (size_t)(r0 + j) * Kw + k);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#ifndef CCSD_EMU
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+#endif
+      if (lane == 0 && warp < 4) part[warp * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 8 && r0 + j < PR1; j += blockDim.x) {
+      float t = 0.f;
+      for (int w = 0; w < nwarp; ++w) t += part[w * 8 + j];
+      g_hu[(size_t)b * PR1 + r0 + j] = t;
+    }
+    __syncthreads();
+  }
 }
 
 CCSD_KERNEL void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__ P, XaArgs a) {
@@ -527,7 +583,11 @@ CCSD_KERNEL void __launch_bounds__(128) hodge_kernel(const DevPlan *__restrict__
 #else
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
 #endif
-    for (int r0 = 0; r0 < PR1; r0 += 8) {
+    if (a.g_hu) {
+      for (int r = threadIdx.x; r < PR1; r += blockDim.x) u[r] = a.g_hu[(size_t)b * PR1 + r];
+      __syncthreads();
+    }
+    for (int r0 = a.g_hu ? PR1 : 0; r0 < PR1; r0 += 8) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int k = threadIdx.x; k < K; k += blockDim.x) {
         if (!(P->cell_mask[k] & zm)) {
