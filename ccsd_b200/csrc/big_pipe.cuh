@@ -473,7 +473,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_final_kernel(const DevPlan *__restri
   mlp_fm(m, P->W, S + (size_t)i * Np + j0, PS, g.ch_out /* planes in the stack */, nullptr, 0, 0, R, hA, hB, BIG_SEG, so, 1, 0,
          ACT_ELU, ACT_NONE);
   const size_t ga = (size_t)b * N * N;
-  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 1];
+  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 1];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
   const float fi = a.flags[(size_t)b * N + i];
   float s2 = 0.f, z2 = 0.f;
@@ -491,7 +491,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_final_kernel(const DevPlan *__restri
     float z = 0.f;
     if (i != j) {
       const int q = i * N + j;
-      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, a.nz.step, a.slot), q)) * fij;
+      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, nz_step(a.nz), a.slot), q)) * fij;
     }
     if (a.mode == MODE_SCORE) {
       a.out_adj[ga + (size_t)i * N + j] = s;
@@ -505,11 +505,12 @@ CCSD_KERNEL void __launch_bounds__(128) big_final_kernel(const DevPlan *__restri
       const float v = mu + ca.pc * z;
       a.out_adj[ga + (size_t)i * N + j] = v;
       a.mean_adj[ga + (size_t)i * N + j] = mu;
-      if (a.traj_adj && b == 0) a.traj_adj[(size_t)i * N + j] = a.denoise ? mu : v;
+      float *tja = a.nz.sd ? a.nz.sd->ta : a.traj_adj;
+      if (tja && b == 0) tja[(size_t)i * N + j] = a.denoise ? mu : v;
       if (i != j) {
         a.out_adj[ga + (size_t)j * N + i] = v;
         a.mean_adj[ga + (size_t)j * N + i] = mu;
-        if (a.traj_adj && b == 0) a.traj_adj[(size_t)j * N + i] = a.denoise ? mu : v;
+        if (tja && b == 0) tja[(size_t)j * N + i] = a.denoise ? mu : v;
       }
     }
   }
@@ -536,7 +537,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restric
   const float *hc = big_ptr(P, g, b, L.big_HC);
   mlp_fm(m, P->W, hc + i0, Np, X.fdim, nullptr, 0, 0, R, hA, hB, BIG_RCX, so, 1, BIG_RCX, ACT_ELU, ACT_NONE);
   const size_t gxo = (size_t)b * N * F;
-  const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 0];
+  const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 0];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
   float s2 = 0.f, z2 = 0.f;
   for (int q = threadIdx.x; q < R * F; q += blockDim.x) {
@@ -545,7 +546,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restric
     const float o = so[f * BIG_RCX + r] * fl;   // mask_x
     if (a.mode == MODE_EVAL) { a.out_x[gxo + p] = o; continue; }
     const float s = cx.score_scale * o;
-    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, a.nz.step, a.slot), p)) * fl;
+    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, nz_step(a.nz), a.slot), p)) * fl;
     if (a.mode == MODE_SCORE) {
       a.out_x[gxo + p] = s;
       s2 += s * s;
@@ -555,7 +556,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restric
       const float v = mu + cx.pc * z;
       a.out_x[gxo + p] = v;
       a.mean_x[gxo + p] = mu;
-      if (a.traj_x && b == 0) a.traj_x[p] = a.denoise ? mu : v;
+      if (b == 0) { float *tjx = a.nz.sd ? a.nz.sd->tx : a.traj_x; if (tjx) tjx[p] = a.denoise ? mu : v; }
     }
   }
   if (a.mode == MODE_SCORE) {

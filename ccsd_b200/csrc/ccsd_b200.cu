@@ -80,6 +80,9 @@ struct ccsd_plan {
   unsigned long long *zmask = nullptr, *zmask_eval = nullptr;
   float *g_stack = nullptr, *g_att = nullptr, *g_hmc = nullptr, *g_x0 = nullptr, *g_x1 = nullptr;
   float *g_big = nullptr;       // scratch of the large-graph pipeline [B][xp.big_total]
+  StepDev *sd_dev = nullptr;    // device-resident step state of a graph replay (ccsd_plan_run)
+  bool graph_capture = false;   // do_step is being captured: kernels read the step / diff_traj slots from sd_dev
+  int use_graph = 0;            // graph-only plans: replay one captured step (latency path of small batches)
   float *g_hu = nullptr;        // [B][n1] hodge_u_kernel's sums for the plan's own flags (valid after ccsd_plan_init)
   bool hu_ready = false;
   float *traj_x = nullptr, *traj_adj = nullptr, *traj_r2 = nullptr;
@@ -101,6 +104,10 @@ struct ccsd_plan {
   bool side_pending = false;
   // x / adj pipeline forks (launch_xa): [0] ScoreNetworkX's final MLP, [1] the hodge branch, [2] the node MLP of each attention
   // layer (beside its per-edge MLP) -- all independent of the attention chain on the caller's stream until the joins
+  cudaGraph_t ggraph = nullptr;             // the captured step of the last graph replay (ccsd_plan_run) ...
+  cudaGraphExec_t gexec = nullptr;          // ... kept until its replays have run (ev_graph)
+  cudaEvent_t ev_graph = nullptr;
+  cudaStream_t gs = nullptr;                // capture stream (the caller's may be the legacy default stream, which cannot capture)
   cudaStream_t xs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_x0 = nullptr, ev_xj[3] = {nullptr, nullptr, nullptr}, ev_xl = nullptr;
   float *Dg = nullptr, *Rs = nullptr;       // [B][E] diag(F F^T), F 1
@@ -469,7 +476,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, hu, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, hu, sd, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -500,6 +507,7 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.ghcat = take(gmh ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16); w.ximg = take(16); w.dg = take(16); w.rs = take(16); w.h2 = take(16);
 #endif
   w.hu = take(p->hp.p1_fold ? B * (size_t)imax(1, d.neta.n_proj_rows[1]) * 4 : 16);
+  w.sd = take(sizeof(StepDev));
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
@@ -682,6 +690,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     }
   }
 #ifndef CCSD_EMU
+  p->use_graph = !d.is_cc && !getenv("CCSD_B200_NO_GRAPH");   // (complexes: the rank-2 passes dominate and a replay measured 8 % slower)
   if (!XL.big && !getenv("CCSD_B200_NO_SIDE_STREAM")) {
     bool ok = cudaEventCreateWithFlags(&p->ev_x0, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&p->ev_xl, cudaEventDisableTiming) == cudaSuccess;
@@ -711,11 +720,25 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
   return 0;
 }
 
+#ifndef CCSD_EMU
+static void drop_graph(ccsd_plan *p) {
+  if (p->gexec) {
+    if (p->ev_graph) cudaEventSynchronize(p->ev_graph);   // its replays have run (normally long ago)
+    cudaGraphExecDestroy(p->gexec);
+    p->gexec = nullptr;
+  }
+  if (p->ggraph) { cudaGraphDestroy(p->ggraph); p->ggraph = nullptr; }
+}
+#endif
+
 void ccsd_plan_destroy(ccsd_plan_t *plan) {
   if (!plan) return;
 #ifndef CCSD_EMU
   for (auto &r : plan->prof) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
   if (plan->side) { cudaStreamSynchronize(plan->side); cudaStreamDestroy(plan->side); }
+  drop_graph(plan);
+  if (plan->ev_graph) cudaEventDestroy(plan->ev_graph);
+  if (plan->gs) cudaStreamDestroy(plan->gs);
   for (int i = 0; i < 3; ++i) {
     if (plan->xs[i]) { cudaStreamSynchronize(plan->xs[i]); cudaStreamDestroy(plan->xs[i]); }
     if (plan->ev_xj[i]) cudaEventDestroy(plan->ev_xj[i]);
@@ -753,6 +776,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
   p->Dg = (float *)(ws + w.dg); p->Rs = (float *)(ws + w.rs); p->H2 = (float *)(ws + w.h2);
 #endif
   p->g_hu = (float *)(ws + w.hu); p->hu_ready = false;
+  p->sd_dev = (StepDev *)(ws + w.sd);
   if (p->hp.xp.big) {
     // pad columns / rows of the planes are read as don't-care operands: make them finite once
     const size_t nb = (size_t)p->hp.d.B * p->hp.xp.big_total * 4;
@@ -812,7 +836,7 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
   }
   InitArgs a;
   a.flags = p->flags; a.px = px; a.padj = padj; a.pr2 = pr2; a.x = p->x; a.adj = p->adj; a.r2 = p->r2;
-  a.nz.seed = seed; a.nz.sample_offset = sample_offset; a.nz.step = -1;
+  a.nz.seed = seed; a.nz.sample_offset = sample_offset; a.nz.step = -1; a.nz.sd = nullptr;
   const size_t units = d.is_cc ? (size_t)d.B * d.E * (p->hp.Kp / 4) : (size_t)d.B * d.N * d.N;
   CCSD_LAUNCH(init_kernel, dim3(grid_for(units), d.is_cc ? 3 : 2, 1), 256, 0, stream, p->dP, a);
   p->launches++;
@@ -1189,8 +1213,9 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
   const size_t sx = (size_t)d.B * d.N * d.F, sa = (size_t)d.B * d.N * d.N, sr = (size_t)d.B * d.E * d.K;
   const int s4 = d.sampler == CCSD_SAMPLER_S4;
   NoiseCtx nz; nz.seed = p->seed; nz.sample_offset = p->sample_offset; nz.step = step;
-  float *tx = p->traj_x ? p->traj_x + (size_t)step * d.N * d.F : nullptr;
-  float *ta = p->traj_adj ? p->traj_adj + (size_t)step * d.N * d.N : nullptr;
+  nz.sd = p->graph_capture ? p->sd_dev : nullptr;   // captured step: index and diff_traj slots live on the device
+  float *tx = (p->traj_x && !p->graph_capture) ? p->traj_x + (size_t)step * d.N * d.F : nullptr;
+  float *ta = (p->traj_adj && !p->graph_capture) ? p->traj_adj + (size_t)step * d.N * d.N : nullptr;
   float *tr = (p->traj_r2 && d.is_cc) ? p->traj_r2 + (size_t)step * d.E * d.K : nullptr;
 
   // rank-2 apply pass: H F + ScoreNetworkF + the mode's epilogue
@@ -1293,7 +1318,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
   // Langevin / S4 step sizes of the objects in obj_mask from the batch means of their norm partials
   auto coef_phase = [&](int obj_mask) -> int {
     if (int r = join_side()) return r;
-    CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4; c.obj_mask = obj_mask;
+    CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4; c.obj_mask = obj_mask; c.sd = nz.sd;
     PROF_BEGIN(p, "coef_kernel", stream);
     CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
     PROF_END(p, stream);
@@ -1371,7 +1396,45 @@ int ccsd_plan_run(ccsd_plan_t *p, int step_begin, int step_end, void *stream) {
   if (!p) return fail(CCSD_ERR_INVALID, "null plan");
   if (!p->inited) return fail(CCSD_ERR_STATE, "ccsd_plan_init must be called before running");
   if (step_begin < 0 || step_end > p->hp.d.n_diff_steps || step_begin > step_end) return fail(CCSD_ERR_INVALID, "step range out of bounds");
-  for (int s = step_begin; s < step_end; ++s)
+  int s = step_begin;
+#ifndef CCSD_EMU
+  // Latency path of small graph-only batches: a step is ~40 dependent launches of 8-30 us kernels, and the gaps between them
+  // are a sixth of the step.  One step is captured as a CUDA graph whose kernels read the step index (schedule row, Philox
+  // draw id) and the diff_traj slots from device memory (StepDev); step_advance_kernel closes the step; the graph is replayed
+  // for every step but the first (eager: it also sets every kernel's shared-memory attribute) and the last (which returns means).
+  if (p->use_graph && !p->profiling && step_end - step_begin >= 8) {
+    const ccsd_plan_desc_t &d = p->hp.d;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = do_step(p, s, nullptr, nullptr, nullptr, 0, stream)) return r;
+    ++s;
+    step_set_kernel<<<1, 1, 0, st>>>(p->sd_dev, s, p->traj_x ? p->traj_x + (size_t)s * d.N * d.F : nullptr,
+                                      p->traj_adj ? p->traj_adj + (size_t)s * d.N * d.N : nullptr);
+    drop_graph(p);
+    if (!p->ev_graph && cudaEventCreateWithFlags(&p->ev_graph, cudaEventDisableTiming) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaEventCreate failed");
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const int64_t l0 = p->launches;
+    if (!p->gs && cudaStreamCreateWithFlags(&p->gs, cudaStreamNonBlocking) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaStreamCreate failed");
+    if (cudaStreamBeginCapture(p->gs, cudaStreamCaptureModeRelaxed) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaStreamBeginCapture failed");
+    p->graph_capture = true;
+    int rc = do_step(p, s, nullptr, nullptr, nullptr, 0, (void *)p->gs);
+    p->graph_capture = false;
+    step_advance_kernel<<<1, 1, 0, p->gs>>>(p->sd_dev, d.N * d.F, d.N * d.N);
+    const cudaError_t ce = cudaStreamEndCapture(p->gs, &graph);
+    const int64_t per_step = p->launches - l0 + 1;
+    p->launches = l0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph) return fail(CCSD_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); return fail(CCSD_ERR_CUDA, "cudaGraphInstantiate failed"); }
+    p->ggraph = graph; p->gexec = exec;   // destroyed by the next run / ccsd_plan_destroy, after ev_graph
+    for (; s < step_end - 1; ++s) {
+      if (cudaGraphLaunch(exec, st) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaGraphLaunch failed");
+      p->launches += per_step;
+    }
+    if (cudaEventRecord(p->ev_graph, st) != cudaSuccess) return fail(CCSD_ERR_CUDA, "cudaEventRecord failed");
+  }
+#endif
+  for (; s < step_end; ++s)
     if (int r = do_step(p, s, nullptr, nullptr, nullptr, s == step_end - 1, stream)) return r;
   return 0;
 }
@@ -1464,6 +1527,7 @@ int ccsd_plan_info(const ccsd_plan_t *p, int what) {
     case 15: return p->use_tc_xfin;
     case 16: return p->use_hnorm;
     case 18: return p->use_tc_big;
+    case 19: return p->use_graph;
     case 17: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_edge[l]; return n; }
     case 14: { int n = 0; for (int l = 0; l < p->hp.d.neta.num_layers; ++l) n += p->use_tc_attn[l]; return n; }   // layers on the tcgen05 attention kernel
 #endif

@@ -79,10 +79,22 @@ struct DevPlan {
 // (rank-2 apply kernels only; x / adj are corrected by update_kernel).
 enum { MODE_EVAL = 0, MODE_SCORE = 1, MODE_PRED = 2, MODE_NORM = 3, MODE_CORR = 4 };
 
+// Device-resident step state of a CUDA-graph replay (ccsd_plan_run): the captured step reads the diffusion step index and the
+// diff_traj destinations from here instead of from kernel arguments, and step_advance_kernel moves them on at its end, so ONE
+// captured step serves every replay.  Eager launches pass sd = nullptr and use the argument values.
+struct StepDev {
+  int step, pad;
+  float *tx, *ta;   // diff_traj destinations of this step (sample 0 of the shard) or nullptr
+};
+
 struct NoiseCtx {
   unsigned long long seed;
   long long sample_offset;
   int step;
+  const StepDev *sd;
 };
+#if defined(__CUDACC__) || defined(CCSD_EMU)
+__host__ __device__ inline int nz_step(const NoiseCtx &nz) { return nz.sd ? nz.sd->step : nz.step; }
+#endif
 
 }  // namespace ccsd

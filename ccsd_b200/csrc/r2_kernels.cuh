@@ -510,7 +510,7 @@ __device__ __forceinline__ void r2_epilogue4(const R2Epi &c, const ApplyArgs &a,
       for (int q = 0; q < 4; ++q)
         if (k0 + q < c.K) z4[q] = a.noise[g0 + q];
     } else {
-      normal4(a.nz.seed, c.gs, draw_id(2, a.nz.step, a.slot), (uint32_t)(e * c.Kg + (k0 >> 2)), z4);
+      normal4(a.nz.seed, c.gs, draw_id(2, nz_step(a.nz), a.slot), (uint32_t)(e * c.Kg + (k0 >> 2)), z4);
     }
   }
 #pragma unroll
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
   R2Epi c;
   c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
   c.gs = (unsigned long long)(a.nz.sample_offset + b);
-  if (a.mode != MODE_EVAL) c.co = P->sched[a.nz.step * 3 + 2];
+  if (a.mode != MODE_EVAL) c.co = P->sched[nz_step(a.nz) * 3 + 2];
   c.b = b; c.E = E; c.K = K; c.Kg = P->Kp >> 2; c.f_nlin = P->f_nlin;
   c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
 
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(256) r2_epi_kernel(const DevPlan *__restrict__
   R2Epi c;
   c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
   c.gs = (unsigned long long)(a.nz.sample_offset + b);
-  if (a.mode != MODE_EVAL) c.co = P->sched[a.nz.step * 3 + 2];
+  if (a.mode != MODE_EVAL) c.co = P->sched[nz_step(a.nz) * 3 + 2];
   c.b = b; c.E = E; c.K = K; c.Kg = Kg; c.f_nlin = P->f_nlin;
   c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
   __syncthreads();
@@ -819,7 +819,20 @@ struct CoefArgs {
   float *coef;             // [3][2]
   int step, s4;
   int obj_mask;            // bit k: compute object k's step sizes (the others keep their previous values)
+  const StepDev *sd;       // graph replay: the step index lives on the device (plan_dev.h)
 };
+
+// graph replay (ccsd_plan_run): set / advance the device-resident step state
+CCSD_KERNEL void step_set_kernel(StepDev *sd, int step, float *tx, float *ta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { sd->step = step; sd->pad = 0; sd->tx = tx; sd->ta = ta; }
+}
+CCSD_KERNEL void step_advance_kernel(StepDev *sd, int stride_x, int stride_adj) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    sd->step += 1;
+    if (sd->tx) sd->tx += stride_x;
+    if (sd->ta) sd->ta += stride_adj;
+  }
+}
 
 CCSD_KERNEL void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ P, CoefArgs a) {
   CCSD_SMEM(sm);
@@ -839,7 +852,7 @@ CCSD_KERNEL void __launch_bounds__(256) coef_kernel(const DevPlan *__restrict__ 
     gs = block_sum(gs, sm);
     zs = block_sum(zs, sm);
     if (threadIdx.x == 0) {
-      const ccsd_objcoef_t co = P->sched[a.step * 3 + obj];
+      const ccsd_objcoef_t co = P->sched[(a.sd ? a.sd->step : a.step) * 3 + obj];
       const float alpha = a.s4 ? co.s4_alpha : co.lg_alpha;
       const float gm = gs / (float)d.B, zm = zs / (float)d.B;
       const float r = d.snr * zm / gm;
@@ -883,7 +896,7 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
   const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
   const int obj = a.obj0 + blockIdx.y;
   const int ndraw = a.s4 ? 3 : 1;
-  const ccsd_objcoef_t co = P->sched[a.nz.step * 3 + obj];
+  const ccsd_objcoef_t co = P->sched[nz_step(a.nz) * 3 + obj];
   const float cs = a.coef[obj * 2], cn = a.coef[obj * 2 + 1];
   const size_t stride = (size_t)gridDim.x * blockDim.x, start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (obj == 0) {
@@ -894,13 +907,13 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
       float z[3] = {0.f, 0.f, 0.f};
       for (int s = 0; s < ndraw; ++s)
         z[s] = f * (a.nx ? a.nx[(size_t)(a.slot0 + s) * tot + g]
-                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, a.nz.step, a.slot0 + s), p));
+                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, nz_step(a.nz), a.slot0 + s), p));
       float mean;
       const float v = upd_elem(co, cs, cn, a.s4, a.x[g], a.sx[g], z, &mean);
       a.x[g] = v;
       if (a.s4) {
         a.mx[g] = mean;
-        if (a.tx && b == 0) a.tx[p] = a.denoise ? mean : v;
+        if (b == 0) { float *tjx = a.nz.sd ? a.nz.sd->tx : a.tx; if (tjx) tjx[p] = a.denoise ? mean : v; }
       }
     }
   } else if (obj == 1) {
@@ -913,14 +926,14 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
         const int q = (i < j) ? i * N + j : j * N + i;
         for (int s = 0; s < ndraw; ++s)
           z[s] = f * (a.nadj ? a.nadj[(size_t)(a.slot0 + s) * tot + (size_t)b * N * N + q]
-                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, a.nz.step, a.slot0 + s), q));
+                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, nz_step(a.nz), a.slot0 + s), q));
       }
       float mean;
       const float v = upd_elem(co, cs, cn, a.s4, a.adj[g], a.sadj[g], z, &mean);
       a.adj[g] = v;
       if (a.s4) {
         a.madj[g] = mean;
-        if (a.tadj && b == 0) a.tadj[p] = a.denoise ? mean : v;
+        if (b == 0) { float *tja = a.nz.sd ? a.nz.sd->ta : a.tadj; if (tja) tja[p] = a.denoise ? mean : v; }
       }
     }
   } else if (d.is_cc) {
@@ -936,7 +949,7 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
         for (int q = 0; q < 4; ++q) zz[s][q] = 0.f;
       if (!a.nr2)
         for (int s = 0; s < ndraw; ++s)
-          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, a.nz.step, a.slot0 + s), (uint32_t)(e * Kg + kg), zz[s]);
+          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, nz_step(a.nz), a.slot0 + s), (uint32_t)(e * Kg + kg), zz[s]);
       for (int q = 0; q < 4; ++q) {
         const int k = kg * 4 + q;
         if (k >= K) break;
@@ -1056,7 +1069,7 @@ CCSD_KERNEL void __launch_bounds__(256) znorm_kernel(const DevPlan *__restrict__
   const float *fl = a.flags + (size_t)b * N;
   const unsigned long long zm = a.zmask[b];
   const unsigned long long gs = (unsigned long long)(a.nz.sample_offset + b);
-  const uint32_t did = draw_id(2, a.nz.step, a.slot);
+  const uint32_t did = draw_id(2, nz_step(a.nz), a.slot);
   // staged once per CTA: edge flags [E]; per tile: the live-cell bits of its 4-cell groups [GPT]
   float *fes = sm + 40;
   unsigned *gm = reinterpret_cast<unsigned *>(fes + ((E + 3) & ~3));

@@ -269,13 +269,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
           a.out_adj[ga + i * N + j] = o;
           a.out_adj[ga + j * N + i] = o;
         } else {
-          const ccsd_objcoef_t ca = P->sched[a.nz.step * 3 + 1];
+          const ccsd_objcoef_t ca = P->sched[nz_step(a.nz) * 3 + 1];
           const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
           const float s = ca.score_scale * o;
           float z = 0.f;
           if (i != j) {
             const int q = i * N + j;
-            z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, a.nz.step, a.slot), q)) * fi * fj;
+            z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, nz_step(a.nz), a.slot), q)) * fi * fj;
           }
           if (a.mode == MODE_SCORE) {
             a.out_adj[ga + i * N + j] = s;
@@ -289,11 +289,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
             const float v = m + ca.pc * z;
             a.out_adj[ga + i * N + j] = v;
             a.mean_adj[ga + i * N + j] = m;
-            if (a.traj_adj && b == 0) a.traj_adj[i * N + j] = a.denoise ? m : v;
+            float *tja = a.nz.sd ? a.nz.sd->ta : a.traj_adj;
+            if (tja && b == 0) tja[i * N + j] = a.denoise ? m : v;
             if (i != j) {
               a.out_adj[ga + j * N + i] = v;
               a.mean_adj[ga + j * N + i] = m;
-              if (a.traj_adj && b == 0) a.traj_adj[j * N + i] = a.denoise ? m : v;
+              if (tja && b == 0) tja[j * N + i] = a.denoise ? m : v;
             }
           }
         }

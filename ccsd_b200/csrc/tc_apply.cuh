@@ -402,14 +402,14 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       ccsd_objcoef_t co;
       memset(&co, 0, sizeof co);
       co.score_scale = 1.f;
-      if (MODE != MODE_EVAL) co = P->sched[a.nz.step * 3 + 2];
+      if (MODE != MODE_EVAL) co = P->sched[nz_step(a.nz) * 3 + 2];
       w.sc = co.score_scale;
       w.k0 = w.sc * d.netf.aff[0]; w.k1 = w.sc * d.netf.aff[1]; w.k2 = w.sc * d.netf.aff[2];
       w.cs = 0.f; w.cn = 0.f;
       if (MODE == MODE_CORR) { w.cs = a.coef[4]; w.cn = a.coef[5]; }
       w.pa = co.pa; w.pb = co.pb; w.pc = co.pc;
     }
-    const uint32_t did = draw_id(2, a.nz.step, a.slot);
+    const uint32_t did = draw_id(2, nz_step(a.nz), a.slot);
     for (int si = 0; si < nmine; ++si) {
       const int b0 = ((int)blockIdx.x + si * (int)gridDim.x) * G;   // first sample of the group
       const int gsz = B - b0 < G ? B - b0 : G;

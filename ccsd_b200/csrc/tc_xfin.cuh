@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(TX_THREADS, 1) tc_xfin_kernel(const DevPlan *_
       tc::tc_fence_before_sync();
       asm volatile("bar.sync 1, 512;" ::: "memory");   // the tile's network output is in `sc`
       // ---- x sampler epilogue: item = (row, feature) of the tile's live rows ----
-      const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[a.nz.step * 3 + 0];
+      const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 0];
       const int nitem = gsz * N * F;
       for (int it2 = threadIdx.x; it2 < nitem; it2 += TX_WORK) {
         const int rr = it2 / F, f = it2 - rr * F;          // rr = row of the tile (graph g2, node i)
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(TX_THREADS, 1) tc_xfin_kernel(const DevPlan *_
         if (a.mode == MODE_EVAL) { a.out_x[gp] = o; continue; }
         const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + bb);
         const float s = cx.score_scale * o;
-        const float z = (a.noise_x ? a.noise_x[gp] : normal1(a.nz.seed, gsid, draw_id(0, a.nz.step, a.slot), p)) * fl;
+        const float z = (a.noise_x ? a.noise_x[gp] : normal1(a.nz.seed, gsid, draw_id(0, nz_step(a.nz), a.slot), p)) * fl;
         if (a.mode == MODE_SCORE) {
           a.out_x[gp] = s;
           sq[it2] = s * s;                 // per-sample norms are summed below in a fixed order (bit-reproducible)
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(TX_THREADS, 1) tc_xfin_kernel(const DevPlan *_
           const float v = m + cx.pc * z;
           a.out_x[gp] = v;
           a.mean_x[gp] = m;
-          if (a.traj_x && bb == 0) a.traj_x[p] = a.denoise ? m : v;
+          if (bb == 0) { float *tjx = a.nz.sd ? a.nz.sd->tx : a.traj_x; if (tjx) tjx[p] = a.denoise ? m : v; }
         }
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");   // `sc` may be overwritten by the next tile; squared entries complete

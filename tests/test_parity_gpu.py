@@ -284,3 +284,32 @@ def test_mol_onehot_on_device():
         xo, ao = mol_onehot(x.to(DEV), adj.to(DEV))
         xr, ar = O.mol_onehot(x, adj)
         assert torch.equal(xo.cpu(), xr) and torch.equal(ao.cpu(), ar)
+
+
+@pytest.mark.parametrize("name,sampler,pred,B", [("community_small", "PC", "Euler", 37), ("qm9", "PC", "Reverse", 64),
+                                                 ("enzymes_small", "S4", "Euler", 16), ("enzymes", "PC", "Reverse", 2)])
+def test_graph_replay_equals_eager(name, sampler, pred, B, monkeypatch):
+    """Graph-only plans replay ONE captured step with the step index / diff_traj slots read from device memory
+    (ccsd_plan_run, StepDev): the same kernels with the same Philox counters, so state, means and the recorded
+    trajectory must equal the eager launch sequence bit for bit."""
+    cfg = Config(name)
+    g = torch.Generator().manual_seed(3)
+    n = torch.randint(max(2, cfg.N // 2), cfg.N + 1, (B,), generator=g)
+    flags = (torch.arange(cfg.N)[None, :] < n[:, None]).float().to(DEV)
+    outs = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("CCSD_B200_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("CCSD_B200_NO_GRAPH", raising=False)
+        eng = make_engine(cfg, B, DEV, sampler=sampler, predictor=pred)
+        assert int(eng.lib.ccsd_plan_info(eng.handle, 19)) == (0 if no_graph else 1)
+        eng.enable_traj()
+        eng.init(flags, seed=11)
+        eng.run(0, 14)
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in eng.read(False)] + [t.clone() for t in eng.read(True)] + [t[:14].clone() for t in eng.traj]
+                    + [eng.launches])
+    assert outs[0][-1] == outs[1][-1] + 12, (outs[0][-1], outs[1][-1])   # one step_advance per replayed step
+    for a, b in zip(outs[0][:-1], outs[1][:-1]):
+        assert torch.equal(a, b)
