@@ -473,7 +473,8 @@ CCSD_KERNEL void __launch_bounds__(128) big_final_kernel(const DevPlan *__restri
   mlp_fm(m, P->W, S + (size_t)i * Np + j0, PS, g.ch_out /* planes in the stack */, nullptr, 0, 0, R, hA, hB, BIG_SEG, so, 1, 0,
          ACT_ELU, ACT_NONE);
   const size_t ga = (size_t)b * N * N;
-  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 1];
+  const int stp = a.mode == MODE_EVAL ? 0 : nz_step(a.nz);
+  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[stp * 3 + 1];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
   const float fi = a.flags[(size_t)b * N + i];
   float s2 = 0.f, z2 = 0.f;
@@ -491,7 +492,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_final_kernel(const DevPlan *__restri
     float z = 0.f;
     if (i != j) {
       const int q = i * N + j;
-      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, nz_step(a.nz), a.slot), q)) * fij;
+      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, stp, a.slot), q)) * fij;
     }
     if (a.mode == MODE_SCORE) {
       a.out_adj[ga + (size_t)i * N + j] = s;
@@ -537,7 +538,8 @@ CCSD_KERNEL void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restric
   const float *hc = big_ptr(P, g, b, L.big_HC);
   mlp_fm(m, P->W, hc + i0, Np, X.fdim, nullptr, 0, 0, R, hA, hB, BIG_RCX, so, 1, BIG_RCX, ACT_ELU, ACT_NONE);
   const size_t gxo = (size_t)b * N * F;
-  const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 0];
+  const int stp = a.mode == MODE_EVAL ? 0 : nz_step(a.nz);
+  const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[stp * 3 + 0];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
   float s2 = 0.f, z2 = 0.f;
   for (int q = threadIdx.x; q < R * F; q += blockDim.x) {
@@ -546,7 +548,7 @@ CCSD_KERNEL void __launch_bounds__(128) big_xfin_kernel(const DevPlan *__restric
     const float o = so[f * BIG_RCX + r] * fl;   // mask_x
     if (a.mode == MODE_EVAL) { a.out_x[gxo + p] = o; continue; }
     const float s = cx.score_scale * o;
-    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, nz_step(a.nz), a.slot), p)) * fl;
+    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, stp, a.slot), p)) * fl;
     if (a.mode == MODE_SCORE) {
       a.out_x[gxo + p] = s;
       s2 += s * s;

@@ -491,6 +491,7 @@ struct R2Epi {
   unsigned long long gs; // global sample index
   ccsd_objcoef_t co;
   int b, E, K, Kg, f_nlin;
+  int step;              // diffusion step (nz_step: argument or device-resident), read once per CTA
   float aff0, aff1, aff2;
 };
 
@@ -510,7 +511,7 @@ __device__ __forceinline__ void r2_epilogue4(const R2Epi &c, const ApplyArgs &a,
       for (int q = 0; q < 4; ++q)
         if (k0 + q < c.K) z4[q] = a.noise[g0 + q];
     } else {
-      normal4(a.nz.seed, c.gs, draw_id(2, nz_step(a.nz), a.slot), (uint32_t)(e * c.Kg + (k0 >> 2)), z4);
+      normal4(a.nz.seed, c.gs, draw_id(2, c.step, a.slot), (uint32_t)(e * c.Kg + (k0 >> 2)), z4);
     }
   }
 #pragma unroll
@@ -568,7 +569,8 @@ __global__ void __launch_bounds__(256) apply_kernel(const DevPlan *__restrict__ 
   R2Epi c;
   c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
   c.gs = (unsigned long long)(a.nz.sample_offset + b);
-  if (a.mode != MODE_EVAL) c.co = P->sched[nz_step(a.nz) * 3 + 2];
+  c.step = a.mode != MODE_EVAL ? nz_step(a.nz) : 0;
+  if (a.mode != MODE_EVAL) c.co = P->sched[c.step * 3 + 2];
   c.b = b; c.E = E; c.K = K; c.Kg = P->Kp >> 2; c.f_nlin = P->f_nlin;
   c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
 
@@ -734,7 +736,8 @@ __global__ void __launch_bounds__(256) r2_epi_kernel(const DevPlan *__restrict__
   R2Epi c;
   c.P = P; c.fl = fl; c.fw = fw; c.zm = zero_mask_of(fl, N);
   c.gs = (unsigned long long)(a.nz.sample_offset + b);
-  if (a.mode != MODE_EVAL) c.co = P->sched[nz_step(a.nz) * 3 + 2];
+  c.step = a.mode != MODE_EVAL ? nz_step(a.nz) : 0;
+  if (a.mode != MODE_EVAL) c.co = P->sched[c.step * 3 + 2];
   c.b = b; c.E = E; c.K = K; c.Kg = Kg; c.f_nlin = P->f_nlin;
   c.aff0 = d.netf.aff[0]; c.aff1 = d.netf.aff[1]; c.aff2 = d.netf.aff[2];
   __syncthreads();
@@ -896,7 +899,8 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
   const int N = d.N, F = d.F, E = d.E, K = d.K, Kg = P->Kp >> 2;
   const int obj = a.obj0 + blockIdx.y;
   const int ndraw = a.s4 ? 3 : 1;
-  const ccsd_objcoef_t co = P->sched[nz_step(a.nz) * 3 + obj];
+  const int stp = nz_step(a.nz);
+  const ccsd_objcoef_t co = P->sched[stp * 3 + obj];
   const float cs = a.coef[obj * 2], cn = a.coef[obj * 2 + 1];
   const size_t stride = (size_t)gridDim.x * blockDim.x, start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (obj == 0) {
@@ -907,7 +911,7 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
       float z[3] = {0.f, 0.f, 0.f};
       for (int s = 0; s < ndraw; ++s)
         z[s] = f * (a.nx ? a.nx[(size_t)(a.slot0 + s) * tot + g]
-                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, nz_step(a.nz), a.slot0 + s), p));
+                         : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(0, stp, a.slot0 + s), p));
       float mean;
       const float v = upd_elem(co, cs, cn, a.s4, a.x[g], a.sx[g], z, &mean);
       a.x[g] = v;
@@ -926,7 +930,7 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
         const int q = (i < j) ? i * N + j : j * N + i;
         for (int s = 0; s < ndraw; ++s)
           z[s] = f * (a.nadj ? a.nadj[(size_t)(a.slot0 + s) * tot + (size_t)b * N * N + q]
-                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, nz_step(a.nz), a.slot0 + s), q));
+                             : normal1(a.nz.seed, a.nz.sample_offset + b, draw_id(1, stp, a.slot0 + s), q));
       }
       float mean;
       const float v = upd_elem(co, cs, cn, a.s4, a.adj[g], a.sadj[g], z, &mean);
@@ -949,7 +953,7 @@ CCSD_KERNEL void __launch_bounds__(256) update_kernel(const DevPlan *__restrict_
         for (int q = 0; q < 4; ++q) zz[s][q] = 0.f;
       if (!a.nr2)
         for (int s = 0; s < ndraw; ++s)
-          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, nz_step(a.nz), a.slot0 + s), (uint32_t)(e * Kg + kg), zz[s]);
+          normal4(a.nz.seed, a.nz.sample_offset + b, draw_id(2, stp, a.slot0 + s), (uint32_t)(e * Kg + kg), zz[s]);
       for (int q = 0; q < 4; ++q) {
         const int k = kg * 4 + q;
         if (k >= K) break;

@@ -269,13 +269,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
           a.out_adj[ga + i * N + j] = o;
           a.out_adj[ga + j * N + i] = o;
         } else {
-          const ccsd_objcoef_t ca = P->sched[nz_step(a.nz) * 3 + 1];
+          const int stp = nz_step(a.nz);
+          const ccsd_objcoef_t ca = P->sched[stp * 3 + 1];
           const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
           const float s = ca.score_scale * o;
           float z = 0.f;
           if (i != j) {
             const int q = i * N + j;
-            z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, nz_step(a.nz), a.slot), q)) * fi * fj;
+            z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, stp, a.slot), q)) * fi * fj;
           }
           if (a.mode == MODE_SCORE) {
             a.out_adj[ga + i * N + j] = s;

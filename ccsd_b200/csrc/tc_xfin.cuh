@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(TX_THREADS, 1) tc_xfin_kernel(const DevPlan *_
       tc::tc_fence_before_sync();
       asm volatile("bar.sync 1, 512;" ::: "memory");   // the tile's network output is in `sc`
       // ---- x sampler epilogue: item = (row, feature) of the tile's live rows ----
-      const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 0];
+      const int stp = a.mode == MODE_EVAL ? 0 : nz_step(a.nz);
+      const ccsd_objcoef_t cx = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[stp * 3 + 0];
       const int nitem = gsz * N * F;
       for (int it2 = threadIdx.x; it2 < nitem; it2 += TX_WORK) {
         const int rr = it2 / F, f = it2 - rr * F;          // rr = row of the tile (graph g2, node i)
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(TX_THREADS, 1) tc_xfin_kernel(const DevPlan *_
         if (a.mode == MODE_EVAL) { a.out_x[gp] = o; continue; }
         const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + bb);
         const float s = cx.score_scale * o;
-        const float z = (a.noise_x ? a.noise_x[gp] : normal1(a.nz.seed, gsid, draw_id(0, nz_step(a.nz), a.slot), p)) * fl;
+        const float z = (a.noise_x ? a.noise_x[gp] : normal1(a.nz.seed, gsid, draw_id(0, stp, a.slot), p)) * fl;
         if (a.mode == MODE_SCORE) {
           a.out_x[gp] = s;
           sq[it2] = s * s;                 // per-sample norms are summed below in a fixed order (bit-reproducible)

@@ -172,7 +172,8 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
     }
     return;
   }
-  const ccsd_objcoef_t cx = P->sched[nz_step(a.nz) * 3 + 0];
+  const int stp = nz_step(a.nz);
+  const ccsd_objcoef_t cx = P->sched[stp * 3 + 0];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
   if (a.mode == MODE_SCORE) {
     // scaled score + per-sample squared norms of score and (masked) noise (solver.py:693-699, 1299-1305)
@@ -181,7 +182,7 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
       const int i = p / F, f = p - i * F;
       const float s = cx.score_scale * sx[f * N4 + i];
       a.out_x[gxo + p] = s;
-      const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, nz_step(a.nz), a.slot), p)) * flags[i];
+      const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, stp, a.slot), p)) * flags[i];
       s2 += s * s;
       z2 += z * z;
     }
@@ -197,7 +198,7 @@ CCSD_KERNEL void __launch_bounds__(128) x_net_kernel(const DevPlan *__restrict__
   for (int p = threadIdx.x; p < N * F; p += blockDim.x) {
     const int i = p / F, f = p - i * F;
     const float s = cx.score_scale * sx[f * N4 + i];
-    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, nz_step(a.nz), a.slot), p)) * flags[i];
+    const float z = (a.noise_x ? a.noise_x[gxo + p] : normal1(a.nz.seed, gsid, draw_id(0, stp, a.slot), p)) * flags[i];
     const float m = cx.pa * x0[f * N4 + i] + cx.pb * s;
     const float v = m + cx.pc * z;
     a.out_x[gxo + p] = v;
@@ -862,7 +863,8 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_M) afinal_kernel(const DevPlan *
   mlp_fm(A.fin, P->W, gs + r0, ldp, a.ch_out /* = channels in the stack */, nullptr, 0, 0, R, fA, fB, RC, so, 1, 0, ACT_ELU,
          ACT_NONE);
   const size_t ga = (size_t)b * NP;
-  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[nz_step(a.nz) * 3 + 1];
+  const int stp = a.mode == MODE_EVAL ? 0 : nz_step(a.nz);
+  const ccsd_objcoef_t ca = a.mode == MODE_EVAL ? ccsd_objcoef_t() : P->sched[stp * 3 + 1];
   const unsigned long long gsid = (unsigned long long)(a.nz.sample_offset + b);
   float s2 = 0.f, z2 = 0.f;
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -878,7 +880,7 @@ CCSD_KERNEL void __launch_bounds__(128, XP_MINB_M) afinal_kernel(const DevPlan *
     float z = 0.f;
     if (i != j) {
       const int q = i * N + j;
-      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, nz_step(a.nz), a.slot), q)) * flags[i] * flags[j];
+      z = (a.noise_adj ? a.noise_adj[ga + q] : normal1(a.nz.seed, gsid, draw_id(1, stp, a.slot), q)) * flags[i] * flags[j];
     }
     if (a.mode == MODE_SCORE) {
       a.out_adj[ga + i * N + j] = s;
