@@ -5,8 +5,10 @@
 //   rows    = node pairs (i <= j) of one graph, 128 per tile (the channel stack [fd][ldp] of the x/adj pipeline
 //             is feature-major, i.e. an MN-major A operand as it lies in memory)
 //   layer 1 : D1[128 x H] = X[128 x fd] . W1          A, B MN-major bf16 hi/lo in shared memory
-//   layer 2 : D2[128 x H] = elu(D1 + b1) . W2          A K-major (written by the epilogue threads, one row
-//                                                      each), B MN-major
+//   layer 2 : D2[128 x H] = elu(D1 + b1) . W2          A in TENSOR MEMORY (tcgen05.mma A-from-TMEM): each row's thread writes
+//                                                      elu(D1 + b1) back to its TMEM lane as packed bf16 hi / lo pairs -- no
+//                                                      64 KB shared-memory operand, so small networks fit TWO CTAs per SM
+//                                                      (the kernel is a chain of dependent phases per tile); B MN-major
 //   layer 3 : out = elu(D2 + b2) . w3 + b3             H FMAs per row in the epilogue
 // bf16x3 (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM) keeps the 1e-4 parity bar.  W1 / W2 are converted
 // once per CTA and stay resident (<= 96 KB); a persistent CTA walks tiles (graph, row block).
@@ -16,13 +18,11 @@
 
 namespace ccsd {
 
-#ifndef TF_PARTS
-#define TF_PARTS 4
-#endif
-constexpr int TF_NP = TF_PARTS;     // column parts: the epilogue of a 128-row tile is split over TF_NP warps per TMEM lane quarter
-constexpr int TF_EPI = 128 * TF_NP; // epilogue / loader warps: TMEM lane quarter = warp % 4, column part = warp / 4
-constexpr int TF_THREADS = TF_EPI + 32;   // + 1 MMA warp
-constexpr int TF_MMAW = TF_EPI / 32;
+// Column parts NP: the epilogue of a 128-row tile is split over NP warps per TMEM lane quarter (TMEM lane quarter = warp % 4,
+// column part = warp / 4), + 1 MMA warp.  NP = 4, one CTA per SM: large networks (grid: 125 KB of shared memory);
+// NP = 2, two CTAs per SM: everything that fits 113 KB.
+constexpr int TF_NP_MAX = 4;
+constexpr uint32_t TF_COL_A2 = 128;   // TMEM columns: D1 / D2 at [0, 128), the layer-2 A operand (bf16 pairs) hi at [128, 192), lo at [192, 256)
 
 struct TcFinLayout {   // byte offsets from the 1024-aligned base; *_half = distance hi -> lo
   int K1p, Hp;         // fd rounded up to 16, hidden width rounded up to 16
@@ -40,8 +40,8 @@ static inline TcFinLayout tc_afinal_layout(int fd, int dhid) {
   L.w1_half = 2u * L.K1p * 128u; L.w1 = o; o += 2 * L.w1_half;     // [2 n-blocks][K1p k-rows][128 B]
   L.w2_half = 2u * L.Hp * 128u;  L.w2 = o; o += 2 * L.w2_half;     // [2 n-blocks][Hp k-rows][128 B]
   L.a1_half = 2u * L.K1p * 128u; L.a1 = o; o += 2 * L.a1_half;     // [2 m-blocks][K1p k-rows][128 B]
-  L.a2_half = 2u * 16384u;       L.a2 = o; o += 2 * L.a2_half;     // [2 k-blocks][128 rows][128 B]
-  L.vec = o; o += 3 * 128 * 4 + 256 + 512 * TF_NP;                 // b1, b2, w3, reduction scratch, [parts][128] partial dot products
+  L.a2_half = 0; L.a2 = 0;                                        // (the layer-2 A operand lives in tensor memory)
+  L.vec = o; o += 3 * 128 * 4 + 256 + 512 * TF_NP_MAX;                 // b1, b2, w3, reduction scratch, [parts][128] partial dot products
   L.bars = o; o += 64;
   L.total = o + 1024;
   return L;
@@ -60,7 +60,9 @@ struct TcFinArgs {
   int big, Np, nseg;   // large-graph path: row pitch, 128-column segments per row
 };
 
-__global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan *__restrict__ P, TcFinArgs ta) {
+template <int TF_NP>
+__global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afinal_kernel(const DevPlan *__restrict__ P, TcFinArgs ta) {
+  constexpr int TF_EPI = 128 * TF_NP, TF_THREADS = TF_EPI + 32, TF_MMAW = TF_EPI / 32;
   extern __shared__ uint8_t tf_smem_raw[];
   const XaArgs &a = ta.x;
   const TcFinLayout &TL = ta.L;
@@ -186,16 +188,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     tc::mbar_wait(bar, phase);
     phase ^= 1u;
     tc::tc_fence_after_sync();
-    // ---- epilogue 1: elu(D1 + b1) -> A2 (K-major, one row per thread) ----
+    // ---- epilogue 1: elu(D1 + b1) -> the layer-2 A operand in this row's TMEM lane (element k in 32-bit column k / 2) ----
     const int lq = warp & 3, cpart = warp >> 2;               // TMEM lane quarter, column part of this warp
     const int nck = Hp >> 4, cper = (nck + TF_NP - 1) / TF_NP;   // 16-column chunks, chunks per part
     const int ck0 = cpart * cper < nck ? cpart * cper : nck, ck1 = ck0 + cper < nck ? ck0 + cper : nck;
     if (warp < TF_MMAW) {
-      const int r = lq * 32 + lane;
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
       for (int c0 = ck0 * 16; c0 < ck1 * 16; c0 += 16) {
         float v[16];
         tc::tmem_ld16(trow + (uint32_t)c0, v);
+        uint32_t hw[8], lw[8];
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
           float x[8];
@@ -206,13 +208,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
           }
           uint4 hi, lo;
           tc::split8(x, hi, lo);
-          const int c = c0 + h8 * 8;
-          const uint32_t off = TL.a2 + (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u + (uint32_t)((((c & 63) >> 3) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4 *>(gen + off) = hi;
-          *reinterpret_cast<uint4 *>(gen + off + TL.a2_half) = lo;
+          hw[h8 * 4 + 0] = hi.x; hw[h8 * 4 + 1] = hi.y; hw[h8 * 4 + 2] = hi.z; hw[h8 * 4 + 3] = hi.w;
+          lw[h8 * 4 + 0] = lo.x; lw[h8 * 4 + 1] = lo.y; lw[h8 * 4 + 2] = lo.z; lw[h8 * 4 + 3] = lo.w;
         }
+        tc::tmem_st8(trow + TF_COL_A2 + (uint32_t)(c0 >> 1), hw);
+        tc::tmem_st8(trow + TF_COL_A2 + 64u + (uint32_t)(c0 >> 1), lw);
       }
-      tc::fence_proxy_async_smem();
+      tc::tmem_st_wait();
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -222,14 +224,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
       if (tc::elect_one()) {
         const uint32_t blk = (uint32_t)Hp * 128u;
         for (int k4 = 0; k4 < Hp / 16; ++k4) {
-          const uint32_t ao = (uint32_t)(k4 >> 2) * 16384u + (uint32_t)(k4 & 3) * 32u;   // 64-wide k block, 32 bytes per step
-          const uint64_t a_hi = tc::make_smem_desc(base + TL.a2 + ao, 0, 1024);
-          const uint64_t a_lo = tc::make_smem_desc(base + TL.a2 + TL.a2_half + ao, 0, 1024);
+          const uint32_t a_hi = tmem_u + TF_COL_A2 + (uint32_t)(k4 * 8), a_lo = a_hi + 64u;   // 16 k values = 8 columns
           const uint64_t b_hi = tc::make_smem_desc(base + TL.w2 + (uint32_t)k4 * 2048u, blk, 1024);
           const uint64_t b_lo = tc::make_smem_desc(base + TL.w2 + TL.w2_half + (uint32_t)k4 * 2048u, blk, 1024);
-          tc::umma_bf16(tmem_u + 128u, a_hi, b_hi, id2, k4 != 0);
-          tc::umma_bf16(tmem_u + 128u, a_hi, b_lo, id2, 1);
-          tc::umma_bf16(tmem_u + 128u, a_lo, b_hi, id2, 1);
+          tc::umma_bf16_ts(tmem_u, a_hi, b_hi, id2, k4 != 0);   // D2 overwrites D1 (consumed by epilogue 1)
+          tc::umma_bf16_ts(tmem_u, a_hi, b_lo, id2, 1);
+          tc::umma_bf16_ts(tmem_u, a_lo, b_hi, id2, 1);
         }
         tc::umma_commit(bar);
       }
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_afinal_kernel(const DevPlan 
     float s2 = 0.f, z2 = 0.f;
     float acc = 0.f;
     if (warp < TF_MMAW) {
-      const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16) + 128u;
+      const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
       for (int c0 = ck0 * 16; c0 < ck1 * 16; c0 += 16) {
         float v[16];
         tc::tmem_ld16(trow + (uint32_t)c0, v);
@@ -337,10 +337,16 @@ static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const X
     ta.gs_base = a.g_stack;          // the caller passes the large-graph stack base in g_stack
     ta.gs_stride = hp.xp.big_total; ta.ldp = hp.xp.big_PS; ta.NT = hp.xp.big_PS;
   }
-  static CcsdSmemAttr attr;
-  if (ccsd_ensure_smem(tc_afinal_kernel, ta.L.total, attr)) return -1;
   const int ntiles = hp.d.B * ta.ntg;
-  tc_afinal_kernel<<<ntiles < 148 ? ntiles : 148, TF_THREADS, ta.L.total, (cudaStream_t)stream>>>(dP, ta);
+  if (ta.L.total <= 113u * 1024u) {   // two CTAs per SM, 288 threads each
+    static CcsdSmemAttr attr2;
+    if (ccsd_ensure_smem(tc_afinal_kernel<2>, ta.L.total, attr2)) return -1;
+    tc_afinal_kernel<2><<<ntiles < 296 ? ntiles : 296, 128 * 2 + 32, ta.L.total, (cudaStream_t)stream>>>(dP, ta);
+  } else {
+    static CcsdSmemAttr attr4;
+    if (ccsd_ensure_smem(tc_afinal_kernel<4>, ta.L.total, attr4)) return -1;
+    tc_afinal_kernel<4><<<ntiles < 148 ? ntiles : 148, 128 * 4 + 32, ta.L.total, (cudaStream_t)stream>>>(dP, ta);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
