@@ -58,6 +58,7 @@ struct TcFinArgs {
   long long gs_stride; // floats per graph
   int ldp, NT;         // plane stride; valid rows of a plane (triangle path)
   int big, Np, nseg;   // large-graph path: row pitch, 128-column segments per row
+  int gpt, rpg;        // tiny graphs (NT <= 64): gpt graphs share one 128-row tile, rpg = NT rounded up to 8 rows each (else 1, 128)
 };
 
 template <int TF_NP>
@@ -122,11 +123,13 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
   const uint32_t id2 = tc::make_idesc_bf16(128, Hp, /*A K-major*/ 0, /*B MN-major*/ 1);
   const float b3 = __ldg(W + fin.b[2]);
   uint32_t phase = 0;
-  const int ntiles = d.B * ta.ntg;
+  const int ntiles = ta.gpt > 1 ? (d.B + ta.gpt - 1) / ta.gpt : d.B * ta.ntg;
 
   for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
-    const int b = w / ta.ntg, tt = w - b * ta.ntg;
-    int t0 = tt * 128, bi = 0, bj0 = 0, rows = NT - t0;   // rows: valid rows of this tile
+    const int gpt = ta.gpt, rpg = ta.rpg;
+    const int b = gpt > 1 ? w * gpt : w / ta.ntg, tt = gpt > 1 ? 0 : w - b * ta.ntg;   // (first) graph of the tile, tile of the graph
+    const int b0t = b;
+    int t0 = tt * 128, bi = 0, bj0 = 0, rows = NT - t0;   // rows: valid rows of this tile (of each graph when gpt > 1)
     if (ta.big) {
       bi = tt / ta.nseg; bj0 = (tt - bi * ta.nseg) * 128;
       if (bj0 + 128 <= bi) {   // wholly below the diagonal: the mirrored tile covers it (uniform branch)
@@ -146,16 +149,24 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
         const int k = t >> 4, mc = t & 15, m0 = mc << 3;
         const float *src = gs + (size_t)k * ldp + t0 + m0;
         float x[8];
-        if (t0 + m0 + 8 <= ldp) {
+        if (gpt > 1) {   // rows [g rpg, g rpg + NT) of the tile = the pairs of graph b + g
+          const int g = m0 / rpg, tg = m0 - g * rpg;
+          const bool ok = g < gpt && b + g < d.B;
+          const float *sg = gs + (size_t)g * ta.gs_stride + (size_t)k * ldp + tg;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = (ok && tg + q < NT) ? sg[q] : 0.f;
+        } else if (t0 + m0 + 8 <= ldp) {
           const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
           x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) x[q] = t0 + m0 + q < ldp ? src[q] : 0.f;
         }
+        if (gpt == 1) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (m0 + q >= rows) x[q] = 0.f;
+          for (int q = 0; q < 8; ++q)
+            if (m0 + q >= rows) x[q] = 0.f;
+        }
         uint4 hi, lo;
         tc::split8(x, hi, lo);
         const uint32_t off = TL.a1 + (uint32_t)(m0 >> 6) * ((uint32_t)K1p * 128u) + (uint32_t)k * 128u +
@@ -253,12 +264,15 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
     }
     __syncthreads();   // the second column half's partial dot products
     if (warp < 4) {
-      const int r = threadIdx.x, t = t0 + r;
+      const int r = threadIdx.x;
+      const int gg = gpt > 1 ? r / rpg : 0;                 // graph of this row inside the tile
+      const int t = gpt > 1 ? r - gg * rpg : t0 + r;
+      const int b = b0t + gg;
 #pragma unroll
       for (int q = 0; q < TF_NP - 1; ++q) acc += part[q * 128 + r];
       acc += b3;
       int i = 0, j = 0;
-      bool live = r < rows;
+      bool live = gpt > 1 ? (gg < gpt && b < d.B && t < NT) : r < rows;
       if (ta.big) { i = bi; j = bj0 + r; live = live && j >= i; }
       else if (live) { const int ij = P->tri_ij[t]; i = ij >> 8; j = ij & 255; }
       if (live) {
@@ -302,20 +316,35 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
       }
     }
     if (a.mode == MODE_SCORE) {
-      // per-tile norm partial (fixed order): warps 0-3 reduce, thread 0 sums the four warp values
+      if (gpt > 1) {
+        // several graphs per tile: per-row values to shared memory (each thread only ever touches its own slots of `part`),
+        // summed per graph in row order after the barrier
+        if (warp < 4) { part[threadIdx.x] = s2; part[128 + threadIdx.x] = z2; }
+      } else {
+        // per-tile norm partial (fixed order): warps 0-3 reduce, thread 0 sums the four warp values
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+        for (int o = 16; o > 0; o >>= 1) {
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+        }
+        if (lane == 0 && warp < 4) { red[warp] = s2; red[8 + warp] = z2; }
       }
-      if (lane == 0 && warp < 4) { red[warp] = s2; red[8 + warp] = z2; }
     }
     tc::tc_fence_before_sync();
     __syncthreads();   // every thread is done with D1 / D2 / A1 / A2 of this tile
-    if (a.mode == MODE_SCORE && threadIdx.x == 0) {
-      float *np = a.norm_part + ((size_t)(1 * d.B + b) * P->ntile_max + tt) * 2;
-      np[0] = red[0] + red[1] + red[2] + red[3];
-      np[1] = red[8] + red[9] + red[10] + red[11];
+    if (a.mode == MODE_SCORE) {
+      if (gpt > 1) {
+        if ((int)threadIdx.x < gpt && b0t + (int)threadIdx.x < d.B) {
+          float t2 = 0.f, u2 = 0.f;
+          for (int q = 0; q < NT; ++q) { t2 += part[threadIdx.x * rpg + q]; u2 += part[128 + threadIdx.x * rpg + q]; }
+          float *np = a.norm_part + ((size_t)(1 * d.B + b0t + threadIdx.x) * P->ntile_max) * 2;
+          np[0] = t2; np[1] = u2;
+        }
+      } else if (threadIdx.x == 0) {
+        float *np = a.norm_part + ((size_t)(1 * d.B + b) * P->ntile_max + tt) * 2;
+        np[0] = red[0] + red[1] + red[2] + red[3];
+        np[1] = red[8] + red[9] + red[10] + red[11];
+      }
     }
   }
   tc::tc_fence_before_sync();
@@ -331,13 +360,15 @@ static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const X
   ta.ntg = (hp.xp.NT + 127) / 128;
   ta.gs_base = a.g_stack; ta.gs_stride = hp.xp.g_stack; ta.ldp = hp.xp.ldp; ta.NT = hp.xp.NT;
   ta.big = 0; ta.Np = 0; ta.nseg = 1;
+  ta.gpt = 1; ta.rpg = 128;
+  if (!hp.xp.big && hp.xp.NT <= 64) { ta.rpg = (hp.xp.NT + 7) & ~7; ta.gpt = 128 / ta.rpg; }
   if (hp.xp.big) {
     ta.big = 1; ta.Np = hp.xp.big_Np; ta.nseg = (hp.d.N + 127) / 128;
     ta.ntg = hp.d.N * ta.nseg;
     ta.gs_base = a.g_stack;          // the caller passes the large-graph stack base in g_stack
     ta.gs_stride = hp.xp.big_total; ta.ldp = hp.xp.big_PS; ta.NT = hp.xp.big_PS;
   }
-  const int ntiles = hp.d.B * ta.ntg;
+  const int ntiles = ta.gpt > 1 ? (hp.d.B + ta.gpt - 1) / ta.gpt : hp.d.B * ta.ntg;
   if (ta.L.total <= 113u * 1024u) {   // two CTAs per SM, 288 threads each
     static CcsdSmemAttr attr2;
     if (ccsd_ensure_smem(tc_afinal_kernel<2>, ta.L.total, attr2)) return -1;
