@@ -434,6 +434,12 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         for (int c16 = h0 * 3; c16 < h1 * 3; ++c16) {
           const int kb = c16 * 32;                       // first e' column of this 32-element (16-column) group
           uint32_t hw[16], lw[16];
+          if (G > 1 && (!frow || kb + 32 <= c_lo || kb >= c_lo + E)) {
+            // stacked samples: this 32-column group lies outside the row's own diagonal block -- zeros, no loads, no split
+            // (5 of 6 groups at QM9_CC).  Per-lane branch: both sides end in the same two warp-wide stores below.
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { hw[j] = 0u; lw[j] = 0u; }
+          } else
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -471,6 +477,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       for (int ct = 0; ct < ntile; ++ct) {
         const int g = si * ntile + ct;
         const int slot = g & 1, stg = g % TA_NS;
+        if (ct == (ntile > 3 ? ntile - 3 : 0) && si + 1 < nmine && fills && mt < mtiles) {
+          // the next group's H row of this thread -> L2, so the refill at the group boundary (which drains the MMA pipeline)
+          // does not wait for HBM three times
+          const int bn = b0 + (int)gridDim.x * G + sg;
+          if (bn < B) {
+            const char *hp = reinterpret_cast<const char *>(a.H + ((size_t)bn * E + e) * Ep);
+            for (int o = 0; o < E * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + o));
+          }
+        }
         tc::mbar_wait_relaxed(stage_full + 8 * stg, (uint32_t)(g / TA_NS) & 1u);   // staging tile + cell flags visible
         if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 6 : 10, g);
         tc::mbar_wait_relaxed(t_full + 8 * slot, (uint32_t)(g >> 1) & 1u);         // accumulators complete

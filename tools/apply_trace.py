@@ -4,10 +4,12 @@ sys.path.insert(0, "/root/repo")
 from tests.helpers import Config
 from tests.parity_cases import make_engine
 from ccsd_b200 import _native as nat
-cfg = Config("community_small_cc"); B = 1024
+name = sys.argv[1] if len(sys.argv) > 1 else "community_small_cc"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+cfg = Config(name)
 g = torch.Generator().manual_seed(0)
-n = torch.randint(10, 21, (B,), generator=g)
-flags = (torch.arange(20)[None, :] < n[:, None]).float()
+n = torch.randint(max(2, cfg.N // 2), cfg.N + 1, (B,), generator=g)
+flags = (torch.arange(cfg.N)[None, :] < n[:, None]).float()
 eng = make_engine(cfg, B, "cuda")
 eng.init(flags.cuda(), seed=1)
 eng.run(0, 2)
