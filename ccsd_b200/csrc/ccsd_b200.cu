@@ -657,6 +657,7 @@ int ccsd_plan_create(const ccsd_plan_desc_t *desc, const ccsd_objcoef_t *schedul
     int G = imin(8, 192 / imax(d.E, 1));
     while (G > 1 && tc_gram_ncols(G * d.E, p->hp.PR0) > 256) --G;
     if (getenv("CCSD_B200_NO_GRAM_GROUP")) G = 1;   // A/B switch for tests and profiling
+    if (const char *e = getenv("CCSD_B200_GRAM_GROUP")) { const int g = atoi(e); if (g >= 1 && g <= G) G = g; }
     p->hp.gram_group = imax(G, 1);
   }
   p->use_tc_apply = (d.is_cc && (d.nets & 4) && !p->apply_big) ? tc_apply_supported(d.E, d.K) : 0;

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
     // strides and the 24 loads of a k-block are independent.
     const float *Wp = P->W + d.neta.proj_w;
     const bool vec = (K & 3) == 0;
+    const bool vec2 = (K & 1) == 0 && (reinterpret_cast<uintptr_t>(a.r2) & 7) == 0;
     constexpr int NT = 192 / TG_RSTEP;          // RSTEP * NT = 192 rows of F per k-block (E <= 192)
     const int grp = warp / (TG_PROD_WARPS / 2), tg = threadIdx.x - grp * TG_GRP;
     const int c = tg & 7, r0 = tg >> 3;
@@ -142,6 +143,13 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
             const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sj + 4));
             x[j][0] = v0.x; x[j][1] = v0.y; x[j][2] = v0.z; x[j][3] = v0.w;
             x[j][4] = v1.x; x[j][5] = v1.y; x[j][6] = v1.z; x[j][7] = v1.w;
+          } else if (vec2) {   // even K (QM9_CC: 466): rows are 8-byte aligned -- four 8-byte loads instead of eight scalar ones
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+              float2 v2 = make_float2(0.f, 0.f);
+              if (k + q < K) v2 = __ldg(reinterpret_cast<const float2 *>(sj + q));   // (K even, k + q even: the pair is whole)
+              x[j][q] = v2.x; x[j][q + 1] = v2.y;
+            }
           } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) x[j][q] = (k + q < K) ? __ldg(sj + q) : 0.f;
