@@ -424,53 +424,56 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       const bool side = MODE == MODE_PRED && (a.write_mean || (a.traj != nullptr && b == 0));
       // ---- H of this sample -> TMEM (A operand).  Every MMA of the previous sample has completed: this
       // warp waited on t_full of its last tile. ----
-      if (mt < mtiles) {
-        // row er of the block-diagonal operand: H of the row's sample in columns [sg E, sg E + E), zeros elsewhere
-        const bool frow = fills && sg < gsz;
-        const float *Hrow = a.H + ((size_t)(frow ? b : b0) * E + (frow ? e : 0)) * Ep;
-        const int c_lo = sg * E;
-        // roles 0 / 1 share the rows of M tile 0 (e' halves); role 2 fills both halves of M tile 1
-        const int h0 = role == 2 ? 0 : role, h1 = role == 2 ? 2 : role + 1;
-        for (int c16 = h0 * 3; c16 < h1 * 3; ++c16) {
+      if (lane == 0 && ew == 0) TA_STAMP(14, si * ntile);
+      {
+        // The A operand is 2 M tiles x 6 groups of 32 e' columns (16 TMEM columns for hi, 16 for lo) per lane quarter.  The three
+        // warps of a quarter (roles 0-2) take every third (M tile, group) pair, whichever tile their entries belong to:
+        // M tile 0 holds edge row 32 q + lane on lane 32 q + lane, M tile 1 holds row 128 + 16 q + lane on the lanes < 16 of
+        // the quarter (zero rows above).  Block-diagonal operand: H of the row's sample in columns [sg E, sg E + E).
+        const int npair = mtiles * 6;
+        for (int idx = role; idx < npair; idx += 3) {
+          const int fm = idx / 6, c16 = idx - fm * 6;
+          int erf = fm == 0 ? q * 32 + lane : (lane < 16 ? 128 + q * 16 + lane : -1);
+          if (erf >= EB) erf = -1;
+          const int sgf = erf >= 0 ? erf / E : 0, ef = erf >= 0 ? erf - sgf * E : 0;
+          const bool frow = erf >= 0 && sgf < gsz;
+          // H is symmetric: element (e, k) is read as (k, e), so that the lanes of a warp (consecutive rows e) read consecutive
+          // addresses -- one 128-byte wavefront per load instead of 32 (a row-wise float4 per lane made the refill at every
+          // sample boundary cost 20-30 k cycles: 16 % of the pass)
+          const float *Hcolp = a.H + (size_t)(b0 + (frow ? sgf : 0)) * E * Ep + ef;
+          const int c_lo = sgf * E;
           const int kb = c16 * 32;                       // first e' column of this 32-element (16-column) group
           uint32_t hw[16], lw[16];
-          if (G > 1 && (!frow || kb + 32 <= c_lo || kb >= c_lo + E)) {
-            // stacked samples: this 32-column group lies outside the row's own diagonal block -- zeros, no loads, no split
-            // (5 of 6 groups at QM9_CC).  Per-lane branch: both sides end in the same two warp-wide stores below.
+          if (!frow || kb + 32 <= c_lo || kb >= c_lo + E) {
+            // outside the row's own diagonal block (or no row): zeros, no loads, no split.  Per-lane branch: both sides end in
+            // the same two warp-wide stores below.
 #pragma unroll
             for (int j = 0; j < 16; ++j) { hw[j] = 0u; lw[j] = 0u; }
-          } else
+          } else {
+            float vv[32];   // all 32 loads in flight before the first split
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int k = kb + 4 * j4 - c_lo;             // column inside the sample's own H
-            if (frow) {
-              if (G == 1) {
-                if (k < Ep) v = __ldg(reinterpret_cast<const float4 *>(Hrow + k));
-                if (k + 0 >= E) v.x = 0.f;
-                if (k + 1 >= E) v.y = 0.f;
-                if (k + 2 >= E) v.z = 0.f;
-                if (k + 3 >= E) v.w = 0.f;
-              } else {
-                if (k + 0 >= 0 && k + 0 < E) v.x = __ldg(Hrow + k + 0);
-                if (k + 1 >= 0 && k + 1 < E) v.y = __ldg(Hrow + k + 1);
-                if (k + 2 >= 0 && k + 2 < E) v.z = __ldg(Hrow + k + 2);
-                if (k + 3 >= 0 && k + 3 < E) v.w = __ldg(Hrow + k + 3);
-              }
+            for (int j = 0; j < 32; ++j) {
+              const int k = kb + j - c_lo;               // column inside the sample's own H
+              vv[j] = (k >= 0 && k < E) ? __ldg(Hcolp + (size_t)k * Ep) : 0.f;
             }
-            uint2 hi, lo;
-            tc::split4(v, hi, lo);
-            hw[2 * j4] = hi.x; hw[2 * j4 + 1] = hi.y;
-            lw[2 * j4] = lo.x; lw[2 * j4 + 1] = lo.y;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              uint2 hi, lo;
+              tc::split4(make_float4(vv[4 * j4], vv[4 * j4 + 1], vv[4 * j4 + 2], vv[4 * j4 + 3]), hi, lo);
+              hw[2 * j4] = hi.x; hw[2 * j4 + 1] = hi.y;
+              lw[2 * j4] = lo.x; lw[2 * j4 + 1] = lo.y;
+            }
           }
-          const uint32_t col = (uint32_t)(mt * 192 + c16 * 16);
+          const uint32_t col = (uint32_t)(fm * 192 + c16 * 16);
           tc::tmem_st16(tmem + lane_base + col, hw);
           tc::tmem_st16(tmem + lane_base + col + 96u, lw);
         }
         tc::tmem_st_wait();
+        if (lane == 0 && ew == 0) TA_STAMP(13, si * ntile);
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(h_ready);
+      if (lane == 0 && ew == 0) TA_STAMP(15, si * ntile);
 
       float s2 = 0.f, z2 = 0.f;
       const float *Nb = a.noise ? a.noise + (size_t)(live ? b : b0) * E * K : nullptr;
@@ -487,10 +490,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
           }
         }
         tc::mbar_wait_relaxed(stage_full + 8 * stg, (uint32_t)(g / TA_NS) & 1u);   // staging tile + cell flags visible
-        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 6 : 10, g);
+        if (lane == 0 && ew == 0) TA_STAMP(6, g);
         tc::mbar_wait_relaxed(t_full + 8 * slot, (uint32_t)(g >> 1) & 1u);         // accumulators complete
         tc::tc_fence_after_sync();
-        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 7 : 11, g);
+        if (lane == 0 && ew == 0) TA_STAMP(7, g);
         float v[16];
         const uint32_t dcol = tmem + lane_base + TA_COL_D + (uint32_t)(slot * 64 + mt * 32);
         if (role < 2) {
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         }
         tc::tc_fence_before_sync();
         tc::mbar_arrive(d_empty + 8 * slot);                          // accumulator slot may be overwritten
-        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 8 : 12, g);
+        if (lane == 0 && ew == 0) TA_STAMP(8, g);
         if (live) {
           uint8_t *row = gen + TA_OPER + (size_t)stg * TA_STAGE + (size_t)er * 128;
           const float *fcp = fcs + (stg * TA_GMAX + sg) * TA_TN + chalf * 16;
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
         }
         if (MODE != MODE_NORM) tc::fence_proxy_async_smem();          // generic writes -> visible to the TMA store
         tc::mbar_arrive(epi_done + 8 * stg);                          // (release) tile may be copied out
-        if (lane == 0 && (ew == 0 || ew == 8)) TA_STAMP(ew == 0 ? 9 : 13, g);
+        if (lane == 0 && ew == 0) TA_STAMP(9, g);
       }
       if (MODE == MODE_SCORE || MODE == MODE_NORM) {
         // per-sample squared norms: every (cell half, row) partial goes to shared memory, then one thread per

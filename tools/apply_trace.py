@@ -30,3 +30,11 @@ for a_, b_, nm in [(0, 1, "cp.async wait"), (1, 2, "opfree wait"), (2, 3, "conve
     print(f"{nm:14s} mean {x.mean():9.0f} median {np.median(x):9.0f}")
 x = t[2:250, 0][1:] - t[2:250, 3][:-1]
 print(f"{'ld full->next issue (copy-out + cp.async issue)':14s} mean {x.mean():9.0f}")
+
+nt = (cfg.K + 31) // 32
+print("group boundaries (first tile of each group): e0.done(prev) -> fill.start -> fill.end -> mma.start -> e0.acc")
+for gi in range(1, min(8, 500 // nt)):
+    r = gi * nt
+    print(f"tile {r:4d}: prev e0.done {t[r-1, 9] - t[r-1, 9]:7d}  fill.start {t[r, 14] - t[r-1, 9]:7d}  fill.end {t[r, 15] - t[r-1, 9]:7d}  "
+          f"mma.start {t[r, 4] - t[r-1, 9]:7d}  e0.acc {t[r, 7] - t[r-1, 9]:7d}  next e0.done {t[r, 9] - t[r-1, 9]:7d}"
+          f"  | rounds {t[r, 10] - t[r, 14]:6d} {t[r, 11] - t[r, 14]:6d} {t[r, 12] - t[r, 14]:6d} st_wait {t[r, 13] - t[r, 14]:6d}")
