@@ -277,6 +277,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       if (threadIdx.x == 0) TA_STAMP(1, g);
       int b, Eg, k0;
       tile_of(g, b, Eg, k0);
+      // (the stage is this tile's since its load landed: the cell flags go first, so that their two dependent global loads
+      // overlap the wait for the operand slot instead of sitting between the conversion and the arrive)
+      for (int t = threadIdx.x; t < G * TA_TN; t += TA_LOAD) {   // cell flags of every sample of the group
+        const int sg = t >> 5, k = k0 + (t & 31);
+        const bool on = b + sg < B && k < K && !(P->cell_mask[k] & a.zmask[b + sg]);
+        fcs[((g % TA_NS) * TA_GMAX + sg) * TA_TN + (t & 31)] = on ? 1.f : 0.f;
+      }
       if (g >= 2) tc::mbar_wait(op_empty + 8 * (g & 1), (uint32_t)(((g >> 1) & 1) ^ 1));
       if (threadIdx.x == 0) TA_STAMP(2, g);
       const uint8_t *st = gen + TA_OPER + (size_t)(g % TA_NS) * TA_STAGE + soff;
@@ -295,11 +302,6 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
             *reinterpret_cast<uint2 *>(op + (size_t)(j0 + u) * JSTR) = hi;
             *reinterpret_cast<uint2 *>(op + TA_OPHALF + (size_t)(j0 + u) * JSTR) = lo;
           }
-      }
-      for (int t = threadIdx.x; t < G * TA_TN; t += TA_LOAD) {   // cell flags of every sample of the group
-        const int sg = t >> 5, k = k0 + (t & 31);
-        const bool on = b + sg < B && k < K && !(P->cell_mask[k] & a.zmask[b + sg]);
-        fcs[((g % TA_NS) * TA_GMAX + sg) * TA_TN + (t & 31)] = on ? 1.f : 0.f;
       }
       tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(full + 8 * (g & 1));
