@@ -1224,7 +1224,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     ApplyArgs q; memset(&q, 0, sizeof q);
     q.r2 = p->r2; q.H = p->H; q.flags = p->flags; q.mode = mode; q.slot = slot; q.denoise = d.denoise; q.nz = nz;
     q.norm_part = p->norm_part; q.coef = p->coef; q.zmask = p->zmask;
-    q.trace = mode == MODE_CORR ? p->trace : nullptr;   // debug timeline of the Langevin-correction pass
+    q.trace = (mode == MODE_CORR || mode == MODE_SCORE) ? p->trace : nullptr;   // debug timeline of the Langevin-correction (S4: score) pass
     q.noise = nr2 ? nr2 + (size_t)slot * sr : nullptr;
     if (mode == MODE_SCORE) q.out = p->sr2;
     else if (mode == MODE_CORR) q.out = p->r2;

@@ -10,7 +10,8 @@ cfg = Config(name)
 g = torch.Generator().manual_seed(0)
 n = torch.randint(max(2, cfg.N // 2), cfg.N + 1, (B,), generator=g)
 flags = (torch.arange(cfg.N)[None, :] < n[:, None]).float()
-eng = make_engine(cfg, B, "cuda")
+samp = sys.argv[3] if len(sys.argv) > 3 else "PC"
+eng = make_engine(cfg, B, "cuda", sampler=samp)
 eng.init(flags.cuda(), seed=1)
 eng.run(0, 2)
 tr = torch.zeros(512, 16, dtype=torch.int64, device="cuda")
