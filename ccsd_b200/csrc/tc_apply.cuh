@@ -116,6 +116,54 @@ __device__ __forceinline__ float r2_entry(const R2Epi &c, const R2Fold &w, float
 // debug timeline (ccsd_debug_apply_trace): stamp `slot` of tile g, CTA 0 only
 #define TA_STAMP(slot_, g_) do { if (a.trace && blockIdx.x == 0 && (g_) < 512) a.trace[(size_t)(g_) * 16 + (slot_)] = clock64(); } while (0)
 
+// H of a work group -> the TMEM A operand (called once per group by every epilogue warp; inlined: as a real call its
+// register save / restore cost the main kernel 4 %).
+// The A operand is 2 M tiles x 6 groups of 32 e' columns (16 TMEM columns for hi, 16 for lo) per lane quarter.  The three
+// warps of a quarter (roles 0-2) take every third (M tile, group) pair, whichever tile their entries belong to:
+// M tile 0 holds edge row 32 q + lane on lane 32 q + lane, M tile 1 holds row 128 + 16 q + lane on the lanes < 16 of
+// the quarter (zero rows above).  Block-diagonal operand: H of the row's sample in columns [sg E, sg E + E).
+__device__ __forceinline__ void ta_fill_h(const float *__restrict__ H, int b0, int gsz, int E, int Ep, int EB, int mtiles, int role, int q,
+                                       int lane, uint32_t tmem_lane) {
+  const int npair = mtiles * 6;
+  for (int idx = role; idx < npair; idx += 3) {
+    const int fm = idx / 6, c16 = idx - fm * 6;
+    int erf = fm == 0 ? q * 32 + lane : (lane < 16 ? 128 + q * 16 + lane : -1);
+    if (erf >= EB) erf = -1;
+    const int sgf = erf >= 0 ? erf / E : 0, ef = erf >= 0 ? erf - sgf * E : 0;
+    const bool frow = erf >= 0 && sgf < gsz;
+    // H is symmetric: element (e, k) is read as (k, e), so that the lanes of a warp (consecutive rows e) read consecutive
+    // addresses -- one 128-byte wavefront per load instead of 32 (a row-wise float4 per lane made the refill at every
+    // sample boundary cost 20-30 k cycles: 16 % of the pass)
+    const float *Hcolp = H + (size_t)(b0 + (frow ? sgf : 0)) * E * Ep + ef;
+    const int c_lo = sgf * E;
+    const int kb = c16 * 32;                       // first e' column of this 32-element (16-column) group
+    uint32_t hw[16], lw[16];
+    if (!frow || kb + 32 <= c_lo || kb >= c_lo + E) {
+      // outside the row's own diagonal block (or no row): zeros, no loads, no split.  Per-lane branch: both sides end in
+      // the same two warp-wide stores below.
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { hw[j] = 0u; lw[j] = 0u; }
+    } else {
+      float vv[32];   // all 32 loads in flight before the first split
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int k = kb + j - c_lo;               // column inside the sample's own H
+        vv[j] = (k >= 0 && k < E) ? __ldg(Hcolp + (size_t)k * Ep) : 0.f;
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        uint2 hi, lo;
+        tc::split4(make_float4(vv[4 * j4], vv[4 * j4 + 1], vv[4 * j4 + 2], vv[4 * j4 + 3]), hi, lo);
+        hw[2 * j4] = hi.x; hw[2 * j4 + 1] = hi.y;
+        lw[2 * j4] = lo.x; lw[2 * j4 + 1] = lo.y;
+      }
+    }
+    const uint32_t col = (uint32_t)(fm * 192 + c16 * 16);
+    tc::tmem_st16(tmem_lane + col, hw);
+    tc::tmem_st16(tmem_lane + col + 96u, lw);
+  }
+}
+
 template <int FMODE, int MODE>
 __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *__restrict__ P, ApplyArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_in,
@@ -182,6 +230,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
     // ===================== loaders =====================
     const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.r2) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+    const bool vec2 = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.r2) & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 7) == 0);
     const int cu = threadIdx.x & 7, r0 = threadIdx.x >> 3;   // 16-byte chunk (4 cells) of rows r0 + RSTEP j
     const bool writes = MODE != MODE_NORM;
     // rows advance by a multiple of 8, so the XOR swizzle term (r & 7) is a per-thread constant and every
@@ -215,12 +264,32 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
           tc::cp_async16(st + (uint32_t)j * JSTR, ok ? (const void *)(src + j * gstr) : (const void *)a.r2, ok ? (uint32_t)nb : 0u);
         }
       } else {
-        for (int j = 0; j < nj; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const bool ok = k + i < K && r0 + j * TA_RSTEP < Eg;
-            tc::cp_async4(st + (uint32_t)j * JSTR + 4u * i, ok ? (const void *)(src + j * gstr + i) : (const void *)a.r2, ok ? 4u : 0u);
+        // Row pitch not 16-byte aligned (QM9_CC: K = 466, ENZYMES_small_CC: K = 715).  The loader warps run at a fraction of an
+        // issue slot beside the epilogue warps, so what counts is instructions per row: the row / cell bounds are hoisted
+        // (njv valid rows, nv valid cells of this thread's chunk), the pointers advance by constant strides, and the copies
+        // are 8-byte ones when K is even.
+        int njv = Eg > r0 ? (Eg - r0 + TA_RSTEP - 1) / TA_RSTEP : 0;
+        if (njv > nj) njv = nj;
+        const int nv = k + 4 <= K ? 4 : (k < K ? K - k : 0);
+        const float *sp = src;
+        uint32_t sa = st;
+        if (vec2 && nv == 4) {
+#pragma unroll 4
+          for (int j = 0; j < njv; ++j, sa += JSTR, sp += gstr) {
+            tc::cp_async8(sa, sp, 8u);
+            tc::cp_async8(sa + 8u, sp + 2, 8u);
           }
+          for (int j = njv; j < nj; ++j, sa += JSTR)   // rows past the group's last sample (short last group): zero fill
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tc::cp_async4(sa + 4u * i, (const void *)a.r2, 0u);
+        } else {
+          for (int j = 0; j < nj; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool ok = k + i < K && r0 + j * TA_RSTEP < Eg;
+              tc::cp_async4(st + (uint32_t)j * JSTR + 4u * i, ok ? (const void *)(src + j * gstr + i) : (const void *)a.r2, ok ? 4u : 0u);
+            }
+        }
       }
     };
     auto copy_out = [&](int g) {
@@ -245,12 +314,24 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
             if (j0 + u < njw) __stcs(reinterpret_cast<float4 *>(dst + (j0 + u) * gstr), v[u]);
         }
       } else {
-        for (int j = 0; j < njw; ++j) {
-          const float4 v = *reinterpret_cast<const float4 *>(st + (size_t)j * JSTR);
-          const float vv[4] = {v.x, v.y, v.z, v.w};
+        const int nv = k + 4 <= K ? 4 : K - k;   // (k < K here)
+        const uint8_t *sp = st;
+        float *dp = dst;
+        if (vec2 && nv == 4) {
+#pragma unroll 4
+          for (int j = 0; j < njw; ++j, sp += JSTR, dp += gstr) {
+            const float4 v = *reinterpret_cast<const float4 *>(sp);
+            __stcs(reinterpret_cast<float2 *>(dp), make_float2(v.x, v.y));
+            __stcs(reinterpret_cast<float2 *>(dp + 2), make_float2(v.z, v.w));
+          }
+        } else {
+          for (int j = 0; j < njw; ++j) {
+            const float4 v = *reinterpret_cast<const float4 *>(st + (size_t)j * JSTR);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (k + i < K) __stcs(dst + j * gstr + i, vv[i]);
+            for (int i = 0; i < 4; ++i)
+              if (k + i < K) __stcs(dst + j * gstr + i, vv[i]);
+          }
         }
       }
     };
@@ -428,48 +509,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) tc_apply_kernel(const DevPlan *
       // warp waited on t_full of its last tile. ----
       if (lane == 0 && ew == 0) TA_STAMP(14, si * ntile);
       {
-        // The A operand is 2 M tiles x 6 groups of 32 e' columns (16 TMEM columns for hi, 16 for lo) per lane quarter.  The three
-        // warps of a quarter (roles 0-2) take every third (M tile, group) pair, whichever tile their entries belong to:
-        // M tile 0 holds edge row 32 q + lane on lane 32 q + lane, M tile 1 holds row 128 + 16 q + lane on the lanes < 16 of
-        // the quarter (zero rows above).  Block-diagonal operand: H of the row's sample in columns [sg E, sg E + E).
-        const int npair = mtiles * 6;
-        for (int idx = role; idx < npair; idx += 3) {
-          const int fm = idx / 6, c16 = idx - fm * 6;
-          int erf = fm == 0 ? q * 32 + lane : (lane < 16 ? 128 + q * 16 + lane : -1);
-          if (erf >= EB) erf = -1;
-          const int sgf = erf >= 0 ? erf / E : 0, ef = erf >= 0 ? erf - sgf * E : 0;
-          const bool frow = erf >= 0 && sgf < gsz;
-          // H is symmetric: element (e, k) is read as (k, e), so that the lanes of a warp (consecutive rows e) read consecutive
-          // addresses -- one 128-byte wavefront per load instead of 32 (a row-wise float4 per lane made the refill at every
-          // sample boundary cost 20-30 k cycles: 16 % of the pass)
-          const float *Hcolp = a.H + (size_t)(b0 + (frow ? sgf : 0)) * E * Ep + ef;
-          const int c_lo = sgf * E;
-          const int kb = c16 * 32;                       // first e' column of this 32-element (16-column) group
-          uint32_t hw[16], lw[16];
-          if (!frow || kb + 32 <= c_lo || kb >= c_lo + E) {
-            // outside the row's own diagonal block (or no row): zeros, no loads, no split.  Per-lane branch: both sides end in
-            // the same two warp-wide stores below.
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { hw[j] = 0u; lw[j] = 0u; }
-          } else {
-            float vv[32];   // all 32 loads in flight before the first split
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int k = kb + j - c_lo;               // column inside the sample's own H
-              vv[j] = (k >= 0 && k < E) ? __ldg(Hcolp + (size_t)k * Ep) : 0.f;
-            }
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              uint2 hi, lo;
-              tc::split4(make_float4(vv[4 * j4], vv[4 * j4 + 1], vv[4 * j4 + 2], vv[4 * j4 + 3]), hi, lo);
-              hw[2 * j4] = hi.x; hw[2 * j4 + 1] = hi.y;
-              lw[2 * j4] = lo.x; lw[2 * j4 + 1] = lo.y;
-            }
-          }
-          const uint32_t col = (uint32_t)(fm * 192 + c16 * 16);
-          tc::tmem_st16(tmem + lane_base + col, hw);
-          tc::tmem_st16(tmem + lane_base + col + 96u, lw);
-        }
+        ta_fill_h(a.H, b0, gsz, E, Ep, EB, mtiles, role, q, lane, tmem + lane_base);
         tc::tmem_st_wait();
         if (lane == 0 && ew == 0) TA_STAMP(13, si * ntile);
       }
