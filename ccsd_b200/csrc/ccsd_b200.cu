@@ -80,6 +80,8 @@ struct ccsd_plan {
   unsigned long long *zmask = nullptr, *zmask_eval = nullptr;
   float *g_stack = nullptr, *g_att = nullptr, *g_hmc = nullptr, *g_x0 = nullptr, *g_x1 = nullptr;
   float *g_big = nullptr;       // scratch of the large-graph pipeline [B][xp.big_total]
+  uint8_t *gimg = nullptr;      // tc_gram: projection rows as operand chunks (tc_gram_prep_kernel)
+  bool gimg_fresh = false;      // built from the CURRENT weight blob (reset by ccsd_plan_init / ccsd_score_eval: the caller may refresh the blob)
   StepDev *sd_dev = nullptr;    // device-resident step state of a graph replay (ccsd_plan_run)
   bool graph_capture = false;   // do_step is being captured: kernels read the step / diff_traj slots from sd_dev
   int use_graph = 0;            // graph-only plans: replay one captured step (latency path of small batches)
@@ -476,7 +478,7 @@ const char *ccsd_version(void) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, hu, sd, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
+  size_t plan, sched, cells, edges, zmask, zmask_eval, tri, gstack, gatt, ghmc, gx0, gx1, ghcat, ximg, dg, rs, h2, hu, sd, gimg, gbig, flags, x, adj, r2, mx, madj, mr2, sx, sadj, sr2, H, P0, P1, norm, coef, total;
 };
 static WsLayout ws_layout(const ccsd_plan *p) {
   const ccsd_plan_desc_t &d = p->hp.d;
@@ -508,6 +510,11 @@ static WsLayout ws_layout(const ccsd_plan *p) {
 #endif
   w.hu = take(p->hp.p1_fold ? B * (size_t)imax(1, d.neta.n_proj_rows[1]) * 4 : 16);
   w.sd = take(sizeof(StepDev));
+#ifndef CCSD_EMU
+  w.gimg = take(p->use_tc ? tc_gram_img_bytes((int)K, p->hp.PR0) : 16);
+#else
+  w.gimg = take(16);
+#endif
   w.gbig = take(p->hp.xp.big ? B * (size_t)p->hp.xp.big_total * 4 : 16);
   w.flags = take(B * N * 4);
   w.x = take(B * N * F * 4); w.adj = take(B * N * N * 4); w.r2 = take(B * E * K * 4 + 16);
@@ -778,6 +785,7 @@ int ccsd_plan_bind(ccsd_plan_t *p, void *workspace_dev, size_t bytes, void *stre
 #endif
   p->g_hu = (float *)(ws + w.hu); p->hu_ready = false;
   p->sd_dev = (StepDev *)(ws + w.sd);
+  p->gimg = (uint8_t *)(ws + w.gimg);
   if (p->hp.xp.big) {
     // pad columns / rows of the planes are read as don't-care operands: make them finite once
     const size_t nb = (size_t)p->hp.d.B * p->hp.xp.big_total * 4;
@@ -825,6 +833,7 @@ int ccsd_plan_init(ccsd_plan_t *p, const float *flags_dev, const float *px, cons
   const ccsd_plan_desc_t &d = p->hp.d;
   if (int r = dev_copy(p->flags, flags_dev, (size_t)d.B * d.N * 4, stream)) return r;
   p->seed = seed; p->sample_offset = sample_offset;
+  p->gimg_fresh = false;
 #ifndef CCSD_EMU
   // the caller may have refreshed the weight blob since the last run: rebuild the bf16 operand image of the X network's MLP
   if (p->use_tc_xfin)
@@ -1059,7 +1068,7 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
 #ifndef CCSD_EMU
     if (p->use_tc_attn[l]) {
       PROF_BEGIN(p, "tc_attn_kernel", stream);
-      a.trace = (l == 1 && a.mode == MODE_PRED) ? p->trace : nullptr;   // debug timeline: layer 1 of the predictor's evaluation
+      a.trace = (l == 1 && a.mode == MODE_PRED && !getenv("CCSD_B200_TRACE_GRAM")) ? p->trace : nullptr;   // debug timeline: layer 1 of the predictor's evaluation
       if (tc_attn_launch(p->dP, p->hp, a, p->tattn[l], stream)) return fail(CCSD_ERR_CUDA, "tc_attn launch failed");
       PROF_END(p, stream);
     } else
@@ -1181,7 +1190,12 @@ static int launch_rank2_pre(ccsd_plan *p, const float *r2, const float *adj, con
 #ifndef CCSD_EMU
   if (p->use_tc) {
     PROF_BEGIN(p, "tc_gram_kernel", stream);
-    if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, p->use_hnorm ? p->Dg : nullptr, p->use_hnorm ? p->Rs : nullptr, stream)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
+    if (p->hp.PR0 > 0 && !p->gimg_fresh) {
+      tc_gram_prep_kernel<<<(d.K + TG_BK - 1) / TG_BK, 128, 0, (cudaStream_t)stream>>>(p->dP, p->gimg);
+      p->gimg_fresh = true;
+      p->launches++;
+    }
+    if (int r = tc_gram_launch(p->dP, p->hp, r2, p->H, p->P0, p->use_hnorm ? p->Dg : nullptr, p->use_hnorm ? p->Rs : nullptr, stream, getenv("CCSD_B200_TRACE_GRAM") ? p->trace : nullptr, p->hp.PR0 > 0 ? p->gimg : nullptr)) return fail(CCSD_ERR_CUDA, "tc_gram launch failed");
     PROF_END(p, stream);
     p->launches++;
   } else
@@ -1457,6 +1471,7 @@ int ccsd_score_eval(ccsd_plan_t *p, int which, const float *x, const float *adj,
   if (d.is_cc && which != CCSD_NET_X && !r2) return fail(CCSD_ERR_INVALID, "rank2 is required for CC plans");
   if (which == CCSD_NET_RANK2 && !d.is_cc) return fail(CCSD_ERR_INVALID, "graph plans have no rank-2 network");
   if (which < 0 || which > 2 || !(d.nets & (1 << which))) return fail(CCSD_ERR_INVALID, "that network is not part of this plan");
+  p->gimg_fresh = false;
   if (which == CCSD_NET_X || which == CCSD_NET_ADJ) {
     if (which == CCSD_NET_ADJ && d.is_cc)
       if (int r = launch_rank2_pre(p, r2, adj, flags, stream)) return r;

@@ -45,6 +45,9 @@ struct TcGramArgs {
   const float *r2;  // [B,E,K]
   float *H;         // [B,E,E]
   float *P0;        // [B,E,PR0]
+  const uint8_t *wimg;   // projection rows of the weight blob as bf16 hi / lo operand chunks: [k-block][row][chunk][hi 16 B | lo 16 B]
+                         // (tc_gram_prep_kernel, once per run), or nullptr: converted from the fp32 blob in the loop
+  long long *trace;  // debug timeline (ccsd_debug_apply_trace): CTA 0, [k-block index < 512][16] clock stamps, or nullptr
   float *Dg, *Rs;   // optional [B,E]: diag(F F^T) (before the (1 - I) mask) and the row sums F 1 (one more all-ones
                     // projection row) -- the Gram quantities the Langevin norm of an affine ScoreNetworkF needs (tc_hnorm.cuh)
 };
@@ -55,6 +58,28 @@ static inline int tc_gram_supported(int E, int K, int PR0) {
   (void)K;
   return E >= 8 && E <= 192 && PR0 <= 64 && tc_gram_ncols(E, PR0) <= 256;
 }
+
+// The projection rows (hodge q / k weights, K-major like F) are the same for every sample: converted once per run into the
+// operand chunks the producers would otherwise rebuild for every k-block of every sample -- behind a synchronous L2 load
+// that sat between the stage wait and the arrive (3 k of the 5.5 k cycles of that section, tools/gram_trace.py).
+static __global__ void tc_gram_prep_kernel(const DevPlan *__restrict__ P, uint8_t *__restrict__ img) {
+  const ccsd_plan_desc_t &d = P->d;
+  const int PR0 = P->PR0, Kw = P->Kp, kb = blockIdx.x;
+  const float *Wp = P->W + d.neta.proj_w;
+  for (int t = threadIdx.x; t < PR0 * 8; t += blockDim.x) {
+    const int rw = t >> 3, c = t & 7, k = kb * TG_BK + c * 8;
+    float y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) y[q] = (k + q < Kw) ? __ldg(Wp + (size_t)rw * Kw + k + q) : 0.f;
+    uint4 hi, lo;
+    tc::split8(y, hi, lo);
+    uint4 *dst = reinterpret_cast<uint4 *>(img + ((size_t)(kb * PR0 + rw) * 8 + c) * 32);
+    dst[0] = hi; dst[1] = lo;
+  }
+}
+static inline size_t tc_gram_img_bytes(int K, int PR0) { return (size_t)((K + TG_BK - 1) / TG_BK) * (size_t)(PR0 > 0 ? PR0 : 1) * 256; }
+
+#define TG_STAMP(slot_, i_) do { if (a.trace && blockIdx.x == 0 && (i_) < 512) a.trace[(size_t)(i_) * 16 + (slot_)] = clock64(); } while (0)
 
 template <bool GROUPED>   // GROUPED = false: one sample per work unit (G = 1 folds away at compile time)
 __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const DevPlan *__restrict__ P, TcGramArgs a) {
@@ -127,48 +152,85 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
     while (kb >= nkb && vb < NV) { kb -= nkb; vb += (int)gridDim.x; }
     int s = grp % TG_STAGES;
     uint32_t ph = (uint32_t)(grp / TG_STAGES) & 1;
-    for (; vb < NV;) {
-      const float *Fb = a.r2 + (size_t)vb * EG * K;
-      const int rows_valid = ((B - vb * G < G) ? B - vb * G : G) * E;   // the last unit may hold fewer samples
-      const int k = kb * TG_BK + c * 8;
-      const bool fast = vec && (kb * TG_BK + TG_BK <= K);
+    int gi = grp;   // k-block index of this CTA (debug timeline)
+    // Software pipeline over the group's k-blocks, in two halves of NT / 2 rows: while one half of the CURRENT k-block is split
+    // and stored, the same half of the NEXT k-block is already being loaded into the registers it frees.  (The first version
+    // issued a k-block's loads, waited for them, converted, and only then issued the next ones: 6.3 k cycles per k-block and
+    // group against 1.9 k of MMA time per k-block -- tools/gram_trace.py.)
+    constexpr int NH = NT / 2;
+    auto load_half = [&](float (&xh)[NH][8], int vb_, int kb_, int h) {
+      const float *Fb = a.r2 + (size_t)vb_ * EG * K;
+      const int rows_valid = ((B - vb_ * G < G) ? B - vb_ * G : G) * E;   // the last unit may hold fewer samples
+      const int k = kb_ * TG_BK + c * 8;
+      const bool fast = vec && (kb_ * TG_BK + TG_BK <= K);
       const float *src = Fb + (size_t)r0 * K + k;
-      float x[NT][8];
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
+      for (int j3 = 0; j3 < NH; ++j3) {
+        const int j = h * NH + j3;
         if (r0 + TG_RSTEP * j < rows_valid) {
           const float *sj = src + (size_t)(TG_RSTEP * j) * K;
           if (fast) {
             const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sj));
             const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sj + 4));
-            x[j][0] = v0.x; x[j][1] = v0.y; x[j][2] = v0.z; x[j][3] = v0.w;
-            x[j][4] = v1.x; x[j][5] = v1.y; x[j][6] = v1.z; x[j][7] = v1.w;
+            xh[j3][0] = v0.x; xh[j3][1] = v0.y; xh[j3][2] = v0.z; xh[j3][3] = v0.w;
+            xh[j3][4] = v1.x; xh[j3][5] = v1.y; xh[j3][6] = v1.z; xh[j3][7] = v1.w;
           } else if (vec2) {   // even K (QM9_CC: 466): rows are 8-byte aligned -- four 8-byte loads instead of eight scalar ones
 #pragma unroll
             for (int q = 0; q < 8; q += 2) {
               float2 v2 = make_float2(0.f, 0.f);
               if (k + q < K) v2 = __ldg(reinterpret_cast<const float2 *>(sj + q));   // (K even, k + q even: the pair is whole)
-              x[j][q] = v2.x; x[j][q + 1] = v2.y;
+              xh[j3][q] = v2.x; xh[j3][q + 1] = v2.y;
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) x[j][q] = (k + q < K) ? __ldg(sj + q) : 0.f;
+            for (int q = 0; q < 8; ++q) xh[j3][q] = (k + q < K) ? __ldg(sj + q) : 0.f;
           }
         }
       }
-      tc::mbar_wait(empty0 + 8 * s, ph ^ 1);
-      uint8_t *st = gen_base + (size_t)s * TG_STAGE;
+    };
+    auto store_half = [&](const float (&xh)[NH][8], uint8_t *st, int rows_valid, int h) {
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
+      for (int j3 = 0; j3 < NH; ++j3) {
+        const int j = h * NH + j3;
         if (r0 + TG_RSTEP * j < rows_valid) {
           uint4 hi, lo;
-          tc::split8(x[j], hi, lo);
+          tc::split8(xh[j3], hi, lo);
           *reinterpret_cast<uint4 *>(st + off0 + j * (TG_RSTEP * 128u)) = hi;
           *reinterpret_cast<uint4 *>(st + TG_HALF + off0 + j * (TG_RSTEP * 128u)) = lo;
         }
       }
-      // projection rows of the weight blob (zero padded to Kw, L1/L2 resident)
-      for (int rw = r0; rw < PR0; rw += TG_RSTEP) {
+    };
+    float xa[NH][8], xb[NH][8];
+    if (vb < NV) { load_half(xa, vb, kb, 0); load_half(xb, vb, kb, 1); }
+    for (; vb < NV; gi += 2) {
+      if (tg == 0) TG_STAMP(grp * 4 + 0, gi);
+      const int rows_valid = ((B - vb * G < G) ? B - vb * G : G) * E;
+      const int k = kb * TG_BK + c * 8;
+      int vbn = vb, kbn = kb + 2;
+      while (kbn >= nkb && vbn < NV) { kbn -= nkb; vbn += (int)gridDim.x; }
+      if (tg == 0) TG_STAMP(grp * 4 + 1, gi);
+      tc::mbar_wait(empty0 + 8 * s, ph ^ 1);
+      if (tg == 0) TG_STAMP(grp * 4 + 2, gi);
+      uint8_t *st = gen_base + (size_t)s * TG_STAGE;
+      // projection rows: asynchronous copies of the prepared operand chunks (no registers, no wait until the arrive) ...
+      const bool img_row = a.wimg != nullptr && r0 < PR0;
+      if (img_row) {
+        const int row = wp0 + r0;
+        const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+        const uint8_t *src = a.wimg + ((size_t)(kb * PR0 + r0) * 8 + c) * 32;
+        const uint32_t sdst = base + (uint32_t)s * TG_STAGE + off;
+        tc::cp_async16(sdst, src, 16u);
+        tc::cp_async16(sdst + TG_HALF, src + 16, 16u);
+      }
+      store_half(xa, st, rows_valid, 0);
+      if (tg == 0 && grp == 0) TG_STAMP(4, gi);
+      if (vbn < NV) load_half(xa, vbn, kbn, 0);
+      store_half(xb, st, rows_valid, 1);
+      if (tg == 0 && grp == 0) TG_STAMP(5, gi);
+      if (vbn < NV) load_half(xb, vbn, kbn, 1);
+      if (tg == 0 && grp == 0) TG_STAMP(6, gi);
+      // ... or, without the image (and for rows past the first sweep), converted from the fp32 blob (zero padded to Kw)
+      for (int rw = a.wimg ? r0 + TG_RSTEP : r0; rw < PR0; rw += TG_RSTEP) {
         const float *sw = Wp + (size_t)rw * Kw + k;
         float y[8];
         if (k + 8 <= Kw) {
@@ -195,10 +257,13 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
         *reinterpret_cast<uint4 *>(st + off) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4 *>(st + TG_HALF + off) = make_uint4(0u, 0u, 0u, 0u);
       }
+      if (tg == 0 && grp == 0) TG_STAMP(7, gi);
+      tc::cp_async_commit();
+      tc::cp_async_wait<0>();
       tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       tc::mbar_arrive(full0 + 8 * s);
-      kb += 2;
-      while (kb >= nkb && vb < NV) { kb -= nkb; vb += (int)gridDim.x; }
+      if (tg == 0) TG_STAMP(grp * 4 + 3, gi);
+      vb = vbn; kb = kbn;
       s += 2;
       if (s >= TG_STAGES) { s -= TG_STAGES; ph ^= 1u; }
     }
@@ -217,8 +282,10 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % TG_STAGES;
         const uint32_t ph = (it / TG_STAGES) & 1;
+        if (lane == 0) TG_STAMP(8, it);
         tc::mbar_wait(full0 + 8 * s, ph);
         tc::tc_fence_after_sync();
+        if (lane == 0) TG_STAMP(9, it);
         if (tc::elect_one()) {
           const uint32_t sb = base + (uint32_t)s * TG_STAGE;
 #pragma unroll
@@ -248,6 +315,7 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
           if (kb == nkb - 1) tc::umma_commit(tfull + 8 * buf);   // accumulators complete
         }
         __syncwarp();
+        if (lane == 0) TG_STAMP(10, it);
       }
     }
   } else {
@@ -260,6 +328,7 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
       const uint32_t buf = dbuf ? (tile & 1u) : 0u, use = dbuf ? (tile >> 1) : tile;
       tc::mbar_wait(tfull + 8 * buf, use & 1u);
       tc::tc_fence_after_sync();
+      if (threadIdx.x == TG_PROD) TG_STAMP(12, tile * nkb);
       for (int mi = 0; mi < mtiles; ++mi) {
         const int mt = mtiles - 1 - mi;   // the second tile first: its single accumulator is what the next unit's MMAs wait for
         const int row = mt * 128 + q * 32 + lane;
@@ -323,6 +392,7 @@ __global__ void __launch_bounds__(tg_threads(GROUPED), 1) tc_gram_kernel(const D
         tc::tc_fence_before_sync();
         if (mt == 1) tc::mbar_arrive(tempty1);
         else tc::mbar_arrive(tempty0 + 8 * buf);
+        if (threadIdx.x == TG_PROD) TG_STAMP(13 + mt, tile * nkb);
       }
     }
   }
@@ -338,9 +408,9 @@ static inline int tc_gram_prepare() {
 }
 
 static inline int tc_gram_launch(const DevPlan *dP, const DevPlan &hp, const float *r2, float *H, float *P0, float *Dg, float *Rs,
-                                 void *stream) {
+                                 void *stream, long long *trace = nullptr, const uint8_t *wimg = nullptr) {
   TcGramArgs a;
-  a.r2 = r2; a.H = H; a.P0 = P0; a.Dg = Dg; a.Rs = Rs;
+  a.r2 = r2; a.H = H; a.P0 = P0; a.Dg = Dg; a.Rs = Rs; a.trace = trace; a.wimg = wimg;
   const int nv = (hp.d.B + hp.gram_group - 1) / hp.gram_group;
   int grid = nv < 148 ? nv : 148;
   if (hp.gram_group > 1) tc_gram_kernel<true><<<grid, tg_threads(true), TG_SMEM, (cudaStream_t)stream>>>(dP, a);
