@@ -26,20 +26,22 @@ constexpr uint32_t TF_COL_A2 = 128;   // TMEM columns: D1 / D2 at [0, 128), the 
 
 struct TcFinLayout {   // byte offsets from the 1024-aligned base; *_half = distance hi -> lo
   int K1p, Hp;         // fd rounded up to 16, hidden width rounded up to 16
+  int KC;              // channels of the X tile staged per layer-1 pass (K1p, or K1p / 2 when only that fits two CTAs per SM)
   uint32_t w1, w1_half, w2, w2_half, a1, a1_half, a2, a2_half, vec, bars, total;
 };
 
 static inline int tc_afinal_supported(const ccsd_neta_t &A, int fd_have) {
   return A.fin.nl == 3 && A.fin.dout == 1 && fd_have >= 1 && fd_have <= 64 && A.fin.dhid >= 8 && A.fin.dhid <= 128;
 }
-static inline TcFinLayout tc_afinal_layout(int fd, int dhid) {
+static inline TcFinLayout tc_afinal_layout(int fd, int dhid, int kc = 0) {
   TcFinLayout L;
   L.K1p = (fd + 15) & ~15;
   L.Hp = (dhid + 15) & ~15;
+  L.KC = kc > 0 ? kc : L.K1p;
   uint32_t o = 0;
   L.w1_half = 2u * L.K1p * 128u; L.w1 = o; o += 2 * L.w1_half;     // [2 n-blocks][K1p k-rows][128 B]
   L.w2_half = 2u * L.Hp * 128u;  L.w2 = o; o += 2 * L.w2_half;     // [2 n-blocks][Hp k-rows][128 B]
-  L.a1_half = 2u * L.K1p * 128u; L.a1 = o; o += 2 * L.a1_half;     // [2 m-blocks][K1p k-rows][128 B]
+  L.a1_half = 2u * L.KC * 128u;  L.a1 = o; o += 2 * L.a1_half;     // [2 m-blocks][KC k-rows][128 B]
   L.a2_half = 0; L.a2 = 0;                                        // (the layer-2 A operand lives in tensor memory)
   L.vec = o; o += 3 * 128 * 4 + 256 + 512 * TF_NP_MAX;                 // b1, b2, w3, reduction scratch, [parts][128] partial dot products
   L.bars = o; o += 64;
@@ -143,13 +145,20 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
       rows = N - bj0;
     }
     const float *gs = ta.gs_base + (size_t)b * ta.gs_stride;
-    // ---- X tile -> A1 (MN-major): chunk = 8 consecutive rows of one channel ----
+    // ---- X tile -> A1 (MN-major): chunk = 8 consecutive rows of one channel.  Large networks (grid: 64 channels) stage the
+    //      tile in two passes of KC channels, so that the kernel fits two CTAs per SM ----
+    const int KC = TL.KC, npass = K1p / KC;
+   for (int pass = 0; pass < npass; ++pass) {
     if (warp < TF_MMAW) {
-      for (int t = threadIdx.x; t < fd * 16; t += TF_EPI) {
-        const int k = t >> 4, mc = t & 15, m0 = mc << 3;
+      const int kend = npass == 1 ? fd : KC;   // (two passes: the pad channels of the last pass are written as zeros)
+      for (int t = threadIdx.x; t < kend * 16; t += TF_EPI) {
+        const int kl = t >> 4, k = pass * KC + kl, mc = t & 15, m0 = mc << 3;
         const float *src = gs + (size_t)k * ldp + t0 + m0;
         float x[8];
-        if (gpt > 1) {   // rows [g rpg, g rpg + NT) of the tile = the pairs of graph b + g
+        if (k >= fd) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = 0.f;
+        } else if (gpt > 1) {   // rows [g rpg, g rpg + NT) of the tile = the pairs of graph b + g
           const int g = m0 / rpg, tg = m0 - g * rpg;
           const bool ok = g < gpt && b + g < d.B;
           const float *sg = gs + (size_t)g * ta.gs_stride + (size_t)k * ldp + tg;
@@ -169,8 +178,8 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
         }
         uint4 hi, lo;
         tc::split8(x, hi, lo);
-        const uint32_t off = TL.a1 + (uint32_t)(m0 >> 6) * ((uint32_t)K1p * 128u) + (uint32_t)k * 128u +
-                             (uint32_t)((((m0 & 63) >> 3) ^ (k & 7)) << 4);
+        const uint32_t off = TL.a1 + (uint32_t)(m0 >> 6) * ((uint32_t)KC * 128u) + (uint32_t)kl * 128u +
+                             (uint32_t)((((m0 & 63) >> 3) ^ (kl & 7)) << 4);
         *reinterpret_cast<uint4 *>(gen + off) = hi;
         *reinterpret_cast<uint4 *>(gen + off + TL.a1_half) = lo;
       }
@@ -182,13 +191,14 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
     if (warp == TF_MMAW) {
       tc::tc_fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t blk = (uint32_t)K1p * 128u;
-        for (int k4 = 0; k4 < K1p / 16; ++k4) {
-          const uint64_t a_hi = tc::make_smem_desc(base + TL.a1 + (uint32_t)k4 * 2048u, blk, 1024);
-          const uint64_t a_lo = tc::make_smem_desc(base + TL.a1 + TL.a1_half + (uint32_t)k4 * 2048u, blk, 1024);
-          const uint64_t b_hi = tc::make_smem_desc(base + TL.w1 + (uint32_t)k4 * 2048u, blk, 1024);
-          const uint64_t b_lo = tc::make_smem_desc(base + TL.w1 + TL.w1_half + (uint32_t)k4 * 2048u, blk, 1024);
-          tc::umma_bf16(tmem_u, a_hi, b_hi, id1, k4 != 0);
+        const uint32_t blk = (uint32_t)K1p * 128u, blka = (uint32_t)KC * 128u;
+        for (int k4 = 0; k4 < KC / 16; ++k4) {
+          const uint32_t kw = (uint32_t)(pass * (KC / 16) + k4);   // k step inside the resident W1
+          const uint64_t a_hi = tc::make_smem_desc(base + TL.a1 + (uint32_t)k4 * 2048u, blka, 1024);
+          const uint64_t a_lo = tc::make_smem_desc(base + TL.a1 + TL.a1_half + (uint32_t)k4 * 2048u, blka, 1024);
+          const uint64_t b_hi = tc::make_smem_desc(base + TL.w1 + kw * 2048u, blk, 1024);
+          const uint64_t b_lo = tc::make_smem_desc(base + TL.w1 + TL.w1_half + kw * 2048u, blk, 1024);
+          tc::umma_bf16(tmem_u, a_hi, b_hi, id1, (pass | k4) != 0);
           tc::umma_bf16(tmem_u, a_hi, b_lo, id1, 1);
           tc::umma_bf16(tmem_u, a_lo, b_hi, id1, 1);
         }
@@ -196,9 +206,10 @@ __global__ void __launch_bounds__(128 * TF_NP + 32, TF_NP == 2 ? 2 : 1) tc_afina
       }
       __syncwarp();
     }
-    tc::mbar_wait(bar, phase);
+    tc::mbar_wait(bar, phase);   // (between passes: the MMAs have read A1 before it is overwritten)
     phase ^= 1u;
     tc::tc_fence_after_sync();
+   }
     // ---- epilogue 1: elu(D1 + b1) -> the layer-2 A operand in this row's TMEM lane (element k in 32-bit column k / 2) ----
     const int lq = warp & 3, cpart = warp >> 2;               // TMEM lane quarter, column part of this warp
     const int nck = Hp >> 4, cper = (nck + TF_NP - 1) / TF_NP;   // 16-column chunks, chunks per part
@@ -356,6 +367,10 @@ static inline int tc_afinal_launch(const DevPlan *dP, const DevPlan &hp, const X
   TcFinArgs ta;
   ta.x = a;
   ta.L = tc_afinal_layout(fd, hp.d.neta.fin.dhid);
+  if (ta.L.total > 113u * 1024u && (ta.L.K1p / 2) % 16 == 0) {   // two channel passes if that is what fits two CTAs per SM
+    const TcFinLayout L2 = tc_afinal_layout(fd, hp.d.neta.fin.dhid, ta.L.K1p / 2);
+    if (L2.total <= 113u * 1024u) ta.L = L2;
+  }
   ta.fd = fd;
   ta.ntg = (hp.xp.NT + 127) / 128;
   ta.gs_base = a.g_stack; ta.gs_stride = hp.xp.g_stack; ta.ldp = hp.xp.ldp; ta.NT = hp.xp.NT;
