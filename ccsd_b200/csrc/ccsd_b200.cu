@@ -1417,7 +1417,7 @@ int ccsd_plan_run(ccsd_plan_t *p, int step_begin, int step_end, void *stream) {
   // are a sixth of the step.  One step is captured as a CUDA graph whose kernels read the step index (schedule row, Philox
   // draw id) and the diff_traj slots from device memory (StepDev); step_advance_kernel closes the step; the graph is replayed
   // for every step but the first (eager: it also sets every kernel's shared-memory attribute) and the last (which returns means).
-  if (p->use_graph && !p->profiling && step_end - step_begin >= 8) {
+  if (p->use_graph && !p->profiling && step_end - step_begin >= 32) {   // (capture + instantiation cost ~1-15 ms: long runs only)
     const ccsd_plan_desc_t &d = p->hp.d;
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = do_step(p, s, nullptr, nullptr, nullptr, 0, stream)) return r;

@@ -306,10 +306,10 @@ def test_graph_replay_equals_eager(name, sampler, pred, B, monkeypatch):
         assert int(eng.lib.ccsd_plan_info(eng.handle, 19)) == (0 if no_graph else 1)
         eng.enable_traj()
         eng.init(flags, seed=11)
-        eng.run(0, 14)
+        eng.run(0, 36)
         torch.cuda.synchronize()
-        outs.append([t.clone() for t in eng.read(False)] + [t.clone() for t in eng.read(True)] + [t[:14].clone() for t in eng.traj]
+        outs.append([t.clone() for t in eng.read(False)] + [t.clone() for t in eng.read(True)] + [t[:36].clone() for t in eng.traj]
                     + [eng.launches])
-    assert outs[0][-1] == outs[1][-1] + 12, (outs[0][-1], outs[1][-1])   # one step_advance per replayed step
+    assert outs[0][-1] == outs[1][-1] + 34, (outs[0][-1], outs[1][-1])   # one step_advance per replayed step
     for a, b in zip(outs[0][:-1], outs[1][:-1]):
         assert torch.equal(a, b)
