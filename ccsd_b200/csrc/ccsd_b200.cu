@@ -1335,7 +1335,7 @@ static int do_step(ccsd_plan *p, int step, const float *nx, const float *nadj, c
     if (int r = join_side()) return r;
     CoefArgs c; c.norm_part = p->norm_part; c.coef = p->coef; c.step = step; c.s4 = s4; c.obj_mask = obj_mask; c.sd = nz.sd;
     PROF_BEGIN(p, "coef_kernel", stream);
-    CCSD_LAUNCH(coef_kernel, dim3(1, 1, 1), 256, 64 * 4, stream, p->dP, c);
+    CCSD_LAUNCH(coef_kernel, dim3(d.is_cc ? 3 : 2, 1, 1), d.B >= 2048 ? 1024 : 256, 64 * 4, stream, p->dP, c);
     PROF_END(p, stream);
     p->launches++;
     return dev_check("coef_kernel");
