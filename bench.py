@@ -552,8 +552,10 @@ def main():
             dom = max((k_ for k_ in R2 if k_ in prof_summary), key=lambda k_: prof_summary[k_][0])
             avg_ms = prof_summary[dom][0] / prof_summary[dom][1]
             fl, by = work.get(dom, (0, 0))
-            if dom == "tc_apply_kernel" and sampler == "PC" and corr == "Langevin":
-                by = (work["tc_apply_kernel:norm"][1] + 2 * work["tc_apply_kernel"][1]) / 3.0   # NORM, CORR, PRED passes
+            if dom == "tc_apply_kernel" and sampler == "PC" and corr == "Langevin" and prof_summary[dom][1] >= 3 * args.profile_steps:
+                # NORM (read only), CORR, PRED passes.  With the Langevin norms from Gram quantities (tc_hnorm) there is no NORM
+                # pass: both launches of a step read and write the state
+                by = (work["tc_apply_kernel:norm"][1] + 2 * work["tc_apply_kernel"][1]) / 3.0
             if dom.startswith("tc_r2big_kernel"):   # real GEMMs: tensor roofline (algorithmic 2mnk; bf16x3 executes three MMAs per product)
                 ach = fl / (avg_ms * 1e-3) / 1e12
                 roofline = {"unit_of_work": "rank2_passes", "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
