@@ -515,20 +515,9 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
     if (warp < TT_MMAW) {
       const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);   // T overwrote AX in the accumulator columns
       float *gh = a.g_hmc + (size_t)(b0 + (live ? gl : 0)) * L.g_hmc + (size_t)c * L.mc_o1_max * N4 + ni;
-      for (int ck0 = part; ck0 < (N1p >> 4); ck0 += 2 * TT_NP) {
-        // two 16-column chunks per round trip to tensor memory
-        uint32_t raw2[2][16];
-        const bool two = ck0 + TT_NP < (N1p >> 4);
-        tc::tmem_ld16_nowait(trow + (uint32_t)(ck0 * 16), raw2[0]);
-        if (two) tc::tmem_ld16_nowait(trow + (uint32_t)((ck0 + TT_NP) * 16), raw2[1]);
-        tc::tmem_ld_wait();
-#pragma unroll
-       for (int cc = 0; cc < 2; ++cc) {
-        if (cc == 1 && !two) break;
-        const int ck = ck0 + cc * TT_NP;
+      for (int ck = part; ck < (N1p >> 4); ck += TT_NP) {
         float v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(raw2[cc][q]);
+        tc::tmem_ld16(trow + (uint32_t)(ck * 16), v);
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
           const int n0 = ck * 16 + h8 * 8;
@@ -546,7 +535,6 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tc_attn_kernel(const DevPlan *_
             }
           }
         }
-       }
       }
     }
     tc::tc_fence_before_sync();
