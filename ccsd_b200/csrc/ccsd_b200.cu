@@ -503,7 +503,7 @@ static WsLayout ws_layout(const ccsd_plan *p) {
   w.dg = take(p->use_hnorm ? B * E * 4 : 16);
   w.rs = take(p->use_hnorm ? B * E * 4 : 16);
   w.h2 = take((p->use_hnorm && p->use_tc_big) ? B * E * (size_t)a4((int)E) * 4 + 64 : 16);
-  w.ghcat = take((p->use_tc_xfin || gmh) ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
+  w.ghcat = take((p->use_tc_xfin || gmh || ((d.nets & 1) && !p->hp.xp.big)) ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16);
   w.ximg = take(p->use_tc_xfin ? (size_t)p->txf.img_bytes : 16);
 #else
   w.ghcat = take(gmh ? B * (size_t)d.netx.fdim * p->hp.xp.N4 * 4 : 16); w.ximg = take(16); w.dg = take(16); w.rs = take(16); w.h2 = take(16);
@@ -992,8 +992,13 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
     a.which &= ~1;
     if (!a.which) return dev_check("ScoreNetworkX_GMH");
   }
+  bool split_x = false;   // the fp32 final MLP of ScoreNetworkX as a second x_net_kernel launch on a forked stream
 #ifndef CCSD_EMU
   if (p->use_tc_xfin && (a.which & 1)) a.g_hcat = p->g_hcat;
+  // Networks the tensor-core final MLP does not cover (fdim > 128: ENZYMES_small(_CC), ego_small): x_net_kernel stops after
+  // the GCN stack and hands [x, h_1 .. h_D] over in global memory, exactly like the tensor-core path; its final MLP + epilogue
+  // (the gmh_phase == 2 entry) then runs beside the hodge branch and the attention chain instead of in front of them.
+  if (!p->use_tc_xfin && !d.netx.gmh && (a.which & 3) == 3 && p->xs[0] && !p->profiling) { a.g_hcat = p->g_hcat; split_x = true; }
 #endif
   PROF_BEGIN(p, "x_net_kernel", stream);
   CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, stream, p->dP, a);
@@ -1012,9 +1017,15 @@ static int launch_xa(ccsd_plan *p, XaArgs a, void *stream) {
       if (cudaStreamWaitEvent(p->xs[0], p->ev_x0, 0) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream fork failed");
       sx = (void *)p->xs[0];
     }
-    PROF_BEGIN(p, "tc_xfin_kernel", stream);
-    if (tc_xfin_launch(p->dP, p->hp, a, p->txf, p->g_hcat, d.netx.fdim * L.N4, p->ximg, sx)) return fail(CCSD_ERR_CUDA, "tc_xfin launch failed");
-    PROF_END(p, stream);
+    if (split_x) {
+      XaArgs a2 = a;
+      a2.which = 1; a2.gmh_phase = 2;
+      CCSD_LAUNCH(x_net_kernel, dim3(d.B, 1, 1), L.Tx, (size_t)L.x_total * 4, sx, p->dP, a2);
+    } else {
+      PROF_BEGIN(p, "tc_xfin_kernel", stream);
+      if (tc_xfin_launch(p->dP, p->hp, a, p->txf, p->g_hcat, d.netx.fdim * L.N4, p->ximg, sx)) return fail(CCSD_ERR_CUDA, "tc_xfin launch failed");
+      PROF_END(p, stream);
+    }
     p->launches++;
     if (forked) {
       if (cudaEventRecord(p->ev_xj[0], p->xs[0]) != cudaSuccess) return fail(CCSD_ERR_CUDA, "stream join failed");
