@@ -20,13 +20,13 @@ eng.run(2, 3)   # the LAST apply pass of the step (PRED) leaves its stamps
 torch.cuda.synchronize()
 t = tr.cpu().numpy()
 t0 = t[0, 0]
-names = ["ld.issue", "ld.landed", "ld.opfree", "ld.full", "mma.start", "mma.issued", "e0.wait", "e0.acc", "e0.ld", "e0.done", "e8.wait", "e8.acc", "e8.ld", "e8.done"]
+names = ["ld.issue", "ld.landed", "ld.opfree", "ld.full", "mma.start", "mma.issued", "e0.wait", "e0.acc", "e0.ld", "e0.done"]
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for gidx in list(range(0, 12)) + list(range(30, 44)) + list(range(100, 108)):
-    print(f"{gidx:4d} " + " ".join(f"{(t[gidx, i] - t0):10d}" for i in range(14)))
+    print(f"{gidx:4d} " + " ".join(f"{(t[gidx, i] - t0):10d}" for i in range(10)))
 d = np.diff(t[:250, 9])
 print("epilogue(e0) tile period: mean", d.mean(), "median", np.median(d))
-for a_, b_, nm in [(0, 1, "cp.async wait"), (1, 2, "opfree wait"), (2, 3, "convert"), (4, 5, "mma issue"), (6, 7, "e0 wait acc"), (7, 8, "e0 tmem ld"), (8, 9, "e0 compute"), (10, 11, "e8 wait acc"), (12, 13, "e8 compute")]:
+for a_, b_, nm in [(0, 1, "cp.async wait"), (1, 2, "opfree wait"), (2, 3, "convert"), (4, 5, "mma issue"), (6, 7, "e0 wait acc"), (7, 8, "e0 tmem ld"), (8, 9, "e0 compute")]:
     x = (t[2:250, b_] - t[2:250, a_])
     print(f"{nm:14s} mean {x.mean():9.0f} median {np.median(x):9.0f}")
 x = t[2:250, 0][1:] - t[2:250, 3][:-1]
@@ -38,4 +38,4 @@ for gi in range(1, min(8, 500 // nt)):
     r = gi * nt
     print(f"tile {r:4d}: prev e0.done {t[r-1, 9] - t[r-1, 9]:7d}  fill.start {t[r, 14] - t[r-1, 9]:7d}  fill.end {t[r, 15] - t[r-1, 9]:7d}  "
           f"mma.start {t[r, 4] - t[r-1, 9]:7d}  e0.acc {t[r, 7] - t[r-1, 9]:7d}  next e0.done {t[r, 9] - t[r-1, 9]:7d}"
-          f"  | rounds {t[r, 10] - t[r, 14]:6d} {t[r, 11] - t[r, 14]:6d} {t[r, 12] - t[r, 14]:6d} st_wait {t[r, 13] - t[r, 14]:6d}")
+          f"  | refill done (warp 0) {t[r, 13] - t[r, 14]:6d}")
